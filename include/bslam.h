@@ -1,0 +1,239 @@
+/* bslam.h -- C ABI of libbslam.so: the B200-native Gauss-Newton / LM inner loop
+ * behind pyslam's `Problem.solve()`.
+ *
+ * The reference (utiasSTARS/pyslam) has NO FFI of its own: its boundary is the
+ * Python `Problem` class plus three duck-typed protocols.  Each
+ * entry point below therefore cites the reference *Python* code whose work it
+ * replaces; pyslam_b200/problem.py (the drop-in `Problem`) is the only caller
+ * and binds these with ctypes (pyslam_b200/engine.py; binding stub for a
+ * reference maintainer in INTEGRATION.md).
+ *
+ * Rules of the ABI
+ *   - every function returns 0 on success, <0 on error (BSLAM_E_*); the message
+ *     is available from bslam_last_error(); nothing throws across the boundary;
+ *   - the caller owns every host buffer; the library copies during the call and
+ *     never retains a host pointer;  the library owns all device memory;
+ *   - one CUDA stream per handle; a handle is not thread-safe, distinct handles
+ *     are independent;
+ *   - all floating point data is IEEE double; indices are int32;
+ *   - matrices are row-major.  An SE(3) pose is 12 doubles [R(3x3) | t(3)]
+ *     (R first, row-major, then t); an SE(2) pose is 6 doubles [R(2x2) | t(2)].
+ *     Tangent vectors are ordered [rho; phi] and perturbations are applied on
+ *     the left, T <- exp(xi) T, as liegroups/pyslam do.
+ *
+ * Life cycle:  create -> set_* parameter tables -> add_* blocks -> finalize ->
+ *              { iterate | linearize/solve/retract | eval_cost }* -> get_* -> destroy
+ */
+#ifndef BSLAM_H_
+#define BSLAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bslam_solver bslam_solver;
+
+#if defined(__GNUC__)
+#define BSLAM_API __attribute__((visibility("default")))
+#else
+#define BSLAM_API
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+#define BSLAM_OK              0
+#define BSLAM_E_INVALID      -1   /* bad argument / call order            */
+#define BSLAM_E_CUDA         -2   /* CUDA runtime error (see last_error)  */
+#define BSLAM_E_STRUCTURE    -3   /* problem structure unsupported        */
+#define BSLAM_E_NUMERIC      -4   /* reduced system not positive definite */
+
+/* ---- pose groups --------------------------------------------------------- */
+#define BSLAM_SE2 2
+#define BSLAM_SE3 3
+
+/* ---- robust losses: pyslam/losses.py:8-214 (element-wise IRLS) -- */
+#define BSLAM_LOSS_L2     0
+#define BSLAM_LOSS_L1     1
+#define BSLAM_LOSS_CAUCHY 2
+#define BSLAM_LOSS_HUBER  3
+#define BSLAM_LOSS_TUKEY  4
+#define BSLAM_LOSS_TDIST  5
+
+/* ---- scalar slots written by bslam_iterate / read by bslam_get_scalars ---- */
+#define BSLAM_S_COST_LIN   0   /* sum rho(r) at the linearisation point (blocks with >=1 variable param) */
+#define BSLAM_S_COST_NEW   1   /* sum rho(r) over ALL blocks at x [+] dx                                 */
+#define BSLAM_S_DX_NORM2   2   /* ||dx||^2 over the whole update vector                                   */
+#define BSLAM_S_CHOL_FAIL  3   /* >0 if a non-positive pivot was met                                       */
+#define BSLAM_S_COST_EVAL  4   /* result of bslam_eval_cost                                                */
+#define BSLAM_N_SCALARS   16
+
+/* ---- timing slots (milliseconds, CUDA events on the handle's stream) ------ */
+#define BSLAM_T_LINEARIZE  0   /* zero + all linearisation kernels                  */
+#define BSLAM_T_REPROJ     1   /* the reprojection linearisation kernel alone       */
+#define BSLAM_T_SCHUR      2   /* landmark inverse + Schur complement               */
+#define BSLAM_T_CHOLESKY   3   /* dense factorisation of the reduced system         */
+#define BSLAM_T_TRSV       4   /* forward / backward substitution                   */
+#define BSLAM_T_BACKSUB    5   /* landmark back-substitution                        */
+#define BSLAM_T_RETRACT    6   /* exp / retract + ||dx||                            */
+#define BSLAM_T_COST       7   /* cost at the new point                             */
+#define BSLAM_T_TOTAL      8
+#define BSLAM_N_TIMINGS   16
+
+/* ---- life cycle ------------------------------------------------------------ */
+
+/* Library/ABI version (major*10000 + minor*100 + patch). */
+BSLAM_API int bslam_version(void);
+
+/* Create a solver bound to CUDA device `device`.  Replaces `Problem.__init__`
+ * (pyslam/problem.py:43-69).  Fails with BSLAM_E_CUDA when no usable GPU exists:
+ * there is no CPU fallback. */
+BSLAM_API int bslam_create(bslam_solver** out, int device);
+BSLAM_API void bslam_destroy(bslam_solver* s);
+
+/* Message of the most recent error on `s` (or of a failed bslam_create when s
+ * is NULL).  The pointer stays valid until the next call on the same handle. */
+BSLAM_API const char* bslam_last_error(const bslam_solver* s);
+
+/* ---- parameter tables: `Problem.initialize_params` +
+ *      `set_parameters_constant/variable` (pyslam/problem.py:83-108) ----------
+ * Each call (re)defines one table: n entries, values, and one byte per entry
+ * that is non-zero for parameters held constant (may be NULL = all variable).
+ * After bslam_finalize, calling a setter again with the same n updates VALUES
+ * only (is_const must be NULL or unchanged). */
+BSLAM_API int bslam_set_poses_se3(bslam_solver* s, int n, const double* Rt /* n x 12 */, const uint8_t* is_const);
+BSLAM_API int bslam_set_poses_se2(bslam_solver* s, int n, const double* Rt /* n x 6  */, const uint8_t* is_const);
+BSLAM_API int bslam_set_points(bslam_solver* s, int n, const double* xyz /* n x 3 */, const uint8_t* is_const);
+/* Generic vector parameters (anything that is `+=`-updated, problem.py:405-409):
+ * n vectors, dims[i] entries each, values concatenated. */
+BSLAM_API int bslam_set_vectors(bslam_solver* s, int n, const int32_t* dims, const double* values, const uint8_t* is_const);
+
+BSLAM_API int bslam_get_poses_se3(bslam_solver* s, double* Rt /* n x 12 */);
+BSLAM_API int bslam_get_poses_se2(bslam_solver* s, double* Rt /* n x 6  */);
+BSLAM_API int bslam_get_points(bslam_solver* s, double* xyz /* n x 3 */);
+BSLAM_API int bslam_get_vectors(bslam_solver* s, double* values);
+
+/* ---- residual blocks: `Problem.add_residual_block` (pyslam/problem.py:72-81) --
+ * `stiffness` holds ONE matrix shared by the n blocks when per_block == 0, or
+ * n matrices when per_block != 0. */
+
+/* ReprojectionResidual + StereoCamera.project (pyslam/residuals/
+ * reprojection_residual.py:13-37, pyslam/sensors/stereo_camera.py:100-134).
+ * pose_idx -> SE3 table, pt_idx -> point table, obs = (u,v,d),
+ * stiffness 3x3, intr = (cu,cv,fu,fv,b). */
+BSLAM_API int bslam_add_reprojection_blocks(bslam_solver* s, int n,
+                                  const int32_t* pose_idx, const int32_t* pt_idx,
+                                  const double* obs /* n x 3 */,
+                                  const double* stiffness, int per_block,
+                                  const double intr[5], int loss_kind, double loss_k);
+
+/* PoseResidual (pyslam/residuals/pose_residual.py:4-27): r = S log(T T_obs^-1),
+ * J = S.  group = BSLAM_SE2 | BSLAM_SE3; T_obs n x (6|12); stiffness dof x dof. */
+BSLAM_API int bslam_add_pose_blocks(bslam_solver* s, int group, int n, const int32_t* pose_idx,
+                          const double* T_obs, const double* stiffness, int per_block,
+                          int loss_kind, double loss_k);
+
+/* PoseToPoseResidual (pyslam/residuals/pose_to_pose_residual.py:4-32):
+ * r = S log(T2 T1^-1 T21_obs^-1), J1 = -S Ad(T2 T1^-1), J2 = S. */
+BSLAM_API int bslam_add_pose_to_pose_blocks(bslam_solver* s, int group, int n,
+                                  const int32_t* idx1, const int32_t* idx2,
+                                  const double* T21_obs, const double* stiffness, int per_block,
+                                  int loss_kind, double loss_k);
+
+/* Host-evaluated blocks (user-defined Python residuals, the plug-in surface of
+ * pyslam/problem.py:338-360).  Declares the STRUCTURE once: n_blocks blocks,
+ * block b has rows[b] residual rows and uses parameters
+ * param_kind/param_index[param_ptr[b] .. param_ptr[b+1]) where kind is
+ * 0 = SE3 table, 1 = SE2 table, 2 = point table, 3 = vector table.
+ * Values are uploaded every iteration with bslam_upload_dense_values. */
+BSLAM_API int bslam_set_dense_blocks(bslam_solver* s, int n_blocks, const int32_t* rows,
+                           const int32_t* param_ptr, const int32_t* param_kind,
+                           const int32_t* param_index);
+/* e: concatenated sqrt(w)*r of all blocks; J: for every block, for every one of
+ * its parameters in order, the row-major (rows x dof) matrix sqrt(w)*J (zeros
+ * for constant parameters); cost = sum rho(r) over these blocks (added to
+ * BSLAM_S_COST_LIN).  Must be called before each bslam_linearize/iterate when
+ * dense blocks exist. */
+BSLAM_API int bslam_upload_dense_values(bslam_solver* s, const double* e, size_t n_e,
+                              const double* J, size_t n_J, double cost);
+
+BSLAM_API int bslam_clear_blocks(bslam_solver* s);
+
+/* Lower the problem: orders observations by landmark, decides which points are
+ * eliminated by the Schur complement, lays out the reduced system, allocates
+ * device memory.  Replaces `_get_update_partition_dict` (problem.py:252-277)
+ * for the internal ordering; see bslam_get_layout for the mapping back. */
+BSLAM_API int bslam_finalize(bslam_solver* s);
+
+/* Internal update-vector layout: for every table entry the offset of its
+ * tangent slice in the internal dx (or -1 if constant).  The host maps this to
+ * the reference ordering (param_dict insertion order, problem.py:252-277).
+ * Any pointer may be NULL.  *dim = total length D of dx, *n_reduced = size of
+ * the reduced (camera) system. */
+BSLAM_API int bslam_get_layout(bslam_solver* s, int32_t* se3_off, int32_t* se2_off, int32_t* pt_off,
+                     int32_t* vec_off, int32_t* dim, int32_t* n_reduced);
+
+/* ---- the hot path -------------------------------------------------------------- */
+
+/* `Problem.eval_cost` (problem.py:110-128): sum of rho(r) over ALL built-in
+ * blocks at the current parameters (dense blocks are the host's to add). */
+BSLAM_API int bslam_eval_cost(bslam_solver* s, double* cost);
+
+/* One Gauss-Newton / LM iteration, entirely on the device, one host sync:
+ *   linearize  (problem.py:279-360)  -> block-sparse J^T W J, -J^T W r, cost
+ *   solve      (problem.py:186)      -> Schur complement + dense Cholesky
+ *   retract    (problem.py:155-156, 400-409) -> x <- x [+] dx
+ *   cost       (problem.py:189-190, 362-398 net effect) if eval_new_cost
+ * lambda = 0 is the reference's Gauss-Newton; lambda > 0 adds lambda*diag(H)
+ * (extension, not in the reference).  Any out pointer may be NULL. */
+BSLAM_API int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost,
+                  double* cost_lin, double* cost_new, double* dx_norm);
+
+/* The same iteration in separately callable phases (parity tests, multi-GPU). */
+BSLAM_API int bslam_linearize(bslam_solver* s, double* cost_lin);          /* no Schur yet          */
+BSLAM_API int bslam_reduce(bslam_solver* s, double lambda);                /* damping + Schur        */
+BSLAM_API int bslam_solve_reduced(bslam_solver* s);                        /* Cholesky + substitution + landmark back-substitution */
+BSLAM_API int bslam_retract(bslam_solver* s, int eval_new_cost);           /* x <- x [+] dx (+ cost) */
+BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS */);   /* syncs */
+
+/* Multi-GPU plumbing: device address/length (in doubles) of the contiguous
+ * [S (n_pad x n_pad) | rhs (n_pad) | scalars (BSLAM_N_SCALARS)] buffer that the
+ * host all-reduces (NCCL, sum) between bslam_reduce and bslam_solve_reduced,
+ * and of the scalar tail alone (second, 16-double all-reduce after retract). */
+BSLAM_API int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles,
+                         void** scalars_dev_ptr, int32_t* n_pad);
+/* Shard rank of this handle when landmarks are partitioned over several GPUs
+ * (rank 0 alone counts the replicated reduced part in ||dx||^2). */
+BSLAM_API int bslam_set_shard(bslam_solver* s, int rank);
+/* The handle's cudaStream_t, so the host can order collectives and record
+ * events on it. */
+BSLAM_API void* bslam_stream(bslam_solver* s);
+
+/* Best-parameter snapshot used by `allow_nondecreasing_steps` (problem.py:163-175). */
+BSLAM_API int bslam_snapshot(bslam_solver* s);
+BSLAM_API int bslam_restore(bslam_solver* s);
+
+/* ---- inspection (parity tests, covariance) ---------------------------------------- */
+
+/* Update vector of the last solve, internal ordering, length D. */
+BSLAM_API int bslam_get_update(bslam_solver* s, double* dx);
+/* Dense D x D normal matrix H = J^T W J and right-hand side b = -J^T W r of the
+ * last bslam_linearize, internal ordering (small problems only: D <= 20000). */
+BSLAM_API int bslam_get_normal_equations(bslam_solver* s, double* H, double* b);
+/* Reduced system after bslam_reduce: S (n_reduced x n_reduced, symmetric, full) and rhs. */
+BSLAM_API int bslam_get_reduced_system(bslam_solver* s, double* S, double* rhs);
+/* Dense covariance (H^-1, D x D, internal ordering) at the current parameters:
+ * `Problem.compute_covariance` (problem.py:196-203). */
+BSLAM_API int bslam_covariance(bslam_solver* s, double* cov);
+
+/* Phase timings of the last bslam_iterate with timing enabled (ms). */
+BSLAM_API int bslam_enable_timing(bslam_solver* s, int on);
+BSLAM_API int bslam_get_timings(bslam_solver* s, double* ms /* BSLAM_N_TIMINGS */);
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+BSLAM_API int64_t bslam_launch_count(const bslam_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSLAM_H_ */

@@ -1,0 +1,53 @@
+// retract.cuh -- apply the update vector on the manifold.
+// Replaces `_perturb_by_key` + liegroups `perturb` (pyslam/problem.py:155-156,
+// 400-409): poses T <- exp(xi) T (left perturbation, xi = [rho; phi]),
+// vector-space parameters p <- p + dp; and np.linalg.norm(dx) (problem.py:160).
+#pragma once
+#include "common.cuh"
+#include "lie.cuh"
+
+namespace bs {
+
+template <int G>
+__global__ void __launch_bounds__(128) retract_poses_kernel(int n, double* __restrict__ poses,
+                                                            const int* __restrict__ off,
+                                                            const double* __restrict__ dx) {
+  using Gr = Group<G>;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = off[i];
+  if (o < 0) return;
+  double xi[Gr::kDof];
+#pragma unroll
+  for (int k = 0; k < Gr::kDof; ++k) xi[k] = dx[o + k];
+  double* p = poses + (size_t)Gr::kStore * i;
+  Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
+}
+
+// entry e of a flat parameter array moves by dx[off[e]] (off < 0: constant)
+__global__ void __launch_bounds__(256) retract_flat_kernel(int n, double* __restrict__ vals,
+                                                           const int* __restrict__ off,
+                                                           const double* __restrict__ dx) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int o = off[e];
+  if (o >= 0) vals[e] += dx[o];
+}
+
+// landmarks: the first n_lm points, update slice starts at dx + n_red
+__global__ void __launch_bounds__(256) retract_landmarks_kernel(int n3, double* __restrict__ pts,
+                                                                const double* __restrict__ dxl) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n3) pts[e] += dxl[e];
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(int n, const double* __restrict__ v, double* __restrict__ dst) {
+  __shared__ double sred[8];
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += v[i] * v[i];
+  block_sum_to(s, dst, sred);
+}
+
+__global__ void add_scalar_kernel(double* dst, double v) { *dst += v; }
+
+}  // namespace bs

@@ -1,0 +1,997 @@
+// solver.cu -- host side of libbslam.so: the device-resident problem, the
+// lowering (ordering / Schur partition / layout), the per-iteration kernel
+// schedule and the C ABI of include/bslam.h.  No CPU fallback exists anywhere
+// in this file: every arithmetic step of the iteration is a kernel launch.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/bslam.h"
+#include "cholesky.cuh"
+#include "common.cuh"
+#include "dense_blocks.cuh"
+#include "posegraph.cuh"
+#include "reproj.cuh"
+#include "retract.cuh"
+#include "schur.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count == n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+struct EdgeBatch {
+  int group = 3;
+  bool binary = false;
+  int n = 0;
+  int per_block = 0;
+  bs::Loss loss{0, 0.0};
+  std::vector<int> i1, i2;
+  std::vector<double> Tobs, stiff;
+  DevBuf<int> d_i1, d_i2;
+  DevBuf<double> d_Tobs, d_stiff;
+};
+
+}  // namespace
+
+struct bslam_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool finalized = false;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[12] = {};
+  double timings[BSLAM_N_TIMINGS] = {};
+  int shard_rank = 0;
+
+  // ---- parameter tables (user order) ----
+  int n_se3 = 0, n_se2 = 0, n_pt = 0, n_vec = 0, n_vec_entries = 0;
+  std::vector<uint8_t> se3_const, se2_const, pt_const, vec_const;
+  std::vector<int> vec_dims, vec_start;
+  std::vector<double> h_se3, h_se2, h_pts, h_vec;   // staging until finalize
+
+  // ---- blocks (host staging) ----
+  std::vector<int> ob_pose, ob_pt, ob_grp;
+  std::vector<double> ob_uvd;
+  std::vector<bs::ReprojGroup> groups;
+  std::vector<EdgeBatch*> edges;
+  // dense (host-evaluated) blocks
+  int dn_blocks = 0;
+  std::vector<int> dn_rows, dn_pptr, dn_pkind, dn_pindex;
+  std::vector<int> dn_row_ptr, dn_col_ptr, dn_col_index;
+  std::vector<long long> dn_j_ptr;
+  bool dn_uploaded = false;
+  double dn_cost = 0.0;
+
+  // ---- layout ----
+  int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0;
+  std::vector<int> pt_perm, pt_iperm;               // user -> internal, internal -> user
+  std::vector<int> se3_off, se2_off, vec_off, pt_off_user, vec_entry_off, pt_red_entry_off;
+
+  // ---- device ----
+  DevBuf<double> d_se3, d_se2, d_pts, d_vec, d_stage;
+  DevBuf<double> b_se3, b_se2, b_pts, b_vec;        // snapshot
+  DevBuf<int> d_se3_off, d_se2_off, d_vec_entry_off, d_ptred_entry_off, d_pt_perm;
+  DevBuf<double> d_ou, d_ov, d_od;
+  DevBuf<int> d_opose, d_opt, d_ogrp, d_lm_start;
+  DevBuf<bs::ReprojGroup> d_groups;
+  DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_y, d_Linv;
+  DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
+  DevBuf<long long> d_dn_j_ptr;
+  DevBuf<double> d_dn_J, d_dn_e;
+  double* h_scalars = nullptr;   // pinned
+
+  double* S() { return d_red.p; }
+  double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
+  double* scalars() { return d_red.p + (size_t)n_pad * n_pad + n_pad; }
+  size_t red_len() const { return (size_t)n_pad * n_pad + n_pad + BSLAM_N_SCALARS; }
+
+  ~bslam_solver() {
+    for (auto* e : edges) delete e;
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (h_scalars) cudaFreeHost(h_scalars);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int fail(bslam_solver* s, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (s) s->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(s, BSLAM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+#define NEED(cond, ...)                                        \
+  do {                                                         \
+    if (!(cond)) return fail(s, BSLAM_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define LAUNCH(s, kernel, grid, block, smem, ...)                 \
+  do {                                                            \
+    kernel<<<grid, block, smem, (s)->stream>>>(__VA_ARGS__);      \
+    (s)->launches++;                                              \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+cudaError_t upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
+  cudaError_t e = d.alloc(h.size());
+  if (e != cudaSuccess || h.empty()) return e;
+  return cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+bool valid_loss(int kind, double k) {
+  if (kind < 0 || kind > BSLAM_LOSS_TDIST) return false;
+  if (kind >= BSLAM_LOSS_CAUCHY && !(k > 0.0)) return false;
+  return true;
+}
+
+// scatter/gather rows between user order and internal (permuted) point order
+__global__ void permute_rows_kernel(int n, int width, const double* __restrict__ src, double* __restrict__ dst,
+                                    const int* __restrict__ perm, int scatter) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * width) return;
+  const int r = e / width, c = e - r * width;
+  if (scatter) dst[(size_t)perm[r] * width + c] = src[e];
+  else dst[e] = src[(size_t)perm[r] * width + c];
+}
+
+void record(bslam_solver* s, int i) {
+  if (s->timing) cudaEventRecord(s->ev[i], s->stream);
+}
+
+bs::ReprojArgs reproj_args(bslam_solver* s) {
+  bs::ReprojArgs a;
+  a.n_obs = s->n_obs;
+  a.n_lm = s->n_lm;
+  a.obs_u = s->d_ou.p; a.obs_v = s->d_ov.p; a.obs_d = s->d_od.p;
+  a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p;
+  a.obs_grp = s->groups.size() > 1 ? s->d_ogrp.p : nullptr;
+  a.groups = s->d_groups.p;
+  a.poses = s->d_se3.p;
+  a.pose_off = s->d_se3_off.p;
+  a.pts = s->d_pts.p;
+  a.W = s->d_W.p; a.Vg = s->d_Vg.p;
+  a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
+  return a;
+}
+
+bs::EdgeArgs edge_args(bslam_solver* s, EdgeBatch* b) {
+  bs::EdgeArgs a;
+  a.n = b->n;
+  a.i1 = b->d_i1.p;
+  a.i2 = b->binary ? b->d_i2.p : nullptr;
+  a.Tobs = b->d_Tobs.p;
+  a.stiff = b->d_stiff.p;
+  a.stiff_per_block = b->per_block;
+  a.loss = b->loss;
+  a.poses = b->group == 3 ? s->d_se3.p : s->d_se2.p;
+  a.pose_off = b->group == 3 ? s->d_se3_off.p : s->d_se2_off.p;
+  a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
+  return a;
+}
+
+template <bool kCostOnly>
+void launch_edges(bslam_solver* s, EdgeBatch* b, int slot) {
+  if (b->n == 0) return;
+  const bs::EdgeArgs a = edge_args(s, b);
+  const int grid = cdiv(b->n, 128);
+  if (b->group == 3) {
+    if (b->binary) LAUNCH(s, (bs::edge_kernel<3, true, kCostOnly>), grid, 128, 0, a, slot);
+    else LAUNCH(s, (bs::edge_kernel<3, false, kCostOnly>), grid, 128, 0, a, slot);
+  } else {
+    if (b->binary) LAUNCH(s, (bs::edge_kernel<2, true, kCostOnly>), grid, 128, 0, a, slot);
+    else LAUNCH(s, (bs::edge_kernel<2, false, kCostOnly>), grid, 128, 0, a, slot);
+  }
+}
+
+// sum rho over all built-in blocks at the current parameters -> scalars[slot]
+void launch_cost(bslam_solver* s, int slot) {
+  if (s->n_obs > 0) {
+    const int grid = std::min(cdiv(s->n_obs, bs::kReprojThreads), 148 * 8);
+    LAUNCH(s, bs::reproj_cost_kernel, grid, bs::kReprojThreads, 0, reproj_args(s), slot);
+  }
+  for (auto* b : s->edges) launch_edges<true>(s, b, slot);
+}
+
+int do_linearize(bslam_solver* s) {
+  NEED(s->finalized, "bslam_finalize has not been called");
+  NEED(s->dn_blocks == 0 || s->dn_uploaded, "dense blocks declared but bslam_upload_dense_values not called");
+  record(s, 0);
+  CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), s->stream));
+  if (s->n_lm > 0) CU(cudaMemsetAsync(s->d_Vg.p, 0, s->d_Vg.n * sizeof(double), s->stream));
+  if (s->n_pad > s->n_red)
+    LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pad - s->n_red, 64), 64, 0, s->S(), s->n_pad, s->n_red, s->n_pad);
+  record(s, 1);
+  if (s->n_obs > 0)
+    LAUNCH(s, bs::reproj_linearize_kernel, cdiv(s->n_obs, bs::kReprojThreads), bs::kReprojThreads, 0, reproj_args(s));
+  record(s, 2);
+  for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
+  if (s->dn_blocks > 0) {
+    bs::DenseArgs a;
+    a.n_blocks = s->dn_blocks;
+    a.row_ptr = s->d_dn_row_ptr.p; a.col_ptr = s->d_dn_col_ptr.p; a.j_ptr = s->d_dn_j_ptr.p;
+    a.col_index = s->d_dn_col_index.p; a.J = s->d_dn_J.p; a.e = s->d_dn_e.p;
+    a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
+    int max_rows = 1;
+    for (int r : s->dn_rows) max_rows = std::max(max_rows, r);
+    dim3 grid(s->dn_blocks, cdiv(max_rows, bs::kDenseRowChunk));
+    LAUNCH(s, bs::dense_blocks_kernel, grid, 256, 0, a);
+    // the host computed sum rho(r) of its own blocks
+    LAUNCH(s, bs::add_scalar_kernel, 1, 1, 0, s->scalars() + BSLAM_S_COST_LIN, s->dn_cost);
+    s->dn_uploaded = false;
+  }
+  record(s, 3);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+int do_reduce(bslam_solver* s, double lambda) {
+  if (lambda > 0.0 && s->n_red > 0)
+    LAUNCH(s, bs::damp_diag_kernel, cdiv(s->n_red, 128), 128, 0, s->S(), s->n_pad, s->n_red, lambda);
+  if (s->n_lm > 0) {
+    LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm, 256), 256, 0, s->n_lm, s->d_Vg.p, lambda, s->d_Vinv.p);
+    bs::SchurArgs a;
+    a.n_obs = s->n_obs; a.n_lm = s->n_lm;
+    a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.lm_start = s->d_lm_start.p;
+    a.pose_off = s->d_se3_off.p;
+    a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
+    a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
+    LAUNCH(s, bs::schur_kernel, cdiv(s->n_obs, 128), 128, 0, a);
+  }
+  record(s, 4);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+constexpr size_t kPanelSmem = 3 * bs::kNB * bs::kLd * sizeof(double);
+constexpr size_t kUpdateSmem = 2 * bs::kNB * bs::kLd * sizeof(double);
+
+int do_solve_reduced(bslam_solver* s) {
+  const int nb = s->nblk, ld = s->n_pad;
+  for (int k = 0; k < nb; ++k) {
+    LAUNCH(s, bs::chol_panel_kernel, nb - k, bs::kCholThreads, kPanelSmem, s->S(), ld, k, s->d_Linv.p, s->scalars());
+    const int t = nb - k - 1;
+    if (t > 0) LAUNCH(s, bs::chol_update_kernel, dim3(t, t), bs::kCholThreads, kUpdateSmem, s->S(), ld, k);
+  }
+  record(s, 5);
+  for (int k = 0; k < nb; ++k)
+    LAUNCH(s, bs::trsv_fwd_kernel, nb - k, bs::kNB, 0, s->S(), ld, k, s->d_Linv.p, s->rhs(), s->d_y.p);
+  for (int k = nb - 1; k >= 0; --k)
+    LAUNCH(s, bs::trsv_bwd_kernel, k + 1, bs::kNB, 0, s->S(), ld, k, s->d_Linv.p, s->d_y.p, s->d_dx.p);
+  record(s, 6);
+  if (s->n_lm > 0) {
+    bs::BacksubArgs a;
+    a.n_lm = s->n_lm; a.lm_off = s->n_pad;
+    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p; a.dx = s->d_dx.p;
+    LAUNCH(s, bs::backsub_kernel, cdiv(s->n_lm, 128), 128, 0, a);
+  }
+  record(s, 7);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+int do_retract(bslam_solver* s, int eval_new_cost) {
+  const double* dx = s->d_dx.p;
+  if (s->n_se3 > 0) LAUNCH(s, bs::retract_poses_kernel<3>, cdiv(s->n_se3, 128), 128, 0, s->n_se3, s->d_se3.p, s->d_se3_off.p, dx);
+  if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
+  if (s->n_vec_entries > 0)
+    LAUNCH(s, bs::retract_flat_kernel, cdiv(s->n_vec_entries, 256), 256, 0, s->n_vec_entries, s->d_vec.p, s->d_vec_entry_off.p, dx);
+  if (s->n_lm > 0)
+    LAUNCH(s, bs::retract_landmarks_kernel, cdiv(3 * s->n_lm, 256), 256, 0, 3 * s->n_lm, s->d_pts.p, dx + s->n_pad);
+  if (s->n_pt > s->n_lm) {
+    const int n3 = 3 * (s->n_pt - s->n_lm);
+    LAUNCH(s, bs::retract_flat_kernel, cdiv(n3, 256), 256, 0, n3, s->d_pts.p + 3 * (size_t)s->n_lm, s->d_ptred_entry_off.p, dx);
+  }
+  // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
+  if (s->n_red > 0 && s->shard_rank == 0)
+    LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(s->n_red, 256), 148), 256, 0, s->n_red, dx, s->scalars() + BSLAM_S_DX_NORM2);
+  if (s->n_lm > 0)
+    LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(3 * s->n_lm, 256), 148 * 4), 256, 0, 3 * s->n_lm, dx + s->n_pad,
+           s->scalars() + BSLAM_S_DX_NORM2);
+  record(s, 8);
+  if (eval_new_cost) launch_cost(s, BSLAM_S_COST_NEW);
+  record(s, 9);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+int fetch_scalars(bslam_solver* s) {
+  CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->timing) {
+    auto el = [&](int a, int b) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s->ev[a], s->ev[b]);
+      return (double)ms;
+    };
+    s->timings[BSLAM_T_LINEARIZE] = el(0, 3);
+    s->timings[BSLAM_T_REPROJ] = el(1, 2);
+    s->timings[BSLAM_T_SCHUR] = el(3, 4);
+    s->timings[BSLAM_T_CHOLESKY] = el(4, 5);
+    s->timings[BSLAM_T_TRSV] = el(5, 6);
+    s->timings[BSLAM_T_BACKSUB] = el(6, 7);
+    s->timings[BSLAM_T_RETRACT] = el(7, 8);
+    s->timings[BSLAM_T_COST] = el(8, 9);
+    s->timings[BSLAM_T_TOTAL] = el(0, 9);
+  }
+  return BSLAM_OK;
+}
+
+}  // namespace
+
+// =============================================================== C ABI ====
+
+extern "C" {
+
+int bslam_version(void) { return 100; }
+
+const char* bslam_last_error(const bslam_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int bslam_create(bslam_solver** out, int device) {
+  bslam_solver* s = nullptr;
+  if (!out) return fail(s, BSLAM_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(s, BSLAM_E_CUDA, "no CUDA device available (%s); libbslam has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= count) return fail(s, BSLAM_E_INVALID, "device %d out of range [0,%d)", device, count);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(s, BSLAM_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  bslam_solver* h = new bslam_solver();
+  h->device = device;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_scalars, BSLAM_N_SCALARS * sizeof(double))) != cudaSuccess) {
+    fail(s, BSLAM_E_CUDA, "stream/pinned allocation: %s", cudaGetErrorString(e));
+    delete h;
+    return BSLAM_E_CUDA;
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  cudaFuncSetAttribute(bs::chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
+  cudaFuncSetAttribute(bs::chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
+  *out = h;
+  return BSLAM_OK;
+}
+
+void bslam_destroy(bslam_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  delete s;
+}
+
+// ---------------------------------------------------------------- parameters
+
+static int set_table(bslam_solver* s, const char* what, int n, int width, const double* vals, const uint8_t* is_const,
+                     int& n_field, std::vector<uint8_t>& cflags, std::vector<double>& host, DevBuf<double>& dev) {
+  NEED(s, "NULL solver");
+  NEED(n >= 0 && (n == 0 || vals), "%s: bad arguments", what);
+  CU(cudaSetDevice(s->device));
+  if (s->finalized) {
+    NEED(n == n_field, "%s: table size changed after finalize (%d -> %d); call bslam_clear_blocks first", what, n_field, n);
+    if (is_const)
+      for (int i = 0; i < n; ++i)
+        NEED((is_const[i] != 0) == (cflags[i] != 0), "%s: constant flags changed after finalize", what);
+    if (n > 0) CU(cudaMemcpyAsync(dev.p, vals, (size_t)n * width * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return BSLAM_OK;
+  }
+  n_field = n;
+  cflags.assign(n, 0);
+  if (is_const)
+    for (int i = 0; i < n; ++i) cflags[i] = is_const[i] ? 1 : 0;
+  host.assign(vals, vals + (size_t)n * width);
+  return BSLAM_OK;
+}
+
+int bslam_set_poses_se3(bslam_solver* s, int n, const double* Rt, const uint8_t* is_const) {
+  NEED(s, "NULL solver");
+  return set_table(s, "bslam_set_poses_se3", n, 12, Rt, is_const, s->n_se3, s->se3_const, s->h_se3, s->d_se3);
+}
+
+int bslam_set_poses_se2(bslam_solver* s, int n, const double* Rt, const uint8_t* is_const) {
+  NEED(s, "NULL solver");
+  return set_table(s, "bslam_set_poses_se2", n, 6, Rt, is_const, s->n_se2, s->se2_const, s->h_se2, s->d_se2);
+}
+
+int bslam_set_points(bslam_solver* s, int n, const double* xyz, const uint8_t* is_const) {
+  NEED(s, "NULL solver");
+  if (!s->finalized) return set_table(s, "bslam_set_points", n, 3, xyz, is_const, s->n_pt, s->pt_const, s->h_pts, s->d_pts);
+  NEED(n == s->n_pt, "bslam_set_points: table size changed after finalize");
+  if (is_const)
+    for (int i = 0; i < n; ++i)
+      NEED((is_const[i] != 0) == (s->pt_const[i] != 0), "bslam_set_points: constant flags changed after finalize");
+  if (n == 0) return BSLAM_OK;
+  CU(cudaSetDevice(s->device));
+  // user order -> internal (landmarks-first) order, permuted on the device
+  CU(cudaMemcpyAsync(s->d_stage.p, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  LAUNCH(s, permute_rows_kernel, cdiv(3LL * n, 256), 256, 0, n, 3, s->d_stage.p, s->d_pts.p, s->d_pt_perm.p, 1);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+int bslam_set_vectors(bslam_solver* s, int n, const int32_t* dims, const double* values, const uint8_t* is_const) {
+  NEED(s, "NULL solver");
+  NEED(n >= 0 && (n == 0 || (dims && values)), "bslam_set_vectors: bad arguments");
+  long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    NEED(dims[i] >= 0, "bslam_set_vectors: negative dimension");
+    total += dims[i];
+  }
+  if (s->finalized) {
+    NEED(n == s->n_vec, "bslam_set_vectors: table size changed after finalize");
+    for (int i = 0; i < n; ++i) NEED(dims[i] == s->vec_dims[i], "bslam_set_vectors: dimensions changed after finalize");
+    CU(cudaSetDevice(s->device));
+    if (total > 0) CU(cudaMemcpyAsync(s->d_vec.p, values, total * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return BSLAM_OK;
+  }
+  s->n_vec = n;
+  s->vec_dims.assign(dims, dims + n);
+  s->vec_start.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) s->vec_start[i + 1] = s->vec_start[i] + dims[i];
+  s->n_vec_entries = (int)total;
+  s->vec_const.assign(n, 0);
+  if (is_const)
+    for (int i = 0; i < n; ++i) s->vec_const[i] = is_const[i] ? 1 : 0;
+  s->h_vec.assign(values, values + total);
+  return BSLAM_OK;
+}
+
+static int get_table(bslam_solver* s, const char* what, int n, int width, double* out, DevBuf<double>& dev) {
+  NEED(s && s->finalized, "%s: solver not finalized", what);
+  if (n == 0) return BSLAM_OK;
+  NEED(out, "%s: NULL output", what);
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(out, dev.p, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return BSLAM_OK;
+}
+
+int bslam_get_poses_se3(bslam_solver* s, double* Rt) {
+  NEED(s, "NULL solver");
+  return get_table(s, "bslam_get_poses_se3", s->n_se3, 12, Rt, s->d_se3);
+}
+int bslam_get_poses_se2(bslam_solver* s, double* Rt) {
+  NEED(s, "NULL solver");
+  return get_table(s, "bslam_get_poses_se2", s->n_se2, 6, Rt, s->d_se2);
+}
+int bslam_get_points(bslam_solver* s, double* xyz) {
+  NEED(s && s->finalized, "bslam_get_points: solver not finalized");
+  if (s->n_pt == 0) return BSLAM_OK;
+  NEED(xyz, "bslam_get_points: NULL output");
+  CU(cudaSetDevice(s->device));
+  LAUNCH(s, permute_rows_kernel, cdiv(3LL * s->n_pt, 256), 256, 0, s->n_pt, 3, s->d_pts.p, s->d_stage.p, s->d_pt_perm.p, 0);
+  CU(cudaMemcpyAsync(xyz, s->d_stage.p, (size_t)s->n_pt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return BSLAM_OK;
+}
+int bslam_get_vectors(bslam_solver* s, double* values) {
+  NEED(s, "NULL solver");
+  return get_table(s, "bslam_get_vectors", s->n_vec_entries, 1, values, s->d_vec);
+}
+
+// -------------------------------------------------------------------- blocks
+
+int bslam_add_reprojection_blocks(bslam_solver* s, int n, const int32_t* pose_idx, const int32_t* pt_idx,
+                                  const double* obs, const double* stiffness, int per_block, const double intr[5],
+                                  int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_add_reprojection_blocks after finalize; call bslam_clear_blocks first");
+  NEED(n >= 0 && (n == 0 || (pose_idx && pt_idx && obs && stiffness && intr)), "bslam_add_reprojection_blocks: bad arguments");
+  NEED(valid_loss(loss_kind, loss_k), "bslam_add_reprojection_blocks: invalid loss (kind %d, k %g)", loss_kind, loss_k);
+  if (n == 0) return BSLAM_OK;
+  for (int i = 0; i < n; ++i) {
+    NEED(pose_idx[i] >= 0 && pose_idx[i] < s->n_se3, "reprojection block %d: pose index %d outside the SE3 table (%d)", i,
+         pose_idx[i], s->n_se3);
+    NEED(pt_idx[i] >= 0 && pt_idx[i] < s->n_pt, "reprojection block %d: point index %d outside the point table (%d)", i,
+         pt_idx[i], s->n_pt);
+  }
+  auto make_group = [&](const double* S9) {
+    bs::ReprojGroup g;
+    g.cu = intr[0]; g.cv = intr[1]; g.fu = intr[2]; g.fv = intr[3]; g.b = intr[4];
+    for (int k = 0; k < 9; ++k) g.S[k] = S9[k];
+    g.loss.kind = loss_kind;
+    g.loss.k = loss_k;
+    return g;
+  };
+  auto find_group = [&](const bs::ReprojGroup& g) {
+    // newest groups first: consecutive blocks nearly always share their constants
+    for (int k = (int)s->groups.size() - 1; k >= 0 && k >= (int)s->groups.size() - 8; --k)
+      if (std::memcmp(&s->groups[k], &g, sizeof g) == 0) return k;
+    s->groups.push_back(g);
+    return (int)s->groups.size() - 1;
+  };
+  int gshared = per_block ? -1 : find_group(make_group(stiffness));
+  s->ob_pose.insert(s->ob_pose.end(), pose_idx, pose_idx + n);
+  s->ob_pt.insert(s->ob_pt.end(), pt_idx, pt_idx + n);
+  s->ob_uvd.insert(s->ob_uvd.end(), obs, obs + 3 * (size_t)n);
+  for (int i = 0; i < n; ++i) s->ob_grp.push_back(per_block ? find_group(make_group(stiffness + 9 * (size_t)i)) : gshared);
+  return BSLAM_OK;
+}
+
+static int add_edges(bslam_solver* s, const char* what, int group, bool binary, int n, const int32_t* i1, const int32_t* i2,
+                     const double* Tobs, const double* stiffness, int per_block, int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "%s after finalize; call bslam_clear_blocks first", what);
+  NEED(group == BSLAM_SE2 || group == BSLAM_SE3, "%s: group must be BSLAM_SE2 or BSLAM_SE3", what);
+  NEED(n >= 0 && (n == 0 || (i1 && (!binary || i2) && Tobs && stiffness)), "%s: bad arguments", what);
+  NEED(valid_loss(loss_kind, loss_k), "%s: invalid loss (kind %d, k %g)", what, loss_kind, loss_k);
+  if (n == 0) return BSLAM_OK;
+  const int table = group == 3 ? s->n_se3 : s->n_se2;
+  for (int i = 0; i < n; ++i) {
+    NEED(i1[i] >= 0 && i1[i] < table, "%s %d: pose index %d outside the table (%d)", what, i, i1[i], table);
+    if (binary) NEED(i2[i] >= 0 && i2[i] < table, "%s %d: pose index %d outside the table (%d)", what, i, i2[i], table);
+  }
+  const int store = group == 3 ? 12 : 6, dof = group == 3 ? 6 : 3;
+  EdgeBatch* b = new EdgeBatch();
+  b->group = group; b->binary = binary; b->n = n; b->per_block = per_block ? 1 : 0;
+  b->loss.kind = loss_kind; b->loss.k = loss_k;
+  b->i1.assign(i1, i1 + n);
+  if (binary) b->i2.assign(i2, i2 + n);
+  b->Tobs.assign(Tobs, Tobs + (size_t)n * store);
+  b->stiff.assign(stiffness, stiffness + (size_t)(per_block ? n : 1) * dof * dof);
+  s->edges.push_back(b);
+  return BSLAM_OK;
+}
+
+int bslam_add_pose_blocks(bslam_solver* s, int group, int n, const int32_t* pose_idx, const double* T_obs,
+                          const double* stiffness, int per_block, int loss_kind, double loss_k) {
+  return add_edges(s, "bslam_add_pose_blocks", group, false, n, pose_idx, nullptr, T_obs, stiffness, per_block, loss_kind, loss_k);
+}
+
+int bslam_add_pose_to_pose_blocks(bslam_solver* s, int group, int n, const int32_t* idx1, const int32_t* idx2,
+                                  const double* T21_obs, const double* stiffness, int per_block, int loss_kind, double loss_k) {
+  return add_edges(s, "bslam_add_pose_to_pose_blocks", group, true, n, idx1, idx2, T21_obs, stiffness, per_block, loss_kind, loss_k);
+}
+
+int bslam_set_dense_blocks(bslam_solver* s, int n_blocks, const int32_t* rows, const int32_t* param_ptr,
+                           const int32_t* param_kind, const int32_t* param_index) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_set_dense_blocks after finalize; call bslam_clear_blocks first");
+  NEED(n_blocks >= 0 && (n_blocks == 0 || (rows && param_ptr && param_kind && param_index)), "bslam_set_dense_blocks: bad arguments");
+  s->dn_blocks = n_blocks;
+  s->dn_rows.assign(rows, rows + n_blocks);
+  s->dn_pptr.assign(param_ptr, param_ptr + n_blocks + (n_blocks ? 1 : 0));
+  const int np = n_blocks ? param_ptr[n_blocks] : 0;
+  s->dn_pkind.assign(param_kind, param_kind + np);
+  s->dn_pindex.assign(param_index, param_index + np);
+  const int tables[4] = {s->n_se3, s->n_se2, s->n_pt, s->n_vec};
+  for (int i = 0; i < np; ++i) {
+    NEED(param_kind[i] >= 0 && param_kind[i] <= 3, "dense block parameter %d: kind %d invalid", i, param_kind[i]);
+    NEED(param_index[i] >= 0 && param_index[i] < tables[param_kind[i]], "dense block parameter %d: index %d outside table", i, param_index[i]);
+  }
+  for (int b = 0; b < n_blocks; ++b) NEED(rows[b] > 0, "dense block %d has %d rows", b, rows[b]);
+  return BSLAM_OK;
+}
+
+int bslam_upload_dense_values(bslam_solver* s, const double* e, size_t n_e, const double* J, size_t n_J, double cost) {
+  NEED(s && s->finalized, "bslam_upload_dense_values: solver not finalized");
+  NEED(s->dn_blocks > 0, "bslam_upload_dense_values: no dense blocks declared");
+  NEED(n_e == (size_t)s->dn_row_ptr.back() && n_J == (size_t)s->dn_j_ptr.back(),
+       "bslam_upload_dense_values: expected %d residual rows and %lld Jacobian entries, got %zu and %zu",
+       s->dn_row_ptr.back(), s->dn_j_ptr.back(), n_e, n_J);
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(s->d_dn_e.p, e, n_e * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaMemcpyAsync(s->d_dn_J.p, J, n_J * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));   // the caller may reuse its buffers immediately
+  s->dn_cost = cost;
+  s->dn_uploaded = true;
+  return BSLAM_OK;
+}
+
+int bslam_clear_blocks(bslam_solver* s) {
+  NEED(s, "NULL solver");
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  s->ob_pose.clear(); s->ob_pt.clear(); s->ob_grp.clear(); s->ob_uvd.clear(); s->groups.clear();
+  for (auto* e : s->edges) delete e;
+  s->edges.clear();
+  s->dn_blocks = 0;
+  s->dn_rows.clear(); s->dn_pptr.clear(); s->dn_pkind.clear(); s->dn_pindex.clear();
+  s->finalized = false;
+  return BSLAM_OK;
+}
+
+// ------------------------------------------------------------------ lowering
+
+int bslam_finalize(bslam_solver* s) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "already finalized");
+  CU(cudaSetDevice(s->device));
+  const int N = (int)s->ob_pose.size();
+  s->n_obs = N;
+
+  // ---- which points are eliminated by the Schur complement ----
+  std::vector<uint8_t> by_reproj(s->n_pt, 0), by_dense(s->n_pt, 0);
+  for (int i = 0; i < N; ++i) by_reproj[s->ob_pt[i]] = 1;
+  for (size_t i = 0; i < s->dn_pkind.size(); ++i)
+    if (s->dn_pkind[i] == 2) by_dense[s->dn_pindex[i]] = 1;
+  s->pt_perm.assign(s->n_pt, -1);
+  s->pt_iperm.clear();
+  s->pt_iperm.reserve(s->n_pt);
+  for (int p = 0; p < s->n_pt; ++p) {
+    if (s->pt_const[p]) continue;
+    if (by_reproj[p] && by_dense[p])
+      return fail(s, BSLAM_E_STRUCTURE,
+                  "point %d is used by both reprojection blocks and host-evaluated blocks; this mix is not supported yet", p);
+    if (!by_reproj[p] && !by_dense[p])
+      return fail(s, BSLAM_E_STRUCTURE, "variable point %d is not referenced by any residual block (singular system)", p);
+    if (by_reproj[p]) {
+      s->pt_perm[p] = (int)s->pt_iperm.size();
+      s->pt_iperm.push_back(p);
+    }
+  }
+  s->n_lm = (int)s->pt_iperm.size();
+  for (int p = 0; p < s->n_pt; ++p)
+    if (s->pt_perm[p] < 0) {
+      s->pt_perm[p] = (int)s->pt_iperm.size();
+      s->pt_iperm.push_back(p);
+    }
+
+  // ---- reduced-system layout: SE3 poses | SE2 poses | vectors | non-eliminated points ----
+  int off = 0;
+  s->se3_off.assign(s->n_se3, -1);
+  for (int i = 0; i < s->n_se3; ++i)
+    if (!s->se3_const[i]) { s->se3_off[i] = off; off += 6; }
+  s->se2_off.assign(s->n_se2, -1);
+  for (int i = 0; i < s->n_se2; ++i)
+    if (!s->se2_const[i]) { s->se2_off[i] = off; off += 3; }
+  s->vec_off.assign(s->n_vec, -1);
+  s->vec_entry_off.assign(s->n_vec_entries, -1);
+  for (int i = 0; i < s->n_vec; ++i)
+    if (!s->vec_const[i]) {
+      s->vec_off[i] = off;
+      for (int k = 0; k < s->vec_dims[i]; ++k) s->vec_entry_off[s->vec_start[i] + k] = off + k;
+      off += s->vec_dims[i];
+    }
+  s->pt_off_user.assign(s->n_pt, -1);
+  s->pt_red_entry_off.assign(3 * (size_t)(s->n_pt - s->n_lm), -1);
+  for (int q = s->n_lm; q < s->n_pt; ++q) {
+    const int p = s->pt_iperm[q];
+    if (s->pt_const[p]) continue;
+    s->pt_off_user[p] = off;
+    for (int k = 0; k < 3; ++k) s->pt_red_entry_off[3 * (size_t)(q - s->n_lm) + k] = off + k;
+    off += 3;
+  }
+  s->n_red = off;
+  s->n_pad = std::max(1, cdiv(off, bs::kNB)) * bs::kNB;
+  s->nblk = s->n_pad / bs::kNB;
+  for (int q = 0; q < s->n_lm; ++q) s->pt_off_user[s->pt_iperm[q]] = s->n_red + 3 * q;
+  s->dim = s->n_red + 3 * s->n_lm;
+
+  // ---- observations sorted by internal point index (stable) ----
+  std::vector<int> order(N);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return s->pt_perm[s->ob_pt[a]] < s->pt_perm[s->ob_pt[b]]; });
+  std::vector<double> ou(N), ov(N), od(N);
+  std::vector<int> opose(N), opt(N), ogrp(N), lm_start(s->n_lm + 1, 0);
+  for (int k = 0; k < N; ++k) {
+    const int i = order[k];
+    ou[k] = s->ob_uvd[3 * (size_t)i]; ov[k] = s->ob_uvd[3 * (size_t)i + 1]; od[k] = s->ob_uvd[3 * (size_t)i + 2];
+    opose[k] = s->ob_pose[i];
+    opt[k] = s->pt_perm[s->ob_pt[i]];
+    ogrp[k] = s->ob_grp[i];
+    if (opt[k] < s->n_lm) lm_start[opt[k] + 1]++;
+  }
+  for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
+
+  // ---- dense-block structure ----
+  s->dn_row_ptr.assign(1, 0); s->dn_col_ptr.assign(1, 0); s->dn_j_ptr.assign(1, 0);
+  s->dn_col_index.clear();
+  for (int b = 0; b < s->dn_blocks; ++b) {
+    int ncols = 0;
+    for (int k = s->dn_pptr[b]; k < s->dn_pptr[b + 1]; ++k) {
+      const int kind = s->dn_pkind[k], idx = s->dn_pindex[k];
+      int dof, o;
+      if (kind == 0) { dof = 6; o = s->se3_off[idx]; }
+      else if (kind == 1) { dof = 3; o = s->se2_off[idx]; }
+      else if (kind == 2) { dof = 3; o = s->pt_off_user[idx]; }
+      else { dof = s->vec_dims[idx]; o = s->vec_off[idx]; }
+      for (int c = 0; c < dof; ++c) s->dn_col_index.push_back(o < 0 ? -1 : o + c);
+      ncols += dof;
+    }
+    s->dn_row_ptr.push_back(s->dn_row_ptr.back() + s->dn_rows[b]);
+    s->dn_col_ptr.push_back(s->dn_col_ptr.back() + ncols);
+    s->dn_j_ptr.push_back(s->dn_j_ptr.back() + (long long)s->dn_rows[b] * ncols);
+  }
+
+  // ---- device memory ----
+  cudaStream_t st = s->stream;
+  std::vector<double> pts_int(3 * (size_t)s->n_pt);
+  for (int q = 0; q < s->n_pt; ++q)
+    for (int k = 0; k < 3; ++k) pts_int[3 * (size_t)q + k] = s->h_pts[3 * (size_t)s->pt_iperm[q] + k];
+  CU(upload(s->d_se3, s->h_se3, st));
+  CU(upload(s->d_se2, s->h_se2, st));
+  CU(upload(s->d_pts, pts_int, st));
+  CU(upload(s->d_vec, s->h_vec, st));
+  CU(s->d_stage.alloc(3 * (size_t)s->n_pt));
+  CU(upload(s->d_pt_perm, s->pt_perm, st));
+  CU(upload(s->d_se3_off, s->se3_off, st));
+  CU(upload(s->d_se2_off, s->se2_off, st));
+  CU(upload(s->d_vec_entry_off, s->vec_entry_off, st));
+  CU(upload(s->d_ptred_entry_off, s->pt_red_entry_off, st));
+  CU(upload(s->d_ou, ou, st)); CU(upload(s->d_ov, ov, st)); CU(upload(s->d_od, od, st));
+  CU(upload(s->d_opose, opose, st)); CU(upload(s->d_opt, opt, st)); CU(upload(s->d_ogrp, ogrp, st));
+  CU(upload(s->d_lm_start, lm_start, st));
+  CU(upload(s->d_groups, s->groups, st));
+  for (auto* b : s->edges) {
+    CU(upload(b->d_i1, b->i1, st));
+    CU(upload(b->d_i2, b->i2, st));
+    CU(upload(b->d_Tobs, b->Tobs, st));
+    CU(upload(b->d_stiff, b->stiff, st));
+  }
+  CU(upload(s->d_dn_row_ptr, s->dn_row_ptr, st));
+  CU(upload(s->d_dn_col_ptr, s->dn_col_ptr, st));
+  CU(upload(s->d_dn_j_ptr, s->dn_j_ptr, st));
+  CU(upload(s->d_dn_col_index, s->dn_col_index, st));
+  CU(s->d_dn_J.alloc((size_t)s->dn_j_ptr.back()));
+  CU(s->d_dn_e.alloc((size_t)s->dn_row_ptr.back()));
+  CU(s->d_W.alloc(18 * (size_t)N));
+  CU(s->d_Vg.alloc(9 * (size_t)s->n_lm));
+  CU(s->d_Vinv.alloc(6 * (size_t)s->n_lm));
+  CU(s->d_red.alloc(s->red_len()));
+  CU(s->d_dx.alloc((size_t)s->n_pad + 3 * (size_t)s->n_lm));
+  CU(s->d_y.alloc(s->n_pad));
+  CU(s->d_Linv.alloc((size_t)s->nblk * bs::kNB * bs::kNB));
+  CU(s->b_se3.alloc(s->d_se3.n)); CU(s->b_se2.alloc(s->d_se2.n));
+  CU(s->b_pts.alloc(s->d_pts.n)); CU(s->b_vec.alloc(s->d_vec.n));
+  CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), st));
+  CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
+  if (N > 0) CU(cudaMemsetAsync(s->d_W.p, 0, s->d_W.n * sizeof(double), st));
+  CU(cudaStreamSynchronize(st));
+  s->finalized = true;
+  s->dn_uploaded = false;
+  return BSLAM_OK;
+}
+
+int bslam_get_layout(bslam_solver* s, int32_t* se3_off, int32_t* se2_off, int32_t* pt_off, int32_t* vec_off, int32_t* dim,
+                     int32_t* n_reduced) {
+  NEED(s && s->finalized, "bslam_get_layout: solver not finalized");
+  if (se3_off) std::copy(s->se3_off.begin(), s->se3_off.end(), se3_off);
+  if (se2_off) std::copy(s->se2_off.begin(), s->se2_off.end(), se2_off);
+  if (pt_off) std::copy(s->pt_off_user.begin(), s->pt_off_user.end(), pt_off);
+  if (vec_off) std::copy(s->vec_off.begin(), s->vec_off.end(), vec_off);
+  if (dim) *dim = s->dim;
+  if (n_reduced) *n_reduced = s->n_red;
+  return BSLAM_OK;
+}
+
+// ------------------------------------------------------------------ hot path
+
+int bslam_eval_cost(bslam_solver* s, double* cost) {
+  NEED(s && s->finalized, "bslam_eval_cost: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemsetAsync(s->scalars() + BSLAM_S_COST_EVAL, 0, sizeof(double), s->stream));
+  launch_cost(s, BSLAM_S_COST_EVAL);
+  CU(cudaGetLastError());
+  const bool t = s->timing;
+  s->timing = false;
+  int rc = fetch_scalars(s);
+  s->timing = t;
+  if (rc) return rc;
+  if (cost) *cost = s->h_scalars[BSLAM_S_COST_EVAL];
+  return BSLAM_OK;
+}
+
+int bslam_linearize(bslam_solver* s, double* cost_lin) {
+  NEED(s, "NULL solver");
+  CU(cudaSetDevice(s->device));
+  int rc = do_linearize(s);
+  if (rc) return rc;
+  if (cost_lin) {
+    CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
+  }
+  return BSLAM_OK;
+}
+
+int bslam_reduce(bslam_solver* s, double lambda) {
+  NEED(s && s->finalized, "bslam_reduce: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_reduce: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  return do_reduce(s, lambda);
+}
+
+int bslam_solve_reduced(bslam_solver* s) {
+  NEED(s && s->finalized, "bslam_solve_reduced: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  return do_solve_reduced(s);
+}
+
+int bslam_retract(bslam_solver* s, int eval_new_cost) {
+  NEED(s && s->finalized, "bslam_retract: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  return do_retract(s, eval_new_cost);
+}
+
+int bslam_get_scalars(bslam_solver* s, double* out) {
+  NEED(s && s->finalized, "bslam_get_scalars: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  int rc = fetch_scalars(s);
+  if (rc) return rc;
+  if (out) std::memcpy(out, s->h_scalars, BSLAM_N_SCALARS * sizeof(double));
+  return BSLAM_OK;
+}
+
+int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost, double* cost_lin, double* cost_new, double* dx_norm) {
+  NEED(s && s->finalized, "bslam_iterate: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_iterate: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if ((rc = do_linearize(s))) return rc;
+  if ((rc = do_reduce(s, lambda))) return rc;
+  if ((rc = do_solve_reduced(s))) return rc;
+  if ((rc = do_retract(s, eval_new_cost))) return rc;
+  if ((rc = fetch_scalars(s))) return rc;
+  if (cost_lin) *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
+  if (cost_new) *cost_new = s->h_scalars[BSLAM_S_COST_NEW];
+  if (dx_norm) *dx_norm = std::sqrt(s->h_scalars[BSLAM_S_DX_NORM2]);
+  return BSLAM_OK;
+}
+
+int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles, void** scalars_dev_ptr, int32_t* n_pad) {
+  NEED(s && s->finalized, "bslam_reduced_buffer: solver not finalized");
+  if (dev_ptr) *dev_ptr = s->d_red.p;
+  if (n_doubles) *n_doubles = s->red_len();
+  if (scalars_dev_ptr) *scalars_dev_ptr = s->scalars();
+  if (n_pad) *n_pad = s->n_pad;
+  return BSLAM_OK;
+}
+
+int bslam_set_shard(bslam_solver* s, int rank) {
+  NEED(s, "NULL solver");
+  s->shard_rank = rank;
+  return BSLAM_OK;
+}
+
+void* bslam_stream(bslam_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int bslam_snapshot(bslam_solver* s) {
+  NEED(s && s->finalized, "bslam_snapshot: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  auto cp = [&](DevBuf<double>& dst, DevBuf<double>& src) {
+    return src.n ? cudaMemcpyAsync(dst.p, src.p, src.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) : cudaSuccess;
+  };
+  CU(cp(s->b_se3, s->d_se3)); CU(cp(s->b_se2, s->d_se2)); CU(cp(s->b_pts, s->d_pts)); CU(cp(s->b_vec, s->d_vec));
+  return BSLAM_OK;
+}
+
+int bslam_restore(bslam_solver* s) {
+  NEED(s && s->finalized, "bslam_restore: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  auto cp = [&](DevBuf<double>& dst, DevBuf<double>& src) {
+    return src.n ? cudaMemcpyAsync(dst.p, src.p, src.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) : cudaSuccess;
+  };
+  CU(cp(s->d_se3, s->b_se3)); CU(cp(s->d_se2, s->b_se2)); CU(cp(s->d_pts, s->b_pts)); CU(cp(s->d_vec, s->b_vec));
+  return BSLAM_OK;
+}
+
+// ---------------------------------------------------------------- inspection
+
+int bslam_get_update(bslam_solver* s, double* dx) {
+  NEED(s && s->finalized && dx, "bslam_get_update: bad arguments");
+  CU(cudaSetDevice(s->device));
+  if (s->n_red) CU(cudaMemcpyAsync(dx, s->d_dx.p, s->n_red * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (s->n_lm)
+    CU(cudaMemcpyAsync(dx + s->n_red, s->d_dx.p + s->n_pad, 3 * (size_t)s->n_lm * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return BSLAM_OK;
+}
+
+int bslam_get_reduced_system(bslam_solver* s, double* Sout, double* rhs) {
+  NEED(s && s->finalized, "bslam_get_reduced_system: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  const int n = s->n_red, ld = s->n_pad;
+  std::vector<double> tmp((size_t)ld * ld);
+  CU(cudaMemcpyAsync(tmp.data(), s->S(), tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (rhs && n) CU(cudaMemcpyAsync(rhs, s->rhs(), n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (Sout)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) Sout[(size_t)i * n + j] = Sout[(size_t)j * n + i] = tmp[(size_t)i * ld + j];
+  return BSLAM_OK;
+}
+
+int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
+  NEED(s && s->finalized && H && b, "bslam_get_normal_equations: bad arguments");
+  NEED(s->dim <= 20000, "bslam_get_normal_equations: D = %d too large for a dense export", s->dim);
+  CU(cudaSetDevice(s->device));
+  const int D = s->dim, n = s->n_red, ld = s->n_pad, N = s->n_obs;
+  std::vector<double> Sd((size_t)ld * ld), W(18 * (size_t)N), Vg(9 * (size_t)s->n_lm);
+  std::vector<int> opose(N), opt(N);
+  CU(cudaMemcpyAsync(Sd.data(), s->S(), Sd.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (n) CU(cudaMemcpyAsync(b, s->rhs(), n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (N) {
+    CU(cudaMemcpyAsync(W.data(), s->d_W.p, W.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(opose.data(), s->d_opose.p, N * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(opt.data(), s->d_opt.p, N * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (s->n_lm) CU(cudaMemcpyAsync(Vg.data(), s->d_Vg.p, Vg.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  std::fill(H, H + (size_t)D * D, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) H[(size_t)i * D + j] = H[(size_t)j * D + i] = Sd[(size_t)i * ld + j];
+  static const int vi[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  for (int q = 0; q < s->n_lm; ++q) {
+    const int o = n + 3 * q;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) H[(size_t)(o + r) * D + o + c] = Vg[9 * (size_t)q + vi[r][c]];
+      b[o + r] = Vg[9 * (size_t)q + 6 + r];
+    }
+  }
+  for (int k = 0; k < N; ++k) {
+    const int po = s->se3_off[opose[k]];
+    if (po < 0 || opt[k] >= s->n_lm) continue;
+    const int o = n + 3 * opt[k];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 3; ++c) {
+        H[(size_t)(po + r) * D + o + c] += W[18 * (size_t)k + 3 * r + c];
+        H[(size_t)(o + c) * D + po + r] += W[18 * (size_t)k + 3 * r + c];
+      }
+  }
+  return BSLAM_OK;
+}
+
+int bslam_covariance(bslam_solver* s, double* cov) {
+  (void)cov;
+  return fail(s, BSLAM_E_INVALID, "bslam_covariance: not implemented yet");
+}
+
+int bslam_enable_timing(bslam_solver* s, int on) {
+  NEED(s, "NULL solver");
+  s->timing = on != 0;
+  return BSLAM_OK;
+}
+
+int bslam_get_timings(bslam_solver* s, double* ms) {
+  NEED(s && ms, "bslam_get_timings: bad arguments");
+  std::memcpy(ms, s->timings, sizeof s->timings);
+  return BSLAM_OK;
+}
+
+int64_t bslam_launch_count(const bslam_solver* s) { return s ? s->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+"""ctypes binding of libbslam.so (include/bslam.h) -- the only door from the
+Python host into the CUDA solver.
+
+There is deliberately no fallback: if the shared library is missing, cannot be
+loaded, or no GPU is present, every entry point raises `EngineError`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbslam.so')
+
+N_SCALARS = 16
+N_TIMINGS = 16
+S_COST_LIN, S_COST_NEW, S_DX_NORM2, S_CHOL_FAIL, S_COST_EVAL = 0, 1, 2, 3, 4
+TIMING_NAMES = ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total')
+SE2, SE3 = 2, 3
+KIND_SE3, KIND_SE2, KIND_POINT, KIND_VEC = 0, 1, 2, 3
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+_h = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol declared in include/bslam.h
+SIGNATURES = {
+    'bslam_version': (C.c_int, []),
+    'bslam_create': (C.c_int, [C.POINTER(_h), C.c_int]),
+    'bslam_destroy': (None, [_h]),
+    'bslam_last_error': (C.c_char_p, [_h]),
+    'bslam_set_poses_se3': (C.c_int, [_h, C.c_int, _dp, _bp]),
+    'bslam_set_poses_se2': (C.c_int, [_h, C.c_int, _dp, _bp]),
+    'bslam_set_points': (C.c_int, [_h, C.c_int, _dp, _bp]),
+    'bslam_set_vectors': (C.c_int, [_h, C.c_int, _ip, _dp, _bp]),
+    'bslam_get_poses_se3': (C.c_int, [_h, _dp]),
+    'bslam_get_poses_se2': (C.c_int, [_h, _dp]),
+    'bslam_get_points': (C.c_int, [_h, _dp]),
+    'bslam_get_vectors': (C.c_int, [_h, _dp]),
+    'bslam_add_reprojection_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double]),
+    'bslam_add_pose_blocks': (C.c_int, [_h, C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    'bslam_add_pose_to_pose_blocks': (C.c_int, [_h, C.c_int, C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    'bslam_set_dense_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _ip, _ip]),
+    'bslam_upload_dense_values': (C.c_int, [_h, _dp, C.c_size_t, _dp, C.c_size_t, C.c_double]),
+    'bslam_clear_blocks': (C.c_int, [_h]),
+    'bslam_finalize': (C.c_int, [_h]),
+    'bslam_get_layout': (C.c_int, [_h, _ip, _ip, _ip, _ip, _ip, _ip]),
+    'bslam_eval_cost': (C.c_int, [_h, _dp]),
+    'bslam_iterate': (C.c_int, [_h, C.c_double, C.c_int, _dp, _dp, _dp]),
+    'bslam_linearize': (C.c_int, [_h, _dp]),
+    'bslam_reduce': (C.c_int, [_h, C.c_double]),
+    'bslam_solve_reduced': (C.c_int, [_h]),
+    'bslam_retract': (C.c_int, [_h, C.c_int]),
+    'bslam_get_scalars': (C.c_int, [_h, _dp]),
+    'bslam_reduced_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), _ip]),
+    'bslam_set_shard': (C.c_int, [_h, C.c_int]),
+    'bslam_stream': (C.c_void_p, [_h]),
+    'bslam_snapshot': (C.c_int, [_h]),
+    'bslam_restore': (C.c_int, [_h]),
+    'bslam_get_update': (C.c_int, [_h, _dp]),
+    'bslam_get_normal_equations': (C.c_int, [_h, _dp, _dp]),
+    'bslam_get_reduced_system': (C.c_int, [_h, _dp, _dp]),
+    'bslam_covariance': (C.c_int, [_h, _dp]),
+    'bslam_enable_timing': (C.c_int, [_h, C.c_int]),
+    'bslam_get_timings': (C.c_int, [_h, _dp]),
+    'bslam_launch_count': (C.c_int64, [_h]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libbslam.so and attach the prototypes.  Raises EngineError when
+    the library has not been built (run `python -c 'import __graft_entry__ as g;
+    g.build()'` or `make -C pyslam_b200/csrc`)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise EngineError('CUDA extension {} not found -- build it with `make -C pyslam_b200/csrc`; '
+                          'there is no CPU fallback'.format(path))
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise EngineError('cannot load {}: {}'.format(path, e))
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise EngineError('{} does not export {}'.format(path, name))
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _b(a):
+    return None if a is None else a.ctypes.data_as(_bp)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _flags(a, n):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(a).astype(bool), dtype=np.uint8)
+    assert a.shape == (n,)
+    return a
+
+
+class Engine:
+    """One libbslam solver handle on one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = _h()
+        rc = self._lib.bslam_create(C.byref(self._h), int(device))
+        if rc != 0:
+            msg = self._lib.bslam_last_error(None)
+            self._h = None
+            raise EngineError('bslam_create failed ({}): {}'.format(rc, (msg or b'').decode()))
+        self.device = int(device)
+        self.n = dict(se3=0, se2=0, pt=0, vec=0, vec_entries=0)
+        self._scal = np.zeros(N_SCALARS)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.bslam_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError('libbslam error {}: {}'.format(rc, (self._lib.bslam_last_error(self._h) or b'').decode()))
+
+    # ---- parameter tables -------------------------------------------------
+    def set_poses_se3(self, Rt, is_const=None):
+        Rt = _f64(Rt, (-1, 12))
+        self.n['se3'] = len(Rt)
+        self._ck(self._lib.bslam_set_poses_se3(self._h, len(Rt), _d(Rt), _b(_flags(is_const, len(Rt)))))
+
+    def set_poses_se2(self, Rt, is_const=None):
+        Rt = _f64(Rt, (-1, 6))
+        self.n['se2'] = len(Rt)
+        self._ck(self._lib.bslam_set_poses_se2(self._h, len(Rt), _d(Rt), _b(_flags(is_const, len(Rt)))))
+
+    def set_points(self, xyz, is_const=None):
+        xyz = _f64(xyz, (-1, 3))
+        self.n['pt'] = len(xyz)
+        self._ck(self._lib.bslam_set_points(self._h, len(xyz), _d(xyz), _b(_flags(is_const, len(xyz)))))
+
+    def set_vectors(self, dims, values, is_const=None):
+        dims = _i32(dims)
+        values = _f64(values).ravel()
+        assert values.size == int(dims.sum())
+        self.n['vec'], self.n['vec_entries'] = len(dims), values.size
+        self._ck(self._lib.bslam_set_vectors(self._h, len(dims), _i(dims), _d(values), _b(_flags(is_const, len(dims)))))
+
+    def get_poses_se3(self):
+        out = np.empty((self.n['se3'], 12))
+        self._ck(self._lib.bslam_get_poses_se3(self._h, _d(out)))
+        return out
+
+    def get_poses_se2(self):
+        out = np.empty((self.n['se2'], 6))
+        self._ck(self._lib.bslam_get_poses_se2(self._h, _d(out)))
+        return out
+
+    def get_points(self):
+        out = np.empty((self.n['pt'], 3))
+        self._ck(self._lib.bslam_get_points(self._h, _d(out)))
+        return out
+
+    def get_vectors(self):
+        out = np.empty(self.n['vec_entries'])
+        self._ck(self._lib.bslam_get_vectors(self._h, _d(out)))
+        return out
+
+    # ---- blocks -------------------------------------------------------------
+    @staticmethod
+    def _stiff(stiffness, n, d):
+        S = _f64(stiffness)
+        if S.size == d * d:
+            return S.reshape(d, d), 0
+        if S.size == n * d * d:
+            return S.reshape(n, d, d), 1
+        raise ValueError('stiffness must hold 1 or {} matrices of {}x{}'.format(n, d, d))
+
+    def add_reprojection_blocks(self, pose_idx, pt_idx, obs, stiffness, intr, loss_kind=0, loss_k=0.):
+        pose_idx, pt_idx, obs = _i32(pose_idx), _i32(pt_idx), _f64(obs, (-1, 3))
+        n = len(pose_idx)
+        assert len(pt_idx) == n and len(obs) == n
+        S, per = self._stiff(stiffness, n, 3)
+        intr = _f64(intr, (5,))
+        self._ck(self._lib.bslam_add_reprojection_blocks(self._h, n, _i(pose_idx), _i(pt_idx), _d(obs), _d(S), per,
+                                                         _d(intr), int(loss_kind), float(loss_k)))
+
+    def add_pose_blocks(self, group, pose_idx, T_obs, stiffness, loss_kind=0, loss_k=0.):
+        store, dof = (12, 6) if group == SE3 else (6, 3)
+        pose_idx, T_obs = _i32(pose_idx), _f64(T_obs, (-1, store))
+        n = len(pose_idx)
+        S, per = self._stiff(stiffness, n, dof)
+        self._ck(self._lib.bslam_add_pose_blocks(self._h, group, n, _i(pose_idx), _d(T_obs), _d(S), per,
+                                                 int(loss_kind), float(loss_k)))
+
+    def add_pose_to_pose_blocks(self, group, idx1, idx2, T21_obs, stiffness, loss_kind=0, loss_k=0.):
+        store, dof = (12, 6) if group == SE3 else (6, 3)
+        idx1, idx2, T21_obs = _i32(idx1), _i32(idx2), _f64(T21_obs, (-1, store))
+        n = len(idx1)
+        S, per = self._stiff(stiffness, n, dof)
+        self._ck(self._lib.bslam_add_pose_to_pose_blocks(self._h, group, n, _i(idx1), _i(idx2), _d(T21_obs), _d(S), per,
+                                                         int(loss_kind), float(loss_k)))
+
+    def set_dense_blocks(self, rows, param_ptr, param_kind, param_index):
+        rows, param_ptr = _i32(rows), _i32(param_ptr)
+        param_kind, param_index = _i32(param_kind), _i32(param_index)
+        self._ck(self._lib.bslam_set_dense_blocks(self._h, len(rows), _i(rows), _i(param_ptr), _i(param_kind),
+                                                  _i(param_index)))
+
+    def upload_dense_values(self, e, J, cost):
+        e, J = _f64(e).ravel(), _f64(J).ravel()
+        self._ck(self._lib.bslam_upload_dense_values(self._h, _d(e), e.size, _d(J), J.size, float(cost)))
+
+    def clear_blocks(self):
+        self._ck(self._lib.bslam_clear_blocks(self._h))
+
+    def finalize(self):
+        self._ck(self._lib.bslam_finalize(self._h))
+
+    def layout(self):
+        """dict(se3=offsets, se2=..., pt=..., vec=..., dim=D, n_reduced=n)."""
+        o = {k: np.empty(self.n[k], np.int32) for k in ('se3', 'se2', 'pt', 'vec')}
+        dim, nred = C.c_int32(), C.c_int32()
+        self._ck(self._lib.bslam_get_layout(self._h, _i(o['se3']), _i(o['se2']), _i(o['pt']), _i(o['vec']),
+                                            C.byref(dim), C.byref(nred)))
+        o['dim'], o['n_reduced'] = dim.value, nred.value
+        return o
+
+    # ---- hot path -----------------------------------------------------------
+    def eval_cost(self):
+        c = C.c_double()
+        self._ck(self._lib.bslam_eval_cost(self._h, C.byref(c)))
+        return c.value
+
+    def iterate(self, lam=0., eval_new_cost=True):
+        """(cost at linearisation point, cost at x [+] dx, ||dx||)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.bslam_iterate(self._h, float(lam), int(bool(eval_new_cost)), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def linearize(self, fetch_cost=True):
+        c = C.c_double()
+        self._ck(self._lib.bslam_linearize(self._h, C.byref(c) if fetch_cost else None))
+        return c.value if fetch_cost else None
+
+    def reduce(self, lam=0.):
+        self._ck(self._lib.bslam_reduce(self._h, float(lam)))
+
+    def solve_reduced(self):
+        self._ck(self._lib.bslam_solve_reduced(self._h))
+
+    def retract(self, eval_new_cost=True):
+        self._ck(self._lib.bslam_retract(self._h, int(bool(eval_new_cost))))
+
+    def scalars(self):
+        self._ck(self._lib.bslam_get_scalars(self._h, _d(self._scal)))
+        return self._scal.copy()
+
+    def reduced_buffer(self):
+        """(device pointer, length in doubles, device pointer of the scalar tail, n_pad)."""
+        p, n, ps, npad = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_int32()
+        self._ck(self._lib.bslam_reduced_buffer(self._h, C.byref(p), C.byref(n), C.byref(ps), C.byref(npad)))
+        return p.value, n.value, ps.value, npad.value
+
+    def set_shard(self, rank):
+        self._ck(self._lib.bslam_set_shard(self._h, int(rank)))
+
+    def stream(self):
+        return self._lib.bslam_stream(self._h)
+
+    def snapshot(self):
+        self._ck(self._lib.bslam_snapshot(self._h))
+
+    def restore(self):
+        self._ck(self._lib.bslam_restore(self._h))
+
+    # ---- inspection -----------------------------------------------------------
+    def get_update(self, dim):
+        out = np.empty(dim)
+        self._ck(self._lib.bslam_get_update(self._h, _d(out)))
+        return out
+
+    def get_normal_equations(self, dim):
+        H, b = np.empty((dim, dim)), np.empty(dim)
+        self._ck(self._lib.bslam_get_normal_equations(self._h, _d(H), _d(b)))
+        return H, b
+
+    def get_reduced_system(self, n):
+        S, r = np.empty((n, n)), np.empty(n)
+        self._ck(self._lib.bslam_get_reduced_system(self._h, _d(S), _d(r)))
+        return S, r
+
+    def covariance(self, dim):
+        out = np.empty((dim, dim))
+        self._ck(self._lib.bslam_covariance(self._h, _d(out)))
+        return out
+
+    def enable_timing(self, on=True):
+        self._ck(self._lib.bslam_enable_timing(self._h, int(bool(on))))
+
+    def timings(self):
+        out = np.zeros(N_TIMINGS)
+        self._ck(self._lib.bslam_get_timings(self._h, _d(out)))
+        return dict(zip(TIMING_NAMES, out[:len(TIMING_NAMES)]))
+
+    def launch_count(self):
+        return int(self._lib.bslam_launch_count(self._h))

@@ -1,0 +1,567 @@
+"""Drop-in replacement for `pyslam.problem` (reference pyslam/problem.py:11-409).
+
+Same public surface -- `Options`, `Problem.add_residual_block`,
+`initialize_params`, `set_parameters_constant/variable`, `eval_cost`, `solve`,
+`solve_one_iter`, `compute_covariance`, `get_covariance_block`, `summary`,
+`param_dict`, `_cost_history` -- and the same iteration/termination semantics
+(problem.py:130-180), but the Gauss-Newton
+iteration itself (linearise, solve, retract, cost) runs on the GPU through
+libbslam.so (pyslam_b200/engine.py).  There is no CPU solve path: without the
+CUDA library or without a GPU, `solve()` raises `EngineError`.
+
+What happens to a residual block at `solve()`:
+  * built-in types (ReprojectionResidual with a StereoCamera, PoseResidual,
+    PoseToPoseResidual) with a built-in loss are packed into SoA batches and
+    linearised by CUDA kernels -- their Python `evaluate` is never called;
+  * anything else (user-defined residuals such as the notebook's
+    CubicResidual, QuadraticResidual, user-defined losses) keeps pyslam's
+    duck-typed protocol: `block.evaluate(params, compute_jacobians)` and
+    `loss.weight/loss.loss` run in Python and the scaled (e, J) rows are
+    uploaded; assembly, solve and retraction still happen on the GPU.
+
+Extensions (default to reference behaviour): `Options.device`,
+`Options.lm_lambda` (Levenberg-Marquardt damping, 0 = Gauss-Newton),
+`Problem.add_reprojection_batch` (bulk block registration for large problems),
+`Problem.last_timings`.
+"""
+import copy
+import warnings
+
+import numpy as np
+
+from . import engine as _engine
+from .lie import group_of
+from .losses import L2Loss, loss_descriptor
+from .residuals.blocks import BLOCK_POSE, BLOCK_POSE_TO_POSE, BLOCK_REPROJECTION
+
+
+class Options:
+    """Optimisation options; the first ten attributes and their defaults are
+    the reference's (pyslam/problem.py:14-37)."""
+
+    def __init__(self):
+        self.max_iters = 100
+        self.min_update_norm = 1e-6
+        self.min_cost = 1e-12
+        self.min_cost_decrease = 0.9
+
+        self.linesearch_alpha = 0.8
+        self.linesearch_max_iters = 10
+        self.linesearch_min_cost_decrease = 0.9
+
+        self.allow_nondecreasing_steps = False
+        self.max_nondecreasing_steps = 3
+
+        self.num_threads = 1          # accepted for compatibility; evaluation is on the GPU
+
+        # --- extensions ---
+        self.device = 0               # CUDA device ordinal
+        self.lm_lambda = 0.           # lambda * diag(H) damping; 0 = the reference's Gauss-Newton
+
+
+class _ReprojectionBatch:
+    """Many ReprojectionResidual blocks registered at once (arrays instead of
+    one Python object per block)."""
+
+    def __init__(self, camera, pose_keys, point_keys, obs, stiffness, loss):
+        self.camera, self.pose_keys, self.point_keys = camera, list(pose_keys), list(point_keys)
+        self.obs = np.ascontiguousarray(obs, dtype=float).reshape(-1, 3)
+        self.stiffness, self.loss = np.asarray(stiffness, dtype=float), loss
+        if not (len(self.pose_keys) == len(self.point_keys) == len(self.obs)):
+            raise ValueError('pose_keys, point_keys and obs must have the same length')
+
+
+def _param_dof(p):
+    """problem.py:257-266."""
+    if hasattr(p, 'dof'):
+        return p.dof
+    if hasattr(p, '__len__'):
+        return len(p)
+    return 1
+
+
+def _pose_row(T, n):
+    return np.concatenate([np.asarray(T.rot.mat, dtype=float).reshape(n * n),
+                           np.asarray(T.trans, dtype=float).reshape(n)])
+
+
+class _Lowered:
+    """Result of lowering a Problem onto the engine's tables and batches."""
+    pass
+
+
+class Problem:
+    """Builds and solves a non-linear least-squares problem (pyslam/problem.py:40)."""
+
+    def __init__(self, options=None):
+        self.options = options if options is not None else Options()
+        self.param_dict = dict()
+        self.residual_blocks = []
+        self.block_param_keys = []
+        self.block_loss_functions = []
+        self.constant_param_keys = []
+        self._update_partition_dict = {}
+        self._covariance_matrix = None
+        self._cost_history = []
+        self._batches = []
+        self._engine = None
+        self._low = None
+        self.last_timings = None
+        self._timing = False
+
+    # ------------------------------------------------------------------ building
+    def add_residual_block(self, block, param_keys, loss=None):
+        """Add a cost block (problem.py:72-81).  `loss` defaults to L2Loss()."""
+        if isinstance(param_keys, str):
+            param_keys = [param_keys]
+        self.residual_blocks.append(block)
+        self.block_param_keys.append(param_keys)
+        self.block_loss_functions.append(loss if loss is not None else L2Loss())
+        self._low = None
+
+    def add_reprojection_batch(self, camera, pose_keys, point_keys, obs, stiffness, loss=None):
+        """Extension: register len(obs) ReprojectionResidual blocks at once."""
+        self._batches.append(_ReprojectionBatch(camera, pose_keys, point_keys, obs, stiffness,
+                                                loss if loss is not None else L2Loss()))
+        self._low = None
+
+    def initialize_params(self, param_dict):
+        """problem.py:83-86 (values are deep-copied)."""
+        self.param_dict.update(copy.deepcopy(param_dict))
+        self._low = None
+
+    def set_parameters_constant(self, param_keys):
+        if isinstance(param_keys, str):
+            param_keys = [param_keys]
+        for key in param_keys:
+            if key not in self.constant_param_keys:
+                self.constant_param_keys.append(key)
+        self._low = None
+
+    def set_parameters_variable(self, param_keys):
+        if isinstance(param_keys, str):
+            param_keys = [param_keys]
+        for key in param_keys:
+            if key in self.constant_param_keys:
+                self.constant_param_keys.remove(key)
+        self._low = None
+
+    # ------------------------------------------------------------------ lowering
+    def _get_update_partition_dict(self):
+        """key -> range in the update vector, param_dict insertion order,
+        constants skipped (problem.py:252-277)."""
+        part, stop = {}, 0
+        for key, param in self.param_dict.items():
+            if key not in self.constant_param_keys:
+                dof = _param_dof(param)
+                part[key] = range(stop, stop + dof)
+                stop += dof
+        return part
+
+    def _lower(self):
+        """Classify parameters and blocks, fill the engine's tables."""
+        pd = self.param_dict
+        const = set(self.constant_param_keys)
+        low = _Lowered()
+
+        # which 3-vectors act as landmarks of built-in reprojection blocks
+        def fusable_reproj(block, keys, loss):
+            if getattr(type(block), 'BLOCK_KIND', None) != BLOCK_REPROJECTION or len(keys) != 2:
+                return False
+            if loss_descriptor(loss) is None or not hasattr(block.camera, 'intrinsics'):
+                return False
+            T, p = pd.get(keys[0]), pd.get(keys[1])
+            return group_of(T) == 'se3' and group_of(p) is None and np.size(p) == 3 and not np.isscalar(p)
+
+        def fusable_pose(block, keys, loss, kind, nkeys):
+            if getattr(type(block), 'BLOCK_KIND', None) != kind or len(keys) != nkeys:
+                return None
+            if loss_descriptor(loss) is None:
+                return None
+            obs = block.T_obs if kind == BLOCK_POSE else block.T_2_1_obs
+            g = group_of(obs)
+            if g not in ('se2', 'se3') or any(group_of(pd.get(k)) != g for k in keys):
+                return None
+            return g
+
+        kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('dense',)
+        point_keys = set()
+        for block, keys, loss in zip(self.residual_blocks, self.block_param_keys, self.block_loss_functions):
+            for k in keys:
+                if k not in pd:
+                    raise KeyError('Parameter {} has not been initialized'.format(k))
+            if fusable_reproj(block, keys, loss):
+                kinds.append(('reproj',))
+                point_keys.add(keys[1])
+                continue
+            g = fusable_pose(block, keys, loss, BLOCK_POSE, 1)
+            if g:
+                kinds.append(('pose', g))
+                continue
+            g = fusable_pose(block, keys, loss, BLOCK_POSE_TO_POSE, 2)
+            if g:
+                kinds.append(('p2p', g))
+                continue
+            kinds.append(('dense',))
+        for bt in self._batches:
+            if loss_descriptor(bt.loss) is None or not hasattr(bt.camera, 'intrinsics'):
+                raise ValueError('add_reprojection_batch needs a built-in camera and loss')
+            for k in set(bt.pose_keys) | set(bt.point_keys):
+                if k not in pd:
+                    raise KeyError('Parameter {} has not been initialized'.format(k))
+            point_keys.update(bt.point_keys)
+
+        # parameter tables, each in param_dict insertion order
+        low.table = {}                      # key -> (kind id, index)
+        low.keys = {'se3': [], 'se2': [], 'pt': [], 'vec': []}
+        low.opaque = set()
+        for key, p in pd.items():
+            g = group_of(p)
+            if g in ('se3', 'se2'):
+                name = g
+            elif g is None and key in point_keys:
+                name = 'pt'
+            else:
+                name = 'vec'
+                if g is not None or (hasattr(p, 'perturb') and hasattr(p, 'dof')):
+                    low.opaque.add(key)     # manifold type the library has no kernel for
+            low.table[key] = (name, len(low.keys[name]))
+            low.keys[name].append(key)
+        low.kinds = kinds
+        low.dense_ids = [i for i, k in enumerate(kinds) if k[0] == 'dense']
+        low.all_fused = not low.dense_ids
+        self._low = low
+
+        eng = self._engine
+        if eng is None:
+            eng = self._engine = _engine.Engine(getattr(self.options, 'device', 0))
+        eng.clear_blocks()
+        self._upload_params(pd, structure=True)
+
+        # --- built-in blocks -> batches grouped by (kind, loss, camera) ---
+        KIND = {'se3': _engine.KIND_SE3, 'se2': _engine.KIND_SE2, 'pt': _engine.KIND_POINT, 'vec': _engine.KIND_VEC}
+        groups = {}
+        for i, (block, keys, loss) in enumerate(zip(self.residual_blocks, self.block_param_keys,
+                                                    self.block_loss_functions)):
+            k = kinds[i]
+            if k[0] == 'dense':
+                continue
+            ld = loss_descriptor(loss)
+            if k[0] == 'reproj':
+                gk = ('reproj', ld, tuple(block.camera.intrinsics()))
+            else:
+                gk = (k[0], k[1], ld)
+            groups.setdefault(gk, []).append(i)
+        for gk, ids in groups.items():
+            if gk[0] == 'reproj':
+                pose_idx = [low.table[self.block_param_keys[i][0]][1] for i in ids]
+                pt_idx = [low.table[self.block_param_keys[i][1]][1] for i in ids]
+                obs = np.array([np.asarray(self.residual_blocks[i].obs, dtype=float).reshape(3) for i in ids])
+                S = np.array([np.asarray(self.residual_blocks[i].stiffness, dtype=float).reshape(3, 3) for i in ids])
+                if np.all(S == S[0]):
+                    S = S[0]
+                eng.add_reprojection_blocks(pose_idx, pt_idx, obs, S, gk[2], gk[1][0], gk[1][1])
+            else:
+                grp = _engine.SE3 if gk[1] == 'se3' else _engine.SE2
+                n = 3 if gk[1] == 'se3' else 2
+                dof = 6 if gk[1] == 'se3' else 3
+                S = np.array([np.asarray(self.residual_blocks[i].stiffness, dtype=float).reshape(dof, dof) for i in ids])
+                if np.all(S == S[0]):
+                    S = S[0]
+                if gk[0] == 'pose':
+                    idx = [low.table[self.block_param_keys[i][0]][1] for i in ids]
+                    Tobs = np.array([_pose_row(self.residual_blocks[i].T_obs, n) for i in ids])
+                    eng.add_pose_blocks(grp, idx, Tobs, S, gk[2][0], gk[2][1])
+                else:
+                    i1 = [low.table[self.block_param_keys[i][0]][1] for i in ids]
+                    i2 = [low.table[self.block_param_keys[i][1]][1] for i in ids]
+                    Tobs = np.array([_pose_row(self.residual_blocks[i].T_2_1_obs, n) for i in ids])
+                    eng.add_pose_to_pose_blocks(grp, i1, i2, Tobs, S, gk[2][0], gk[2][1])
+        for bt in self._batches:
+            ld = loss_descriptor(bt.loss)
+            pose_idx = np.fromiter((low.table[k][1] for k in bt.pose_keys), np.int32, len(bt.pose_keys))
+            pt_idx = np.fromiter((low.table[k][1] for k in bt.point_keys), np.int32, len(bt.point_keys))
+            for k in bt.pose_keys[:1]:
+                if low.table[k][0] != 'se3':
+                    raise ValueError('reprojection batch pose keys must be SE3 parameters')
+            eng.add_reprojection_blocks(pose_idx, pt_idx, bt.obs, bt.stiffness, bt.camera.intrinsics(), ld[0], ld[1])
+
+        # --- host-evaluated blocks: structure ---
+        # (the reference drops blocks whose parameters are all constant from the
+        #  normal equations, problem.py:343-348, but still counts them in eval_cost)
+        low.dense_active = [i for i in low.dense_ids
+                            if any(k not in const for k in self.block_param_keys[i])]
+        if low.dense_active:
+            rows, pptr, pkind, pindex = [], [0], [], []
+            for i in low.dense_active:
+                keys = self.block_param_keys[i]
+                r = np.atleast_1d(self.residual_blocks[i].evaluate([pd[k] for k in keys]))
+                rows.append(r.size)
+                for k in keys:
+                    name, idx = low.table[k]
+                    pkind.append(KIND[name])
+                    pindex.append(idx)
+                pptr.append(len(pkind))
+            eng.set_dense_blocks(rows, pptr, pkind, pindex)
+            low.dense_rows = rows
+        eng.finalize()
+
+        # --- map the engine's internal update ordering to the reference's ---
+        lay = eng.layout()
+        self._update_partition_dict = self._get_update_partition_dict()
+        D = lay['dim']
+        total = sum(len(r) for r in self._update_partition_dict.values())
+        if total != D:
+            raise RuntimeError('internal layout mismatch: {} vs {}'.format(total, D))
+        src = np.empty(D, np.int64)
+        for key, r in self._update_partition_dict.items():
+            name, idx = low.table[key]
+            o = int(lay[name][idx])
+            src[r.start:r.stop] = np.arange(o, o + len(r))
+        low.ref_from_internal = src
+        low.dim = D
+        low.layout = lay
+        return low
+
+    def _vec_values(self, key, p):
+        if key in self._low.opaque:
+            return np.zeros(_param_dof(p))
+        return np.atleast_1d(np.asarray(p, dtype=float)).ravel()
+
+    def _upload_params(self, pd, structure=False):
+        """Host parameter objects -> device tables."""
+        low, eng = self._low, self._engine
+        const = set(self.constant_param_keys)
+        flags = (lambda keys: [k in const for k in keys]) if structure else (lambda keys: None)
+        ks = low.keys
+        if ks['se3'] or structure:
+            eng.set_poses_se3(np.array([_pose_row(pd[k], 3) for k in ks['se3']]).reshape(-1, 12), flags(ks['se3']))
+        if ks['se2'] or structure:
+            eng.set_poses_se2(np.array([_pose_row(pd[k], 2) for k in ks['se2']]).reshape(-1, 6), flags(ks['se2']))
+        if ks['pt'] or structure:
+            eng.set_points(np.array([np.asarray(pd[k], dtype=float).reshape(3) for k in ks['pt']]).reshape(-1, 3),
+                           flags(ks['pt']))
+        if ks['vec'] or structure:
+            vals = [self._vec_values(k, pd[k]) for k in ks['vec']]
+            dims = [v.size for v in vals]
+            eng.set_vectors(dims, np.concatenate(vals) if vals else np.zeros(0), flags(ks['vec']))
+
+    def _download_params(self, dx_ref=None):
+        """Device tables -> the objects in `param_dict` (in place where the type
+        allows, as the reference's perturb / += do, problem.py:400-409).
+        Opaque manifold parameters are perturbed on the host with `dx_ref`."""
+        low, eng, pd = self._low, self._engine, self.param_dict
+        const = set(self.constant_param_keys)
+        ks = low.keys
+        if ks['se3']:
+            for k, row in zip(ks['se3'], eng.get_poses_se3()):
+                if k not in const:
+                    pd[k].rot.mat = row[:9].reshape(3, 3).copy()
+                    pd[k].trans = row[9:].copy()
+        if ks['se2']:
+            for k, row in zip(ks['se2'], eng.get_poses_se2()):
+                if k not in const:
+                    pd[k].rot.mat = row[:4].reshape(2, 2).copy()
+                    pd[k].trans = row[4:].copy()
+        if ks['pt']:
+            for k, row in zip(ks['pt'], eng.get_points()):
+                if k not in const:
+                    self._assign_vector(k, row)
+        if ks['vec']:
+            vals, pos = eng.get_vectors(), 0
+            for k in ks['vec']:
+                n = _param_dof(pd[k])
+                if k not in const:
+                    if k in low.opaque:
+                        if dx_ref is not None:
+                            pd[k].perturb(dx_ref[self._update_partition_dict[k]])
+                    else:
+                        self._assign_vector(k, vals[pos:pos + n])
+                pos += n
+
+    def _assign_vector(self, key, values):
+        p = self.param_dict[key]
+        if isinstance(p, np.ndarray) and p.dtype.kind == 'f' and p.shape == np.shape(values):
+            p[...] = values
+        elif isinstance(p, np.ndarray):
+            self.param_dict[key] = np.array(values, dtype=float).reshape(p.shape)
+        else:
+            # python scalars / lists become float arrays after `+=`, as in the reference
+            self.param_dict[key] = np.array(values, dtype=float)
+
+    # ------------------------------------------------ host-evaluated (plug-in) blocks
+    def _dense_linearize(self):
+        """problem.py:338-360 for the blocks that only exist as Python code."""
+        low, pd = self._low, self.param_dict
+        const = set(self.constant_param_keys)
+        e_parts, J_parts, cost = [], [], 0.
+        for i, nrows in zip(low.dense_active, low.dense_rows):
+            block, keys, loss = self.residual_blocks[i], self.block_param_keys[i], self.block_loss_functions[i]
+            cj = [k not in const for k in keys]
+            residual, jacs = block.evaluate([pd[k] for k in keys], cj)
+            residual = np.atleast_1d(np.asarray(residual, dtype=float)).ravel()
+            if residual.size != nrows:
+                raise ValueError('residual block {} changed its size ({} -> {})'.format(i, nrows, residual.size))
+            sqrt_w = np.sqrt(np.asarray(loss.weight(residual), dtype=float)).ravel()
+            cols = []
+            for k, want, jac in zip(keys, cj, jacs):
+                dof = _param_dof(pd[k])
+                if not want or jac is None:
+                    cols.append(np.zeros((nrows, dof)))
+                else:
+                    cols.append(sqrt_w[:, None] * np.asarray(jac, dtype=float).reshape(nrows, dof))
+            J_parts.append(np.hstack(cols).ravel())
+            e_parts.append(sqrt_w * residual)
+            cost += float(np.sum(loss.loss(residual)))
+        self._engine.upload_dense_values(np.concatenate(e_parts), np.concatenate(J_parts), cost)
+
+    def _dense_cost(self, ids, pd):
+        cost = 0.
+        for i in ids:
+            r = self.residual_blocks[i].evaluate([pd[k] for k in self.block_param_keys[i]])
+            cost += float(np.sum(self.block_loss_functions[i].loss(np.asarray(r, dtype=float))))
+        return cost
+
+    # ------------------------------------------------------------------ public API
+    def _ensure_lowered(self, upload=True):
+        if self._low is None:
+            self._lower()
+        elif upload:
+            self._upload_params(self.param_dict)
+        return self._low
+
+    def eval_cost(self, param_dict=None):
+        """Sum of loss(residual) over all blocks (problem.py:110-128)."""
+        low = self._ensure_lowered()
+        eng = self._engine
+        pd = self.param_dict
+        if param_dict is not None and param_dict is not self.param_dict:
+            pd = dict(self.param_dict)
+            pd.update(param_dict)
+            self._upload_params(pd)
+        cost = eng.eval_cost() + self._dense_cost(low.dense_ids, pd)
+        if pd is not self.param_dict:
+            self._upload_params(self.param_dict)
+        return cost
+
+    def _step(self, apply):
+        """One iteration on the device.  Returns (dx in reference order or None,
+        ||dx||, cost as `solve_one_iter` reports it)."""
+        low, eng, opt = self._low, self._engine, self.options
+        linesearch = opt.linesearch_max_iters > 0
+        if low.dense_active:
+            self._dense_linearize()
+        if not apply:
+            eng.snapshot()
+        cost_lin, cost_new, dx_norm = eng.iterate(getattr(opt, 'lm_lambda', 0.), linesearch)
+        self.last_timings = eng.timings() if getattr(self, '_timing', False) else None
+        dx_ref = None
+        need_host = bool(low.dense_ids) or bool(low.opaque)
+        if not apply or need_host:
+            dx_ref = eng.get_update(low.dim)[low.ref_from_internal]
+        if not apply:
+            if linesearch and low.dense_ids:
+                trial = copy.deepcopy(self.param_dict)
+                saved, self.param_dict = self.param_dict, trial
+                self._download_params(dx_ref)
+                self.param_dict = saved
+                cost_new += self._dense_cost(low.dense_ids, trial)
+            eng.restore()
+        elif need_host:
+            self._download_params(dx_ref)
+            if linesearch:
+                cost_new += self._dense_cost(low.dense_ids, self.param_dict)
+        if eng.scalars()[_engine.S_CHOL_FAIL] > 0:
+            warnings.warn('reduced normal matrix is not positive definite; the update is unreliable')
+        if linesearch:
+            cost = cost_new if np.isfinite(cost_new) else np.inf     # problem.py:362-398 net effect
+        else:
+            cost = cost_lin
+        return dx_ref, dx_norm, cost
+
+    def solve_one_iter(self):
+        """(dx, cost) of one Gauss-Newton iteration without applying it
+        (problem.py:182-194).  dx is in the reference's ordering."""
+        self._ensure_lowered()
+        dx, _, cost = self._step(apply=False)
+        return dx, cost
+
+    def solve(self):
+        """Gauss-Newton with the reference's termination logic (problem.py:130-180)."""
+        opt = self.options
+        low = self._ensure_lowered()
+        eng = self._engine
+        cost = eng.eval_cost() + self._dense_cost(low.dense_ids, self.param_dict)
+        iters, nondecreasing = 0, 0
+        self._cost_history = [cost]
+        best_host = None
+        done = False
+        while not done:
+            iters += 1
+            prev_cost = cost
+            _, dx_norm, cost = self._step(apply=True)
+            self._cost_history.append(cost)
+            done = iters > opt.max_iters or dx_norm < opt.min_update_norm or cost < opt.min_cost
+            if opt.allow_nondecreasing_steps:
+                if nondecreasing == 0:
+                    eng.snapshot()
+                    if low.opaque:
+                        best_host = {k: copy.deepcopy(self.param_dict[k]) for k in low.opaque}
+                if cost >= opt.min_cost_decrease * prev_cost:
+                    nondecreasing += 1
+                else:
+                    nondecreasing = 0
+                if nondecreasing >= opt.max_nondecreasing_steps:
+                    done = True
+                    eng.restore()
+                    if best_host:
+                        self.param_dict.update(best_host)
+            else:
+                done = done or cost >= opt.min_cost_decrease * prev_cost
+        self._download_params()
+        return self.param_dict
+
+    def compute_covariance(self):
+        """Covariance of the final estimate = inverse of the normal matrix at the
+        current parameters (problem.py:196-203)."""
+        try:
+            low = self._ensure_lowered()
+            if low.dense_active:
+                self._dense_linearize()
+            cov_int = self._engine.covariance(low.dim)
+            idx = low.ref_from_internal
+            self._covariance_matrix = cov_int[np.ix_(idx, idx)]
+        except Exception as e:       # the reference swallows and prints (problem.py:202-203)
+            print('Covariance computation failed!\n{}'.format(e))
+
+    def get_covariance_block(self, param0, param1):
+        """problem.py:205-216."""
+        try:
+            r0 = self._update_partition_dict[param0]
+            r1 = self._update_partition_dict[param1]
+            return np.squeeze(self._covariance_matrix[r0.start:r0.stop, r1.start:r1.stop])
+        except KeyError as e:
+            print('Cannot compute covariance for constant parameter {}'.format(e.args[0]))
+        return None
+
+    def summary(self, format='brief'):
+        """Same text as the reference's summary (problem.py:218-250)."""
+        if not self._cost_history:
+            raise ValueError('solve has not yet been called')
+        h = self._cost_history
+        if format == 'brief':
+            return 'Iterations: {:3} | Cost: {:12e} --> {:12e}'.format(len(h), h[0], h[-1])
+        if format == 'full':
+            header = '{:>5s} | {:>12s} --> {:>12s} | {:>10s}\n'.format('Iter', 'Initial cost', 'Final cost', 'Rel change')
+            lines = [header, '-' * len(header) + '\n']
+            for i, (ic, fc) in enumerate(zip(h[:-1], h[1:])):
+                lines.append('{:5} | {:12e} --> {:12e} | {:+10f}\n'.format(i, ic, fc, (fc - ic) / ic))
+            return ''.join(lines)
+        raise ValueError('Invalid summary format \'{}\'.'.format(format) +
+                         'Valid formats are \'brief\' and \'full\'')
+
+    def enable_timing(self, on=True):
+        """Extension: record per-phase CUDA-event timings into `last_timings`."""
+        self._timing = bool(on)
+        self._ensure_lowered(upload=False)
+        self._engine.enable_timing(on)

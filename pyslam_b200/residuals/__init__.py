@@ -1,0 +1,10 @@
+"""Residual plug-ins (reference pyslam/residuals/).
+
+`from pyslam_b200.residuals import ReprojectionResidual, PoseResidual, ...`
+resolves the same names as `from pyslam.residuals import ...`.
+"""
+from .blocks import (ReprojectionResidual, PoseResidual, PoseToPoseResidual,
+                     QuadraticResidual)
+
+__all__ = ['ReprojectionResidual', 'PoseResidual', 'PoseToPoseResidual',
+           'QuadraticResidual']
