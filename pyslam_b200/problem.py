@@ -160,6 +160,15 @@ class Problem:
 
     def _lower(self):
         """Classify parameters and blocks, fill the engine's tables."""
+        if self._engine is None:      # raises EngineError without the CUDA library / a GPU
+            self._engine = _engine.Engine(getattr(self.options, 'device', 0))
+        try:
+            return self._lower_impl()
+        except Exception:
+            self._low = None
+            raise
+
+    def _lower_impl(self):
         pd = self.param_dict
         const = set(self.constant_param_keys)
         low = _Lowered()
@@ -233,8 +242,6 @@ class Problem:
         self._low = low
 
         eng = self._engine
-        if eng is None:
-            eng = self._engine = _engine.Engine(getattr(self.options, 'device', 0))
         eng.clear_blocks()
         self._upload_params(pd, structure=True)
 

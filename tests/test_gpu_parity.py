@@ -1,0 +1,223 @@
+"""GPU: the CUDA path (through pyslam_b200.Problem -> ctypes -> libbslam.so)
+against (i) fixtures produced by the unmodified reference and (ii) the CPU
+oracle on the same seeded inputs.
+
+Tolerances.  north_star asks for 1e-6 relative on the update vector and the
+final cost.  The tests below hold the first linearisation (H, g, cost) to
+1e-11, update vectors to 1e-7 and cost histories to 1e-7 -- all arithmetic is
+fp64; the residual difference is summation order (atomics) and Schur+Cholesky
+versus SuperLU.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err
+import builders as B
+
+pytestmark = pytest.mark.gpu
+
+TOL_LIN = 1e-11      # first linearisation: H, g, cost
+TOL_DX = 1e-7        # update vector (north_star: 1e-6)
+TOL_COST = 1e-7      # cost history / final cost (north_star: 1e-6)
+
+
+def normal_equations_ref_order(pr):
+    """Dense (H, b, cost) of the product at its current parameters, permuted to
+    the reference's update ordering."""
+    low = pr._ensure_lowered()
+    if low.dense_active:
+        pr._dense_linearize()
+    cost = pr._engine.linearize()
+    H, b = pr._engine.get_normal_equations(low.dim)
+    idx = low.ref_from_internal
+    return H[np.ix_(idx, idx)], b[idx], cost
+
+
+@pytest.mark.parametrize('name', ['ba_huber', 'ba_cauchy'])
+@pytest.mark.parametrize('bulk', [False, True])
+def test_ba_against_reference_golden(name, bulk):
+    g = load_golden(name)
+    pr = B.product_ba_problem(g, bulk=bulk)
+    H, b, cost = normal_equations_ref_order(pr)
+    ones = np.ones(len(b))
+    assert np.allclose(H, H.T, rtol=0, atol=0)
+    assert rel_err(np.diag(H), g['H0_diag']) < TOL_LIN
+    assert rel_err(H @ ones, g['H0_ones']) < TOL_LIN
+    assert abs(np.sqrt((H * H).sum()) - g['H0_fro']) < TOL_LIN * g['H0_fro']
+    assert int((H != 0).sum()) == int(g['H0_nnz'])
+    assert rel_err(b, g['g0']) < TOL_LIN
+    assert abs(cost - g['cost0']) < TOL_LIN * g['cost0']
+    dx0, c1 = pr.solve_one_iter()
+    assert rel_err(dx0, g['dx0']) < TOL_DX
+    assert abs(c1 - g['cost_history'][1]) < TOL_COST * g['cost_history'][1]
+    # solve_one_iter must not move the parameters
+    dx0b, _ = pr.solve_one_iter()
+    assert rel_err(dx0b, dx0) < 1e-12
+    pr.solve()
+    assert len(pr._cost_history) == len(g['cost_history'])
+    np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=TOL_COST)
+    pk, qk = B.ba_keys(g)
+    R = np.array([pr.param_dict[k].rot.mat for k in pk])
+    t = np.array([pr.param_dict[k].trans for k in pk])
+    pts = np.array([pr.param_dict[k] for k in qk])
+    assert rel_err(R, g['R_final']) < 1e-7 and rel_err(t, g['t_final']) < 1e-6 and rel_err(pts, g['pts_final']) < 1e-7
+
+
+@pytest.mark.parametrize('name,group', [('posegraph_se2', 'se2'), ('posegraph_se3', 'se3')])
+def test_pose_graph_against_reference_golden(name, group):
+    g = load_golden(name)
+    pr = B.product_pose_graph(g, group)
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, g['H0']) < TOL_LIN
+    assert rel_err(b, g['g0']) < TOL_LIN
+    assert abs(cost - g['cost0']) < TOL_LIN * g['cost0']
+    dx0, _ = pr.solve_one_iter()
+    assert rel_err(dx0, g['dx0']) < TOL_DX
+    pr.solve()
+    assert len(pr._cost_history) == len(g['cost_history'])
+    np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=TOL_COST)
+    Tf = B.rows_of([pr.param_dict[k] for k in B.pose_graph_keys(g)])
+    assert rel_err(Tf, g['T_final']) < 1e-7
+
+
+@pytest.mark.parametrize('loss', [('huber', 0.4), ('cauchy', 0.5), ('tukey', 2.0), ('tdist', 3.0)])
+def test_pose_graph_robust_losses_against_oracle(loss):
+    from pyslam_b200 import synthetic
+    d = synthetic.se2_pose_graph(40, 5, seed=11, loop_span=13)
+    o = B.oracle_pose_graph(d, 'se2', loss)
+    o._update_partition_dict = o._get_update_partition_dict()
+    Ho, bo, co = o.get_precision_information_and_cost()
+    pr = B.product_pose_graph(d, 'se2', loss)
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    o.solve()
+    pr.solve()
+    assert len(pr._cost_history) == len(o._cost_history)
+    np.testing.assert_allclose(pr._cost_history, o._cost_history, rtol=TOL_COST)
+
+
+def test_reference_bundle_adjust_test_case():
+    # reference tests/test_problem.py:239-282, trace of examples/stereo_ba.py
+    import pyslam_b200
+    from pyslam_b200.lie import SE3
+    from pyslam_b200.residuals import ReprojectionResidual
+    from pyslam_b200.sensors import StereoCamera
+    g = load_golden('ba_reference_test')
+    cam = StereoCamera(640, 480, 1000, 1000, 0.25, 1280, 960)
+    pr = pyslam_b200.Problem(B.nondecreasing_options(pyslam_b200.Options))
+    for i in range(4):
+        for j in range(3):
+            pr.add_residual_block(ReprojectionResidual(cam, g['obs'][i, j], g['stiffness']),
+                                  ['T_cam%d_w' % i, 'pt%d_w' % j])
+    init = {'pt%d_w' % j: g['pts_init'][j].copy() for j in range(3)}
+    init.update({'T_cam%d_w' % i: SE3.identity() for i in range(4)})
+    pr.initialize_params(init)
+    pr.set_parameters_constant('T_cam0_w')
+    dx0, _ = pr.solve_one_iter()
+    assert rel_err(dx0, g['dx0']) < TOL_DX
+    out = pr.solve()
+    assert len(pr._cost_history) == len(g['cost_history'])
+    np.testing.assert_allclose(pr._cost_history[:4], g['cost_history'][:4], rtol=1e-6)
+    assert ['%.6e' % c for c in pr._cost_history[:3]] == ['4.209652e+05', '1.921859e+04', '3.924267e+01']
+    for j in range(3):
+        assert np.linalg.norm(out['pt%d_w' % j] - g['pts_true'][j]) < 1e-4
+    for i in range(4):
+        assert np.linalg.norm(out['T_cam%d_w' % i].inv().dot(B.p_se3(g['T_true'][i])).log()) < 1e-4
+
+
+@pytest.mark.parametrize('n', [10, 20])
+def test_cubic_fit_plugin_path(n):
+    """BASELINE config 1: user-defined Python residual (notebook's CubicResidual)
+    through the generic plug-in path; assembly/solve/update on the GPU."""
+    import pyslam_b200
+    g = load_golden('cubic')
+    pr = pyslam_b200.Problem()
+    for xi, yi in zip(g['n%d_x' % n], g['n%d_y' % n]):
+        pr.add_residual_block(B.CubicResidual(xi, yi, 1.), ['a', 'b', 'c', 'd'])
+    pr.initialize_params({'a': -2., 'b': 10., 'c': -6., 'd': -140.})
+    dx0, _ = pr.solve_one_iter()
+    assert rel_err(dx0, g['n%d_dx0' % n]) < 1e-9
+    out = pr.solve()
+    assert len(pr._cost_history) == len(g['n%d_cost_history' % n])
+    assert abs(pr._cost_history[0] - g['n%d_cost_history' % n][0]) < 1e-12 * pr._cost_history[0]
+    np.testing.assert_allclose([float(np.squeeze(out[k])) for k in 'abcd'], [2., 4., -4., 0.], atol=1e-8)
+    if n == 10:
+        assert pr.summary().startswith('Iterations:   2 | Cost: 3.735817e+05 -->')
+
+
+def test_quadratic_reference_tests():
+    # reference tests/test_problem.py:45-79
+    import pyslam_b200
+    from pyslam_b200.residuals import QuadraticResidual
+    pr = pyslam_b200.Problem()
+    pr.add_residual_block(QuadraticResidual(1., 4., 0.5), ['a', 'b', 'c'])
+    pr.add_residual_block(QuadraticResidual(0., 1., 2.), ['a', 'b', 'c'])
+    pr.initialize_params({'a': 1., 'b': 2., 'c': 1.})
+    assert pr.eval_cost() == 0.
+    assert pr.eval_cost({'a': 1., 'b': 0., 'c': 0.}) == 3.125
+    x = np.linspace(-5, 5, 10)
+    y = x * x - 2. * x + 3.
+    pr = pyslam_b200.Problem()
+    for xi, yi in zip(x, y):
+        pr.add_residual_block(QuadraticResidual(xi, yi, 1.), ['a', 'b', 'c'])
+    pr.initialize_params({'a': -20., 'b': 10., 'c': -30.})
+    dx0, _ = pr.solve_one_iter()
+    np.testing.assert_allclose(dx0, [21., -12., 33.], rtol=1e-9)
+    out = pr.solve()
+    for k, v in {'a': 1., 'b': -2., 'c': 3.}.items():
+        assert np.allclose(out[k], v)
+
+
+def test_constant_parameters_and_mixed_blocks():
+    """Constant landmarks / constant poses inside reprojection blocks, and a
+    prior on a pose next to reprojection blocks (pose block + BA in one problem)."""
+    from oracle import gn_oracle as O
+    from oracle import liegroups as OL
+    import pyslam_b200
+    from pyslam_b200 import synthetic
+    from pyslam_b200.lie import SE3, SO3
+    from pyslam_b200.residuals import PoseResidual
+    d = synthetic.stereo_ba(5, 40, track=4, seed=21)
+    op = B.oracle_ba_problem(d)
+    pp = B.product_ba_problem(d)
+    pk, qk = B.ba_keys(d)
+    S6 = np.diag([30., 30., 30., 80., 80., 80.])
+    op.add_residual_block(O.PoseResidual(OL.SE3(OL.SO3(d['R_true'][2]), d['t_true'][2]), S6), pk[2])
+    pp.add_residual_block(PoseResidual(SE3(SO3(d['R_true'][2]), d['t_true'][2]), S6), pk[2])
+    for pr in (op, pp):
+        pr.set_parameters_constant([qk[3], qk[17], pk[4]])
+    op._update_partition_dict = op._get_update_partition_dict()
+    Ho, bo, co = op.get_precision_information_and_cost()
+    H, b, cost = normal_equations_ref_order(pp)
+    assert H.shape == Ho.shape
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    assert abs(pp.eval_cost() - op.eval_cost()) < 1e-12 * co
+    op.solve()
+    pp.solve()
+    assert len(pp._cost_history) == len(op._cost_history)
+    np.testing.assert_allclose(pp._cost_history, op._cost_history, rtol=TOL_COST)
+    assert np.array_equal(pp.param_dict[qk[3]], d['pts0'][3])          # constants untouched
+
+
+def test_config3_against_oracle():
+    """BASELINE config 3: 50 keyframes x 5 000 landmarks x 30 000 reprojections, Huber(1.5)."""
+    from oracle import gn_oracle as O
+    from pyslam_b200 import synthetic
+    d = synthetic.stereo_ba(50, 5000, seed=0)
+    ba = B.oracle_ba_arrays(d)
+    pr = B.product_ba_problem(d, bulk=True)
+    low = pr._ensure_lowered()
+    cost0 = pr._engine.eval_cost()
+    assert abs(cost0 - O.ba_cost(ba)) < 1e-12 * cost0
+    for it in range(2):
+        ref = O.ba_iteration(ba)
+        cost_lin, cost_new, dx_norm = pr._engine.iterate(0., True)
+        dx = pr._engine.get_update(low.dim)[low.ref_from_internal]
+        assert abs(cost_lin - ref['cost_lin']) < 1e-10 * ref['cost_lin']
+        assert rel_err(dx, ref['dx']) < 1e-6, 'iteration %d' % it
+        assert abs(dx_norm - np.linalg.norm(ref['dx'])) < 1e-6 * dx_norm
+        assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
