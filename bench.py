@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- Gauss-Newton/LM iterations per second on the stereo bundle
+adjustment of BASELINE.json (config 4: 500 keyframes x 100 000 landmarks x
+600 000 reprojections, Huber(1.5), Schur complement), landmarks sharded over
+N GPUs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full iteration of the hot path: linearise (residuals,
+Jacobians, robust weights, J^T W J / J^T W r assembly) + Schur complement +
+dense reduced Cholesky + back-substitution + manifold retraction + cost at the
+new point -- what `Problem.solve_one_iter()` + the update does in the
+reference (pyslam/problem.py:143-156,182-194).
+
+Prints ONE JSON line (see the keys at the bottom).  `value` is measured with
+the problem resident in HBM; `e2e` goes through the C-ABI calls with HOST
+buffers (pinned): every step uploads the parameters, iterates and downloads the
+updated parameters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'LM iterations/sec on stereo BA (500 keyframes x 100000 landmarks x 600000 reprojections)'
+N_KF, N_LM, TRACK = 500, 100000, 6
+LOSS_NAMES = {'l2': 0, 'l1': 1, 'cauchy': 2, 'huber': 3, 'tukey': 4, 'tdist': 5}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.path = gpu, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_engine(d, device):
+    """Upload one (sharded) BA problem through the C ABI."""
+    from pyslam_b200 import engine as E
+    eng = E.Engine(device)
+    Rt = np.concatenate([d['R0'].reshape(-1, 9), d['t0']], axis=1)
+    eng.set_poses_se3(Rt, d['pose_const'])
+    eng.set_points(d['pts0'])
+    eng.add_reprojection_blocks(d['pose_idx'], d['pt_idx'], d['obs'], d['stiffness'], d['intr'],
+                                LOSS_NAMES[d['loss'][0]], d['loss'][1])
+    eng.finalize()
+    return eng, Rt
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pyslam_b200 import synthetic
+    from pyslam_b200.dist import ShardedSolver, shard_stereo_ba
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run --nproc-per-node %d' % args.gpus)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    full = synthetic.stereo_ba(N_KF, N_LM, track=TRACK, seed=0)
+    d = shard_stereo_ba(full, rank, world) if world > 1 else full
+    eng, Rt0 = build_engine(d, local)
+    solver = ShardedSolver(eng, rank, world)
+    stream = eng.torch_stream()
+    n_obs_total, n_obs = len(full['obs']), len(d['obs'])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reset():
+        eng.set_poses_se3(Rt0)
+        eng.set_points(d['pts0'])
+
+    # ---- device-resident: K iterations of Gauss-Newton from the initial guess ----
+    for _ in range(args.warmup):
+        solver.iterate(0., True)
+    reset()
+    eng.enable_timing(True)
+    t_phase = {k: 0. for k in ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total')}
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    costs = []
+    for _ in range(args.steps):
+        c_lin, c_new, dxn = solver.iterate(0., True)
+        costs.append((c_lin, c_new, dxn))
+        if world == 1:
+            for k, v in eng.timings().items():
+                t_phase[k] += v
+    e1.record(stream)
+    barrier()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    eng.enable_timing(False)
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step
+
+    # ---- end to end through the C ABI with host buffers (pinned) ----
+    pin_Rt = torch.from_numpy(Rt0.copy()).pin_memory()
+    pin_pts = torch.from_numpy(np.ascontiguousarray(d['pts0'])).pin_memory()
+    out_Rt = torch.empty_like(pin_Rt).pin_memory()
+    out_pts = torch.empty_like(pin_pts).pin_memory()
+    h2d = pin_Rt.numel() * 8 + pin_pts.numel() * 8
+    d2h = out_Rt.numel() * 8 + out_pts.numel() * 8 + 16 * 8
+    np_Rt, np_pts, np_oRt, np_opts = pin_Rt.numpy(), pin_pts.numpy(), out_Rt.numpy(), out_pts.numpy()
+
+    def e2e_step():
+        eng.set_poses_se3(np_Rt)
+        eng.set_points(np_pts)
+        r = solver.iterate(0., True)
+        eng.get_poses_se3(np_oRt)
+        eng.get_points(np_opts)
+        np_Rt[...] = np_oRt          # next step starts from the updated host copy
+        np_pts[...] = np_opts
+        return r
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    np_Rt[...] = Rt0
+    np_pts[...] = d['pts0']
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    # the e2e region contains host work between device ops: report the wall clock (>= device time)
+    e2e_ms = max(e2e_ms, wall_ms)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = 1000.0 * args.steps / e2e_ms
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    n_cam = N_KF
+    alg_bytes = 176 * n_obs + 312 * n_cam + 96 * len(d['pts0'])       # DESIGN.md "algorithmic bytes"
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'stereo BA config 4: %d keyframes x %d landmarks x %d reprojections, track %d, '
+                               'Huber(1.5), pose 0 constant, Gauss-Newton (lambda=0) with Schur complement'
+                               % (N_KF, N_LM, n_obs_total, TRACK),
+                   'parallelism': 'landmarks sharded over %d GPU(s), one NCCL all-reduce of the reduced system per iteration' % world
+                   if world > 1 else 'single GPU',
+                   'l2_policy': 'inputs+outputs per iteration (%.0f MB obs/W/points + 72 MB reduced matrix) exceed the 126 MB L2'
+                                % (alg_bytes / 1e6),
+                   'reduced_system_dim': 6 * (N_KF - 1)},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'iterations/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': int(launches),
+        'final_cost': costs[-1][1], 'first_cost': costs[0][0],
+    }
+    if world == 1:
+        t_reproj = t_phase['reproj'] / args.steps * 1e-3
+        achieved = alg_bytes / t_reproj / 1e9 if t_reproj > 0 else None
+        out['roofline'] = {'kernel': 'reproj_linearize_kernel', 'bound': 'hbm', 'achieved': achieved,
+                           'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'] if achieved else None,
+                           'traffic': None, 'peak_source': pk_src, 'algorithmic_bytes_per_launch': alg_bytes,
+                           'avg_launch_ms': t_reproj * 1e3}
+        n = 6 * (N_KF - 1)
+        t_chol = t_phase['cholesky'] / args.steps * 1e-3
+        out['roofline_cholesky'] = {'kernel': 'chol_panel_kernel+chol_update_kernel', 'bound': 'fp64 (DMMA)',
+                                    'flops': n ** 3 / 3.0, 'avg_ms': t_chol * 1e3,
+                                    'achieved_tflops': n ** 3 / 3.0 / t_chol / 1e12 if t_chol > 0 else None}
+        out['phase_ms'] = {k: v / args.steps for k, v in t_phase.items()}
+        out['cpu_baseline'] = cpu_baseline(budget_s=25.0)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------- CPU legs (oracle as the reported baseline)
+SAMPLES = [(50, 10000), (25, 5000), (10, 2000)]          # same landmark density as the full problem (200 / keyframe)
+
+
+def oracle_step_seconds(n_kf, n_lm, steps=1, warmup=0):
+    """Seconds per Gauss-Newton iteration of the CPU oracle (numpy assembly +
+    scipy.sparse spsolve on the full system, i.e. the reference's algorithm,
+    pyslam/problem.py:279-336,186) on an n_kf x n_lm sample."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import builders as B
+    from oracle import gn_oracle as O
+    from pyslam_b200 import synthetic
+    d = synthetic.stereo_ba(n_kf, n_lm, track=TRACK, seed=0)
+    ba = B.oracle_ba_arrays(d)
+    for _ in range(warmup):
+        O.ba_iteration(ba)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.ba_iteration(ba)
+    return (time.perf_counter() - t0) / steps
+
+
+def pick_sample(budget_s, n_steps):
+    t_small = oracle_step_seconds(*SAMPLES[-1])
+    # measured in the build container: 0.25 s, 2.1 s, 13.2 s per iteration for the three samples
+    rel = {SAMPLES[0]: 13.2 / 0.25, SAMPLES[1]: 2.07 / 0.25, SAMPLES[2]: 1.0}
+    for s in SAMPLES:
+        if t_small * rel[s] * n_steps <= budget_s:
+            return s
+    return SAMPLES[-1]
+
+
+def cpu_baseline(budget_s):
+    n_kf, n_lm = pick_sample(budget_s, 1)
+    t = oracle_step_seconds(n_kf, n_lm)
+    scale = N_LM / n_lm
+    import scipy
+    return {'value': 1.0 / (t * scale), 'unit': 'iterations/s', 'cores': 1, 'kind': 'port',
+            'sample': 'one Gauss-Newton iteration of the numpy/scipy oracle (vectorised assembly + SuperLU spsolve on the '
+                      'full system, the reference algorithm) on a 1/%d-scale problem (%d kf x %d lm x %d obs, same density): '
+                      '%.2f s; value = 1/(%d x that), i.e. LINEAR extrapolation to full size -- optimistic for the CPU '
+                      '(measured scaling of spsolve here is ~n^2.6). The unmodified reference itself needs 94 s/iteration '
+                      'at 1/20 scale and cannot run the full size (SURVEY F7).'
+                      % (scale, n_kf, n_lm, n_lm * TRACK, t, scale),
+            'host_cpus': os.cpu_count(), 'scipy': scipy.__version__}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_steps = args.steps + args.warmup
+    n_kf, n_lm = pick_sample(150.0, n_steps)
+    t = oracle_step_seconds(n_kf, n_lm, steps=args.steps, warmup=args.warmup)
+    scale = N_LM / n_lm
+    value = 1.0 / (t * scale)
+    sample = ('each step = one Gauss-Newton iteration of the numpy/scipy oracle port of pyslam (vectorised assembly + '
+              'scipy SuperLU spsolve on the full system) on a 1/%d-scale sample (%d kf x %d lm x %d obs, same density); '
+              'value = 1/(%d x seconds per step): linear extrapolation to the full problem, optimistic for the CPU'
+              % (scale, n_kf, n_lm, n_lm * TRACK, scale))
+    out = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'iterations/s', 'n_gpus': args.gpus,
+           'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * scale * 1e3, 'higher_is_better': True,
+           'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+           'config': {'workload': 'stereo BA config 4: %d keyframes x %d landmarks x %d reprojections, track %d, Huber(1.5)'
+                                  % (N_KF, N_LM, N_LM * TRACK, TRACK), 'sample': sample},
+           'cpu_baseline': {'value': value, 'unit': 'iterations/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+                            'host_cpus': os.cpu_count()},
+           'e2e': {'value': value, 'unit': 'iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -180,8 +180,8 @@ class Engine:
         self.n['vec'], self.n['vec_entries'] = len(dims), values.size
         self._ck(self._lib.bslam_set_vectors(self._h, len(dims), _i(dims), _d(values), _b(_flags(is_const, len(dims)))))
 
-    def get_poses_se3(self):
-        out = np.empty((self.n['se3'], 12))
+    def get_poses_se3(self, out=None):
+        out = np.empty((self.n['se3'], 12)) if out is None else out
         self._ck(self._lib.bslam_get_poses_se3(self._h, _d(out)))
         return out
 
@@ -190,8 +190,8 @@ class Engine:
         self._ck(self._lib.bslam_get_poses_se2(self._h, _d(out)))
         return out
 
-    def get_points(self):
-        out = np.empty((self.n['pt'], 3))
+    def get_points(self, out=None):
+        out = np.empty((self.n['pt'], 3)) if out is None else out
         self._ck(self._lib.bslam_get_points(self._h, _d(out)))
         return out
 
@@ -339,3 +339,36 @@ class Engine:
 
     def launch_count(self):
         return int(self._lib.bslam_launch_count(self._h))
+
+
+# ---- torch interop (multi-GPU plumbing and event timing only) -----------------
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias library memory."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr='<f8', data=(int(ptr), False), version=2)
+
+
+def _engine_reduced_tensor(self):
+    """torch.float64 tensor aliasing the device buffer [S | rhs | scalars] that is
+    all-reduced across GPUs between `reduce` and `solve_reduced`."""
+    import torch
+    p, n, _, _ = self.reduced_buffer()
+    return torch.as_tensor(_DevArray(p, n), device='cuda:%d' % self.device)
+
+
+def _engine_scalars_tensor(self):
+    import torch
+    _, _, ps, _ = self.reduced_buffer()
+    return torch.as_tensor(_DevArray(ps, N_SCALARS), device='cuda:%d' % self.device)
+
+
+def _engine_torch_stream(self):
+    """The handle's CUDA stream as a torch stream (order collectives / record events on it)."""
+    import torch
+    return torch.cuda.ExternalStream(self.stream(), device='cuda:%d' % self.device)
+
+
+Engine.reduced_tensor = _engine_reduced_tensor
+Engine.scalars_tensor = _engine_scalars_tensor
+Engine.torch_stream = _engine_torch_stream
