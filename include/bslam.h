@@ -203,6 +203,12 @@ BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS 
  * and of the scalar tail alone (second, 16-double all-reduce after retract). */
 BSLAM_API int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles,
                          void** scalars_dev_ptr, int32_t* n_pad);
+/* Tile structure (64x64 tiles, (n_pad/64 + 1) x (n_pad/64) bytes, row-major) of
+ * the reduced system as seen by THIS handle's residual blocks.  set == 0 copies it
+ * out; set != 0 ORs `mask` into it -- with sharded landmarks the host ORs the
+ * masks of all ranks (all-reduce MAX) once after bslam_finalize, because the
+ * summed matrix has the union structure. */
+BSLAM_API int bslam_tile_structure(bslam_solver* s, uint8_t* mask, size_t n, int set);
 /* Shard rank of this handle when landmarks are partitioned over several GPUs
  * (rank 0 alone counts the replicated reduced part in ||dx||^2). */
 BSLAM_API int bslam_set_shard(bslam_solver* s, int rank);

@@ -1,25 +1,56 @@
-// cholesky.cuh -- dense fp64 Cholesky of the reduced camera system and the two
-// triangular solves.  Together with schur.cuh this replaces
-// `splinalg.spsolve(precision, information)` (pyslam/problem.py:186).
+// cholesky.cuh -- dense/tile-sparse fp64 Cholesky of the reduced camera system
+// plus both triangular solves, as ONE persistent kernel.  Together with
+// schur.cuh this replaces `splinalg.spsolve(precision, information)`
+// (pyslam/problem.py:186).
 //
-// S is n_pad x n_pad row-major (n_pad a multiple of NB = 64, padding rows carry
-// an identity diagonal), only the lower triangle is referenced.  Right-looking
-// blocked factorisation, two launches per 64-column panel:
-//   chol_panel_kernel  every CTA re-factorises the 64x64 diagonal tile in shared
-//                      memory and forms its triangular inverse; CTA 0 stores L_kk
-//                      and L_kk^-1, CTA b>0 turns tile (k+b,k) into L = A L_kk^-T
-//                      with fp64 tensor-core MMAs (mma.sync.m8n8k4.f64 -> DMMA);
-//   chol_update_kernel A_ij -= L_ik L_jk^T for all tiles i >= j > k, DMMA.
-// tcgen05 has no fp64 kind, so DMMA is the tensor path available to an fp64
-// factorisation on sm_100a.
+// Layout: S is n_pad x n_pad row-major (n_pad = 64 * nt, identity on the padding
+// diagonal, lower triangle referenced); the right-hand side is stored as row
+// n_pad of the same buffer, i.e. it is tile-row `nt` of a (nt+1) x nt grid of
+// 64x64 tiles.  Carrying b as an extra row makes the forward substitution part
+// of the factorisation:  [L; y^T] [L^T] = [S; b^T].
+//
+// Schedule: left-looking, one task per non-zero tile (i,j) of L, dispatched in
+// column-major order through an atomic ticket; the structure (which tiles are
+// non-zero after fill-in) is computed once on the host from the co-visibility
+// graph, so banded / sparse camera systems skip their zero tiles.
+//     C   = S_ij - sum_{k<j} L_ik L_jk^T       fp64 tensor-core MMAs (DMMA m8n8k4),
+//                                              waiting per k on the producers' flags
+//     i==j: L_jj = chol(C), X_jj = L_jj^-1      (two 32x32 register-resident warp
+//                                              factorisations + DMMA for the rest)
+//     i>j : L_ij = C X_jj^T                      DMMA
+// followed by nt backward-substitution tasks x_k = X_kk^T (y_k - sum_{i>k} L_ik^T x_i).
+// Dependencies are epoch flags in global memory (st.release / ld.acquire at gpu
+// scope); all CTAs are co-resident and take tickets in increasing order, so a
+// waiting CTA always waits on a ticket held by a running CTA (no deadlock).
+//
+// tcgen05 has no fp64 kind: DMMA (mma.sync.m8n8k4.f64) is the tensor path an
+// fp64 factorisation can use on sm_100a.
 #pragma once
 #include "common.cuh"
 
 namespace bs {
 
-constexpr int kNB = 64;           // panel width / tile edge
+constexpr int kNB = 64;           // tile edge
 constexpr int kLd = 68;           // smem leading dimension (doubles): rows shift by 8 banks
 constexpr int kCholThreads = 256;
+
+struct CholTask {
+  int i, j;        // tile row / column (i == nt: right-hand-side row)
+  int kbeg, kend;  // range in klist: columns k < j with L_ik and L_jk both non-zero
+};
+
+struct CholPlan {
+  int nt;
+  int n_tile_tasks;
+  const CholTask* tasks;
+  const int* klist;
+  const int* bwd_ptr;    // [nt+1]
+  const int* bwd_rows;   // rows i > k with a non-zero tile (i,k), descending
+  int* ready;            // [(nt+1)*nt] epoch flags: tile final
+  int* xready;           // [nt]       epoch flags: x_k final
+  int* ticket;
+  int epoch;
+};
 
 BS_D void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -27,29 +58,56 @@ BS_D void dmma_8x8x4(double& d0, double& d1, double a, double b) {
                : "d"(a), "d"(b));
 }
 
-// acc(64x64) = A(64x64) * B(64x64)^T, both tiles in shared memory with leading
-// dimension kLd.  8 warps; warp w owns rows 16*(w/2).., cols 32*(w%2)..
-// Lane mapping of m8n8k4: a = A[g][t], b = B^T[t][g] = B[g][t], c = C[g][2t..2t+1]
-// with g = lane/4, t = lane%4.
+BS_D int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+BS_D void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Block-wide wait until *flag == epoch.
+BS_D void wait_flag(const int* flag, int epoch) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire(flag) != epoch) __nanosleep(20);
+  }
+  __syncthreads();
+}
+// Block-wide publish: every thread's global writes become visible, then the flag.
+BS_D void post_flag(int* flag, int epoch) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release(flag, epoch);
+}
+
+// 64x64 accumulator of the CTA: 8 warps, warp w owns rows 16*(w/2).., cols 32*(w%2)..
+// m8n8k4 lane mapping: a = A[g][t], b = B[g][t] (B^T operand), c = C[g][2t..2t+1],
+// g = lane/4, t = lane%4.
 struct TileAcc {
   double c[2][4][2];
 };
 
-BS_D void tile_mma_abt(const double* __restrict__ sA, const double* __restrict__ sB, TileAcc& acc) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int m0 = 16 * (warp >> 1), n0 = 32 * (warp & 1);
+BS_D void acc_zero(TileAcc& acc) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc.c[i][j][0] = acc.c[i][j][1] = 0.0;
+}
+
+// acc += A(64x64) * B(64x64)^T, both in shared memory (leading dimension kLd)
+BS_D void tile_mma_abt(const double* __restrict__ sA, const double* __restrict__ sB, TileAcc& acc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* pa = sA + (16 * (warp >> 1) + g) * kLd + t;
+  const double* pb = sB + (32 * (warp & 1) + g) * kLd + t;
 #pragma unroll 4
   for (int k0 = 0; k0 < kNB; k0 += 4) {
     double a[2], b[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) a[i] = sA[(m0 + 8 * i + g) * kLd + k0 + t];
+    for (int i = 0; i < 2; ++i) a[i] = pa[8 * i * kLd + k0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = sB[(n0 + 8 * j + g) * kLd + k0 + t];
+    for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * kLd + k0];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -57,177 +115,269 @@ BS_D void tile_mma_abt(const double* __restrict__ sA, const double* __restrict__
   }
 }
 
-// global (row-major, leading dimension ld) 64x64 tile <-> shared tile
-BS_D void tile_load(double* __restrict__ s, const double* __restrict__ gsrc, int ld) {
+// global tile (row-major, leading dimension ld) -> shared tile; rows >= nrows are zero-filled.
+// L2-coherent loads (ld.global.cg): the data may have been produced by another CTA of this launch.
+BS_D void tile_load(double* __restrict__ s, const double* __restrict__ gsrc, int ld, int nrows) {
   for (int e = threadIdx.x; e < kNB * kNB / 2; e += kCholThreads) {
     const int r = e >> 5, c2 = (e & 31) << 1;
-    const double2 v = *reinterpret_cast<const double2*>(gsrc + (size_t)r * ld + c2);
+    double2 v = make_double2(0.0, 0.0);
+    if (r < nrows) v = __ldcg(reinterpret_cast<const double2*>(gsrc + (size_t)r * ld + c2));
     s[r * kLd + c2] = v.x;
     s[r * kLd + c2 + 1] = v.y;
   }
 }
 
-// Factorise the 64x64 tile in sA (lower triangle) in place, and write the
-// inverse of the factor into sX (lower triangular, zeros above).  Returns the
-// number of non-positive pivots seen (same value in every thread).
-BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX) {
-  __shared__ int s_bad;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_bad = 0;
-  for (int j = 0; j < kNB; ++j) {
-    __syncthreads();
-    if (tid == 0) {
-      const double p = sA[j * kLd + j];
-      if (!(p > 0.0)) s_bad += 1;
-      sA[j * kLd + j] = sqrt(p);
-    }
-    __syncthreads();
-    const double d = sA[j * kLd + j];
-    if (tid > j && tid < kNB) sA[tid * kLd + j] /= d;
-    __syncthreads();
-    const int rem = kNB - 1 - j;
-    for (int e = tid; e < rem * rem; e += kCholThreads) {
-      const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= i) sA[i * kLd + c] -= sA[i * kLd + j] * sA[c * kLd + j];
-    }
-  }
-  __syncthreads();
-  // X = L^-1: thread c owns column c (forward substitution)
-  for (int e = tid; e < kNB * kLd; e += kCholThreads) sX[e] = 0.0;
-  __syncthreads();
-  if (tid < kNB) {
-    const int c = tid;
-    sX[c * kLd + c] = 1.0 / sA[c * kLd + c];
-    for (int i = c + 1; i < kNB; ++i) {
-      double s0 = 0.0, s1 = 0.0;
-      int m = c;
-      for (; m + 1 < i; m += 2) {
-        s0 += sA[i * kLd + m] * sX[m * kLd + c];
-        s1 += sA[i * kLd + m + 1] * sX[(m + 1) * kLd + c];
-      }
-      if (m < i) s0 += sA[i * kLd + m] * sX[m * kLd + c];
-      sX[i * kLd + c] = -(s0 + s1) / sA[i * kLd + i];
-    }
-  }
-  __syncthreads();
-  return s_bad;
-}
-
-// Panel k: grid = (#tiles below k) + 1.
-__global__ void __launch_bounds__(kCholThreads)
-chol_panel_kernel(double* __restrict__ S, int ld, int k, double* __restrict__ Linv, double* __restrict__ scalars) {
-  extern __shared__ double smem[];
-  double* sA = smem;                 // diagonal tile -> L_kk
-  double* sX = smem + kNB * kLd;     // L_kk^-1
-  double* sP = smem + 2 * kNB * kLd; // panel tile
-  double* Akk = S + (size_t)k * kNB * ld + (size_t)k * kNB;
-  tile_load(sA, Akk, ld);
-  const int b = blockIdx.x;
-  if (b > 0) tile_load(sP, S + (size_t)(k + b) * kNB * ld + (size_t)k * kNB, ld);
-  const int bad = tile_potrf_inv(sA, sX);
-  if (b == 0) {
-    if (bad && threadIdx.x == 0) red_add(scalars + 3 /*CHOL_FAIL*/, (double)bad);
-    double* Lk = Linv + (size_t)k * kNB * kNB;
-    for (int e = threadIdx.x; e < kNB * kNB; e += kCholThreads) {
-      const int r = e >> 6, c = e & 63;
-      if (c <= r) Akk[(size_t)r * ld + c] = sA[r * kLd + c];
-      Lk[e] = sX[r * kLd + c];
-    }
-    return;
-  }
-  // L_ik = A_ik * L_kk^-T   ->  C[m][n] = sum_c A[m][c] X[n][c]
-  TileAcc acc;
-  tile_mma_abt(sP, sX, acc);
+// accumulator <-> memory in the MMA C layout
+template <typename F>
+BS_D void acc_foreach(F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = 16 * (warp >> 1), n0 = 32 * (warp & 1);
-  double* P = S + (size_t)(k + b) * kNB * ld + (size_t)k * kNB;
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double2 v = make_double2(acc.c[i][j][0], acc.c[i][j][1]);
-      *reinterpret_cast<double2*>(P + (size_t)(m0 + 8 * i + g) * ld + n0 + 8 * j + 2 * t) = v;
-    }
+    for (int j = 0; j < 4; ++j) f(i, j, m0 + 8 * i + g, n0 + 8 * j + 2 * t);
 }
 
-// Trailing update after panel k: tile (k+1+by, k+1+bx) -= L_(i,k) L_(j,k)^T, by >= bx.
-__global__ void __launch_bounds__(kCholThreads)
-chol_update_kernel(double* __restrict__ S, int ld, int k) {
-  const int bx = blockIdx.x, by = blockIdx.y;
-  if (bx > by) return;
+// ---- 32x32 building blocks of the diagonal-tile factorisation -------------------
+
+// In-place Cholesky of the 32x32 block at `s` (leading dimension kLd) by ONE warp:
+// lane = row, the row lives in registers, the current column is exchanged through
+// `scol`.  Writes 1/L_jj to `srcp`.  Returns the number of non-positive pivots.
+BS_D int potrf32_warp(double* __restrict__ s, double* __restrict__ scol, double* __restrict__ srcp) {
+  const int lane = threadIdx.x & 31;
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = s[lane * kLd + c];
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double d = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(d > 0.0)) ++bad;
+    const double r = rsqrt(d);
+    const double l = (lane == j) ? d * r : a[j] * r;
+    a[j] = l;
+    scol[lane] = l;
+    if (lane == j) srcp[j] = r;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, scol[c], a[c]);
+    __syncwarp();
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s[lane * kLd + c] = (c <= lane) ? a[c] : 0.0;
+  return bad;
+}
+
+// X = L^-1 for the 32x32 lower-triangular block at `sL` (reciprocal diagonal in
+// srcp) by ONE warp: lane = column of X, forward substitution down the rows.
+BS_D void trtri32_warp(const double* __restrict__ sL, const double* __restrict__ srcp, double* __restrict__ sX) {
+  const int lane = threadIdx.x & 31;
+  double x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int m = 0; m < i; ++m) {
+      const double l = sL[i * kLd + m];
+      if ((m & 3) == 0) s0 = fma(-l, x[m], s0);
+      else if ((m & 3) == 1) s1 = fma(-l, x[m], s1);
+      else if ((m & 3) == 2) s2 = fma(-l, x[m], s2);
+      else s3 = fma(-l, x[m], s3);
+    }
+    x[i] = ((s0 + s1) + (s2 + s3)) * srcp[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sX[i * kLd + lane] = x[i];
+}
+
+// C(32x32) = alpha * A(32x32) * op(B)(32x32) + beta * C, all in shared memory
+// (leading dimension kLd), 8 warps: warp w computes the 8x8 output blocks 2w, 2w+1.
+// kTransB: op(B) = B^T (C[m][n] = sum_c A[m][c] B[n][c]); else op(B) = B.
+template <bool kTransB>
+BS_D void gemm32(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, double alpha,
+                 double beta) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int blk = 2 * warp + q, bm = 8 * (blk >> 2), bn = 8 * (blk & 3);
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 4) {
+      const double a = A[(bm + g) * kLd + k0 + t];
+      const double b = kTransB ? B[(bn + g) * kLd + k0 + t] : B[(k0 + t) * kLd + bn + g];
+      dmma_8x8x4(c0, c1, a, b);
+    }
+    double* p = C + (bm + g) * kLd + bn + 2 * t;
+    p[0] = alpha * c0 + (beta != 0.0 ? beta * p[0] : 0.0);
+    p[1] = alpha * c1 + (beta != 0.0 ? beta * p[1] : 0.0);
+  }
+}
+
+// Factorise the 64x64 tile in sA (lower triangle) in place and build X = L^-1 in
+// sX (lower triangular, zeros above the diagonal).  Returns #non-positive pivots.
+BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double* __restrict__ scol,
+                        double* __restrict__ srcp, int* __restrict__ sbad) {
+  const int warp = threadIdx.x >> 5;
+  double* A11 = sA;
+  double* A21 = sA + 32 * kLd;
+  double* A22 = sA + 32 * kLd + 32;
+  double* X11 = sX;
+  double* X12 = sX + 32;
+  double* X21 = sX + 32 * kLd;
+  double* X22 = sX + 32 * kLd + 32;
+  if (threadIdx.x == 0) *sbad = 0;
+  __syncthreads();
+  if (warp == 0) {
+    const int bad = potrf32_warp(A11, scol, srcp);
+    __syncwarp();
+    trtri32_warp(A11, srcp, X11);
+    if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
+  } else {
+    // X12 = 0 (and the part of the tile above the diagonal blocks is never read)
+    for (int e = threadIdx.x - 32; e < 32 * 32; e += kCholThreads - 32) X12[(e >> 5) * kLd + (e & 31)] = 0.0;
+  }
+  __syncthreads();
+  gemm32<true>(A21, X11, X21, 1.0, 0.0);          // X21 <- L21 = A21 X11^T   (scratch use of X21)
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 32; e += kCholThreads) A21[(e >> 5) * kLd + (e & 31)] = X21[(e >> 5) * kLd + (e & 31)];
+  __syncthreads();
+  gemm32<true>(A21, A21, A22, -1.0, 1.0);         // A22 -= L21 L21^T
+  __syncthreads();
+  if (warp == 0) {
+    const int bad = potrf32_warp(A22, scol, srcp + 32);
+    __syncwarp();
+    trtri32_warp(A22, srcp + 32, X22);
+    if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
+  }
+  __syncthreads();
+  gemm32<false>(A21, X11, X12, 1.0, 0.0);         // X12 (scratch) <- L21 X11
+  __syncthreads();
+  gemm32<false>(X22, X12, X21, -1.0, 0.0);        // X21 = -X22 L21 X11
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 32; e += kCholThreads) X12[(e >> 5) * kLd + (e & 31)] = 0.0;
+  __syncthreads();
+  return *sbad;
+}
+
+// ---- the persistent kernel ---------------------------------------------------------
+__global__ void __launch_bounds__(kCholThreads, 1)
+chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, double* __restrict__ x,
+                  double* __restrict__ scalars, const CholPlan p) {
   extern __shared__ double smem[];
   double* sA = smem;
   double* sB = smem + kNB * kLd;
-  const int ti = k + 1 + by, tj = k + 1 + bx;
-  tile_load(sA, S + (size_t)ti * kNB * ld + (size_t)k * kNB, ld);
-  if (bx != by) tile_load(sB, S + (size_t)tj * kNB * ld + (size_t)k * kNB, ld);
-  else sB = sA;
-  __syncthreads();
-  TileAcc acc;
-  tile_mma_abt(sA, sB, acc);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int m0 = 16 * (warp >> 1), n0 = 32 * (warp & 1);
-  double* C = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
+  double* scol = smem + 2 * kNB * kLd;      // 64
+  double* srcp = scol + 64;                 // 64
+  double* sred = srcp + 64;                 // 4 * 64
+  __shared__ int s_ticket, s_bad;
+  const int tid = threadIdx.x;
+  const int nt = p.nt;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int tk = s_ticket;
+    if (tk >= p.n_tile_tasks + nt) break;
+
+    if (tk < p.n_tile_tasks) {
+      // ------------------------------------------------ tile task (i, j)
+      const CholTask task = p.tasks[tk];
+      const int ti = task.i, tj = task.j;
+      const int rows_i = (ti == nt) ? 1 : kNB;
+      TileAcc acc;
+      acc_zero(acc);
+      for (int kk = task.kbeg; kk < task.kend; ++kk) {
+        const int k = p.klist[kk];
+        if (tid == 0) {
+          while (ld_acquire(p.ready + ti * nt + k) != p.epoch) __nanosleep(20);
+          while (ld_acquire(p.ready + tj * nt + k) != p.epoch) __nanosleep(20);
+        }
+        __syncthreads();   // also protects sA/sB of the previous round
+        tile_load(sA, S + (size_t)ti * kNB * ld + (size_t)k * kNB, ld, rows_i);
+        if (ti != tj) tile_load(sB, S + (size_t)tj * kNB * ld + (size_t)k * kNB, ld, kNB);
+        __syncthreads();
+        tile_mma_abt(sA, ti != tj ? sB : sA, acc);
+      }
+      __syncthreads();
+      // C = S_ij - acc  -> sA
+      double* Cij = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
+      acc_foreach([&](int i, int j, int r, int c) {
+        double2 v = make_double2(0.0, 0.0);
+        if (r < rows_i) v = *reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c);
+        sA[r * kLd + c] = v.x - acc.c[i][j][0];
+        sA[r * kLd + c + 1] = v.y - acc.c[i][j][1];
+      });
+      __syncthreads();
+      if (ti == tj) {
+        const int bad = tile_potrf_inv(sA, sB, scol, srcp, &s_bad);
+        if (bad && tid == 0) red_add(scalars + 3 /*CHOL_FAIL*/, (double)bad);
+        double* Lk = Linv + (size_t)tj * kNB * kNB;
+        for (int e = tid; e < kNB * kNB; e += kCholThreads) {
+          const int r = e >> 6, c = e & 63;
+          if (c <= r) Cij[(size_t)r * ld + c] = sA[r * kLd + c];
+          Lk[e] = sB[r * kLd + c];
+        }
+      } else {
+        wait_flag(p.ready + tj * nt + tj, p.epoch);
+        tile_load(sB, Linv + (size_t)tj * kNB * kNB, kNB, kNB);
+        __syncthreads();
+        acc_zero(acc);
+        tile_mma_abt(sA, sB, acc);            // L_ij = C X_jj^T
+        acc_foreach([&](int i, int j, int r, int c) {
+          if (r < rows_i)
+            *reinterpret_cast<double2*>(Cij + (size_t)r * ld + c) = make_double2(acc.c[i][j][0], acc.c[i][j][1]);
+        });
+      }
+      post_flag(p.ready + ti * nt + tj, p.epoch);
+    } else {
+      // ------------------------------------------------ backward substitution, column k
+      const int k = nt - 1 - (tk - p.n_tile_tasks);
+      const int c = tid & 63, grp = tid >> 6;        // 4 row groups of 16
+      // X_kk rows of this thread, prefetched: x_k[c] = sum_r X_kk[r][c] v[r]
+      wait_flag(p.ready + k * nt + k, p.epoch);
+      double xr[16];
+      {
+        const double* X = Linv + (size_t)k * kNB * kNB + (size_t)(16 * grp) * kNB + c;
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+        for (int r = 0; r < 16; ++r) xr[r] = __ldcg(X + (size_t)r * kNB);
+      }
+      double part = 0.0;
+      for (int q = p.bwd_ptr[k]; q < p.bwd_ptr[k + 1]; ++q) {
+        const int i = p.bwd_rows[q];
+        wait_flag(p.ready + i * nt + k, p.epoch);
+        double lr[16];
+        const double* L = S + (size_t)(i * kNB + 16 * grp) * ld + (size_t)k * kNB + c;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double2* p = reinterpret_cast<double2*>(C + (size_t)(m0 + 8 * i + g) * ld + n0 + 8 * j + 2 * t);
-      double2 v = *p;
-      v.x -= acc.c[i][j][0];
-      v.y -= acc.c[i][j][1];
-      *p = v;
+        for (int r = 0; r < 16; ++r) lr[r] = __ldcg(L + (size_t)r * ld);
+        wait_flag(p.xready + i, p.epoch);
+        const double* xi = x + (size_t)i * kNB + 16 * grp;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) part = fma(lr[r], __ldcg(xi + r), part);
+      }
+      wait_flag(p.ready + nt * nt + k, p.epoch);     // y_k (row 0 of the right-hand-side tile)
+      sred[grp * 64 + c] = part;
+      __syncthreads();
+      if (grp == 0) {
+        const double y = __ldcg(S + (size_t)nt * kNB * ld + (size_t)k * kNB + c);
+        scol[c] = y - (sred[c] + sred[64 + c] + sred[128 + c] + sred[192 + c]);
+      }
+      __syncthreads();
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v = fma(xr[r], scol[16 * grp + r], v);
+      __syncthreads();
+      sred[grp * 64 + c] = v;
+      __syncthreads();
+      if (grp == 0) x[(size_t)k * kNB + c] = sred[c] + sred[64 + c] + sred[128 + c] + sred[192 + c];
+      post_flag(p.xready + k, p.epoch);
     }
+  }
 }
 
-// Forward substitution step k (L y = b), grid = (#tiles below k) + 1:
-//   every CTA recomputes y_k = L_kk^-1 b_k; CTA 0 stores it, CTA b>0 applies
-//   b_(k+b) -= L_(k+b,k) y_k.
-__global__ void __launch_bounds__(kNB) trsv_fwd_kernel(const double* __restrict__ S, int ld, int k,
-                                                        const double* __restrict__ Linv,
-                                                        double* __restrict__ bvec, double* __restrict__ y) {
-  __shared__ double sb[kNB], sy[kNB];
-  const int t = threadIdx.x, b = blockIdx.x;
-  sb[t] = bvec[k * kNB + t];
-  __syncthreads();
-  const double* X = Linv + (size_t)k * kNB * kNB + (size_t)t * kNB;
-  double v = 0.0;
-  for (int c = 0; c <= t; ++c) v += X[c] * sb[c];
-  sy[t] = v;
-  __syncthreads();
-  if (b == 0) { y[k * kNB + t] = v; return; }
-  const double* Lr = S + (size_t)((k + b) * kNB + t) * ld + (size_t)k * kNB;
-  double acc = 0.0;
-#pragma unroll 8
-  for (int c = 0; c < kNB; ++c) acc += Lr[c] * sy[c];
-  bvec[(k + b) * kNB + t] -= acc;
-}
-
-// Backward substitution step k (L^T x = y), grid = k + 1:
-//   every CTA recomputes x_k = L_kk^-T y_k; CTA 0 stores it, CTA b>0 applies
-//   y_(b-1) -= L_(k,b-1)^T x_k.
-__global__ void __launch_bounds__(kNB) trsv_bwd_kernel(const double* __restrict__ S, int ld, int k,
-                                                        const double* __restrict__ Linv,
-                                                        double* __restrict__ y, double* __restrict__ x) {
-  __shared__ double sy[kNB], sx[kNB];
-  const int t = threadIdx.x, b = blockIdx.x;
-  sy[t] = y[k * kNB + t];
-  __syncthreads();
-  const double* X = Linv + (size_t)k * kNB * kNB;
-  double v = 0.0;
-  for (int r = t; r < kNB; ++r) v += X[(size_t)r * kNB + t] * sy[r];
-  sx[t] = v;
-  __syncthreads();
-  if (b == 0) { x[k * kNB + t] = v; return; }
-  const int j = b - 1;
-  const double* Lt = S + (size_t)k * kNB * ld + (size_t)j * kNB + t;   // column t of tile (k,j)
-  double acc = 0.0;
-#pragma unroll 8
-  for (int r = 0; r < kNB; ++r) acc += Lt[(size_t)r * ld] * sx[r];
-  y[j * kNB + t] -= acc;
-}
+constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + 4 * 64) * sizeof(double);
 
 // identity on the padding diagonal so the padded factorisation is well defined
 __global__ void pad_diag_kernel(double* __restrict__ S, int ld, int n, int n_pad) {

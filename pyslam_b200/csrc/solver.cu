@@ -100,11 +100,18 @@ struct bslam_solver {
   DevBuf<double> d_ou, d_ov, d_od;
   DevBuf<int> d_opose, d_opt, d_ogrp, d_lm_start;
   DevBuf<bs::ReprojGroup> d_groups;
-  DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_y, d_Linv;
+  DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_Linv;
   DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
   DevBuf<long long> d_dn_j_ptr;
   DevBuf<double> d_dn_J, d_dn_e;
   double* h_scalars = nullptr;   // pinned
+
+  // ---- tile structure of the reduced system and the Cholesky task plan ----
+  std::vector<uint8_t> tile_mask;                   // [(nblk+1) * nblk], lower triangle + rhs row
+  bool plan_valid = false;
+  int chol_epoch = 0, chol_grid = 0, n_tile_tasks = 0;
+  DevBuf<bs::CholTask> d_tasks;
+  DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_ticket;
 
   double* S() { return d_red.p; }
   double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
@@ -285,21 +292,121 @@ int do_reduce(bslam_solver* s, double lambda) {
   return BSLAM_OK;
 }
 
-constexpr size_t kPanelSmem = 3 * bs::kNB * bs::kLd * sizeof(double);
-constexpr size_t kUpdateSmem = 2 * bs::kNB * bs::kLd * sizeof(double);
+// Tile-level structure of the reduced matrix from the co-visibility graph:
+// tile (a,b) is non-zero if some residual block couples a parameter in tile a
+// with one in tile b.
+void mark_tiles(bslam_solver* s, const std::vector<int>& tiles) {
+  const int nt = s->nblk;
+  for (int a : tiles)
+    for (int b : tiles)
+      if (a >= b) s->tile_mask[(size_t)a * nt + b] = 1;
+}
+
+void tiles_of(int off, int dof, std::vector<int>& out) {
+  if (off < 0) return;
+  for (int t = off / bs::kNB; t <= (off + dof - 1) / bs::kNB; ++t)
+    if (std::find(out.begin(), out.end(), t) == out.end()) out.push_back(t);
+}
+
+void build_tile_mask(bslam_solver* s, const std::vector<int>& opose, const std::vector<int>& lm_start) {
+  const int nt = s->nblk;
+  s->tile_mask.assign((size_t)(nt + 1) * nt, 0);
+  for (int t = 0; t < nt; ++t) s->tile_mask[(size_t)t * nt + t] = 1;
+  for (int t = 0; t < nt; ++t) s->tile_mask[(size_t)nt * nt + t] = 1;      // right-hand side row
+  std::vector<int> tiles;
+  for (int q = 0; q < s->n_lm; ++q) {                                      // Schur fill: poses sharing a landmark
+    tiles.clear();
+    for (int k = lm_start[q]; k < lm_start[q + 1]; ++k) tiles_of(s->se3_off[opose[k]], 6, tiles);
+    mark_tiles(s, tiles);
+  }
+  for (auto* b : s->edges) {
+    if (!b->binary) continue;
+    const std::vector<int>& off = b->group == 3 ? s->se3_off : s->se2_off;
+    const int dof = b->group == 3 ? 6 : 3;
+    for (int e = 0; e < b->n; ++e) {
+      tiles.clear();
+      tiles_of(off[b->i1[e]], dof, tiles);
+      tiles_of(off[b->i2[e]], dof, tiles);
+      mark_tiles(s, tiles);
+    }
+  }
+  for (int b = 0; b < s->dn_blocks; ++b) {
+    tiles.clear();
+    for (int c = s->dn_col_ptr[b]; c < s->dn_col_ptr[b + 1]; ++c) tiles_of(s->dn_col_index[c], 1, tiles);
+    mark_tiles(s, tiles);
+  }
+  s->plan_valid = false;
+}
+
+// Symbolic factorisation on the tile grid + task list of chol_solve_kernel.
+int build_chol_plan(bslam_solver* s) {
+  const int nt = s->nblk;
+  std::vector<uint8_t> m = s->tile_mask;
+  auto at = [&](int i, int j) -> uint8_t& { return m[(size_t)i * nt + j]; };
+  std::vector<int> rows;
+  for (int k = 0; k < nt; ++k) {
+    rows.clear();
+    for (int i = k + 1; i <= nt; ++i)
+      if (at(i, k)) rows.push_back(i);
+    for (int a : rows)
+      for (int b : rows)
+        if (a >= b && b < nt) at(a, b) = 1;
+  }
+  std::vector<bs::CholTask> tasks;
+  std::vector<int> klist, bwd_ptr(nt + 1, 0), bwd_rows;
+  for (int j = 0; j < nt; ++j)
+    for (int i = j; i <= nt; ++i) {
+      if (!at(i, j)) continue;
+      bs::CholTask t;
+      t.i = i; t.j = j; t.kbeg = (int)klist.size();
+      for (int k = 0; k < j; ++k)
+        if (at(i, k) && at(j, k)) klist.push_back(k);
+      t.kend = (int)klist.size();
+      tasks.push_back(t);
+    }
+  for (int k = 0; k < nt; ++k) {
+    for (int i = nt - 1; i > k; --i)
+      if (at(i, k)) bwd_rows.push_back(i);
+    bwd_ptr[k + 1] = (int)bwd_rows.size();
+  }
+  if (klist.empty()) klist.push_back(0);
+  if (bwd_rows.empty()) bwd_rows.push_back(0);
+  s->n_tile_tasks = (int)tasks.size();
+  cudaStream_t st = s->stream;
+  CU(upload(s->d_tasks, tasks, st));
+  CU(upload(s->d_klist, klist, st));
+  CU(upload(s->d_bwd_ptr, bwd_ptr, st));
+  CU(upload(s->d_bwd_rows, bwd_rows, st));
+  CU(s->d_ready.alloc((size_t)(nt + 1) * nt));
+  CU(s->d_xready.alloc(nt));
+  CU(s->d_ticket.alloc(1));
+  CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), st));
+  CU(cudaMemsetAsync(s->d_xready.p, 0, s->d_xready.n * sizeof(int), st));
+  s->chol_epoch = 0;
+  int per_sm = 0, sms = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bs::chol_solve_kernel, bs::kCholThreads, bs::kCholSmem));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  if (per_sm < 1) return fail(s, BSLAM_E_CUDA, "chol_solve_kernel does not fit on an SM");
+  s->chol_grid = std::min(per_sm * sms, s->n_tile_tasks + nt);
+  s->plan_valid = true;
+  return BSLAM_OK;
+}
 
 int do_solve_reduced(bslam_solver* s) {
-  const int nb = s->nblk, ld = s->n_pad;
-  for (int k = 0; k < nb; ++k) {
-    LAUNCH(s, bs::chol_panel_kernel, nb - k, bs::kCholThreads, kPanelSmem, s->S(), ld, k, s->d_Linv.p, s->scalars());
-    const int t = nb - k - 1;
-    if (t > 0) LAUNCH(s, bs::chol_update_kernel, dim3(t, t), bs::kCholThreads, kUpdateSmem, s->S(), ld, k);
+  if (!s->plan_valid) {
+    int rc = build_chol_plan(s);
+    if (rc) return rc;
   }
+  bs::CholPlan p;
+  p.nt = s->nblk;
+  p.n_tile_tasks = s->n_tile_tasks;
+  p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
+  p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
+  p.epoch = ++s->chol_epoch;
+  CU(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(int), s->stream));
+  LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
+         s->d_dx.p, s->scalars(), p);
   record(s, 5);
-  for (int k = 0; k < nb; ++k)
-    LAUNCH(s, bs::trsv_fwd_kernel, nb - k, bs::kNB, 0, s->S(), ld, k, s->d_Linv.p, s->rhs(), s->d_y.p);
-  for (int k = nb - 1; k >= 0; --k)
-    LAUNCH(s, bs::trsv_bwd_kernel, k + 1, bs::kNB, 0, s->S(), ld, k, s->d_Linv.p, s->d_y.p, s->d_dx.p);
   record(s, 6);
   if (s->n_lm > 0) {
     bs::BacksubArgs a;
@@ -390,8 +497,7 @@ int bslam_create(bslam_solver** out, int device) {
     return BSLAM_E_CUDA;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
-  cudaFuncSetAttribute(bs::chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem);
-  cudaFuncSetAttribute(bs::chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
+  cudaFuncSetAttribute(bs::chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::kCholSmem);
   *out = h;
   return BSLAM_OK;
 }
@@ -773,7 +879,6 @@ int bslam_finalize(bslam_solver* s) {
   CU(s->d_Vinv.alloc(6 * (size_t)s->n_lm));
   CU(s->d_red.alloc(s->red_len()));
   CU(s->d_dx.alloc((size_t)s->n_pad + 3 * (size_t)s->n_lm));
-  CU(s->d_y.alloc(s->n_pad));
   CU(s->d_Linv.alloc((size_t)s->nblk * bs::kNB * bs::kNB));
   CU(s->b_se3.alloc(s->d_se3.n)); CU(s->b_se2.alloc(s->d_se2.n));
   CU(s->b_pts.alloc(s->d_pts.n)); CU(s->b_vec.alloc(s->d_vec.n));
@@ -781,6 +886,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
   if (N > 0) CU(cudaMemsetAsync(s->d_W.p, 0, s->d_W.n * sizeof(double), st));
   CU(cudaStreamSynchronize(st));
+  build_tile_mask(s, opose, lm_start);
   s->finalized = true;
   s->dn_uploaded = false;
   return BSLAM_OK;
@@ -884,6 +990,18 @@ int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles, voi
 int bslam_set_shard(bslam_solver* s, int rank) {
   NEED(s, "NULL solver");
   s->shard_rank = rank;
+  return BSLAM_OK;
+}
+
+int bslam_tile_structure(bslam_solver* s, uint8_t* mask, size_t n, int set) {
+  NEED(s && s->finalized && mask, "bslam_tile_structure: bad arguments");
+  NEED(n == s->tile_mask.size(), "bslam_tile_structure: expected %zu bytes, got %zu", s->tile_mask.size(), n);
+  if (set) {
+    for (size_t i = 0; i < n; ++i) s->tile_mask[i] = s->tile_mask[i] || mask[i];
+    s->plan_valid = false;
+  } else {
+    std::memcpy(mask, s->tile_mask.data(), n);
+  }
   return BSLAM_OK;
 }
 

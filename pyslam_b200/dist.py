@@ -43,6 +43,19 @@ class ShardedSolver:
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
         engine.set_shard(rank)
         self._buf = self._tail = self._stream = None
+        if world > 1:
+            self._merge_structure()
+
+    def _merge_structure(self):
+        """The summed reduced matrix has the UNION of the ranks' tile structures."""
+        import torch
+        import torch.distributed as dist
+        m = self.engine.tile_structure()
+        t = torch.from_numpy(m.astype(np.int32))
+        if dist.get_backend(self.group) == 'nccl':
+            t = t.cuda(self.engine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.engine.merge_tile_structure(t.cpu().numpy().astype(np.uint8))
 
     def _tensors(self):
         if self._buf is None:

@@ -59,6 +59,7 @@ SIGNATURES = {
     'bslam_retract': (C.c_int, [_h, C.c_int]),
     'bslam_get_scalars': (C.c_int, [_h, _dp]),
     'bslam_reduced_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), _ip]),
+    'bslam_tile_structure': (C.c_int, [_h, _bp, C.c_size_t, C.c_int]),
     'bslam_set_shard': (C.c_int, [_h, C.c_int]),
     'bslam_stream': (C.c_void_p, [_h]),
     'bslam_snapshot': (C.c_int, [_h]),
@@ -295,6 +296,18 @@ class Engine:
         p, n, ps, npad = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_int32()
         self._ck(self._lib.bslam_reduced_buffer(self._h, C.byref(p), C.byref(n), C.byref(ps), C.byref(npad)))
         return p.value, n.value, ps.value, npad.value
+
+    def tile_structure(self):
+        """uint8 mask [(nt+1), nt] of the non-zero 64x64 tiles of the reduced system."""
+        _, _, _, npad = self.reduced_buffer()
+        nt = npad // 64
+        m = np.zeros((nt + 1, nt), np.uint8)
+        self._ck(self._lib.bslam_tile_structure(self._h, _b(m), m.size, 0))
+        return m
+
+    def merge_tile_structure(self, mask):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self._lib.bslam_tile_structure(self._h, _b(m), m.size, 1))
 
     def set_shard(self, rank):
         self._ck(self._lib.bslam_set_shard(self._h, int(rank)))
