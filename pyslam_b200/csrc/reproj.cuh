@@ -11,13 +11,25 @@
 // Data layout (all fp64, device resident, built once by Solver::finalize):
 //   observations sorted by landmark, SoA:  obs_u/obs_v/obs_d[N], obs_pose[N], obs_pt[N]
 //   poses   [K][12] = R row-major | t      (K small: L1/L2 resident)
-//   points  [P][3], landmarks to be eliminated first (index < n_lm)
+//   points  [P][3], landmarks to be eliminated first (index < n_lm), ordered by the
+//           first pose that sees them so that neighbouring landmarks share cameras
+//   "landmark blocks": runs of whole landmarks with <= 128 observations; per block the
+//           distinct variable poses ("slots"), a per-observation slot id and the
+//           block's observations grouped by slot (cam_perm / seg_start)
 // Outputs per launch:
-//   W   [N][18]   J_T^T w J_p   (6x3 row-major)   -- pose/landmark coupling blocks
+//   W   [18][N]   J_T^T w J_p (6x3 row-major index k = 3r+c), SoA planes of N doubles
 //   Vg  [n_lm][9] V_p (xx,xy,xz,yy,yz,zz) | b_p   -- landmark blocks
 //   S   lower triangle of the dense reduced matrix: U_c added at the pose's offset
 //   rhs b_c = -J_T^T w r
 //   scalars[COST_LIN] += sum rho(r)
+//
+// reproj_block_kernel (the fast path): one CTA per landmark block, one thread per
+// observation.  Each thread leaves its 27 camera values (U_c lower triangle, b_c)
+// and 9 landmark values (V_p, b_p) in a shared-memory row; the CTA then reduces
+// them per slot / per landmark, so HBM sees one fp64 atomic per (slot, value) and
+// a plain store per landmark value instead of 36 atomics per observation.
+// reproj_generic_kernel: same arithmetic with global atomics for the tail
+// (landmarks with more than 128 observations, observations of constant points).
 #pragma once
 #include "common.cuh"
 #include "loss.cuh"
@@ -30,8 +42,16 @@ struct ReprojGroup {     // constants shared by a batch of blocks
   Loss loss;
 };
 
+struct LmBlock {         // a run of whole landmarks
+  int obs_begin, n_obs;  // n_obs <= kBlkObs
+  int lm_begin, n_lms;
+  int slot_begin, n_slots;   // into slot_pose[] / (slot_begin + block index) into seg_start[]
+  int seg_begin;             // into seg_start[]: n_slots + 1 entries (local positions in cam_perm order)
+  int pad;
+};
+
 struct ReprojArgs {
-  int n_obs;
+  int n_obs;                      // all observations (SoA stride of W)
   int n_lm;                       // points with index < n_lm are eliminated landmarks
   const double* __restrict__ obs_u;
   const double* __restrict__ obs_v;
@@ -43,7 +63,16 @@ struct ReprojArgs {
   const double* __restrict__ poses;         // [K][12]
   const int* __restrict__ pose_off;         // reduced offset of the pose or -1 (constant)
   const double* __restrict__ pts;           // [P][3]
-  double* __restrict__ W;                   // [N][18]
+  const int* __restrict__ lm_start;         // [n_lm+1]
+  // landmark blocks
+  int n_blocks;
+  const LmBlock* __restrict__ blocks;
+  const int* __restrict__ slot_pose;
+  const unsigned char* __restrict__ cam_perm;   // [N] local obs index, grouped by slot inside each block
+  const unsigned char* __restrict__ seg_start;
+  // tail processed by the generic kernel
+  int tail_begin;
+  double* __restrict__ W;                   // [18][N]
   double* __restrict__ Vg;                  // [n_lm][9]
   double* __restrict__ S;                   // [n_pad][ldS]
   int ldS;
@@ -51,8 +80,10 @@ struct ReprojArgs {
   double* __restrict__ scalars;
 };
 
-constexpr int kReprojThreads = 256;
-constexpr int kWStride = 19;      // 18 doubles + 1 pad: conflict-free 64-bit smem rows
+constexpr int kBlkObs = 128;      // observations per landmark block = threads per CTA
+constexpr int kMaxTrack = 64;     // longer tracks go through the generic (atomic) kernels
+constexpr int kSchurCap = 768;    // n_slots * ldk cap of a multi-landmark block (96 KB of Schur operands)
+constexpr int kRow = 37;          // 27 camera + 9 landmark values + 1 pad (odd stride: conflict-free rows)
 
 // Residual and the two Jacobians of one observation.
 struct ReprojLin {
@@ -107,31 +138,116 @@ BS_D void reproj_linearize_one(const ReprojGroup& g, const double* __restrict__ 
   }
 }
 
-// One thread per observation.  W is staged through shared memory so the
-// 144-byte rows leave the SM as fully coalesced 8-byte-per-lane stores.
-__global__ void __launch_bounds__(kReprojThreads)
-reproj_linearize_kernel(const ReprojArgs a) {
-  __shared__ double sW[kReprojThreads * kWStride];
-  __shared__ double sred[kReprojThreads / 32];
-  const int tid = threadIdx.x;
-  const int base = blockIdx.x * kReprojThreads;
-  const int i = base + tid;
-  double cost = 0.0;
-  double w18[18];
-#pragma unroll
-  for (int k = 0; k < 18; ++k) w18[k] = 0.0;
+// value index 0..20 -> (row, col) of the lower triangle of a 6x6 block, row-major
+__device__ __constant__ unsigned char kTriRow[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
+__device__ __constant__ unsigned char kTriCol[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
 
-  if (i < a.n_obs) {
+__global__ void __launch_bounds__(kBlkObs, 4)
+reproj_block_kernel(const ReprojArgs a) {
+  __shared__ double sT[kBlkObs * kRow];
+  __shared__ double sred[kBlkObs / 32];
+  const int tid = threadIdx.x;
+  const LmBlock blk = a.blocks[blockIdx.x];
+  const int N = a.n_obs;
+  double cost = 0.0;
+
+  if (tid < blk.n_obs) {
+    const int i = blk.obs_begin + tid;
+    const int pi = a.obs_pose[i];
+    const int qi = a.obs_pt[i];
+    const bool pose_var = a.pose_off[pi] >= 0;
+    const ReprojGroup& g = a.groups[a.obs_grp ? a.obs_grp[i] : 0];
+    ReprojLin L;
+    reproj_linearize_one(g, a.poses + 12 * (size_t)pi, a.pts + 3 * (size_t)qi, ld_stream(a.obs_u + i),
+                         ld_stream(a.obs_v + i), ld_stream(a.obs_d + i), L);
+    double w[3], wr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      w[k] = loss_weight(g.loss, L.r[k]);
+      wr[k] = w[k] * L.r[k];
+      cost += loss_rho(g.loss, L.r[k]);
+    }
+    double* row = sT + tid * kRow;
+    // weighted Jacobian rows, reused by all three products
+    double wJT[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) wJT[k] = w[k / 6] * L.JT[k];
+    if (pose_var) {
+      int v = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c)
+          row[v++] = wJT[r] * L.JT[c] + wJT[6 + r] * L.JT[6 + c] + wJT[12 + r] * L.JT[12 + c];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) row[21 + r] = -(L.JT[r] * wr[0] + L.JT[6 + r] * wr[1] + L.JT[12 + r] * wr[2]);
+      // W = J_T^T w J_p, SoA planes
+      double* Wp = a.W + i;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          Wp[(size_t)(3 * r + c) * N] = wJT[r] * L.Jp[c] + wJT[6 + r] * L.Jp[3 + c] + wJT[12 + r] * L.Jp[6 + c];
+    }
+    {
+      int v = 27;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = r; c < 3; ++c)
+          row[v++] = w[0] * L.Jp[r] * L.Jp[c] + w[1] * L.Jp[3 + r] * L.Jp[3 + c] + w[2] * L.Jp[6 + r] * L.Jp[6 + c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) row[33 + r] = -(L.Jp[r] * wr[0] + L.Jp[3 + r] * wr[1] + L.Jp[6 + r] * wr[2]);
+    }
+  }
+  __syncthreads();
+
+  // camera side: one task per (slot, value); observations of a slot are contiguous in cam_perm order
+  {
+    const unsigned char* perm = a.cam_perm + blk.obs_begin;
+    const unsigned char* seg = a.seg_start + blk.seg_begin;
+    const int n_tasks = blk.n_slots * 27;
+    for (int t = tid; t < n_tasks; t += kBlkObs) {
+      const int s = t / 27, v = t - 27 * s;
+      double acc = 0.0;
+      for (int k = seg[s]; k < seg[s + 1]; ++k) acc += sT[perm[k] * kRow + v];
+      const int off = a.pose_off[a.slot_pose[blk.slot_begin + s]];
+      if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
+      else red_add(a.rhs + off + (v - 21), acc);
+    }
+  }
+  // landmark side: one task per (landmark, value); a landmark's observations are contiguous
+  {
+    const int n_tasks = blk.n_lms * 9;
+    for (int t = tid; t < n_tasks; t += kBlkObs) {
+      const int l = t / 9, v = t - 9 * l;
+      const int q = blk.lm_begin + l;
+      const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
+      double acc = 0.0;
+      for (int k = k0; k < k1; ++k) acc += sT[k * kRow + 27 + v];
+      a.Vg[9 * (size_t)q + v] = acc;
+    }
+  }
+  block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
+}
+
+// Tail observations [tail_begin, n_obs): one thread per observation, global atomics.
+__global__ void __launch_bounds__(128)
+reproj_generic_kernel(const ReprojArgs a) {
+  __shared__ double sred[4];
+  const int i = a.tail_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = a.n_obs;
+  double cost = 0.0;
+  if (i < N) {
     const int pi = a.obs_pose[i];
     const int qi = a.obs_pt[i];
     const int poff = a.pose_off[pi];
     const bool pt_var = qi < a.n_lm;
     if (poff >= 0 || pt_var) {
       const ReprojGroup& g = a.groups[a.obs_grp ? a.obs_grp[i] : 0];
-      const double* P = a.poses + 12 * (size_t)pi;
-      const double* X = a.pts + 3 * (size_t)qi;
       ReprojLin L;
-      reproj_linearize_one(g, P, X, a.obs_u[i], a.obs_v[i], a.obs_d[i], L);
+      reproj_linearize_one(g, a.poses + 12 * (size_t)pi, a.pts + 3 * (size_t)qi, a.obs_u[i], a.obs_v[i], a.obs_d[i], L);
       double w[3], wr[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -140,16 +256,13 @@ reproj_linearize_kernel(const ReprojArgs a) {
         cost += loss_rho(g.loss, L.r[k]);
       }
       if (poff >= 0) {
-        // U_c (lower triangle incl. diagonal) and b_c
         double* Sd = a.S + (size_t)poff * a.ldS + poff;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
 #pragma unroll
-          for (int c = 0; c <= r; ++c) {
-            const double v = w[0] * L.JT[r] * L.JT[c] + w[1] * L.JT[6 + r] * L.JT[6 + c] +
-                             w[2] * L.JT[12 + r] * L.JT[12 + c];
-            red_add(Sd + (size_t)r * a.ldS + c, v);
-          }
+          for (int c = 0; c <= r; ++c)
+            red_add(Sd + (size_t)r * a.ldS + c, w[0] * L.JT[r] * L.JT[c] + w[1] * L.JT[6 + r] * L.JT[6 + c] +
+                                                    w[2] * L.JT[12 + r] * L.JT[12 + c]);
           red_add(a.rhs + poff + r, -(L.JT[r] * wr[0] + L.JT[6 + r] * wr[1] + L.JT[12 + r] * wr[2]));
         }
       }
@@ -167,33 +280,24 @@ reproj_linearize_kernel(const ReprojArgs a) {
           red_add(vg + 6 + r, -(L.Jp[r] * wr[0] + L.Jp[3 + r] * wr[1] + L.Jp[6 + r] * wr[2]));
       }
       if (poff >= 0 && pt_var) {
+        double* Wp = a.W + i;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            w18[3 * r + c] = w[0] * L.JT[r] * L.Jp[c] + w[1] * L.JT[6 + r] * L.Jp[3 + c] +
-                             w[2] * L.JT[12 + r] * L.Jp[6 + c];
+            Wp[(size_t)(3 * r + c) * N] = w[0] * L.JT[r] * L.Jp[c] + w[1] * L.JT[6 + r] * L.Jp[3 + c] +
+                                          w[2] * L.JT[12 + r] * L.Jp[6 + c];
       }
     }
-  }
-  // stage W rows, then stream them out coalesced
-#pragma unroll
-  for (int k = 0; k < 18; ++k) sW[tid * kWStride + k] = w18[k];
-  __syncthreads();
-  const int n_here = min(kReprojThreads, a.n_obs - base);
-  double* Wg = a.W + 18 * (size_t)base;
-  for (int e = tid; e < 18 * n_here; e += kReprojThreads) {
-    const int o = e / 18, k = e - 18 * o;
-    Wg[e] = sW[o * kWStride + k];
   }
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
 }
 
 // Cost only: sum rho(r) over ALL reprojection blocks (Problem.eval_cost,
 // pyslam/problem.py:110-128) -> scalars[slot].
-__global__ void __launch_bounds__(kReprojThreads)
+__global__ void __launch_bounds__(256)
 reproj_cost_kernel(const ReprojArgs a, int slot) {
-  __shared__ double sred[kReprojThreads / 32];
+  __shared__ double sred[8];
   double cost = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += gridDim.x * blockDim.x) {
     const ReprojGroup& g = a.groups[a.obs_grp ? a.obs_grp[i] : 0];

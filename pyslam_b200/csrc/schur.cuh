@@ -5,16 +5,14 @@
 // is formed in the dense lower triangle of S, and after the dense solve the
 // landmark updates follow from  dx_p = V_p^-1 (b_p - W_p^T dx_c).
 #pragma once
+#include "cholesky.cuh"
 #include "common.cuh"
+#include "reproj.cuh"
 
 namespace bs {
 
 // Vg[q] = (xx,xy,xz,yy,yz,zz | b0,b1,b2)  ->  Vinv[q] = (xx,xy,xz,yy,yz,zz) of (V + lambda diag V)^-1
-__global__ void __launch_bounds__(256) landmark_invert_kernel(int n_lm, const double* __restrict__ Vg,
-                                                              double lambda, double* __restrict__ Vinv) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_lm) return;
-  const double* v = Vg + 9 * (size_t)q;
+BS_D void sym3_inverse(const double* __restrict__ v, double lambda, double* __restrict__ o) {
   const double s = 1.0 + lambda;
   const double a = v[0] * s, b = v[1], c = v[2], d = v[3] * s, e = v[4], f = v[5] * s;
   // cofactors of the symmetric matrix [[a,b,c],[b,d,e],[c,e,f]]
@@ -26,19 +24,33 @@ __global__ void __launch_bounds__(256) landmark_invert_kernel(int n_lm, const do
   const double c22 = a * d - b * b;
   const double det = a * c00 + b * c01 + c * c02;
   const double id = 1.0 / det;
-  double* o = Vinv + 6 * (size_t)q;
   o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
   o[3] = c11 * id; o[4] = c12 * id; o[5] = c22 * id;
+}
+
+// landmarks [q_begin, n_lm)
+__global__ void __launch_bounds__(256) landmark_invert_kernel(int q_begin, int n_lm, const double* __restrict__ Vg,
+                                                              double lambda, double* __restrict__ Vinv) {
+  const int q = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_lm) return;
+  sym3_inverse(Vg + 9 * (size_t)q, lambda, Vinv + 6 * (size_t)q);
 }
 
 struct SchurArgs {
   int n_obs;
   int n_lm;
+  int obs_begin;                      // generic kernel: first observation it handles
+  double lambda;
+  int n_blocks;
+  const LmBlock* __restrict__ blocks;
+  const int* __restrict__ slot_pose;
+  const unsigned char* __restrict__ obs_slot;   // [N] slot of the observation inside its block (255: constant pose)
+  double* __restrict__ Vinv_out;
   const int* __restrict__ obs_pose;
   const int* __restrict__ obs_pt;
   const int* __restrict__ lm_start;   // [n_lm+1] observation range of each landmark
   const int* __restrict__ pose_off;
-  const double* __restrict__ W;       // [N][18]
+  const double* __restrict__ W;       // [18][N] (SoA planes)
   const double* __restrict__ Vg;      // [n_lm][9]
   const double* __restrict__ Vinv;    // [n_lm][6]
   double* __restrict__ S;
@@ -48,8 +60,8 @@ struct SchurArgs {
 
 // One thread per observation i: Y_i = W_i V^-1, then for every observation j of
 // the same landmark whose pose block does not lie above i's:  S(i,j) -= Y_i W_j^T.
-__global__ void __launch_bounds__(128) schur_kernel(const SchurArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
+  const int i = a.obs_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_obs) return;
   const int q = a.obs_pt[i];
   if (q >= a.n_lm) return;
@@ -57,11 +69,12 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurArgs a) {
   if (oi < 0) return;
   const double* vi = a.Vinv + 6 * (size_t)q;
   const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-  const double* Wi = a.W + 18 * (size_t)i;
+  const size_t N = (size_t)a.n_obs;
+  const double* Wi = a.W + i;
   double Y[18];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    const double w0 = Wi[3 * r], w1 = Wi[3 * r + 1], w2 = Wi[3 * r + 2];
+    const double w0 = Wi[(3 * r) * N], w1 = Wi[(3 * r + 1) * N], w2 = Wi[(3 * r + 2) * N];
     Y[3 * r + 0] = w0 * m00 + w1 * m01 + w2 * m02;
     Y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
     Y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
@@ -75,10 +88,10 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurArgs a) {
   for (int j = j0; j < j1; ++j) {
     const int oj = a.pose_off[a.obs_pose[j]];
     if (oj < 0 || oj > oi) continue;
-    const double* Wj = a.W + 18 * (size_t)j;
+    const double* Wj = a.W + j;
     double wj[18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) wj[k] = Wj[k];
+    for (int k = 0; k < 18; ++k) wj[k] = Wj[k * N];
     double* Sd = a.S + (size_t)oi * a.ldS + oj;
     const bool diag = (oj == oi);
 #pragma unroll
@@ -92,8 +105,109 @@ __global__ void __launch_bounds__(128) schur_kernel(const SchurArgs a) {
   }
 }
 
+
+// ---- fast path: one CTA per landmark block, Schur products on the fp64 tensor cores ----
+// For the block's landmarks l and pose slots a the CTA builds two zero-padded operand
+// matrices in shared memory (8 rows per slot, K = 3*l + c):
+//     Yt[8a + r][K] = (W_{l,a} V_l^-1)[r][c]      Wt[8a + r][K] = W_{l,a}[r][c]
+// so that for every slot pair   S(a,b) -= sum_K Yt[8a+.][K] Wt[8b+.][K]   is a
+// chain of mma.sync.m8n8k4.f64; one fp64 atomic per output element leaves the CTA
+// (instead of one per landmark and element).  b_c -= Y b_p rides along as a mat-vec.
+BS_HD int schur_ldk(int n_lms) {              // row stride: >= 3*n_lms (+pad), = 4 mod 16 -> conflict-free fragments
+  return ((3 * n_lms + 3 + 11) / 16) * 16 + 4;
+}
+
+__global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a) {
+  extern __shared__ double sm[];
+  __shared__ double sVinv[6 * kBlkObs];
+  __shared__ double sG[3 * kBlkObs + 8];
+  const int tid = threadIdx.x;
+  const LmBlock blk = a.blocks[blockIdx.x];
+  const int ldk = schur_ldk(blk.n_lms);
+  const int rows = 8 * blk.n_slots;
+  double* Yt = sm;
+  double* Wt = sm + (size_t)rows * ldk;
+  const size_t N = (size_t)a.n_obs;
+
+  // zero the operands (pairs (slot, landmark) without an observation contribute nothing)
+  {
+    double2* z = reinterpret_cast<double2*>(sm);
+    const int n2 = rows * ldk;            // 2 * rows * ldk doubles = rows*ldk double2
+    for (int e = tid; e < n2; e += kBlkObs) z[e] = make_double2(0.0, 0.0);
+  }
+  // V^-1 and b_p of the block's landmarks
+  for (int l = tid; l < blk.n_lms; l += kBlkObs) {
+    const int q = blk.lm_begin + l;
+    double vi[6];
+    sym3_inverse(a.Vg + 9 * (size_t)q, a.lambda, vi);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sVinv[6 * l + k] = vi[k]; a.Vinv_out[6 * (size_t)q + k] = vi[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sG[3 * l + k] = a.Vg[9 * (size_t)q + 6 + k];
+  }
+  __syncthreads();
+  if (tid < blk.n_obs) {
+    const int i = blk.obs_begin + tid;
+    const int sl = a.obs_slot[i];
+    if (sl != 255) {
+      const int l = a.obs_pt[i] - blk.lm_begin;
+      const double* vi = sVinv + 6 * l;
+      const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
+      double* yr = Yt + (size_t)(8 * sl) * ldk + 3 * l;
+      double* wr = Wt + (size_t)(8 * sl) * ldk + 3 * l;
+      const double* Wi = a.W + i;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double w0 = Wi[(3 * r) * N], w1 = Wi[(3 * r + 1) * N], w2 = Wi[(3 * r + 2) * N];
+        wr[r * ldk] = w0; wr[r * ldk + 1] = w1; wr[r * ldk + 2] = w2;
+        yr[r * ldk] = w0 * m00 + w1 * m01 + w2 * m02;
+        yr[r * ldk + 1] = w0 * m01 + w1 * m11 + w2 * m12;
+        yr[r * ldk + 2] = w0 * m02 + w1 * m12 + w2 * m22;
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int kdim = (3 * blk.n_lms + 3) & ~3;
+  // slot pairs (sa, sb) with sb <= sa, dealt round-robin to the 4 warps
+  const int n_pairs = blk.n_slots * (blk.n_slots + 1) / 2;
+  for (int pidx = warp; pidx < n_pairs; pidx += kBlkObs / 32) {
+    // invert pidx = sa*(sa+1)/2 + sb
+    int sa = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
+    while ((sa + 1) * (sa + 2) / 2 <= pidx) ++sa;
+    while (sa * (sa + 1) / 2 > pidx) --sa;
+    const int sb = pidx - sa * (sa + 1) / 2;
+    int oa = a.pose_off[a.slot_pose[blk.slot_begin + sa]];
+    int ob = a.pose_off[a.slot_pose[blk.slot_begin + sb]];
+    // rows must belong to the pose with the larger reduced offset (lower triangle)
+    const int ra = oa >= ob ? sa : sb, rb = oa >= ob ? sb : sa;
+    if (oa < ob) { const int tmp = oa; oa = ob; ob = tmp; }
+    const double* pa = Yt + (size_t)(8 * ra + g) * ldk + t;
+    const double* pb = Wt + (size_t)(8 * rb + g) * ldk + t;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = 0; k0 < kdim; k0 += 4) dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
+    // C[g][2t], C[g][2t+1] = sum_K Y_ra[g][K] W_rb[2t(+1)][K]
+    if (g < 6 && 2 * t < 6) {
+      const bool diag = (sa == sb);
+      double* Sd = a.S + (size_t)(oa + g) * a.ldS + ob + 2 * t;
+      if (!diag || 2 * t <= g) red_add(Sd, -c0);
+      if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
+    }
+  }
+  // right-hand side: b_c(slot) -= Y b_p
+  for (int e = tid; e < 6 * blk.n_slots; e += kBlkObs) {
+    const int sl = e / 6, r = e - 6 * sl;
+    const double* y = Yt + (size_t)(8 * sl + r) * ldk;
+    double acc = 0.0;
+    for (int k = 0; k < 3 * blk.n_lms; ++k) acc += y[k] * sG[k];
+    red_add(a.rhs + a.pose_off[a.slot_pose[blk.slot_begin + sl]] + r, -acc);
+  }
+}
+
 struct BacksubArgs {
   int n_lm;
+  int n_obs;
   int lm_off;                         // landmark slice of dx starts here
   const int* __restrict__ obs_pose;
   const int* __restrict__ lm_start;
@@ -113,14 +227,15 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   for (int j = a.lm_start[q]; j < a.lm_start[q + 1]; ++j) {
     const int oj = a.pose_off[a.obs_pose[j]];
     if (oj < 0) continue;
-    const double* Wj = a.W + 18 * (size_t)j;
+    const double* Wj = a.W + j;
+    const size_t N = (size_t)a.n_obs;
     const double* d = a.dx + oj;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       const double dr = d[r];
-      s0 -= Wj[3 * r] * dr;
-      s1 -= Wj[3 * r + 1] * dr;
-      s2 -= Wj[3 * r + 2] * dr;
+      s0 -= Wj[(3 * r) * N] * dr;
+      s1 -= Wj[(3 * r + 1) * N] * dr;
+      s2 -= Wj[(3 * r + 2) * N] * dr;
     }
   }
   const double* vi = a.Vinv + 6 * (size_t)q;

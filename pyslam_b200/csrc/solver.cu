@@ -99,6 +99,13 @@ struct bslam_solver {
   DevBuf<int> d_se3_off, d_se2_off, d_vec_entry_off, d_ptred_entry_off, d_pt_perm;
   DevBuf<double> d_ou, d_ov, d_od;
   DevBuf<int> d_opose, d_opt, d_ogrp, d_lm_start;
+  // landmark blocks of the fast reprojection / Schur kernels
+  int n_lmblocks = 0, tail_begin = 0, n_regular = 0;
+  size_t schur_smem = 0;
+  DevBuf<unsigned char> d_obs_slot;
+  DevBuf<bs::LmBlock> d_blocks;
+  DevBuf<int> d_slot_pose;
+  DevBuf<unsigned char> d_cam_perm, d_seg_start;
   DevBuf<bs::ReprojGroup> d_groups;
   DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_Linv;
   DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
@@ -199,6 +206,11 @@ bs::ReprojArgs reproj_args(bslam_solver* s) {
   a.poses = s->d_se3.p;
   a.pose_off = s->d_se3_off.p;
   a.pts = s->d_pts.p;
+  a.lm_start = s->d_lm_start.p;
+  a.n_blocks = s->n_lmblocks;
+  a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p;
+  a.cam_perm = s->d_cam_perm.p; a.seg_start = s->d_seg_start.p;
+  a.tail_begin = s->tail_begin;
   a.W = s->d_W.p; a.Vg = s->d_Vg.p;
   a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
   return a;
@@ -236,8 +248,8 @@ void launch_edges(bslam_solver* s, EdgeBatch* b, int slot) {
 // sum rho over all built-in blocks at the current parameters -> scalars[slot]
 void launch_cost(bslam_solver* s, int slot) {
   if (s->n_obs > 0) {
-    const int grid = std::min(cdiv(s->n_obs, bs::kReprojThreads), 148 * 8);
-    LAUNCH(s, bs::reproj_cost_kernel, grid, bs::kReprojThreads, 0, reproj_args(s), slot);
+    const int grid = std::min(cdiv(s->n_obs, 256), 148 * 8);
+    LAUNCH(s, bs::reproj_cost_kernel, grid, 256, 0, reproj_args(s), slot);
   }
   for (auto* b : s->edges) launch_edges<true>(s, b, slot);
 }
@@ -251,9 +263,10 @@ int do_linearize(bslam_solver* s) {
   if (s->n_pad > s->n_red)
     LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pad - s->n_red, 64), 64, 0, s->S(), s->n_pad, s->n_red, s->n_pad);
   record(s, 1);
-  if (s->n_obs > 0)
-    LAUNCH(s, bs::reproj_linearize_kernel, cdiv(s->n_obs, bs::kReprojThreads), bs::kReprojThreads, 0, reproj_args(s));
+  if (s->n_lmblocks > 0) LAUNCH(s, bs::reproj_block_kernel, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
   record(s, 2);
+  if (s->n_obs > s->tail_begin)
+    LAUNCH(s, bs::reproj_generic_kernel, cdiv(s->n_obs - s->tail_begin, 128), 128, 0, reproj_args(s));
   for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
   if (s->dn_blocks > 0) {
     bs::DenseArgs a;
@@ -278,14 +291,21 @@ int do_reduce(bslam_solver* s, double lambda) {
   if (lambda > 0.0 && s->n_red > 0)
     LAUNCH(s, bs::damp_diag_kernel, cdiv(s->n_red, 128), 128, 0, s->S(), s->n_pad, s->n_red, lambda);
   if (s->n_lm > 0) {
-    LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm, 256), 256, 0, s->n_lm, s->d_Vg.p, lambda, s->d_Vinv.p);
     bs::SchurArgs a;
-    a.n_obs = s->n_obs; a.n_lm = s->n_lm;
+    a.n_obs = s->n_obs; a.n_lm = s->n_lm; a.obs_begin = s->tail_begin; a.lambda = lambda;
+    a.n_blocks = s->n_lmblocks; a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_slot = s->d_obs_slot.p;
+    a.Vinv_out = s->d_Vinv.p;
     a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.lm_start = s->d_lm_start.p;
     a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
-    LAUNCH(s, bs::schur_kernel, cdiv(s->n_obs, 128), 128, 0, a);
+    if (s->n_lmblocks > 0) LAUNCH(s, bs::schur_block_kernel, s->n_lmblocks, bs::kBlkObs, s->schur_smem, a);
+    if (s->n_lm > s->n_regular) {
+      LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm - s->n_regular, 256), 256, 0, s->n_regular, s->n_lm, s->d_Vg.p,
+             lambda, s->d_Vinv.p);
+      const int lm_obs_end = s->n_obs;   // generic kernel skips observations of non-eliminated points itself
+      if (lm_obs_end > s->tail_begin) LAUNCH(s, bs::schur_generic_kernel, cdiv(lm_obs_end - s->tail_begin, 128), 128, 0, a);
+    }
   }
   record(s, 4);
   CU(cudaGetLastError());
@@ -410,7 +430,7 @@ int do_solve_reduced(bslam_solver* s) {
   record(s, 6);
   if (s->n_lm > 0) {
     bs::BacksubArgs a;
-    a.n_lm = s->n_lm; a.lm_off = s->n_pad;
+    a.n_lm = s->n_lm; a.n_obs = s->n_obs; a.lm_off = s->n_pad;
     a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p; a.dx = s->d_dx.p;
     LAUNCH(s, bs::backsub_kernel, cdiv(s->n_lm, 128), 128, 0, a);
@@ -753,27 +773,38 @@ int bslam_finalize(bslam_solver* s) {
   for (int i = 0; i < N; ++i) by_reproj[s->ob_pt[i]] = 1;
   for (size_t i = 0; i < s->dn_pkind.size(); ++i)
     if (s->dn_pkind[i] == 2) by_dense[s->dn_pindex[i]] = 1;
-  s->pt_perm.assign(s->n_pt, -1);
-  s->pt_iperm.clear();
-  s->pt_iperm.reserve(s->n_pt);
-  for (int p = 0; p < s->n_pt; ++p) {
-    if (s->pt_const[p]) continue;
-    if (by_reproj[p] && by_dense[p])
-      return fail(s, BSLAM_E_STRUCTURE,
-                  "point %d is used by both reprojection blocks and host-evaluated blocks; this mix is not supported yet", p);
-    if (!by_reproj[p] && !by_dense[p])
-      return fail(s, BSLAM_E_STRUCTURE, "variable point %d is not referenced by any residual block (singular system)", p);
-    if (by_reproj[p]) {
-      s->pt_perm[p] = (int)s->pt_iperm.size();
-      s->pt_iperm.push_back(p);
-    }
+  // Landmark order: regular landmarks (<= kMaxTrack observations) sorted by the first
+  // pose that sees them (neighbouring landmarks then share cameras), then "big"
+  // landmarks, then the points that are not eliminated.
+  std::vector<int> n_obs_of(s->n_pt, 0), first_pose(s->n_pt, 1 << 30);
+  for (int i = 0; i < N; ++i) {
+    n_obs_of[s->ob_pt[i]]++;
+    first_pose[s->ob_pt[i]] = std::min(first_pose[s->ob_pt[i]], s->ob_pose[i]);
   }
-  s->n_lm = (int)s->pt_iperm.size();
-  for (int p = 0; p < s->n_pt; ++p)
-    if (s->pt_perm[p] < 0) {
-      s->pt_perm[p] = (int)s->pt_iperm.size();
-      s->pt_iperm.push_back(p);
+  std::vector<int> regular, big, rest;
+  for (int p = 0; p < s->n_pt; ++p) {
+    bool elim = false;
+    if (!s->pt_const[p]) {
+      if (by_reproj[p] && by_dense[p])
+        return fail(s, BSLAM_E_STRUCTURE,
+                    "point %d is used by both reprojection blocks and host-evaluated blocks; this mix is not supported yet", p);
+      if (!by_reproj[p] && !by_dense[p])
+        return fail(s, BSLAM_E_STRUCTURE, "variable point %d is not referenced by any residual block (singular system)", p);
+      elim = by_reproj[p] != 0;
     }
+    if (!elim) rest.push_back(p);
+    else if (n_obs_of[p] <= bs::kMaxTrack) regular.push_back(p);
+    else big.push_back(p);
+  }
+  std::stable_sort(regular.begin(), regular.end(), [&](int a, int b) { return first_pose[a] < first_pose[b]; });
+  s->pt_iperm.clear();
+  s->pt_iperm.insert(s->pt_iperm.end(), regular.begin(), regular.end());
+  s->pt_iperm.insert(s->pt_iperm.end(), big.begin(), big.end());
+  s->n_lm = (int)s->pt_iperm.size();
+  const int n_regular = (int)regular.size();
+  s->pt_iperm.insert(s->pt_iperm.end(), rest.begin(), rest.end());
+  s->pt_perm.assign(s->n_pt, -1);
+  for (int q = 0; q < s->n_pt; ++q) s->pt_perm[s->pt_iperm[q]] = q;
 
   // ---- reduced-system layout: SE3 poses | SE2 poses | vectors | non-eliminated points ----
   int off = 0;
@@ -823,6 +854,56 @@ int bslam_finalize(bslam_solver* s) {
   }
   for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
 
+  // ---- landmark blocks: whole landmarks, <= kBlkObs observations, bounded Schur operands ----
+  std::vector<bs::LmBlock> blocks;
+  std::vector<int> slot_pose;
+  std::vector<unsigned char> cam_perm(N, 0), seg_start, obs_slot(N, 255);
+  size_t schur_smem = 0;
+  {
+    int q = 0;
+    std::vector<int> cur;                       // distinct variable poses of the block under construction
+    while (q < n_regular) {
+      bs::LmBlock b{};
+      b.obs_begin = lm_start[q]; b.lm_begin = q;
+      cur.clear();
+      int q1 = q;
+      while (q1 < n_regular && lm_start[q1 + 1] - b.obs_begin <= bs::kBlkObs) {
+        std::vector<int> trial = cur;
+        for (int k = lm_start[q1]; k < lm_start[q1 + 1]; ++k)
+          if (s->se3_off[opose[k]] >= 0 && std::find(trial.begin(), trial.end(), opose[k]) == trial.end())
+            trial.push_back(opose[k]);
+        if (q1 > q && (int)trial.size() * bs::schur_ldk(q1 + 1 - q) > bs::kSchurCap) break;
+        cur.swap(trial);
+        ++q1;
+      }
+      b.n_lms = q1 - q; b.n_obs = lm_start[q1] - b.obs_begin;
+      b.slot_begin = (int)slot_pose.size(); b.seg_begin = (int)seg_start.size();
+      slot_pose.insert(slot_pose.end(), cur.begin(), cur.end());
+      b.n_slots = (int)cur.size();
+      for (int k = 0; k < b.n_obs; ++k) {
+        const int pose = opose[b.obs_begin + k];
+        if (s->se3_off[pose] < 0) continue;
+        obs_slot[b.obs_begin + k] = (unsigned char)(std::find(cur.begin(), cur.end(), pose) - cur.begin());
+      }
+      int pos = 0;
+      for (int sl = 0; sl < b.n_slots; ++sl) {
+        seg_start.push_back((unsigned char)pos);
+        for (int k = 0; k < b.n_obs; ++k)
+          if (obs_slot[b.obs_begin + k] == sl) cam_perm[b.obs_begin + pos++] = (unsigned char)k;
+      }
+      seg_start.push_back((unsigned char)pos);
+      schur_smem = std::max(schur_smem, (size_t)16 * 8 * b.n_slots * bs::schur_ldk(b.n_lms));
+      blocks.push_back(b);
+      q = q1;
+    }
+  }
+  s->schur_smem = schur_smem;
+  s->n_regular = n_regular;
+  s->n_lmblocks = (int)blocks.size();
+  s->tail_begin = lm_start[n_regular];
+  if (slot_pose.empty()) slot_pose.push_back(0);
+  if (seg_start.empty()) seg_start.push_back(0);
+
   // ---- dense-block structure ----
   s->dn_row_ptr.assign(1, 0); s->dn_col_ptr.assign(1, 0); s->dn_j_ptr.assign(1, 0);
   s->dn_col_index.clear();
@@ -861,6 +942,13 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_ou, ou, st)); CU(upload(s->d_ov, ov, st)); CU(upload(s->d_od, od, st));
   CU(upload(s->d_opose, opose, st)); CU(upload(s->d_opt, opt, st)); CU(upload(s->d_ogrp, ogrp, st));
   CU(upload(s->d_lm_start, lm_start, st));
+  CU(upload(s->d_blocks, blocks, st));
+  CU(upload(s->d_slot_pose, slot_pose, st));
+  CU(upload(s->d_cam_perm, cam_perm, st));
+  CU(upload(s->d_seg_start, seg_start, st));
+  CU(upload(s->d_obs_slot, obs_slot, st));
+  if (s->schur_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(bs::schur_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->schur_smem));
   CU(upload(s->d_groups, s->groups, st));
   for (auto* b : s->edges) {
     CU(upload(b->d_i1, b->i1, st));
@@ -1086,8 +1174,8 @@ int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
     const int o = n + 3 * opt[k];
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 3; ++c) {
-        H[(size_t)(po + r) * D + o + c] += W[18 * (size_t)k + 3 * r + c];
-        H[(size_t)(o + c) * D + po + r] += W[18 * (size_t)k + 3 * r + c];
+        H[(size_t)(po + r) * D + o + c] += W[(size_t)(3 * r + c) * N + k];
+        H[(size_t)(o + c) * D + po + r] += W[(size_t)(3 * r + c) * N + k];
       }
   }
   return BSLAM_OK;

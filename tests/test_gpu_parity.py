@@ -33,6 +33,16 @@ def normal_equations_ref_order(pr):
     return H[np.ix_(idx, idx)], b[idx], cost
 
 
+def reduced_system_ref_order(pr, n):
+    """(S, rhs) after `reduce`, restricted/permuted to the first n entries of the
+    reference ordering (valid when those are the non-eliminated parameters)."""
+    low = pr._low
+    Sfull, rfull = pr._engine.get_reduced_system(low.layout['n_reduced'])
+    idx = low.ref_from_internal[:n]
+    assert idx.max() < low.layout['n_reduced']
+    return Sfull[np.ix_(idx, idx)], rfull[idx]
+
+
 @pytest.mark.parametrize('name', ['ba_huber', 'ba_cauchy'])
 @pytest.mark.parametrize('bulk', [False, True])
 def test_ba_against_reference_golden(name, bulk):
@@ -220,4 +230,74 @@ def test_config3_against_oracle():
         assert abs(cost_lin - ref['cost_lin']) < 1e-10 * ref['cost_lin']
         assert rel_err(dx, ref['dx']) < 1e-6, 'iteration %d' % it
         assert abs(dx_norm - np.linalg.norm(ref['dx'])) < 1e-6 * dx_norm
+        assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
+
+
+def test_long_tracks_use_the_tail_path():
+    """Landmarks with more than 128 observations (beyond one landmark block) are
+    linearised by the generic atomic kernel; mixed here with regular landmarks."""
+    from oracle import gn_oracle as O
+    from pyslam_b200 import synthetic
+    d = synthetic.stereo_ba(140, 200, track=5, seed=1)
+    d2 = synthetic.stereo_ba(140, 6, track=140, seed=2)
+    n1 = len(d['pts0'])
+    d['pts0'] = np.vstack([d['pts0'], d2['pts0']])
+    d['pose_idx'] = np.concatenate([d['pose_idx'], d2['pose_idx']])
+    d['pt_idx'] = np.concatenate([d['pt_idx'], d2['pt_idx'] + n1]).astype(np.int32)
+    d['obs'] = np.vstack([d['obs'], d2['obs']])
+    ba = B.oracle_ba_arrays(d)
+    pr = B.product_ba_problem(d, bulk=True)
+    Ho, bo, co = O.ba_linearize(ba)
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    low = pr._low
+    for it in range(2):
+        ref = O.ba_iteration(ba)
+        cost_lin, cost_new, dx_norm = pr._engine.iterate(0., True)
+        dx = pr._engine.get_update(low.dim)[low.ref_from_internal]
+        assert rel_err(dx, ref['dx']) < 1e-6
+        assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
+
+
+def test_random_visibility_blocks():
+    """Landmarks seen by random subsets of poses (3..40 observations, poor camera
+    locality): exercises many landmark-block shapes of the fast kernels."""
+    from oracle import gn_oracle as O
+    from pyslam_b200 import synthetic
+    rng = np.random.default_rng(5)
+    d = synthetic.stereo_ba(60, 300, track=6, seed=6)
+    pose_idx, pt_idx = [], []
+    for q in range(300):
+        n = int(rng.integers(3, 41))
+        pose_idx.append(rng.choice(60, size=n, replace=False))
+        pt_idx.append(np.full(n, q))
+    d['pose_idx'] = np.concatenate(pose_idx).astype(np.int32)
+    d['pt_idx'] = np.concatenate(pt_idx).astype(np.int32)
+    cam = O.StereoCamera(*d['camera'])
+    pc = np.einsum('nij,nj->ni', d['R_true'][d['pose_idx']], d['pts_true'][d['pt_idx']]) + d['t_true'][d['pose_idx']]
+    d['obs'] = cam.project(pc) + 0.3 * rng.standard_normal((len(pc), 3))
+    ba = B.oracle_ba_arrays(d)
+    pr = B.product_ba_problem(d, bulk=True)
+    Ho, bo, co = O.ba_linearize(ba)
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    low = pr._low
+    # reduced system against the Schur complement of the oracle's H (poses come first in the reference order)
+    pr._engine.reduce(0.)
+    n = 6 * 59
+    S, rhs = reduced_system_ref_order(pr, n)
+    Hd = Ho.toarray()
+    Sref = Hd[:n, :n] - Hd[:n, n:] @ np.linalg.solve(Hd[n:, n:], Hd[n:, :n])
+    rref = bo[:n] - Hd[:n, n:] @ np.linalg.solve(Hd[n:, n:], bo[n:])
+    assert rel_err(S, Sref) < 1e-10
+    assert rel_err(rhs, rref) < 1e-10
+    for it in range(2):
+        ref = O.ba_iteration(ba)
+        cost_lin, cost_new, dx_norm = pr._engine.iterate(0., True)
+        dx = pr._engine.get_update(low.dim)[low.ref_from_internal]
+        assert rel_err(dx, ref['dx']) < 1e-6
         assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
