@@ -380,9 +380,9 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
 constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + 4 * 64) * sizeof(double);
 
 // identity on the padding diagonal so the padded factorisation is well defined
-__global__ void pad_diag_kernel(double* __restrict__ S, int ld, int n, int n_pad) {
-  const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) S[(size_t)i * ld + i] = 1.0;
+__global__ void pad_diag_kernel(double* __restrict__ S, int ld, const int* __restrict__ pad_idx, int n_pads) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_pads) S[(size_t)pad_idx[k] * ld + pad_idx[k]] = 1.0;
 }
 
 // S_ii *= (1 + lambda) for i < n  (LM damping lambda * diag(H); extension)

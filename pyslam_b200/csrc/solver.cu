@@ -89,7 +89,8 @@ struct bslam_solver {
   double dn_cost = 0.0;
 
   // ---- layout ----
-  int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0;
+  int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0, n_pads = 0;
+  DevBuf<int> d_pad_idx;
   std::vector<int> pt_perm, pt_iperm;               // user -> internal, internal -> user
   std::vector<int> se3_off, se2_off, vec_off, pt_off_user, vec_entry_off, pt_red_entry_off;
 
@@ -260,8 +261,8 @@ int do_linearize(bslam_solver* s) {
   record(s, 0);
   CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), s->stream));
   if (s->n_lm > 0) CU(cudaMemsetAsync(s->d_Vg.p, 0, s->d_Vg.n * sizeof(double), s->stream));
-  if (s->n_pad > s->n_red)
-    LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pad - s->n_red, 64), 64, 0, s->S(), s->n_pad, s->n_red, s->n_pad);
+  if (s->n_pads > 0)
+    LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
   record(s, 1);
   if (s->n_lmblocks > 0) LAUNCH(s, bs::reproj_block_kernel, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
   record(s, 2);
@@ -806,34 +807,181 @@ int bslam_finalize(bslam_solver* s) {
   s->pt_perm.assign(s->n_pt, -1);
   for (int q = 0; q < s->n_pt; ++q) s->pt_perm[s->pt_iperm[q]] = q;
 
-  // ---- reduced-system layout: SE3 poses | SE2 poses | vectors | non-eliminated points ----
-  int off = 0;
+  // ---- reduced-system layout ----------------------------------------------------------
+  // The non-eliminated parameter blocks (SE3 poses, SE2 poses, vectors, remaining points,
+  // in table order) are packed into "supernodes" of <= 64 tangent dimensions; every
+  // supernode starts on a 64x64 tile boundary of the reduced matrix (unused entries are
+  // padding: identity diagonal, zero right-hand side).  The supernodes are then ordered by
+  // nested dissection of their coupling graph, so that the tile Cholesky's dependency DAG
+  // is a bushy tree instead of a chain (trajectory-like problems are banded in table order).
+  struct Item { int kind, idx, dof; };
+  std::vector<Item> items;
+  for (int i = 0; i < s->n_se3; ++i) if (!s->se3_const[i]) items.push_back({0, i, 6});
+  for (int i = 0; i < s->n_se2; ++i) if (!s->se2_const[i]) items.push_back({1, i, 3});
+  for (int i = 0; i < s->n_vec; ++i) if (!s->vec_const[i] && s->vec_dims[i] > 0) items.push_back({3, i, s->vec_dims[i]});
+  for (int q = s->n_lm; q < s->n_pt; ++q) if (!s->pt_const[s->pt_iperm[q]]) items.push_back({2, s->pt_iperm[q], 3});
+  std::vector<int> sn_first, sn_tiles;          // supernode -> first item, number of tiles
+  std::vector<int> item_sn(items.size());
+  {
+    int fill = bs::kNB + 1;
+    for (size_t k = 0; k < items.size(); ++k) {
+      if (fill + items[k].dof > bs::kNB) {       // open a new supernode
+        sn_first.push_back((int)k);
+        sn_tiles.push_back(std::max(1, cdiv(items[k].dof, bs::kNB)));
+        fill = 0;
+      }
+      fill += items[k].dof;
+      item_sn[k] = (int)sn_first.size() - 1;
+    }
+  }
+  const int n_sn = (int)sn_first.size();
+  std::vector<int> se3_sn(s->n_se3, -1), se2_sn(s->n_se2, -1), vec_sn(s->n_vec, -1), pt_sn(s->n_pt, -1);
+  for (size_t k = 0; k < items.size(); ++k) {
+    std::vector<int>& m = items[k].kind == 0 ? se3_sn : items[k].kind == 1 ? se2_sn : items[k].kind == 3 ? vec_sn : pt_sn;
+    m[items[k].idx] = item_sn[k];
+  }
+  // coupling graph of the supernodes
+  std::vector<std::vector<int>> adj(n_sn);
+  {
+    auto couple = [&](std::vector<int>& g) {
+      std::sort(g.begin(), g.end());
+      g.erase(std::unique(g.begin(), g.end()), g.end());
+      for (int a : g)
+        for (int b : g)
+          if (a != b) adj[a].push_back(b);
+    };
+    std::vector<int> g;
+    // poses that share an eliminated landmark (observations grouped by user point index)
+    std::vector<int> ptr(s->n_pt + 1, 0), members(N);
+    for (int i = 0; i < N; ++i) ptr[s->ob_pt[i] + 1]++;
+    for (int p = 0; p < s->n_pt; ++p) ptr[p + 1] += ptr[p];
+    {
+      std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+      for (int i = 0; i < N; ++i) members[cur[s->ob_pt[i]]++] = s->ob_pose[i];
+    }
+    std::vector<int> last_sig;
+    for (int p = 0; p < s->n_pt; ++p) {
+      if (s->pt_perm[p] >= s->n_lm) continue;
+      g.clear();
+      for (int k = ptr[p]; k < ptr[p + 1]; ++k)
+        if (se3_sn[members[k]] >= 0) g.push_back(se3_sn[members[k]]);
+      std::sort(g.begin(), g.end());
+      g.erase(std::unique(g.begin(), g.end()), g.end());
+      if (g == last_sig) continue;               // same supernode set as the previous landmark
+      last_sig = g;
+      couple(g);
+    }
+    for (auto* b : s->edges) {
+      if (!b->binary) continue;
+      const std::vector<int>& m = b->group == 3 ? se3_sn : se2_sn;
+      for (int e = 0; e < b->n; ++e) {
+        g.clear();
+        if (m[b->i1[e]] >= 0) g.push_back(m[b->i1[e]]);
+        if (m[b->i2[e]] >= 0) g.push_back(m[b->i2[e]]);
+        couple(g);
+      }
+    }
+    for (int b = 0; b < s->dn_blocks; ++b) {
+      g.clear();
+      for (int k = s->dn_pptr[b]; k < s->dn_pptr[b + 1]; ++k) {
+        const int kind = s->dn_pkind[k], idx = s->dn_pindex[k];
+        const int sn = kind == 0 ? se3_sn[idx] : kind == 1 ? se2_sn[idx] : kind == 2 ? pt_sn[idx] : vec_sn[idx];
+        if (sn >= 0) g.push_back(sn);
+      }
+      couple(g);
+    }
+    for (auto& a : adj) {
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+    }
+  }
+  // nested dissection by recursive bisection of the table order
+  std::vector<int> sn_order;
+  {
+    std::vector<int> side(n_sn, 0);
+    std::vector<std::vector<int>> stack;
+    std::vector<int> all(n_sn);
+    std::iota(all.begin(), all.end(), 0);
+    // explicit recursion: each work item is (nodes, separator to append after its children)
+    struct Work { std::vector<int> nodes; bool emit; };
+    std::vector<Work> todo;
+    todo.push_back({all, false});
+    while (!todo.empty()) {
+      Work w = std::move(todo.back());
+      todo.pop_back();
+      if (w.emit || w.nodes.size() <= 2) {
+        sn_order.insert(sn_order.end(), w.nodes.begin(), w.nodes.end());
+        continue;
+      }
+      const size_t mid = w.nodes.size() / 2;
+      std::vector<int> left(w.nodes.begin(), w.nodes.begin() + mid), right(w.nodes.begin() + mid, w.nodes.end());
+      for (int u : left) side[u] = 1;
+      for (int u : right) side[u] = 2;
+      std::vector<int> sepL, sepR;
+      for (int u : left)
+        for (int v : adj[u])
+          if (side[v] == 2) { sepL.push_back(u); break; }
+      for (int u : right)
+        for (int v : adj[u])
+          if (side[v] == 1) { sepR.push_back(u); break; }
+      for (int u : w.nodes) side[u] = 0;
+      const bool useL = sepL.size() <= sepR.size();
+      std::vector<int>& sep = useL ? sepL : sepR;
+      if (sep.size() * 2 >= w.nodes.size()) {      // no useful separator: keep the table order
+        sn_order.insert(sn_order.end(), w.nodes.begin(), w.nodes.end());
+        continue;
+      }
+      std::vector<int>& cut = useL ? left : right;
+      std::vector<int> rest;
+      for (int u : cut)
+        if (!std::binary_search(sep.begin(), sep.end(), u)) rest.push_back(u);
+      // order: left part, right part, separator  (stack is LIFO -> push in reverse)
+      todo.push_back({sep, true});
+      todo.push_back({useL ? right : rest, false});
+      todo.push_back({useL ? rest : left, false});
+    }
+  }
+  // offsets
   s->se3_off.assign(s->n_se3, -1);
-  for (int i = 0; i < s->n_se3; ++i)
-    if (!s->se3_const[i]) { s->se3_off[i] = off; off += 6; }
   s->se2_off.assign(s->n_se2, -1);
-  for (int i = 0; i < s->n_se2; ++i)
-    if (!s->se2_const[i]) { s->se2_off[i] = off; off += 3; }
   s->vec_off.assign(s->n_vec, -1);
   s->vec_entry_off.assign(s->n_vec_entries, -1);
-  for (int i = 0; i < s->n_vec; ++i)
-    if (!s->vec_const[i]) {
-      s->vec_off[i] = off;
-      for (int k = 0; k < s->vec_dims[i]; ++k) s->vec_entry_off[s->vec_start[i] + k] = off + k;
-      off += s->vec_dims[i];
-    }
   s->pt_off_user.assign(s->n_pt, -1);
   s->pt_red_entry_off.assign(3 * (size_t)(s->n_pt - s->n_lm), -1);
-  for (int q = s->n_lm; q < s->n_pt; ++q) {
-    const int p = s->pt_iperm[q];
-    if (s->pt_const[p]) continue;
-    s->pt_off_user[p] = off;
-    for (int k = 0; k < 3; ++k) s->pt_red_entry_off[3 * (size_t)(q - s->n_lm) + k] = off + k;
-    off += 3;
+  std::vector<uint8_t> used;
+  int tile = 0;
+  for (int sn : sn_order) {
+    int off = tile * bs::kNB;
+    const size_t k1 = sn + 1 < n_sn ? sn_first[sn + 1] : items.size();
+    for (size_t k = sn_first[sn]; k < k1; ++k) {
+      const Item& it = items[k];
+      if (it.kind == 0) s->se3_off[it.idx] = off;
+      else if (it.kind == 1) s->se2_off[it.idx] = off;
+      else if (it.kind == 3) {
+        s->vec_off[it.idx] = off;
+        for (int c = 0; c < it.dof; ++c) s->vec_entry_off[s->vec_start[it.idx] + c] = off + c;
+      } else {
+        s->pt_off_user[it.idx] = off;
+        for (int c = 0; c < 3; ++c) s->pt_red_entry_off[3 * (size_t)(s->pt_perm[it.idx] - s->n_lm) + c] = off + c;
+      }
+      off += it.dof;
+    }
+    tile += sn_tiles[sn];
   }
-  s->n_red = off;
-  s->n_pad = std::max(1, cdiv(off, bs::kNB)) * bs::kNB;
-  s->nblk = s->n_pad / bs::kNB;
+  s->nblk = std::max(1, tile);
+  s->n_pad = s->nblk * bs::kNB;
+  s->n_red = s->n_pad;                         // the reduced span includes the padding entries
+  used.assign(s->n_pad, 0);
+  auto mark_used = [&](int off, int dof) { for (int c = 0; c < dof; ++c) used[off + c] = 1; };
+  for (const Item& it : items) {
+    const int off = it.kind == 0 ? s->se3_off[it.idx] : it.kind == 1 ? s->se2_off[it.idx] : it.kind == 3 ? s->vec_off[it.idx]
+                                                                                                            : s->pt_off_user[it.idx];
+    mark_used(off, it.dof);
+  }
+  std::vector<int> pad_idx;
+  for (int i = 0; i < s->n_pad; ++i)
+    if (!used[i]) pad_idx.push_back(i);
+  s->n_pads = (int)pad_idx.size();
   for (int q = 0; q < s->n_lm; ++q) s->pt_off_user[s->pt_iperm[q]] = s->n_red + 3 * q;
   s->dim = s->n_red + 3 * s->n_lm;
 
@@ -935,6 +1083,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_vec, s->h_vec, st));
   CU(s->d_stage.alloc(3 * (size_t)s->n_pt));
   CU(upload(s->d_pt_perm, s->pt_perm, st));
+  CU(upload(s->d_pad_idx, pad_idx, st));
   CU(upload(s->d_se3_off, s->se3_off, st));
   CU(upload(s->d_se2_off, s->se2_off, st));
   CU(upload(s->d_vec_entry_off, s->vec_entry_off, st));

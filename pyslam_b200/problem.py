@@ -318,9 +318,9 @@ class Problem:
         self._update_partition_dict = self._get_update_partition_dict()
         D = lay['dim']
         total = sum(len(r) for r in self._update_partition_dict.values())
-        if total != D:
+        if total > D:      # D may exceed the sum of dofs: the reduced span contains padding entries
             raise RuntimeError('internal layout mismatch: {} vs {}'.format(total, D))
-        src = np.empty(D, np.int64)
+        src = np.empty(total, np.int64)
         for key, r in self._update_partition_dict.items():
             name, idx = low.table[key]
             o = int(lay[name][idx])
