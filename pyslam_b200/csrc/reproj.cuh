@@ -60,6 +60,8 @@ struct ReprojArgs {
   const int* __restrict__ obs_pt;
   const int* __restrict__ obs_grp;          // nullptr when there is a single group
   const ReprojGroup* __restrict__ groups;
+  ReprojGroup g0;                           // groups[0] by value (constant bank) for the single-group fast path
+  const unsigned char* __restrict__ obs_slot;   // [N] slot of the observation inside its block (255: constant pose)
   const double* __restrict__ poses;         // [K][12]
   const int* __restrict__ pose_off;         // reduced offset of the pose or -1 (constant)
   const double* __restrict__ pts;           // [P][3]
@@ -72,6 +74,7 @@ struct ReprojArgs {
   const unsigned char* __restrict__ seg_start;
   // tail processed by the generic kernel
   int tail_begin;
+  int dbg;                                  // profiling aid (BSLAM_DBG): 1 no atomics, 2 no W stores, 4 no reductions
   double* __restrict__ W;                   // [18][N]
   double* __restrict__ Vg;                  // [n_lm][9]
   double* __restrict__ S;                   // [n_pad][ldS]
@@ -138,11 +141,93 @@ BS_D void reproj_linearize_one(const ReprojGroup& g, const double* __restrict__ 
   }
 }
 
+// Structured linearisation of one observation.  With e = pi(p_c) - z, r = S e,
+// w = loss weights, Q = S^T diag(w) S, Jc the (sparse) camera Jacobian and
+// B = -p_c^, the reference's J_T = S Jc [I | B] and J_p = S Jc R give
+//     M = Jc^T Q Jc  (3x3 symmetric),   t = Jc^T Q e,
+//     U_c = [I|B]^T M [I|B],  b_c = -[I|B]^T t,
+//     V_p = R^T M R,          b_p = -R^T t,        W = [I|B]^T M R,
+// which needs ~40% of the flops of forming the 3x6 / 3x3 Jacobians and their
+// weighted outer products entry by entry (same values up to rounding).
+struct ReprojBlocks {
+  double M[6];     // xx xy xz yy yz zz
+  double t[3];
+  double MB[9];    // M B   (row-major 3x3)
+  double BMB[6];   // B^T M B (xx xy xz yy yz zz)
+  double MR[9];    // M R   (row-major 3x3)
+  double x, y, z;  // p_c
+  double cost;
+};
+
+BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, const double* __restrict__ X,
+                        double u, double v, double d, ReprojBlocks& o) {
+  const double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9];
+  const double y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10];
+  const double z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
+  o.x = x; o.y = y; o.z = z;
+  const double iz = 1.0 / z;
+  const double iz2 = iz * iz;
+  const double e0 = g.fu * x * iz + g.cu - u;
+  const double e1 = g.fv * y * iz + g.cv - v;
+  const double e2 = g.fu * g.b * iz - d;
+  // residual, weights, cost;  Q = S^T diag(w) S
+  double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0;
+  double cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double s0 = g.S[3 * k], s1 = g.S[3 * k + 1], s2 = g.S[3 * k + 2];
+    const double r = s0 * e0 + s1 * e1 + s2 * e2;
+    const double w = loss_weight(g.loss, r);
+    cost += loss_rho(g.loss, r);
+    const double ws0 = w * s0, ws1 = w * s1, ws2 = w * s2;
+    q00 = fma(ws0, s0, q00); q01 = fma(ws0, s1, q01); q02 = fma(ws0, s2, q02);
+    q11 = fma(ws1, s1, q11); q12 = fma(ws1, s2, q12); q22 = fma(ws2, s2, q22);
+  }
+  o.cost = cost;
+  const double qe0 = q00 * e0 + q01 * e1 + q02 * e2;
+  const double qe1 = q01 * e0 + q11 * e1 + q12 * e2;
+  const double qe2 = q02 * e0 + q12 * e1 + q22 * e2;
+  // camera Jacobian non-zeros (stereo_camera.py:112-134): [[a,0,c0],[0,b,c1],[0,0,c2]]
+  const double a = g.fu * iz, b = g.fv * iz;
+  const double c0 = -g.fu * x * iz2, c1 = -g.fv * y * iz2, c2 = -g.fu * g.b * iz2;
+  // QJ = Q Jc (only the entries M needs), M = Jc^T QJ
+  const double k02 = c0 * q00 + c1 * q01 + c2 * q02;
+  const double k12 = c0 * q01 + c1 * q11 + c2 * q12;
+  const double k22 = c0 * q02 + c1 * q12 + c2 * q22;
+  const double m00 = a * a * q00, m01 = a * b * q01, m02 = a * k02;
+  const double m11 = b * b * q11, m12 = b * k12;
+  const double m22 = c0 * k02 + c1 * k12 + c2 * k22;
+  o.M[0] = m00; o.M[1] = m01; o.M[2] = m02; o.M[3] = m11; o.M[4] = m12; o.M[5] = m22;
+  o.t[0] = a * qe0; o.t[1] = b * qe1; o.t[2] = c0 * qe0 + c1 * qe1 + c2 * qe2;
+  // M B with B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
+  const double Mr[9] = {m00, m01, m02, m01, m11, m12, m02, m12, m22};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o.MB[3 * i + 0] = y * Mr[3 * i + 2] - z * Mr[3 * i + 1];
+    o.MB[3 * i + 1] = z * Mr[3 * i + 0] - x * Mr[3 * i + 2];
+    o.MB[3 * i + 2] = x * Mr[3 * i + 1] - y * Mr[3 * i + 0];
+  }
+  // B^T (M B): rows of B^T are [0,-z,y], [z,0,-x], [-y,x,0]
+  o.BMB[0] = y * o.MB[6] - z * o.MB[3];
+  o.BMB[1] = y * o.MB[7] - z * o.MB[4];
+  o.BMB[2] = y * o.MB[8] - z * o.MB[5];
+  o.BMB[3] = z * o.MB[1] - x * o.MB[7];
+  o.BMB[4] = z * o.MB[2] - x * o.MB[8];
+  o.BMB[5] = x * o.MB[5] - y * o.MB[2];
+  // M R
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o.MR[3 * i + j] = Mr[3 * i] * P[j] + Mr[3 * i + 1] * P[3 + j] + Mr[3 * i + 2] * P[6 + j];
+}
+
 // value index 0..20 -> (row, col) of the lower triangle of a 6x6 block, row-major
 __device__ __constant__ unsigned char kTriRow[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
 __device__ __constant__ unsigned char kTriCol[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
 
-__global__ void __launch_bounds__(kBlkObs, 4)
+template <bool kSingleGroup>
+__global__ void __launch_bounds__(kBlkObs, 5)
 reproj_block_kernel(const ReprojArgs a) {
   __shared__ double sT[kBlkObs * kRow];
   __shared__ double sred[kBlkObs / 32];
@@ -151,60 +236,89 @@ reproj_block_kernel(const ReprojArgs a) {
   const int N = a.n_obs;
   double cost = 0.0;
 
+  // Every global load of the block is issued up front (one DRAM round trip): the
+  // observation, its slot / landmark index, and -- cooperatively -- the poses of
+  // the block's slots and its (contiguous) landmark coordinates, staged in sT.
+  double ou = 0.0, ov = 0.0, od = 0.0;
+  int sl = 255, ql = 0, gi = 0;
+  const int i = blk.obs_begin + tid;
   if (tid < blk.n_obs) {
-    const int i = blk.obs_begin + tid;
-    const int pi = a.obs_pose[i];
-    const int qi = a.obs_pt[i];
-    const bool pose_var = a.pose_off[pi] >= 0;
-    const ReprojGroup& g = a.groups[a.obs_grp ? a.obs_grp[i] : 0];
-    ReprojLin L;
-    reproj_linearize_one(g, a.poses + 12 * (size_t)pi, a.pts + 3 * (size_t)qi, ld_stream(a.obs_u + i),
-                         ld_stream(a.obs_v + i), ld_stream(a.obs_d + i), L);
-    double w[3], wr[3];
+    ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
+    sl = a.obs_slot[i];
+    ql = a.obs_pt[i] - blk.lm_begin;
+    if (!kSingleGroup) gi = a.obs_grp[i];
+  }
+  double* sPose = sT;                               // [n_slots + 1][12]; last row: scratch for constant poses
+  double* sPts = sT + 12 * (kBlkObs + 1);           // [n_lms][3]
+  for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) {
+    const int s = e / 12;
+    sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + s] + (e - 12 * s)];
+  }
+  for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
+  __syncthreads();
+  double P[12], X[3];
+  if (tid < blk.n_obs) {
+    if (sl != 255) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      w[k] = loss_weight(g.loss, L.r[k]);
-      wr[k] = w[k] * L.r[k];
-      cost += loss_rho(g.loss, L.r[k]);
+      for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
+    } else {                                        // constant pose: not a slot, read it directly
+      const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
     }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) X[k] = sPts[3 * ql + k];
+  }
+  __syncthreads();                                  // sT is reused for the per-observation rows below
+
+  if (tid < blk.n_obs) {
+    const bool pose_var = sl != 255;
+    const ReprojGroup& g = kSingleGroup ? a.g0 : a.groups[gi];
+    ReprojBlocks o;
+    reproj_blocks(g, P, X, ou, ov, od, o);
+    cost = o.cost;
     double* row = sT + tid * kRow;
-    // weighted Jacobian rows, reused by all three products
-    double wJT[18];
-#pragma unroll
-    for (int k = 0; k < 18; ++k) wJT[k] = w[k / 6] * L.JT[k];
     if (pose_var) {
-      int v = 0;
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-#pragma unroll
-        for (int c = 0; c <= r; ++c)
-          row[v++] = wJT[r] * L.JT[c] + wJT[6 + r] * L.JT[6 + c] + wJT[12 + r] * L.JT[12 + c];
-      }
-#pragma unroll
-      for (int r = 0; r < 6; ++r) row[21 + r] = -(L.JT[r] * wr[0] + L.JT[6 + r] * wr[1] + L.JT[12 + r] * wr[2]);
-      // W = J_T^T w J_p, SoA planes
+      // U_c lower triangle, rows 0-2: M; rows 3-5: [(M B)^T | B^T M B]
+      row[0] = o.M[0];
+      row[1] = o.M[1]; row[2] = o.M[3];
+      row[3] = o.M[2]; row[4] = o.M[4]; row[5] = o.M[5];
+      row[6] = o.MB[0]; row[7] = o.MB[3]; row[8] = o.MB[6]; row[9] = o.BMB[0];
+      row[10] = o.MB[1]; row[11] = o.MB[4]; row[12] = o.MB[7]; row[13] = o.BMB[1]; row[14] = o.BMB[3];
+      row[15] = o.MB[2]; row[16] = o.MB[5]; row[17] = o.MB[8]; row[18] = o.BMB[2]; row[19] = o.BMB[4]; row[20] = o.BMB[5];
+      // b_c = -[t; B^T t]
+      row[21] = -o.t[0]; row[22] = -o.t[1]; row[23] = -o.t[2];
+      row[24] = -(o.y * o.t[2] - o.z * o.t[1]);
+      row[25] = -(o.z * o.t[0] - o.x * o.t[2]);
+      row[26] = -(o.x * o.t[1] - o.y * o.t[0]);
+      // W = [M R; B^T M R], SoA planes
       double* Wp = a.W + i;
+      if (!(a.dbg & 2)) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+      for (int k = 0; k < 9; ++k) Wp[(size_t)k * N] = o.MR[k];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          Wp[(size_t)(3 * r + c) * N] = wJT[r] * L.Jp[c] + wJT[6 + r] * L.Jp[3 + c] + wJT[12 + r] * L.Jp[6 + c];
+      for (int j = 0; j < 3; ++j) {
+        Wp[(size_t)(9 + j) * N] = o.y * o.MR[6 + j] - o.z * o.MR[3 + j];
+        Wp[(size_t)(12 + j) * N] = o.z * o.MR[j] - o.x * o.MR[6 + j];
+        Wp[(size_t)(15 + j) * N] = o.x * o.MR[3 + j] - o.y * o.MR[j];
+      }
+      }
     }
-    {
-      int v = 27;
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = r; c < 3; ++c)
-          row[v++] = w[0] * L.Jp[r] * L.Jp[c] + w[1] * L.Jp[3 + r] * L.Jp[3 + c] + w[2] * L.Jp[6 + r] * L.Jp[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) row[33 + r] = -(L.Jp[r] * wr[0] + L.Jp[3 + r] * wr[1] + L.Jp[6 + r] * wr[2]);
-    }
+    // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
+    row[27] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
+    row[28] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
+    row[29] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
+    row[30] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
+    row[31] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
+    row[32] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
+    row[33] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
+    row[34] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
+    row[35] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
   }
   __syncthreads();
 
   // camera side: one task per (slot, value); observations of a slot are contiguous in cam_perm order
-  {
+  if (!(a.dbg & 4)) {
     const unsigned char* perm = a.cam_perm + blk.obs_begin;
     const unsigned char* seg = a.seg_start + blk.seg_begin;
     const int n_tasks = blk.n_slots * 27;
@@ -213,12 +327,13 @@ reproj_block_kernel(const ReprojArgs a) {
       double acc = 0.0;
       for (int k = seg[s]; k < seg[s + 1]; ++k) acc += sT[perm[k] * kRow + v];
       const int off = a.pose_off[a.slot_pose[blk.slot_begin + s]];
-      if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
+      if (a.dbg & 1) { if (acc == 1.2345e-300) a.Vg[0] = acc; }
+      else if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
       else red_add(a.rhs + off + (v - 21), acc);
     }
   }
   // landmark side: one task per (landmark, value); a landmark's observations are contiguous
-  {
+  if (!(a.dbg & 4)) {
     const int n_tasks = blk.n_lms * 9;
     for (int t = tid; t < n_tasks; t += kBlkObs) {
       const int l = t / 9, v = t - 9 * l;

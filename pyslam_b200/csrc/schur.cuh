@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
 // so that for every slot pair   S(a,b) -= sum_K Yt[8a+.][K] Wt[8b+.][K]   is a
 // chain of mma.sync.m8n8k4.f64; one fp64 atomic per output element leaves the CTA
 // (instead of one per landmark and element).  b_c -= Y b_p rides along as a mat-vec.
+constexpr int kSlotRows = 6;        // rows per slot; MMA fragments read 8 rows, rows 6-7 only feed discarded outputs
 BS_HD int schur_ldk(int n_lms) {              // row stride: >= 3*n_lms (+pad), = 4 mod 16 -> conflict-free fragments
   return ((3 * n_lms + 3 + 11) / 16) * 16 + 4;
 }
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   const int tid = threadIdx.x;
   const LmBlock blk = a.blocks[blockIdx.x];
   const int ldk = schur_ldk(blk.n_lms);
-  const int rows = 8 * blk.n_slots;
+  const int rows = kSlotRows * blk.n_slots + 2;     // +2: the last slot's fragment rows 6-7
   double* Yt = sm;
   double* Wt = sm + (size_t)rows * ldk;
   const size_t N = (size_t)a.n_obs;
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
       const int l = a.obs_pt[i] - blk.lm_begin;
       const double* vi = sVinv + 6 * l;
       const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-      double* yr = Yt + (size_t)(8 * sl) * ldk + 3 * l;
-      double* wr = Wt + (size_t)(8 * sl) * ldk + 3 * l;
+      double* yr = Yt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
+      double* wr = Wt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
       const double* Wi = a.W + i;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
@@ -171,20 +172,17 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   const int g = lane >> 2, t = lane & 3;
   const int kdim = (3 * blk.n_lms + 3) & ~3;
   // slot pairs (sa, sb) with sb <= sa, dealt round-robin to the 4 warps
-  const int n_pairs = blk.n_slots * (blk.n_slots + 1) / 2;
-  for (int pidx = warp; pidx < n_pairs; pidx += kBlkObs / 32) {
-    // invert pidx = sa*(sa+1)/2 + sb
-    int sa = (int)((sqrt(8.0 * pidx + 1.0) - 1.0) * 0.5);
-    while ((sa + 1) * (sa + 2) / 2 <= pidx) ++sa;
-    while (sa * (sa + 1) / 2 > pidx) --sa;
-    const int sb = pidx - sa * (sa + 1) / 2;
+  int pidx = 0;
+  for (int sa = 0; sa < blk.n_slots; ++sa)
+   for (int sb = 0; sb <= sa; ++sb, ++pidx) {
+    if ((pidx & 3) != warp) continue;
     int oa = a.pose_off[a.slot_pose[blk.slot_begin + sa]];
     int ob = a.pose_off[a.slot_pose[blk.slot_begin + sb]];
     // rows must belong to the pose with the larger reduced offset (lower triangle)
     const int ra = oa >= ob ? sa : sb, rb = oa >= ob ? sb : sa;
     if (oa < ob) { const int tmp = oa; oa = ob; ob = tmp; }
-    const double* pa = Yt + (size_t)(8 * ra + g) * ldk + t;
-    const double* pb = Wt + (size_t)(8 * rb + g) * ldk + t;
+    const double* pa = Yt + (size_t)(kSlotRows * ra + g) * ldk + t;
+    const double* pb = Wt + (size_t)(kSlotRows * rb + g) * ldk + t;
     double c0 = 0.0, c1 = 0.0;
     for (int k0 = 0; k0 < kdim; k0 += 4) dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
     // C[g][2t], C[g][2t+1] = sum_K Y_ra[g][K] W_rb[2t(+1)][K]
@@ -198,7 +196,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   // right-hand side: b_c(slot) -= Y b_p
   for (int e = tid; e < 6 * blk.n_slots; e += kBlkObs) {
     const int sl = e / 6, r = e - 6 * sl;
-    const double* y = Yt + (size_t)(8 * sl + r) * ldk;
+    const double* y = Yt + (size_t)(kSlotRows * sl + r) * ldk;
     double acc = 0.0;
     for (int k = 0; k < 3 * blk.n_lms; ++k) acc += y[k] * sG[k];
     red_add(a.rhs + a.pose_off[a.slot_pose[blk.slot_begin + sl]] + r, -acc);

@@ -204,6 +204,8 @@ bs::ReprojArgs reproj_args(bslam_solver* s) {
   a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p;
   a.obs_grp = s->groups.size() > 1 ? s->d_ogrp.p : nullptr;
   a.groups = s->d_groups.p;
+  if (!s->groups.empty()) a.g0 = s->groups[0];
+  a.obs_slot = s->d_obs_slot.p;
   a.poses = s->d_se3.p;
   a.pose_off = s->d_se3_off.p;
   a.pts = s->d_pts.p;
@@ -212,6 +214,7 @@ bs::ReprojArgs reproj_args(bslam_solver* s) {
   a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p;
   a.cam_perm = s->d_cam_perm.p; a.seg_start = s->d_seg_start.p;
   a.tail_begin = s->tail_begin;
+  { const char* e = getenv("BSLAM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.W = s->d_W.p; a.Vg = s->d_Vg.p;
   a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
   return a;
@@ -264,7 +267,10 @@ int do_linearize(bslam_solver* s) {
   if (s->n_pads > 0)
     LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
   record(s, 1);
-  if (s->n_lmblocks > 0) LAUNCH(s, bs::reproj_block_kernel, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
+  if (s->n_lmblocks > 0) {
+    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
+    else LAUNCH(s, bs::reproj_block_kernel<false>, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
+  }
   record(s, 2);
   if (s->n_obs > s->tail_begin)
     LAUNCH(s, bs::reproj_generic_kernel, cdiv(s->n_obs - s->tail_begin, 128), 128, 0, reproj_args(s));
@@ -1040,7 +1046,7 @@ int bslam_finalize(bslam_solver* s) {
           if (obs_slot[b.obs_begin + k] == sl) cam_perm[b.obs_begin + pos++] = (unsigned char)k;
       }
       seg_start.push_back((unsigned char)pos);
-      schur_smem = std::max(schur_smem, (size_t)16 * 8 * b.n_slots * bs::schur_ldk(b.n_lms));
+      schur_smem = std::max(schur_smem, (size_t)16 * (bs::kSlotRows * b.n_slots + 2) * bs::schur_ldk(b.n_lms));
       blocks.push_back(b);
       q = q1;
     }
@@ -1096,7 +1102,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_cam_perm, cam_perm, st));
   CU(upload(s->d_seg_start, seg_start, st));
   CU(upload(s->d_obs_slot, obs_slot, st));
-  if (s->schur_smem > 48 * 1024)
+  if (s->schur_smem > 0)   // static + dynamic shared memory may exceed the 48 KB default
     CU(cudaFuncSetAttribute(bs::schur_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->schur_smem));
   CU(upload(s->d_groups, s->groups, st));
   for (auto* b : s->edges) {

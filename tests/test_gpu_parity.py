@@ -301,3 +301,44 @@ def test_random_visibility_blocks():
         dx = pr._engine.get_update(low.dim)[low.ref_from_internal]
         assert rel_err(dx, ref['dx']) < 1e-6
         assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
+
+
+def test_mixed_groups_losses_and_stiffness():
+    """Reprojection blocks with different losses and per-block stiffness in one
+    problem (several constant groups inside one kernel launch)."""
+    import pyslam_b200
+    from oracle import gn_oracle as O
+    from oracle import liegroups as OL
+    from pyslam_b200 import synthetic
+    from pyslam_b200.lie import SE3, SO3
+    from pyslam_b200.residuals import ReprojectionResidual
+    from pyslam_b200.sensors import StereoCamera
+    d = synthetic.stereo_ba(6, 60, track=4, seed=9)
+    rng = np.random.default_rng(9)
+    pk, qk = B.ba_keys(d)
+    ocam, pcam = O.StereoCamera(*d['camera']), StereoCamera(*d['camera'])
+    op = O.OracleProblem(B.nondecreasing_options(O.Options))
+    pp = pyslam_b200.Problem(B.nondecreasing_options(pyslam_b200.Options))
+    for k, (ci, qi, o) in enumerate(zip(d['pose_idx'], d['pt_idx'], d['obs'])):
+        S = d['stiffness'] * (1.0 + 0.1 * (k % 3)) + (0.01 * rng.standard_normal((3, 3)) if k % 5 == 0 else 0.)
+        name, kk = [('huber', 1.5), ('cauchy', 2.0), ('l2', 0.), ('tdist', 4.0)][k % 4]
+        op.add_residual_block(O.ReprojectionResidual(ocam, o, S), [pk[ci], qk[qi]], B.oracle_loss(name, kk))
+        pp.add_residual_block(ReprojectionResidual(pcam, o, S), [pk[ci], qk[qi]], B.product_loss(name, kk))
+    po = {k: OL.SE3(OL.SO3(R), t) for k, R, t in zip(pk, d['R0'], d['t0'])}
+    po.update({k: np.array(p) for k, p in zip(qk, d['pts0'])})
+    ppar = {k: SE3(SO3(R), t) for k, R, t in zip(pk, d['R0'], d['t0'])}
+    ppar.update({k: np.array(p) for k, p in zip(qk, d['pts0'])})
+    op.initialize_params(po)
+    pp.initialize_params(ppar)
+    op.set_parameters_constant(pk[0])
+    pp.set_parameters_constant(pk[0])
+    op._update_partition_dict = op._get_update_partition_dict()
+    Ho, bo, co = op.get_precision_information_and_cost()
+    H, b, cost = normal_equations_ref_order(pp)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    op.solve()
+    pp.solve()
+    assert len(pp._cost_history) == len(op._cost_history)
+    np.testing.assert_allclose(pp._cost_history, op._cost_history, rtol=TOL_COST)
