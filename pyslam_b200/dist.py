@@ -42,7 +42,6 @@ class ShardedSolver:
     def __init__(self, engine, rank=0, world=1, group=None):
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
         engine.set_shard(rank)
-        self._buf = self._tail = self._stream = None
         if world > 1:
             self._merge_structure()
 
@@ -57,21 +56,13 @@ class ShardedSolver:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         self.engine.merge_tile_structure(t.cpu().numpy().astype(np.uint8))
 
-    def _tensors(self):
-        if self._buf is None:
-            self._buf = self.engine.reduced_tensor()
-            self._tail = self.engine.scalars_tensor()[1:3]        # COST_NEW, DX_NORM2
-            self._stream = self.engine.torch_stream()
-        return self._buf, self._tail, self._stream
-
     def eval_cost(self):
         import torch
         import torch.distributed as dist
         c = self.engine.eval_cost()
         if self.world == 1:
             return c
-        buf, _, _ = self._tensors()
-        t = torch.tensor([c], dtype=torch.float64, device=buf.device)
+        t = torch.tensor([c], dtype=torch.float64, device=self.engine.scalars_tensor().device)
         dist.all_reduce(t, group=self.group)
         return float(t.item())
 
@@ -81,15 +72,15 @@ class ShardedSolver:
         if self.world == 1:
             return eng.iterate(lam, eval_new_cost)
         import torch.distributed as dist
-        buf, tail, stream = self._tensors()
+        stream = eng.torch_stream()
         eng.linearize(fetch_cost=False)
         eng.reduce(lam)
         with _on_stream(stream):
-            dist.all_reduce(buf, group=self.group)
+            dist.all_reduce(eng.reduced_tensor(), group=self.group)
         eng.solve_reduced()
         eng.retract(eval_new_cost)
         with _on_stream(stream):
-            dist.all_reduce(tail, group=self.group)
+            dist.all_reduce(eng.scalars_tensor()[1:3], group=self.group)      # COST_NEW, DX_NORM2
         s = eng.scalars()
         return float(s[0]), float(s[1]), float(np.sqrt(s[2]))
 

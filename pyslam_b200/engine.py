@@ -367,19 +367,23 @@ def _engine_reduced_tensor(self):
     all-reduced across GPUs between `reduce` and `solve_reduced`."""
     import torch
     p, n, _, _ = self.reduced_buffer()
-    return torch.as_tensor(_DevArray(p, n), device='cuda:%d' % self.device)
+    key = ('red', p, n)
+    if getattr(self, '_tcache_key', None) != key:
+        self._tcache = torch.as_tensor(_DevArray(p, n), device='cuda:%d' % self.device)
+        self._tcache_key = key
+    return self._tcache
 
 
 def _engine_scalars_tensor(self):
-    import torch
-    _, _, ps, _ = self.reduced_buffer()
-    return torch.as_tensor(_DevArray(ps, N_SCALARS), device='cuda:%d' % self.device)
+    return self.reduced_tensor()[-N_SCALARS:]
 
 
 def _engine_torch_stream(self):
     """The handle's CUDA stream as a torch stream (order collectives / record events on it)."""
     import torch
-    return torch.cuda.ExternalStream(self.stream(), device='cuda:%d' % self.device)
+    if getattr(self, '_tstream', None) is None:
+        self._tstream = torch.cuda.ExternalStream(self.stream(), device='cuda:%d' % self.device)
+    return self._tstream
 
 
 Engine.reduced_tensor = _engine_reduced_tensor

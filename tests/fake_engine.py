@@ -248,7 +248,64 @@ class FakeEngine:
         self._scal[:4] = [c, cn, float(self.dx @ self.dx), 0.]
         return c, cn, float(np.linalg.norm(self.dx))
 
+    # ---- phase-wise iteration (multi-GPU plumbing) ----
+    def set_shard(self, rank):
+        self.rank = rank
+
+    def tile_structure(self):
+        return np.ones((2, 1), np.uint8)
+
+    def merge_tile_structure(self, mask):
+        self.merged_mask = np.array(mask)
+
+    def reduce(self, lam=0.):
+        """Schur complement of the points out of (H, b) -> torch buffer [S | rhs | scalars]."""
+        import torch
+        n = self.n_reduced
+        H = self.H + lam * np.diag(np.diag(self.H))
+        Hcc, Hcp, Hpp = H[:n, :n], H[:n, n:], H[n:, n:]
+        self._Hpp, self._Hpc, self._bp = Hpp, Hcp.T, self.b[n:]
+        if Hpp.size:
+            X = np.linalg.solve(Hpp, np.column_stack([Hcp.T, self.b[n:]]))
+            S = Hcc - Hcp @ X[:, :n]
+            rhs = self.b[:n] - Hcp @ X[:, n]
+        else:
+            S, rhs = Hcc.copy(), self.b[:n].copy()
+        buf = np.concatenate([S.ravel(), rhs, np.zeros(N_SCALARS)])
+        buf[n * n + n] = self._scal[0]
+        self._buf = torch.from_numpy(buf)
+
+    def reduced_tensor(self):
+        return self._buf
+
+    def scalars_tensor(self):
+        import torch
+        if getattr(self, '_buf', None) is None:
+            return torch.zeros(N_SCALARS, dtype=torch.float64)
+        n = self.n_reduced
+        return self._buf[n * n + n:]
+
+    def torch_stream(self):
+        return None
+
+    def solve_reduced(self):
+        n = self.n_reduced
+        buf = self._buf.numpy()
+        S, rhs = buf[:n * n].reshape(n, n), buf[n * n:n * n + n]
+        dxc = np.linalg.solve(S, rhs) if n else np.zeros(0)
+        dxp = np.linalg.solve(self._Hpp, self._bp - self._Hpc @ dxc) if self._Hpp.size else np.zeros(0)
+        self.dx = np.concatenate([dxc, dxp])
+
+    def retract(self, eval_new_cost=True):
+        n = self.n_reduced
+        self._retract()
+        tail = self.scalars_tensor().numpy()
+        tail[1] = self.eval_cost() if eval_new_cost else 0.
+        tail[2] = float(self.dx[n:] @ self.dx[n:]) + (float(self.dx[:n] @ self.dx[:n]) if getattr(self, 'rank', 0) == 0 else 0.)
+
     def scalars(self):
+        if getattr(self, '_buf', None) is not None:
+            return self.scalars_tensor().numpy().copy()
         return self._scal.copy()
 
     def snapshot(self):

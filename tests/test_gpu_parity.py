@@ -342,3 +342,28 @@ def test_mixed_groups_losses_and_stiffness():
     pp.solve()
     assert len(pp._cost_history) == len(op._cost_history)
     np.testing.assert_allclose(pp._cost_history, op._cost_history, rtol=TOL_COST)
+
+
+def test_config2_se2_pose_graph_full_size():
+    """BASELINE config 2: SE(2) pose graph, 1 000 poses, prior + 999 odometry + 100
+    loop-closure PoseToPoseResidual blocks, against the block-by-block oracle."""
+    from pyslam_b200 import synthetic
+    d = synthetic.se2_pose_graph(1000, 100, seed=0)
+    o = B.oracle_pose_graph(d, 'se2')
+    p = B.product_pose_graph(d, 'se2')
+    o._update_partition_dict = o._get_update_partition_dict()
+    Ho, bo, co = o.get_precision_information_and_cost()
+    H, b, cost = normal_equations_ref_order(p)
+    assert H.shape == (3000, 3000)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    dx0, _ = p.solve_one_iter()
+    o.solve()
+    assert rel_err(dx0, o.dx_history[0]) < 1e-6
+    p.solve()
+    assert len(p._cost_history) == len(o._cost_history)
+    np.testing.assert_allclose(p._cost_history, o._cost_history, rtol=1e-6)
+    Tp = B.rows_of([p.param_dict[k] for k in B.pose_graph_keys(d)])
+    To = B.rows_of([o.param_dict[k] for k in B.pose_graph_keys(d)])
+    assert rel_err(Tp, To) < 1e-6
