@@ -141,6 +141,18 @@ BSLAM_API int bslam_add_pose_to_pose_blocks(bslam_solver* s, int group, int n,
                                   const double* T21_obs, const double* stiffness, int per_block,
                                   int loss_kind, double loss_k);
 
+/* PhotometricResidualSE3 with a single SE3 parameter (pyslam/residuals/
+ * photometric_residual.py:38-161): dense direct alignment of a reference image
+ * (pixels already filtered by the constructor: valid disparity, gradient >= min_grad)
+ * against `im_track` (height x width, row-major).  uvd_ref n x 3 (pixel u, v,
+ * disparity), im_ref n, im_jac n x 2 (dI/du, dI/dv); stiffness = 1/sigma of the
+ * intensity and of the disparity.  pose_idx -> SE3 table (T_track_ref). */
+BSLAM_API int bslam_add_photometric_block(bslam_solver* s, int pose_idx, int n_px, const double* uvd_ref,
+                                          const double* im_ref, const double* im_jac, const double* im_track,
+                                          int width, int height, const double intr[5],
+                                          double intensity_stiffness, double depth_stiffness,
+                                          int loss_kind, double loss_k);
+
 /* Host-evaluated blocks (user-defined Python residuals, the plug-in surface of
  * pyslam/problem.py:338-360).  Declares the STRUCTURE once: n_blocks blocks,
  * block b has rows[b] residual rows and uses parameters

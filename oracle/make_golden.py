@@ -28,8 +28,8 @@ ref = load_reference()
 warnings.simplefilter('ignore')
 from liegroups import SE2, SE3, SO2, SO3  # noqa: E402  (oracle/liegroups)
 from pyslam.problem import Options, Problem  # noqa: E402  (verbatim reference)
-from pyslam.residuals import (PoseResidual, PoseToPoseResidual, QuadraticResidual,  # noqa: E402
-                              ReprojectionResidual)
+from pyslam.residuals import (PhotometricResidualSE3, PoseResidual, PoseToPoseResidual,  # noqa: E402
+                              QuadraticResidual, ReprojectionResidual)
 from pyslam.sensors import StereoCamera  # noqa: E402
 from pyslam.utils import invsqrt, bilinear_interpolate  # noqa: E402
 import pyslam.losses as ref_losses  # noqa: E402
@@ -296,7 +296,49 @@ def golden_covariance():
                         T_final=pose_rows([problem.param_dict['T0'], problem.param_dict['T1']], 3))
 
 
+# ------------------------------------------------------------------ dense photometric alignment (C5 shape)
+def dense_options():
+    o = Options()                     # pyslam/pipelines/dense.py:31-36
+    o.allow_nondecreasing_steps = True
+    o.max_nondecreasing_steps = 5
+    o.min_cost_decrease = 0.99
+    o.max_iters = 30
+    o.num_threads = 1
+    o.linesearch_max_iters = 0
+    return o
+
+
+def golden_photometric():
+    d = synthetic.photometric_pair(64, 48, seed=1)
+    cam = StereoCamera(*d['camera'])
+    cam.compute_pixel_grid()
+    disp = d['disparity'].copy()
+    disp[5:9, 7:12] = np.nan                     # invalid disparities are dropped by the constructor
+    res = PhotometricResidualSE3(cam, d['im_ref'], disp, d['im_track'], d['im_jac'], d['intensity_stiffness'],
+                                 d['depth_stiffness'], min_grad=0.002)
+    xi = np.array([0.01, -0.005, 0.02, 0.001, -0.002, 0.0015])
+    r, (J,) = res.evaluate([SE3.exp(xi)], [True])
+    problem = Problem(dense_options())
+    problem.add_residual_block(res, ['T_1_0'], ref_losses.CauchyLoss(d['loss'][1]))
+    problem.initialize_params({'T_1_0': SE3.identity()})
+    problem._update_partition_dict = problem._get_update_partition_dict()
+    H, g, cost = problem._get_precision_information_and_cost()
+    dxs = traced_solve(problem)
+    np.savez_compressed(os.path.join(OUT, 'photometric.npz'), camera=np.array(d['camera']), im_ref=d['im_ref'],
+                        im_track=d['im_track'], disparity=disp, im_jac=d['im_jac'],
+                        intensity_stiffness=np.float64(d['intensity_stiffness']),
+                        depth_stiffness=np.float64(d['depth_stiffness']), min_grad=np.float64(0.002),
+                        loss_k=np.float64(d['loss'][1]), xi=xi, n_ref=np.int64(len(res.im_ref)), r=r, J=J,
+                        H0=H.toarray(), g0=np.asarray(g).ravel(), cost0=np.float64(cost), dx0=dxs[0], n_iters=len(dxs),
+                        cost_history=np.array(problem._cost_history), T_final=pose_rows([problem.param_dict['T_1_0']], 3)[0])
+    print('photometric n_ref', len(res.im_ref), 'valid', len(r), 'iters', len(dxs), problem._cost_history[:3], '...',
+          problem._cost_history[-1])
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'photometric':
+        golden_photometric()
+        sys.exit(0)
     golden_losses()
     golden_camera()
     golden_residuals()
@@ -307,5 +349,6 @@ if __name__ == '__main__':
     golden_covariance()
     golden_ba('ba_huber', 8, 120, 'huber', 1.5)
     golden_ba('ba_cauchy', 6, 60, 'cauchy', 2.0)
+    golden_photometric()
     for f in sorted(os.listdir(OUT)):
         print('%8d  %s' % (os.path.getsize(os.path.join(OUT, f)), f))

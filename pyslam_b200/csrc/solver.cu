@@ -15,6 +15,7 @@
 #include "cholesky.cuh"
 #include "common.cuh"
 #include "dense_blocks.cuh"
+#include "photometric.cuh"
 #include "posegraph.cuh"
 #include "reproj.cuh"
 #include "retract.cuh"
@@ -56,6 +57,14 @@ struct EdgeBatch {
   DevBuf<double> d_Tobs, d_stiff;
 };
 
+struct PhotoBlock {
+  int pose_idx = 0, n_px = 0, w = 0, h = 0;
+  double intr[5] = {}, intensity_covar = 0, depth_covar = 0;
+  bs::Loss loss{0, 0.0};
+  std::vector<double> uvd, im_ref, im_jac, im_track;
+  DevBuf<double> d_uvd, d_im_ref, d_im_jac, d_im_track;
+};
+
 }  // namespace
 
 struct bslam_solver {
@@ -80,6 +89,7 @@ struct bslam_solver {
   std::vector<double> ob_uvd;
   std::vector<bs::ReprojGroup> groups;
   std::vector<EdgeBatch*> edges;
+  std::vector<PhotoBlock*> photos;
   // dense (host-evaluated) blocks
   int dn_blocks = 0;
   std::vector<int> dn_rows, dn_pptr, dn_pkind, dn_pindex;
@@ -128,6 +138,7 @@ struct bslam_solver {
 
   ~bslam_solver() {
     for (auto* e : edges) delete e;
+    for (auto* e : photos) delete e;
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (h_scalars) cudaFreeHost(h_scalars);
@@ -249,6 +260,30 @@ void launch_edges(bslam_solver* s, EdgeBatch* b, int slot) {
   }
 }
 
+bs::PhotoArgs photo_args(bslam_solver* s, PhotoBlock* b) {
+  bs::PhotoArgs a;
+  a.n_px = b->n_px;
+  a.uvd = b->d_uvd.p; a.im_ref = b->d_im_ref.p; a.im_jac = b->d_im_jac.p; a.im_track = b->d_im_track.p;
+  a.w = b->w; a.h = b->h;
+  a.cu = b->intr[0]; a.cv = b->intr[1]; a.fu = b->intr[2]; a.fv = b->intr[3]; a.b = b->intr[4];
+  a.intensity_covar = b->intensity_covar; a.depth_covar = b->depth_covar;
+  a.loss = b->loss;
+  a.pose = s->d_se3.p + 12 * (size_t)b->pose_idx;
+  a.pose_off = s->se3_off[b->pose_idx];
+  a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
+  return a;
+}
+
+template <bool kCostOnly>
+void launch_photos(bslam_solver* s, int slot) {
+  for (auto* b : s->photos) {
+    if (b->n_px == 0) continue;
+    if (!kCostOnly && s->se3_off[b->pose_idx] < 0) continue;    // all parameters constant: dropped (problem.py:343-348)
+    const int grid = std::min(cdiv(b->n_px, bs::kPhotoThreads), 148 * 2);
+    LAUNCH(s, bs::photometric_kernel<kCostOnly>, grid, bs::kPhotoThreads, 0, photo_args(s, b), slot);
+  }
+}
+
 // sum rho over all built-in blocks at the current parameters -> scalars[slot]
 void launch_cost(bslam_solver* s, int slot) {
   if (s->n_obs > 0) {
@@ -256,6 +291,7 @@ void launch_cost(bslam_solver* s, int slot) {
     LAUNCH(s, bs::reproj_cost_kernel, grid, 256, 0, reproj_args(s), slot);
   }
   for (auto* b : s->edges) launch_edges<true>(s, b, slot);
+  launch_photos<true>(s, slot);
 }
 
 int do_linearize(bslam_solver* s) {
@@ -275,6 +311,7 @@ int do_linearize(bslam_solver* s) {
   if (s->n_obs > s->tail_begin)
     LAUNCH(s, bs::reproj_generic_kernel, cdiv(s->n_obs - s->tail_begin, 128), 128, 0, reproj_args(s));
   for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
+  launch_photos<false>(s, BSLAM_S_COST_LIN);
   if (s->dn_blocks > 0) {
     bs::DenseArgs a;
     a.n_blocks = s->dn_blocks;
@@ -719,6 +756,30 @@ int bslam_add_pose_to_pose_blocks(bslam_solver* s, int group, int n, const int32
   return add_edges(s, "bslam_add_pose_to_pose_blocks", group, true, n, idx1, idx2, T21_obs, stiffness, per_block, loss_kind, loss_k);
 }
 
+int bslam_add_photometric_block(bslam_solver* s, int pose_idx, int n_px, const double* uvd_ref, const double* im_ref,
+                                const double* im_jac, const double* im_track, int width, int height, const double intr[5],
+                                double intensity_stiffness, double depth_stiffness, int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_add_photometric_block after finalize; call bslam_clear_blocks first");
+  NEED(n_px >= 0 && width > 0 && height > 0 && im_track && intr && (n_px == 0 || (uvd_ref && im_ref && im_jac)),
+       "bslam_add_photometric_block: bad arguments");
+  NEED(pose_idx >= 0 && pose_idx < s->n_se3, "photometric block: pose index %d outside the SE3 table (%d)", pose_idx, s->n_se3);
+  NEED(intensity_stiffness > 0.0 && depth_stiffness > 0.0, "photometric block: stiffness must be positive");
+  NEED(valid_loss(loss_kind, loss_k), "bslam_add_photometric_block: invalid loss (kind %d, k %g)", loss_kind, loss_k);
+  PhotoBlock* b = new PhotoBlock();
+  b->pose_idx = pose_idx; b->n_px = n_px; b->w = width; b->h = height;
+  for (int k = 0; k < 5; ++k) b->intr[k] = intr[k];
+  b->intensity_covar = 1.0 / (intensity_stiffness * intensity_stiffness);     // stiffness ** -2 (photometric_residual.py:59-60)
+  b->depth_covar = 1.0 / (depth_stiffness * depth_stiffness);
+  b->loss.kind = loss_kind; b->loss.k = loss_k;
+  b->uvd.assign(uvd_ref, uvd_ref + 3 * (size_t)n_px);
+  b->im_ref.assign(im_ref, im_ref + n_px);
+  b->im_jac.assign(im_jac, im_jac + 2 * (size_t)n_px);
+  b->im_track.assign(im_track, im_track + (size_t)width * height);
+  s->photos.push_back(b);
+  return BSLAM_OK;
+}
+
 int bslam_set_dense_blocks(bslam_solver* s, int n_blocks, const int32_t* rows, const int32_t* param_ptr,
                            const int32_t* param_kind, const int32_t* param_index) {
   NEED(s, "NULL solver");
@@ -760,6 +821,8 @@ int bslam_clear_blocks(bslam_solver* s) {
   s->ob_pose.clear(); s->ob_pt.clear(); s->ob_grp.clear(); s->ob_uvd.clear(); s->groups.clear();
   for (auto* e : s->edges) delete e;
   s->edges.clear();
+  for (auto* e : s->photos) delete e;
+  s->photos.clear();
   s->dn_blocks = 0;
   s->dn_rows.clear(); s->dn_pptr.clear(); s->dn_pkind.clear(); s->dn_pindex.clear();
   s->finalized = false;
@@ -1110,6 +1173,12 @@ int bslam_finalize(bslam_solver* s) {
     CU(upload(b->d_i2, b->i2, st));
     CU(upload(b->d_Tobs, b->Tobs, st));
     CU(upload(b->d_stiff, b->stiff, st));
+  }
+  for (auto* b : s->photos) {
+    CU(upload(b->d_uvd, b->uvd, st));
+    CU(upload(b->d_im_ref, b->im_ref, st));
+    CU(upload(b->d_im_jac, b->im_jac, st));
+    CU(upload(b->d_im_track, b->im_track, st));
   }
   CU(upload(s->d_dn_row_ptr, s->dn_row_ptr, st));
   CU(upload(s->d_dn_col_ptr, s->dn_col_ptr, st));

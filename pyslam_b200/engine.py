@@ -46,6 +46,8 @@ SIGNATURES = {
     'bslam_add_reprojection_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double]),
     'bslam_add_pose_blocks': (C.c_int, [_h, C.c_int, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
     'bslam_add_pose_to_pose_blocks': (C.c_int, [_h, C.c_int, C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    'bslam_add_photometric_block': (C.c_int, [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_double,
+                                              C.c_double, C.c_int, C.c_double]),
     'bslam_set_dense_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _ip, _ip]),
     'bslam_upload_dense_values': (C.c_int, [_h, _dp, C.c_size_t, _dp, C.c_size_t, C.c_double]),
     'bslam_clear_blocks': (C.c_int, [_h]),
@@ -235,6 +237,15 @@ class Engine:
         S, per = self._stiff(stiffness, n, dof)
         self._ck(self._lib.bslam_add_pose_to_pose_blocks(self._h, group, n, _i(idx1), _i(idx2), _d(T21_obs), _d(S), per,
                                                          int(loss_kind), float(loss_k)))
+
+    def add_photometric_block(self, pose_idx, uvd_ref, im_ref, im_jac, im_track, intr, intensity_stiffness,
+                              depth_stiffness, loss_kind=0, loss_k=0.):
+        uvd_ref, im_ref, im_jac = _f64(uvd_ref, (-1, 3)), _f64(im_ref).ravel(), _f64(im_jac, (-1, 2))
+        im_track, intr = _f64(im_track), _f64(intr, (5,))
+        assert im_track.ndim == 2 and len(im_ref) == len(uvd_ref) == len(im_jac)
+        self._ck(self._lib.bslam_add_photometric_block(
+            self._h, int(pose_idx), len(uvd_ref), _d(uvd_ref), _d(im_ref), _d(im_jac), _d(im_track), im_track.shape[1],
+            im_track.shape[0], _d(intr), float(intensity_stiffness), float(depth_stiffness), int(loss_kind), float(loss_k)))
 
     def set_dense_blocks(self, rows, param_ptr, param_kind, param_index):
         rows, param_ptr = _i32(rows), _i32(param_ptr)

@@ -33,6 +33,7 @@ from . import engine as _engine
 from .lie import group_of
 from .losses import L2Loss, loss_descriptor
 from .residuals.blocks import BLOCK_POSE, BLOCK_POSE_TO_POSE, BLOCK_REPROJECTION
+from .residuals.photometric import BLOCK_PHOTOMETRIC
 
 
 class Options:
@@ -193,7 +194,12 @@ class Problem:
                 return None
             return g
 
-        kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('dense',)
+        def fusable_photo(block, keys, loss):
+            return (getattr(type(block), 'BLOCK_KIND', None) == BLOCK_PHOTOMETRIC and len(keys) == 1
+                    and loss_descriptor(loss) is not None and hasattr(block.camera, 'intrinsics')
+                    and group_of(pd.get(keys[0])) == 'se3')
+
+        kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('photo',) | ('dense',)
         point_keys = set()
         for block, keys, loss in zip(self.residual_blocks, self.block_param_keys, self.block_loss_functions):
             for k in keys:
@@ -202,6 +208,9 @@ class Problem:
             if fusable_reproj(block, keys, loss):
                 kinds.append(('reproj',))
                 point_keys.add(keys[1])
+                continue
+            if fusable_photo(block, keys, loss):
+                kinds.append(('photo',))
                 continue
             g = fusable_pose(block, keys, loss, BLOCK_POSE, 1)
             if g:
@@ -254,6 +263,11 @@ class Problem:
             if k[0] == 'dense':
                 continue
             ld = loss_descriptor(loss)
+            if k[0] == 'photo':
+                eng.add_photometric_block(low.table[keys[0]][1], block.uvd_ref, block.im_ref, block.im_jac, block.im_track,
+                                          block.camera.intrinsics(), block.intensity_stiffness, block.depth_stiffness,
+                                          ld[0], ld[1])
+                continue
             if k[0] == 'reproj':
                 gk = ('reproj', ld, tuple(block.camera.intrinsics()))
             else:

@@ -5,6 +5,7 @@ resolves the same names as `from pyslam.residuals import ...`.
 """
 from .blocks import (ReprojectionResidual, PoseResidual, PoseToPoseResidual,
                      QuadraticResidual)
+from .photometric import PhotometricResidualSE3
 
 __all__ = ['ReprojectionResidual', 'PoseResidual', 'PoseToPoseResidual',
-           'QuadraticResidual']
+           'QuadraticResidual', 'PhotometricResidualSE3']

@@ -105,3 +105,25 @@ def se3_pose_graph(n=40, n_loops=6, seed=0, loop_span=10):
                 prior_stiffness=np.real(invsqrt(1e-6 * np.eye(6))),
                 odo_stiffness=np.real(invsqrt(1e-3 * np.eye(6))),
                 loop_stiffness=np.real(invsqrt(1e-2 * np.eye(6))))
+
+
+def photometric_pair(w=640, h=480, seed=0, shift=1):
+    """Dense stereo photometric alignment, SURVEY 8(d) C5: a smooth random
+    reference image (Gaussian-blurred noise, normalised to [0,1]), a tracking
+    image = the reference shifted horizontally by `shift` pixels, disparity
+    20 + U[0,10], image Jacobian 0.5 * Sobel (pyslam/pipelines/keyframes.py:44-45).
+    Returns a dict; camera = (cu, cv, fu, fv, b, w, h)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(seed)
+    big = ndimage.gaussian_filter(rng.random((h, w + 8)), 3.0)
+    big = (big - big.min()) / (big.max() - big.min())
+    im_ref = np.ascontiguousarray(big[:, 4:4 + w])
+    im_track = np.ascontiguousarray(big[:, 4 + shift:4 + shift + w])
+    disp = 20. + 10. * rng.random((h, w))
+    kx = np.array([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]])
+    gradx = 0.5 * ndimage.correlate(im_ref, kx, mode='reflect')
+    grady = 0.5 * ndimage.correlate(im_ref, kx.T, mode='reflect')
+    scale = w / 640.
+    camera = (320. * scale, 240. * scale, 500. * scale, 500. * scale, 0.5, w, h)
+    return dict(camera=camera, im_ref=im_ref, im_track=im_track, disparity=disp, im_jac=np.array([gradx, grady]),
+                intensity_stiffness=100., depth_stiffness=2., loss=('cauchy', 5.0))

@@ -143,3 +143,38 @@ class CubicResidual:
             full = [self.stiffness * self.x**3, self.stiffness * self.x**2, self.stiffness * self.x, self.stiffness]
             return r, [np.array(j) if cj else None for j, cj in zip(full, compute_jacobians)]
         return r
+
+
+# ------------------------------------------------------------------ dense photometric alignment
+def dense_options(cls):
+    """pyslam/pipelines/dense.py:31-36"""
+    o = cls()
+    o.allow_nondecreasing_steps = True
+    o.max_nondecreasing_steps = 5
+    o.min_cost_decrease = 0.99
+    o.max_iters = 30
+    o.linesearch_max_iters = 0
+    return o
+
+
+def oracle_photometric_problem(d, min_grad=0., options=None):
+    cam = O.StereoCamera(*np.asarray(d['camera']))
+    cam.compute_pixel_grid()
+    res = O.PhotometricResidualSE3(cam, d['im_ref'], d['disparity'], d['im_track'], d['im_jac'],
+                                   float(d['intensity_stiffness']), float(d['depth_stiffness']), min_grad=min_grad)
+    pr = O.OracleProblem(options or dense_options(O.Options))
+    pr.add_residual_block(res, ['T_1_0'], O.CauchyLoss(float(d['loss_k'])))
+    pr.initialize_params({'T_1_0': OL.SE3.identity()})
+    return pr, res
+
+
+def product_photometric_problem(d, min_grad=0., options=None):
+    from pyslam_b200.residuals import PhotometricResidualSE3
+    cam = StereoCamera(*[float(v) for v in np.asarray(d['camera'])])
+    cam.compute_pixel_grid()
+    res = PhotometricResidualSE3(cam, d['im_ref'], d['disparity'], d['im_track'], d['im_jac'],
+                                 float(d['intensity_stiffness']), float(d['depth_stiffness']), min_grad=min_grad)
+    pr = pyslam_b200.Problem(options or dense_options(pyslam_b200.Options))
+    pr.add_residual_block(res, ['T_1_0'], PLoss.CauchyLoss(float(d['loss_k'])))
+    pr.initialize_params({'T_1_0': PL.SE3.identity()})
+    return pr, res

@@ -76,7 +76,7 @@ class FakeEngine:
 
     # ---- blocks
     def clear_blocks(self):
-        self.reproj, self.pose_b, self.p2p_b, self.dense = [], [], [], None
+        self.reproj, self.pose_b, self.p2p_b, self.photo_b, self.dense = [], [], [], [], None
         self.finalized = False
 
     @staticmethod
@@ -107,6 +107,17 @@ class FakeEngine:
         T = np.asarray(T21_obs, float).reshape(n, -1)
         for i in range(n):
             self.p2p_b.append((group, int(idx1[i]), int(idx2[i]), T[i], S[i], self._loss(loss_kind, loss_k)))
+
+    def add_photometric_block(self, pose_idx, uvd_ref, im_ref, im_jac, im_track, intr, intensity_stiffness,
+                              depth_stiffness, loss_kind=0, loss_k=0.):
+        im_track = np.asarray(im_track, float)
+        blk = O.PhotometricResidualSE3.__new__(O.PhotometricResidualSE3)
+        blk.camera = O.StereoCamera(*intr, im_track.shape[1], im_track.shape[0])
+        blk.uvd_ref, blk.im_ref = np.asarray(uvd_ref, float).reshape(-1, 3), np.asarray(im_ref, float).ravel()
+        blk.im_jac, blk.im_track = np.asarray(im_jac, float).reshape(-1, 2), im_track
+        blk.intensity_covar, blk.depth_covar = intensity_stiffness ** -2, depth_stiffness ** -2
+        blk.pt_ref, blk.triang_jac = blk.camera.triangulate(blk.uvd_ref, compute_jacobians=True)
+        self.photo_b.append((int(pose_idx), blk, self._loss(loss_kind, loss_k)))
 
     def set_dense_blocks(self, rows, param_ptr, param_kind, param_index):
         self.dense = (list(rows), list(param_ptr), list(param_kind), list(param_index))
@@ -164,6 +175,8 @@ class FakeEngine:
         for grp, i, j, T, S, loss in self.p2p_b:
             name, objs, mk = ('se3', se3, _se3) if grp == 3 else ('se2', se2, _se2)
             yield O.PoseToPoseResidual(mk(T), S), [(name, i, objs[i]), (name, j, objs[j])], loss
+        for i, blk, loss in self.photo_b:
+            yield blk, [('se3', i, se3[i])], loss
 
     def eval_cost(self):
         return float(sum(np.sum(loss.loss(blk.evaluate([p for _, _, p in ps]))) for blk, ps, loss in self._blocks()))

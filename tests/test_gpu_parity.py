@@ -367,3 +367,41 @@ def test_config2_se2_pose_graph_full_size():
     Tp = B.rows_of([p.param_dict[k] for k in B.pose_graph_keys(d)])
     To = B.rows_of([o.param_dict[k] for k in B.pose_graph_keys(d)])
     assert rel_err(Tp, To) < 1e-6
+
+
+def test_photometric_against_reference_golden():
+    """BASELINE config 5 shape (small image): PhotometricResidualSE3 + CauchyLoss
+    through the fused kernel against the unmodified reference."""
+    g = load_golden('photometric')
+    pr, _ = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, g['H0']) < 1e-10
+    assert rel_err(b, g['g0']) < 1e-10
+    assert abs(cost - g['cost0']) < 1e-11 * g['cost0']
+    dx0, _ = pr.solve_one_iter()
+    assert rel_err(dx0, g['dx0']) < TOL_DX
+    pr.solve()
+    assert len(pr._cost_history) == len(g['cost_history'])
+    np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=1e-6)
+    assert rel_err(B.rows_of([pr.param_dict['T_1_0']])[0], g['T_final']) < 1e-6
+
+
+def test_config5_photometric_full_size():
+    """BASELINE config 5: 640x480 dense stereo photometric alignment, Cauchy(5),
+    against the numpy oracle (first linearisation and the first update)."""
+    from pyslam_b200 import synthetic
+    d = synthetic.photometric_pair(640, 480, seed=0)
+    d['loss_k'] = d['loss'][1]
+    o, _ = B.oracle_photometric_problem(d)
+    p, res = B.product_photometric_problem(d)
+    assert len(res.im_ref) > 300000
+    o._update_partition_dict = o._get_update_partition_dict()
+    Ho, bo, co = o.get_precision_information_and_cost()
+    H, b, cost = normal_equations_ref_order(p)
+    assert rel_err(H, Ho.toarray()) < 1e-10
+    assert rel_err(b, bo) < 1e-10
+    assert abs(cost - co) < 1e-11 * co
+    dxo, _ = o.solve_one_iter()
+    dx, _ = p.solve_one_iter()
+    assert rel_err(dx, dxo) < 1e-6
+    assert abs(p.eval_cost() - o.eval_cost()) < 1e-11 * co

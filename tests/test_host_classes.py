@@ -91,3 +91,16 @@ def test_quadratic_residual():
     _, j1 = r.evaluate([1., -2., 3.], compute_jacobians=[True, True, True])
     _, j2 = r.evaluate([1., -2., 3.], compute_jacobians=[False, False, False])
     assert np.allclose(j1, [4., 2., 1.]) and not any(j2) and len(j1) == len(j2) == 3
+
+
+def test_photometric_residual_numpy_evaluate():
+    g = load_golden('photometric')
+    _, res = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
+    assert len(res.im_ref) == int(g['n_ref'])
+    r, (J,) = res.evaluate([lie.SE3.exp(g['xi'])], [True])
+    np.testing.assert_allclose(r, g['r'], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(J, g['J'], rtol=1e-11, atol=1e-11)
+    T = lie.SE3.exp(g['xi'])
+    r2, (Jr, Jt) = res.evaluate([T.rot, T.trans], [True, True])         # (SO3, t) form
+    np.testing.assert_allclose(r2, r)
+    np.testing.assert_allclose(np.hstack([Jt, Jr]), J)

@@ -222,3 +222,28 @@ def test_no_gpu_fails_loudly():
         pr.solve()
     with pytest.raises(E.EngineError):
         pr.eval_cost()
+
+
+def test_photometric_lowering_and_dense_options():
+    """Config-5 shape through the host: PhotometricResidualSE3 is lowered to a
+    photometric batch, linesearch_max_iters = 0 (cost history lags one
+    iteration), nondecreasing-steps bookkeeping of dense.py."""
+    g = load_golden('photometric')
+    pr, _ = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
+    pr.solve()
+    assert pr._low.kinds == [('photo',)] and pr._engine.photo_b
+    assert len(pr._cost_history) - 1 == int(g['n_iters'])
+    np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=1e-7)
+    assert pr._cost_history[0] == pr._cost_history[1]
+    assert rel_err(B.rows_of([pr.param_dict['T_1_0']])[0], g['T_final']) < 1e-7
+    # the (SO3, t) two-parameter form is not a GPU batch: it must fall back to the plug-in path
+    from pyslam_b200.lie import SE3
+    pr2, res = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
+    pr2.residual_blocks, pr2.block_param_keys, pr2.block_loss_functions = [], [], []
+    pr2.param_dict = {}
+    pr2.add_residual_block(res, ['R_1_0', 't_1_0_1'], O.CauchyLoss(float(g['loss_k'])))
+    pr2.initialize_params({'R_1_0': SE3.identity().rot, 't_1_0_1': np.zeros(3)})
+    pr2.options.max_iters = 3
+    pr2.solve()
+    assert pr2._low.kinds == [('dense',)] and 'R_1_0' in pr2._low.opaque
+    assert pr2._cost_history[-1] < 0.5 * pr2._cost_history[0]

@@ -228,3 +228,20 @@ def test_ba_reference_test_trace():
         assert np.linalg.norm(out['pt%d_w' % j] - g['pts_true'][j]) < 1e-4
     for i in range(4):
         assert np.linalg.norm(OL.SE3.log(out['T_cam%d_w' % i].inv().dot(B.o_se3(g['T_true'][i])))) < 1e-4
+
+
+def test_photometric_matches_reference():
+    g = load_golden('photometric')
+    pr, res = B.oracle_photometric_problem(g, min_grad=float(g['min_grad']))
+    assert len(res.im_ref) == int(g['n_ref'])
+    r, (J,) = res.evaluate([OL.SE3.exp(g['xi'])], [True])
+    np.testing.assert_allclose(r, g['r'], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(J, g['J'], rtol=1e-11, atol=1e-11)
+    pr._update_partition_dict = pr._get_update_partition_dict()
+    H, b, cost = pr.get_precision_information_and_cost()
+    assert rel_err(H.toarray(), g['H0']) < 1e-12 and rel_err(b, g['g0']) < 1e-12
+    pr.solve()
+    assert len(pr.dx_history) == int(g['n_iters'])
+    assert rel_err(pr.dx_history[0], g['dx0']) < 1e-9
+    np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=1e-7)
+    assert rel_err(B.rows_of([pr.param_dict['T_1_0']])[0], g['T_final']) < 1e-7
