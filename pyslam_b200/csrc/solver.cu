@@ -14,6 +14,7 @@
 #include "../../include/bslam.h"
 #include "cholesky.cuh"
 #include "common.cuh"
+#include "covariance.cuh"
 #include "dense_blocks.cuh"
 #include "photometric.cuh"
 #include "posegraph.cuh"
@@ -130,6 +131,7 @@ struct bslam_solver {
   int chol_epoch = 0, chol_grid = 0, n_tile_tasks = 0;
   DevBuf<bs::CholTask> d_tasks;
   DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_ticket;
+  DevBuf<unsigned char> d_fill_mask;               // tile mask after symbolic fill-in
 
   double* S() { return d_red.p; }
   double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
@@ -437,6 +439,7 @@ int build_chol_plan(bslam_solver* s) {
   if (bwd_rows.empty()) bwd_rows.push_back(0);
   s->n_tile_tasks = (int)tasks.size();
   cudaStream_t st = s->stream;
+  CU(upload(s->d_fill_mask, m, st));
   CU(upload(s->d_tasks, tasks, st));
   CU(upload(s->d_klist, klist, st));
   CU(upload(s->d_bwd_ptr, bwd_ptr, st));
@@ -1406,8 +1409,37 @@ int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
 }
 
 int bslam_covariance(bslam_solver* s, double* cov) {
-  (void)cov;
-  return fail(s, BSLAM_E_INVALID, "bslam_covariance: not implemented yet");
+  NEED(s && s->finalized && cov, "bslam_covariance: bad arguments");
+  NEED(s->dim <= 8192, "bslam_covariance: D = %d too large for a dense covariance (limit 8192)", s->dim);
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if ((rc = do_linearize(s))) return rc;
+  if ((rc = do_reduce(s, 0.0))) return rc;
+  if ((rc = do_solve_reduced(s))) return rc;          // factor L (in S), diagonal inverses (Linv)
+  const size_t D = (size_t)s->dim;
+  const int nt = s->nblk, ld = s->n_pad;
+  DevBuf<double> d_cov, d_G;
+  CU(d_cov.alloc(D * D));
+  CU(d_G.alloc((size_t)ld * ld));
+  CU(cudaMemsetAsync(d_cov.p, 0, D * D * sizeof(double), s->stream));
+  CU(cudaMemsetAsync(d_G.p, 0, (size_t)ld * ld * sizeof(double), s->stream));
+  const size_t smem = 2 * bs::kNB * bs::kLd * sizeof(double);
+  CU(cudaFuncSetAttribute(bs::cov_linv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(bs::cov_gtg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LAUNCH(s, bs::cov_linv_kernel, nt, bs::kCholThreads, smem, s->S(), ld, s->d_Linv.p, nt, s->d_fill_mask.p, d_G.p);
+  LAUNCH(s, bs::cov_gtg_kernel, dim3(nt, nt), bs::kCholThreads, smem, d_G.p, ld, nt, d_cov.p, D);
+  if (s->n_lm > 0) {
+    bs::CovLmArgs a;
+    a.n_lm = s->n_lm; a.n_obs = s->n_obs; a.n_pad = s->n_pad; a.D = D;
+    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.W = s->d_W.p; a.Vinv = s->d_Vinv.p; a.cov = d_cov.p;
+    LAUNCH(s, bs::cov_lm_pose_kernel, dim3(cdiv(s->n_pad, 128), 3 * s->n_lm), 128, 0, a);
+    LAUNCH(s, bs::cov_lm_lm_kernel, dim3(cdiv(s->n_lm, 128), 3 * s->n_lm), 128, 0, a);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cov, d_cov.p, D * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return BSLAM_OK;
 }
 
 int bslam_enable_timing(bslam_solver* s, int on) {

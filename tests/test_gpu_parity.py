@@ -405,3 +405,47 @@ def test_config5_photometric_full_size():
     dx, _ = p.solve_one_iter()
     assert rel_err(dx, dxo) < 1e-6
     assert abs(p.eval_cost() - o.eval_cost()) < 1e-11 * co
+
+
+def test_covariance_reference_cases():
+    """Problem.compute_covariance / get_covariance_block."""
+    import pyslam_b200
+    from pyslam_b200.lie import SE3
+    from pyslam_b200.residuals import PoseResidual, PoseToPoseResidual
+    from pyslam_b200.utils import invsqrt
+    # (1) reference tests/test_problem.py:294-321
+    g = load_golden('covariance_se3')
+    pr = pyslam_b200.Problem(B.nondecreasing_options(pyslam_b200.Options))
+    odom = SE3.exp(0.1 * np.ones(6))
+    So, S0 = invsqrt(1e-3 * np.eye(6)), invsqrt(1e-6 * np.eye(6))
+    pr.add_residual_block(PoseResidual(SE3.identity(), S0), 'T0')
+    pr.add_residual_block(PoseToPoseResidual(odom, So), ['T0', 'T1'])
+    pr.initialize_params({'T0': SE3.identity(), 'T1': SE3.identity()})
+    pr.solve()
+    pr.compute_covariance()
+    est = pr.get_covariance_block('T1', 'T1')
+    expected = np.linalg.inv(So.dot(So)) + odom.adjoint().dot(np.linalg.inv(S0.dot(S0)).dot(odom.adjoint().T))
+    assert np.allclose(est, expected)
+    np.testing.assert_allclose(pr._covariance_matrix, g['cov'], rtol=1e-6, atol=1e-12)
+    # (2) cubic notebook (plug-in residuals), cells 8-12
+    c = load_golden('cubic')
+    pr = pyslam_b200.Problem()
+    for xi, yi in zip(c['n10_x'], c['n10_y']):
+        pr.add_residual_block(B.CubicResidual(xi, yi, 1.), ['a', 'b', 'c', 'd'])
+    pr.initialize_params({'a': -2., 'b': 10., 'c': -6., 'd': -140.})
+    pr.solve()
+    pr.compute_covariance()
+    np.testing.assert_allclose(pr._covariance_matrix, c['n10_cov'], rtol=1e-7, atol=1e-14)
+    assert abs(pr.get_covariance_block('a', 'a') - 0.00017205419580419603) < 1e-11
+    # (3) stereo BA with eliminated landmarks against the oracle's dense inverse
+    gb = load_golden('ba_cauchy')
+    o = B.oracle_ba_problem(gb)
+    p = B.product_ba_problem(gb)
+    o._update_partition_dict = o._get_update_partition_dict()
+    o.compute_covariance()
+    p._ensure_lowered()
+    p.compute_covariance()
+    assert rel_err(p._covariance_matrix, o._covariance_matrix) < 1e-6
+    pk, qk = B.ba_keys(gb)
+    np.testing.assert_allclose(p.get_covariance_block(pk[2], qk[5]), o.get_covariance_block(pk[2], qk[5]), rtol=1e-5, atol=1e-9)
+    assert p.get_covariance_block(pk[0], pk[0]) is None        # constant parameter

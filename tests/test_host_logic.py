@@ -247,3 +247,15 @@ def test_photometric_lowering_and_dense_options():
     pr2.solve()
     assert pr2._low.kinds == [('dense',)] and 'R_1_0' in pr2._low.opaque
     assert pr2._cost_history[-1] < 0.5 * pr2._cost_history[0]
+
+
+def test_covariance_block_mapping():
+    gb = load_golden('ba_cauchy')
+    o = B.oracle_ba_problem(gb)
+    p = B.product_ba_problem(gb)
+    o._update_partition_dict = o._get_update_partition_dict()
+    o.compute_covariance()
+    p.compute_covariance()
+    assert rel_err(p._covariance_matrix, o._covariance_matrix) < 1e-7
+    pk, qk = B.ba_keys(gb)
+    np.testing.assert_allclose(p.get_covariance_block(pk[2], qk[5]), o.get_covariance_block(pk[2], qk[5]), rtol=1e-6, atol=1e-10)
