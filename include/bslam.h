@@ -245,6 +245,10 @@ BSLAM_API int bslam_get_reduced_system(bslam_solver* s, double* S, double* rhs);
  * `Problem.compute_covariance` (problem.py:196-203). */
 BSLAM_API int bslam_covariance(bslam_solver* s, double* cov);
 
+/* Debug aid: run one reduced solve with per-task tracing of the Cholesky kernel.
+ * out[6*t..] = (tile row | -1, tile column, start ns, dependencies-ready ns, end ns, SM id). */
+BSLAM_API int bslam_debug_chol_trace(bslam_solver* s, int64_t* out, int max_tasks, int* n_tasks);
+
 /* Phase timings of the last bslam_iterate with timing enabled (ms). */
 BSLAM_API int bslam_enable_timing(bslam_solver* s, int on);
 BSLAM_API int bslam_get_timings(bslam_solver* s, double* ms /* BSLAM_N_TIMINGS */);

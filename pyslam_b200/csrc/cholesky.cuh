@@ -50,12 +50,19 @@ struct CholPlan {
   int* xready;           // [nt]       epoch flags: x_k final
   int* ticket;
   int epoch;
+  long long* trace;      // optional [n_tasks][4]: start, dependencies satisfied, end (globaltimer ns), SM id
 };
 
 BS_D void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
+}
+
+BS_D long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 
 BS_D int ld_acquire(const int* p) {
@@ -282,6 +289,8 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
     const int tk = s_ticket;
     if (tk >= p.n_tile_tasks + nt) break;
 
+    long long t0 = 0, t1 = 0;
+    if (p.trace && tid == 0) t0 = gtime();
     if (tk < p.n_tile_tasks) {
       // ------------------------------------------------ tile task (i, j)
       const CholTask task = p.tasks[tk];
@@ -302,6 +311,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         tile_mma_abt(sA, ti != tj ? sB : sA, acc);
       }
       __syncthreads();
+      if (p.trace && tid == 0) t1 = gtime();
       // C = S_ij - acc  -> sA
       double* Cij = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
       acc_foreach([&](int i, int j, int r, int c) {
@@ -322,6 +332,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         }
       } else {
         wait_flag(p.ready + tj * nt + tj, p.epoch);
+        if (p.trace && tid == 0) t1 = gtime();
         tile_load(sB, Linv + (size_t)tj * kNB * kNB, kNB, kNB);
         __syncthreads();
         acc_zero(acc);
@@ -358,6 +369,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         for (int r = 0; r < 16; ++r) part = fma(lr[r], __ldcg(xi + r), part);
       }
       wait_flag(p.ready + nt * nt + k, p.epoch);     // y_k (row 0 of the right-hand-side tile)
+      if (p.trace && tid == 0) t1 = gtime();
       sred[grp * 64 + c] = part;
       __syncthreads();
       if (grp == 0) {
@@ -374,10 +386,26 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       if (grp == 0) x[(size_t)k * kNB + c] = sred[c] + sred[64 + c] + sred[128 + c] + sred[192 + c];
       post_flag(p.xready + k, p.epoch);
     }
+    if (p.trace && tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      long long* tr = p.trace + 4 * (size_t)tk;
+      tr[0] = t0; tr[1] = t1; tr[2] = gtime(); tr[3] = smid;
+    }
   }
 }
 
 constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + 4 * 64) * sizeof(double);
+
+// zero the listed 64x64 tiles (tile id = i * nt + j) of S
+__global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S, int ld, int nt, const int* __restrict__ tiles) {
+  const int id = tiles[blockIdx.x];
+  double* T = S + (size_t)(id / nt) * kNB * ld + (size_t)(id % nt) * kNB;
+  for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
+    const int r = e >> 5, c2 = (e & 31) << 1;
+    *reinterpret_cast<double2*>(T + (size_t)r * ld + c2) = make_double2(0.0, 0.0);
+  }
+}
 
 // identity on the padding diagonal so the padded factorisation is well defined
 __global__ void pad_diag_kernel(double* __restrict__ S, int ld, const int* __restrict__ pad_idx, int n_pads) {

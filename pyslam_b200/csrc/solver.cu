@@ -132,6 +132,10 @@ struct bslam_solver {
   DevBuf<bs::CholTask> d_tasks;
   DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_ticket;
   DevBuf<unsigned char> d_fill_mask;               // tile mask after symbolic fill-in
+  DevBuf<long long> d_trace;                       // debug: per-task timestamps (bslam_debug_chol_trace)
+  std::vector<bs::CholTask> h_tasks;
+  DevBuf<int> d_dirty_tiles;                       // tiles (i*nt+j) that carry data: zeroed before every linearisation
+  int n_dirty_tiles = 0;
 
   double* S() { return d_red.p; }
   double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
@@ -181,6 +185,8 @@ int fail(bslam_solver* s, int code, const char* fmt, ...) {
   } while (0)
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int build_chol_plan(bslam_solver* s);
 
 template <typename T>
 cudaError_t upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
@@ -300,8 +306,14 @@ int do_linearize(bslam_solver* s) {
   NEED(s->finalized, "bslam_finalize has not been called");
   NEED(s->dn_blocks == 0 || s->dn_uploaded, "dense blocks declared but bslam_upload_dense_values not called");
   record(s, 0);
-  CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), s->stream));
-  if (s->n_lm > 0) CU(cudaMemsetAsync(s->d_Vg.p, 0, s->d_Vg.n * sizeof(double), s->stream));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  // zero only what the iteration dirties: the structurally non-zero tiles (after fill-in), rhs, scalars;
+  // the rest of S was zeroed at finalize and is never written
+  if (s->n_dirty_tiles > 0)
+    LAUNCH(s, bs::zero_tiles_kernel, s->n_dirty_tiles, 256, 0, s->S(), s->n_pad, s->nblk, s->d_dirty_tiles.p);
+  CU(cudaMemsetAsync(s->rhs(), 0, (s->n_pad + BSLAM_N_SCALARS) * sizeof(double), s->stream));
+  if (s->n_lm > s->n_regular)
+    CU(cudaMemsetAsync(s->d_Vg.p + 9 * (size_t)s->n_regular, 0, 9 * (size_t)(s->n_lm - s->n_regular) * sizeof(double), s->stream));
   if (s->n_pads > 0)
     LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
   record(s, 1);
@@ -438,7 +450,17 @@ int build_chol_plan(bslam_solver* s) {
   if (klist.empty()) klist.push_back(0);
   if (bwd_rows.empty()) bwd_rows.push_back(0);
   s->n_tile_tasks = (int)tasks.size();
+  s->h_tasks = tasks;
   cudaStream_t st = s->stream;
+  {
+    std::vector<int> dirty;
+    for (int i = 0; i < nt; ++i)
+      for (int j = 0; j <= i; ++j)
+        if (at(i, j)) dirty.push_back(i * nt + j);
+    s->n_dirty_tiles = (int)dirty.size();
+    if (dirty.empty()) dirty.push_back(0);
+    CU(upload(s->d_dirty_tiles, dirty, st));
+  }
   CU(upload(s->d_fill_mask, m, st));
   CU(upload(s->d_tasks, tasks, st));
   CU(upload(s->d_klist, klist, st));
@@ -470,6 +492,7 @@ int do_solve_reduced(bslam_solver* s) {
   p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
   p.epoch = ++s->chol_epoch;
+  p.trace = s->d_trace.p;
   CU(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(int), s->stream));
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
          s->d_dx.p, s->scalars(), p);
@@ -1439,6 +1462,28 @@ int bslam_covariance(bslam_solver* s, double* cov) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(cov, d_cov.p, D * D * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  return BSLAM_OK;
+}
+
+int bslam_debug_chol_trace(bslam_solver* s, int64_t* out, int max_tasks, int* n_tasks) {
+  NEED(s && s->finalized && out && n_tasks, "bslam_debug_chol_trace: bad arguments");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  const int n = s->n_tile_tasks + s->nblk;
+  *n_tasks = n;
+  NEED(max_tasks >= n, "bslam_debug_chol_trace: need room for %d tasks", n);
+  CU(s->d_trace.alloc(4 * (size_t)n));
+  int rc = do_solve_reduced(s);
+  if (rc) return rc;
+  std::vector<long long> h(4 * (size_t)n);
+  CU(cudaMemcpyAsync(h.data(), s->d_trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->d_trace.release();
+  for (int t = 0; t < n; ++t) {
+    out[6 * t + 0] = t < s->n_tile_tasks ? s->h_tasks[t].i : -1;
+    out[6 * t + 1] = t < s->n_tile_tasks ? s->h_tasks[t].j : s->nblk - 1 - (t - s->n_tile_tasks);
+    for (int k = 0; k < 4; ++k) out[6 * t + 2 + k] = h[4 * (size_t)t + k];
+  }
   return BSLAM_OK;
 }
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     'bslam_get_normal_equations': (C.c_int, [_h, _dp, _dp]),
     'bslam_get_reduced_system': (C.c_int, [_h, _dp, _dp]),
     'bslam_covariance': (C.c_int, [_h, _dp]),
+    'bslam_debug_chol_trace': (C.c_int, [_h, C.POINTER(C.c_int64), C.c_int, _ip]),
     'bslam_enable_timing': (C.c_int, [_h, C.c_int]),
     'bslam_get_timings': (C.c_int, [_h, _dp]),
     'bslam_launch_count': (C.c_int64, [_h]),
@@ -352,6 +353,13 @@ class Engine:
         out = np.empty((dim, dim))
         self._ck(self._lib.bslam_covariance(self._h, _d(out)))
         return out
+
+    def chol_trace(self, max_tasks=20000):
+        """[(tile_row|-1, tile_col, start, deps_ready, end, sm)] of one traced reduced solve (ns)."""
+        out = np.zeros((max_tasks, 6), np.int64)
+        n = C.c_int32()
+        self._ck(self._lib.bslam_debug_chol_trace(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), max_tasks, C.byref(n)))
+        return out[:n.value]
 
     def enable_timing(self, on=True):
         self._ck(self._lib.bslam_enable_timing(self._h, int(bool(on))))
