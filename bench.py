@@ -140,8 +140,6 @@ def run_ours(args):
     for _ in range(args.warmup):
         solver.iterate(0., True)
     reset()
-    eng.enable_timing(True)
-    t_phase = {k: 0. for k in ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total')}
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -151,11 +149,7 @@ def run_ours(args):
     e0.record(stream)
     costs = []
     for _ in range(args.steps):
-        c_lin, c_new, dxn = solver.iterate(0., True)
-        costs.append((c_lin, c_new, dxn))
-        if world == 1:
-            for k, v in eng.timings().items():
-                t_phase[k] += v
+        costs.append(solver.iterate(0., True))
     e1.record(stream)
     barrier()
     launches = eng.launch_count() - l0
@@ -165,9 +159,20 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    eng.enable_timing(False)
     ms_per_step = ms / args.steps
     value = 1000.0 / ms_per_step
+
+    # ---- the same K steps again with the library's per-phase CUDA events (the timed loop above runs
+    #      each iteration as one CUDA graph, inside which events cannot be read back) ----
+    t_phase = {k: 0. for k in ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total')}
+    if world == 1:
+        reset()
+        eng.enable_timing(True)
+        for _ in range(args.steps):
+            solver.iterate(0., True)
+            for k, v in eng.timings().items():
+                t_phase[k] += v
+        eng.enable_timing(False)
 
     # ---- end to end through the C ABI with host buffers (pinned) ----
     pin_Rt = torch.from_numpy(Rt0.copy()).pin_memory()
@@ -238,16 +243,20 @@ def run_ours(args):
     if world == 1:
         t_reproj = t_phase['reproj'] / args.steps * 1e-3
         achieved = alg_bytes / t_reproj / 1e9 if t_reproj > 0 else None
-        out['roofline'] = {'kernel': 'reproj_linearize_kernel', 'bound': 'hbm', 'achieved': achieved,
+        out['roofline'] = {'kernel': 'reproj_block_kernel', 'bound': 'hbm', 'achieved': achieved,
                            'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'] if achieved else None,
                            'traffic': None, 'peak_source': pk_src, 'algorithmic_bytes_per_launch': alg_bytes,
+                           'timed_in': 'second pass of the same K steps with per-kernel CUDA events on the launching stream',
                            'avg_launch_ms': t_reproj * 1e3}
         n = 6 * (N_KF - 1)
         t_chol = t_phase['cholesky'] / args.steps * 1e-3
-        out['roofline_cholesky'] = {'kernel': 'chol_panel_kernel+chol_update_kernel', 'bound': 'fp64 (DMMA)',
-                                    'flops': n ** 3 / 3.0, 'avg_ms': t_chol * 1e3,
-                                    'achieved_tflops': n ** 3 / 3.0 / t_chol / 1e12 if t_chol > 0 else None}
+        out['roofline_cholesky'] = {'kernel': 'chol_solve_kernel', 'bound': 'fp64 DMMA if dense; latency-bound at this tile sparsity',
+                                    'dense_flops': n ** 3 / 3.0, 'avg_ms': t_chol * 1e3,
+                                    'note': 'reduced matrix is tile-sparse after nested dissection (~150 of 1275 lower tiles); '
+                                            'dense-equivalent rate would be %.1f TFLOP/s' % (n ** 3 / 3.0 / t_chol / 1e12 if t_chol > 0 else 0.)}
         out['phase_ms'] = {k: v / args.steps for k, v in t_phase.items()}
+        out['phase_ms_note'] = ('un-graphed pass; backsub = long-track tail only, retract = poses/vectors, '
+                                'cost = fused landmark back-substitution + retraction + cost at the new point')
         out['cpu_baseline'] = cpu_baseline(budget_s=25.0)
     print(json.dumps(out))
     if world > 1:

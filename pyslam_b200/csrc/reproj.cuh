@@ -411,10 +411,10 @@ reproj_generic_kernel(const ReprojArgs a) {
 // Cost only: sum rho(r) over ALL reprojection blocks (Problem.eval_cost,
 // pyslam/problem.py:110-128) -> scalars[slot].
 __global__ void __launch_bounds__(256)
-reproj_cost_kernel(const ReprojArgs a, int slot) {
+reproj_cost_kernel(const ReprojArgs a, int slot, int obs_begin) {
   __shared__ double sred[8];
   double cost = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += gridDim.x * blockDim.x) {
+  for (int i = obs_begin + blockIdx.x * blockDim.x + threadIdx.x; i < a.n_obs; i += gridDim.x * blockDim.x) {
     const ReprojGroup& g = a.groups[a.obs_grp ? a.obs_grp[i] : 0];
     double r[3];
     reproj_residual_only(g, a.poses + 12 * (size_t)a.obs_pose[i], a.pts + 3 * (size_t)a.obs_pt[i],

@@ -8,6 +8,7 @@
 #include "cholesky.cuh"
 #include "common.cuh"
 #include "reproj.cuh"
+#include "lie.cuh"
 
 namespace bs {
 
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
 
 struct BacksubArgs {
   int n_lm;
+  int q_begin;                        // first landmark handled by the generic kernel
   int n_obs;
   int lm_off;                         // landmark slice of dx starts here
   const int* __restrict__ obs_pose;
@@ -218,7 +220,7 @@ struct BacksubArgs {
 
 // One thread per landmark: dx_p = V^-1 (b_p - sum_j W_j^T dx_c(j)).
 __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = a.q_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.n_lm) return;
   const double* g = a.Vg + 9 * (size_t)q + 6;
   double s0 = g[0], s1 = g[1], s2 = g[2];
@@ -241,6 +243,137 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   o[0] = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
   o[1] = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
   o[2] = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
+}
+
+// ---- fused tail of the iteration for the landmark blocks ------------------------------
+// back-substitution dx_p = V^-1 (b_p - W^T dx_c), retraction p <- p + dx_p, ||dx_p||^2 and the
+// cost at the new point (pyslam/problem.py:155-156, 189-190, 400-409) in one pass over W and
+// the observations.  The poses must already be retracted (retract_poses_kernel).
+struct FinishArgs {
+  int n_obs;
+  int lm_off;
+  int eval_cost;
+  int n_blocks;
+  const LmBlock* __restrict__ blocks;
+  const int* __restrict__ slot_pose;
+  const unsigned char* __restrict__ obs_slot;
+  const int* __restrict__ obs_pose;
+  const int* __restrict__ obs_pt;
+  const int* __restrict__ obs_grp;
+  const ReprojGroup* __restrict__ groups;
+  ReprojGroup g0;
+  const int* __restrict__ lm_start;
+  const int* __restrict__ pose_off;
+  const double* __restrict__ obs_u;
+  const double* __restrict__ obs_v;
+  const double* __restrict__ obs_d;
+  const double* __restrict__ poses;     // retracted
+  double* __restrict__ pts;
+  const double* __restrict__ W;
+  const double* __restrict__ Vg;
+  const double* __restrict__ Vinv;
+  double* __restrict__ dx;
+  double* __restrict__ scalars;
+};
+
+template <bool kSingleGroup>
+__global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) {
+  __shared__ double sPose[12 * (kBlkObs + 1)];
+  __shared__ double sDx[6 * kBlkObs];
+  __shared__ double sPts[3 * kBlkObs];
+  __shared__ double sAcc[3 * kBlkObs];
+  __shared__ double sred[2 * (kBlkObs / 32)];
+  const int tid = threadIdx.x;
+  const LmBlock blk = a.blocks[blockIdx.x];
+  const size_t N = (size_t)a.n_obs;
+  const int i = blk.obs_begin + tid;
+  double w18[18];
+  double ou = 0.0, ov = 0.0, od = 0.0;
+  int sl = 255, ql = 0, gi = 0;
+  if (tid < blk.n_obs) {
+    sl = a.obs_slot[i];
+    ql = a.obs_pt[i] - blk.lm_begin;
+    if (sl != 255) {
+#pragma unroll
+      for (int k = 0; k < 18; ++k) w18[k] = ld_stream(a.W + k * N + i);
+    }
+    if (a.eval_cost) {
+      ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
+      if (!kSingleGroup) gi = a.obs_grp[i];
+    }
+  }
+  for (int e = tid; e < blk.n_slots; e += kBlkObs) {
+    const int pose = a.slot_pose[blk.slot_begin + e];
+    const int off = a.pose_off[pose];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sDx[6 * e + k] = a.dx[off + k];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sPose[12 * e + k] = a.poses[12 * (size_t)pose + k];
+  }
+  for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
+  __syncthreads();
+  if (tid < blk.n_obs) {
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    if (sl != 255) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const double d = sDx[6 * sl + r];
+        c0 = fma(w18[3 * r], d, c0); c1 = fma(w18[3 * r + 1], d, c1); c2 = fma(w18[3 * r + 2], d, c2);
+      }
+    }
+    sAcc[3 * tid] = c0; sAcc[3 * tid + 1] = c1; sAcc[3 * tid + 2] = c2;
+  }
+  __syncthreads();
+  double dx2 = 0.0;
+  if (tid < blk.n_lms) {
+    const int q = blk.lm_begin + tid;
+    const double* g = a.Vg + 9 * (size_t)q + 6;
+    double s0 = g[0], s1 = g[1], s2 = g[2];
+    const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
+    for (int k = k0; k < k1; ++k) { s0 -= sAcc[3 * k]; s1 -= sAcc[3 * k + 1]; s2 -= sAcc[3 * k + 2]; }
+    const double* vi = a.Vinv + 6 * (size_t)q;
+    const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
+    const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
+    const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
+    double* o = a.dx + a.lm_off + 3 * (size_t)q;
+    o[0] = d0; o[1] = d1; o[2] = d2;
+    dx2 = d0 * d0 + d1 * d1 + d2 * d2;
+    const double p0 = sPts[3 * tid] + d0, p1 = sPts[3 * tid + 1] + d1, p2 = sPts[3 * tid + 2] + d2;
+    sPts[3 * tid] = p0; sPts[3 * tid + 1] = p1; sPts[3 * tid + 2] = p2;
+    double* P = a.pts + 3 * (size_t)q;
+    P[0] = p0; P[1] = p1; P[2] = p2;
+  }
+  __syncthreads();
+  double cost = 0.0;
+  if (a.eval_cost && tid < blk.n_obs) {
+    const ReprojGroup& g = kSingleGroup ? a.g0 : a.groups[gi];
+    double P[12];
+    if (sl != 255) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
+    } else {
+      const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+    }
+    double r[3];
+    reproj_residual_only(g, P, sPts + 3 * ql, ou, ov, od, r);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cost += loss_rho(g.loss, r[k]);
+  }
+  // two block sums -> two atomics
+  cost = warp_sum(cost);
+  dx2 = warp_sum(dx2);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) { sred[warp] = cost; sred[kBlkObs / 32 + warp] = dx2; }
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, d = 0.0;
+#pragma unroll
+    for (int w = 0; w < kBlkObs / 32; ++w) { c += sred[w]; d += sred[kBlkObs / 32 + w]; }
+    if (a.eval_cost) red_add(a.scalars + 1 /*COST_NEW*/, c);
+    red_add(a.scalars + 2 /*DX_NORM2*/, d);
+  }
 }
 
 }  // namespace bs

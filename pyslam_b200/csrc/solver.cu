@@ -125,6 +125,13 @@ struct bslam_solver {
   DevBuf<double> d_dn_J, d_dn_e;
   double* h_scalars = nullptr;   // pinned
 
+  // ---- CUDA graph of one whole iteration (single GPU, built-in blocks only) ----
+  cudaGraphExec_t graph_exec = nullptr;
+  double graph_lambda = -1.0;
+  int graph_eval = -1;
+  int64_t graph_launches = 0;
+  bool use_graph = true;
+
   // ---- tile structure of the reduced system and the Cholesky task plan ----
   std::vector<uint8_t> tile_mask;                   // [(nblk+1) * nblk], lower triangle + rhs row
   bool plan_valid = false;
@@ -147,6 +154,7 @@ struct bslam_solver {
     for (auto* e : photos) delete e;
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (h_scalars) cudaFreeHost(h_scalars);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -209,6 +217,11 @@ __global__ void permute_rows_kernel(int n, int width, const double* __restrict__
   const int r = e / width, c = e - r * width;
   if (scatter) dst[(size_t)perm[r] * width + c] = src[e];
   else dst[e] = src[(size_t)perm[r] * width + c];
+}
+
+void drop_graph(bslam_solver* s) {
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  s->graph_exec = nullptr;
 }
 
 void record(bslam_solver* s, int i) {
@@ -296,7 +309,7 @@ void launch_photos(bslam_solver* s, int slot) {
 void launch_cost(bslam_solver* s, int slot) {
   if (s->n_obs > 0) {
     const int grid = std::min(cdiv(s->n_obs, 256), 148 * 8);
-    LAUNCH(s, bs::reproj_cost_kernel, grid, 256, 0, reproj_args(s), slot);
+    LAUNCH(s, bs::reproj_cost_kernel, grid, 256, 0, reproj_args(s), slot, 0);
   }
   for (auto* b : s->edges) launch_edges<true>(s, b, slot);
   launch_photos<true>(s, slot);
@@ -491,19 +504,21 @@ int do_solve_reduced(bslam_solver* s) {
   p.n_tile_tasks = s->n_tile_tasks;
   p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
-  p.epoch = ++s->chol_epoch;
+  p.epoch = 1;
   p.trace = s->d_trace.p;
   CU(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(int), s->stream));
+  CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), s->stream));
+  CU(cudaMemsetAsync(s->d_xready.p, 0, s->d_xready.n * sizeof(int), s->stream));
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
          s->d_dx.p, s->scalars(), p);
   record(s, 5);
   record(s, 6);
-  if (s->n_lm > 0) {
+  if (s->n_lm > s->n_regular) {      // regular landmarks are back-substituted by lm_finish_kernel (do_retract)
     bs::BacksubArgs a;
-    a.n_lm = s->n_lm; a.n_obs = s->n_obs; a.lm_off = s->n_pad;
+    a.n_lm = s->n_lm; a.q_begin = s->n_regular; a.n_obs = s->n_obs; a.lm_off = s->n_pad;
     a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p; a.dx = s->d_dx.p;
-    LAUNCH(s, bs::backsub_kernel, cdiv(s->n_lm, 128), 128, 0, a);
+    LAUNCH(s, bs::backsub_kernel, cdiv(s->n_lm - s->n_regular, 128), 128, 0, a);
   }
   record(s, 7);
   CU(cudaGetLastError());
@@ -516,8 +531,6 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
   if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
   if (s->n_vec_entries > 0)
     LAUNCH(s, bs::retract_flat_kernel, cdiv(s->n_vec_entries, 256), 256, 0, s->n_vec_entries, s->d_vec.p, s->d_vec_entry_off.p, dx);
-  if (s->n_lm > 0)
-    LAUNCH(s, bs::retract_landmarks_kernel, cdiv(3 * s->n_lm, 256), 256, 0, 3 * s->n_lm, s->d_pts.p, dx + s->n_pad);
   if (s->n_pt > s->n_lm) {
     const int n3 = 3 * (s->n_pt - s->n_lm);
     LAUNCH(s, bs::retract_flat_kernel, cdiv(n3, 256), 256, 0, n3, s->d_pts.p + 3 * (size_t)s->n_lm, s->d_ptred_entry_off.p, dx);
@@ -525,11 +538,37 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
   // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
   if (s->n_red > 0 && s->shard_rank == 0)
     LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(s->n_red, 256), 148), 256, 0, s->n_red, dx, s->scalars() + BSLAM_S_DX_NORM2);
-  if (s->n_lm > 0)
-    LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(3 * s->n_lm, 256), 148 * 4), 256, 0, 3 * s->n_lm, dx + s->n_pad,
-           s->scalars() + BSLAM_S_DX_NORM2);
   record(s, 8);
-  if (eval_new_cost) launch_cost(s, BSLAM_S_COST_NEW);
+  // landmark blocks: back-substitution + retraction + ||dx_p||^2 + cost at the new point, fused
+  if (s->n_lmblocks > 0) {
+    bs::FinishArgs a;
+    a.n_obs = s->n_obs; a.lm_off = s->n_pad; a.eval_cost = eval_new_cost; a.n_blocks = s->n_lmblocks;
+    a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_slot = s->d_obs_slot.p;
+    a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.obs_grp = s->d_ogrp.p; a.groups = s->d_groups.p;
+    if (!s->groups.empty()) a.g0 = s->groups[0];
+    a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.obs_u = s->d_ou.p; a.obs_v = s->d_ov.p; a.obs_d = s->d_od.p;
+    a.poses = s->d_se3.p; a.pts = s->d_pts.p; a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
+    a.dx = s->d_dx.p; a.scalars = s->scalars();
+    if (s->groups.size() == 1) LAUNCH(s, bs::lm_finish_kernel<true>, s->n_lmblocks, bs::kBlkObs, 0, a);
+    else LAUNCH(s, bs::lm_finish_kernel<false>, s->n_lmblocks, bs::kBlkObs, 0, a);
+  }
+  // tail: landmarks with long tracks (already back-substituted), then everything that is not a landmark block
+  if (s->n_lm > s->n_regular) {
+    const int n3 = 3 * (s->n_lm - s->n_regular);
+    LAUNCH(s, bs::retract_landmarks_kernel, cdiv(n3, 256), 256, 0, n3, s->d_pts.p + 3 * (size_t)s->n_regular,
+           dx + s->n_pad + 3 * (size_t)s->n_regular);
+    LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(n3, 256), 148 * 4), 256, 0, n3, dx + s->n_pad + 3 * (size_t)s->n_regular,
+           s->scalars() + BSLAM_S_DX_NORM2);
+  }
+  if (eval_new_cost) {
+    if (s->n_obs > s->tail_begin) {
+      const int n = s->n_obs - s->tail_begin;
+      LAUNCH(s, bs::reproj_cost_kernel, std::min(cdiv(n, 256), 148 * 8), 256, 0, reproj_args(s), BSLAM_S_COST_NEW, s->tail_begin);
+    }
+    for (auto* b : s->edges) launch_edges<true>(s, b, BSLAM_S_COST_NEW);
+    launch_photos<true>(s, BSLAM_S_COST_NEW);
+  }
   record(s, 9);
   CU(cudaGetLastError());
   return BSLAM_OK;
@@ -587,6 +626,7 @@ int bslam_create(bslam_solver** out, int device) {
     return BSLAM_E_CUDA;
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  { const char* e = getenv("BSLAM_NO_GRAPH"); if (e && atoi(e)) h->use_graph = false; }
   cudaFuncSetAttribute(bs::chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::kCholSmem);
   *out = h;
   return BSLAM_OK;
@@ -851,6 +891,7 @@ int bslam_clear_blocks(bslam_solver* s) {
   s->photos.clear();
   s->dn_blocks = 0;
   s->dn_rows.clear(); s->dn_pptr.clear(); s->dn_pkind.clear(); s->dn_pindex.clear();
+  drop_graph(s);
   s->finalized = false;
   return BSLAM_OK;
 }
@@ -1305,11 +1346,44 @@ int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost, double* cos
   NEED(lambda >= 0.0, "bslam_iterate: lambda must be >= 0");
   CU(cudaSetDevice(s->device));
   int rc;
-  if ((rc = do_linearize(s))) return rc;
-  if ((rc = do_reduce(s, lambda))) return rc;
-  if ((rc = do_solve_reduced(s))) return rc;
-  if ((rc = do_retract(s, eval_new_cost))) return rc;
-  if ((rc = fetch_scalars(s))) return rc;
+  const bool graphable = s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr;
+  if (graphable) {
+    // the whole iteration (~15 kernels + memsets + the scalar read-back) is one graph launch
+    if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+    if (s->graph_exec && (s->graph_lambda != lambda || s->graph_eval != eval_new_cost)) drop_graph(s);
+    if (!s->graph_exec) {
+      cudaGraph_t graph = nullptr;
+      const int64_t l0 = s->launches;
+      CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      rc = do_linearize(s);
+      if (!rc) rc = do_reduce(s, lambda);
+      if (!rc) rc = do_solve_reduced(s);
+      if (!rc) rc = do_retract(s, eval_new_cost);
+      cudaError_t ce = cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+      cudaError_t ee = cudaStreamEndCapture(s->stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess || ee != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail(s, BSLAM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+      }
+      ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { s->graph_exec = nullptr; return fail(s, BSLAM_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+      s->graph_launches = s->launches - l0;
+      s->launches = l0;
+      s->graph_lambda = lambda;
+      s->graph_eval = eval_new_cost;
+    }
+    CU(cudaGraphLaunch(s->graph_exec, s->stream));
+    s->launches += s->graph_launches;
+    CU(cudaStreamSynchronize(s->stream));
+  } else {
+    if ((rc = do_linearize(s))) return rc;
+    if ((rc = do_reduce(s, lambda))) return rc;
+    if ((rc = do_solve_reduced(s))) return rc;
+    if ((rc = do_retract(s, eval_new_cost))) return rc;
+    if ((rc = fetch_scalars(s))) return rc;
+  }
   if (cost_lin) *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
   if (cost_new) *cost_new = s->h_scalars[BSLAM_S_COST_NEW];
   if (dx_norm) *dx_norm = std::sqrt(s->h_scalars[BSLAM_S_DX_NORM2]);
@@ -1337,6 +1411,7 @@ int bslam_tile_structure(bslam_solver* s, uint8_t* mask, size_t n, int set) {
   if (set) {
     for (size_t i = 0; i < n; ++i) s->tile_mask[i] = s->tile_mask[i] || mask[i];
     s->plan_valid = false;
+    drop_graph(s);
   } else {
     std::memcpy(mask, s->tile_mask.data(), n);
   }
