@@ -222,48 +222,173 @@ BS_D void gemm32(const double* __restrict__ A, const double* __restrict__ B, dou
   }
 }
 
-// Factorise the 64x64 tile in sA (lower triangle) in place and build X = L^-1 in
-// sX (lower triangular, zeros above the diagonal).  Returns #non-positive pivots.
+// 1/sqrt(d) to full double precision: hardware approximation (MUFU.RSQ64H, ~2^-22) + two
+// Newton steps; ~2x shorter dependency chain than the library rsqrt() on the pivot critical path.
+BS_D double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
+// ---- 16x16 building blocks (one warp each) ------------------------------------------------
+// In-place Cholesky of the 16x16 block at `s` (lanes 0..15 = rows, the row lives in registers).
+// The next pivot is formed and its rsqrt started BEFORE the trailing update of the current column,
+// so the per-pivot critical chain is mul -> fma -> shfl -> rsqrt only.  `scol` holds 2 x 16 doubles
+// (double-buffered column broadcast); 1/L_jj goes to srcp.  Returns #non-positive pivots.
+BS_D int potrf16_warp(double* __restrict__ s, double* __restrict__ scol, double* __restrict__ srcp) {
+  const int lane = threadIdx.x & 31, row = lane & 15;
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = s[row * kLd + c];
+  int bad = 0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double r = fast_rsqrt(d);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (!(d > 0.0)) ++bad;
+    const double l = (row == j) ? d * r : a[j] * r;
+    a[j] = l;
+    if (lane == j) srcp[j] = r;
+    double dn = 0.0, rn = 0.0;
+    if (j + 1 < 16) {
+      dn = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
+      rn = fast_rsqrt(dn);
+    }
+    double* sc = scol + (j & 1) * 16;
+    if (lane < 16) sc[row] = l;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < 16; ++c) a[c] = fma(-l, sc[c], a[c]);
+    d = dn;
+    r = rn;
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s[row * kLd + c] = (c <= row) ? a[c] : 0.0;
+  }
+  return bad;
+}
+
+// X = L^-1 of the 16x16 lower-triangular block at sL (lanes 0..15 = columns of X).
+BS_D void trtri16_warp(const double* __restrict__ sL, const double* __restrict__ srcp, double* __restrict__ sX) {
+  const int lane = threadIdx.x & 31, col = lane & 15;
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double s0 = (i == col) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < i; ++m) {
+      const double l = sL[i * kLd + m];
+      if (m & 1) s1 = fma(-l, x[m], s1);
+      else s0 = fma(-l, x[m], s0);
+    }
+    x[i] = (s0 + s1) * srcp[i];
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sX[i * kLd + col] = x[i];
+  }
+}
+
+// C(16x16) = alpha * A(16x16) * op(B) + beta * C by ONE warp (DMMA), shared memory, leading
+// dimension kLd.  Safe when C aliases A or B: every operand is read before anything is stored.
+template <bool kTransB>
+BS_D void gemm16_warp(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, double alpha,
+                      double beta) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double c[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+#pragma unroll
+  for (int k0 = 0; k0 < 16; k0 += 4) {
+    const double a0 = A[g * kLd + k0 + t], a1 = A[(8 + g) * kLd + k0 + t];
+    const double b0 = kTransB ? B[g * kLd + k0 + t] : B[(k0 + t) * kLd + g];
+    const double b1 = kTransB ? B[(8 + g) * kLd + k0 + t] : B[(k0 + t) * kLd + 8 + g];
+    dmma_8x8x4(c[0][0][0], c[0][0][1], a0, b0);
+    dmma_8x8x4(c[0][1][0], c[0][1][1], a0, b1);
+    dmma_8x8x4(c[1][0][0], c[1][0][1], a1, b0);
+    dmma_8x8x4(c[1][1][0], c[1][1][1], a1, b1);
+  }
+  double old[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double* p = C + (8 * i + g) * kLd + 8 * j + 2 * t;
+      old[i][j][0] = beta != 0.0 ? p[0] : 0.0;
+      old[i][j][1] = beta != 0.0 ? p[1] : 0.0;
+    }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double* p = C + (8 * i + g) * kLd + 8 * j + 2 * t;
+      p[0] = alpha * c[i][j][0] + beta * old[i][j][0];
+      p[1] = alpha * c[i][j][1] + beta * old[i][j][1];
+    }
+}
+
+// Factorise the 64x64 tile in sA (lower triangle) in place and build X = L^-1 in sX (lower
+// triangular, zeros above the diagonal), blocked by 16: per block column a register-resident
+// potrf16 + trtri16 on warp 0, then the panel and trailing updates as one 16x16 DMMA product
+// per warp; the off-diagonal blocks of X follow by block back-substitution.  Returns #bad pivots.
 BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double* __restrict__ scol,
                         double* __restrict__ srcp, int* __restrict__ sbad) {
   const int warp = threadIdx.x >> 5;
-  double* A11 = sA;
-  double* A21 = sA + 32 * kLd;
-  double* A22 = sA + 32 * kLd + 32;
-  double* X11 = sX;
-  double* X12 = sX + 32;
-  double* X21 = sX + 32 * kLd;
-  double* X22 = sX + 32 * kLd + 32;
+  auto Ab = [&](int i, int j) { return sA + (16 * i) * kLd + 16 * j; };
+  auto Xb = [&](int i, int j) { return sX + (16 * i) * kLd + 16 * j; };
   if (threadIdx.x == 0) *sbad = 0;
   __syncthreads();
-  if (warp == 0) {
-    const int bad = potrf32_warp(A11, scol, srcp);
-    __syncwarp();
-    trtri32_warp(A11, srcp, X11);
-    if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
-  } else {
-    // X12 = 0 (and the part of the tile above the diagonal blocks is never read)
-    for (int e = threadIdx.x - 32; e < 32 * 32; e += kCholThreads - 32) X12[(e >> 5) * kLd + (e & 31)] = 0.0;
+  for (int b = 0; b < 4; ++b) {
+    if (warp == 0) {
+      const int bad = potrf16_warp(Ab(b, b), scol, srcp + 16 * b);
+      __syncwarp();
+      trtri16_warp(Ab(b, b), srcp + 16 * b, Xb(b, b));
+      if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
+    }
+    __syncthreads();
+    if (b == 3) break;
+    // panel: L_ib = A_ib X_bb^T
+    if (warp < 3 - b) gemm16_warp<true>(Ab(b + 1 + warp, b), Xb(b, b), Ab(b + 1 + warp, b), 1.0, 0.0);
+    __syncthreads();
+    // trailing update: A_ij -= L_ib L_jb^T for b < j <= i <= 3  (at most 6 blocks, one per warp)
+    {
+      int w = 0;
+      for (int i = b + 1; i < 4; ++i)
+        for (int j = b + 1; j <= i; ++j, ++w)
+          if (w == warp) gemm16_warp<true>(Ab(i, b), Ab(j, b), Ab(i, j), -1.0, 1.0);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  gemm32<true>(A21, X11, X21, 1.0, 0.0);          // X21 <- L21 = A21 X11^T   (scratch use of X21)
-  __syncthreads();
-  for (int e = threadIdx.x; e < 32 * 32; e += kCholThreads) A21[(e >> 5) * kLd + (e & 31)] = X21[(e >> 5) * kLd + (e & 31)];
-  __syncthreads();
-  gemm32<true>(A21, A21, A22, -1.0, 1.0);         // A22 -= L21 L21^T
-  __syncthreads();
-  if (warp == 0) {
-    const int bad = potrf32_warp(A22, scol, srcp + 32);
-    __syncwarp();
-    trtri32_warp(A22, srcp + 32, X22);
-    if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
+  // off-diagonal blocks of X by distance from the diagonal; the mirror block (j, i) is scratch
+  for (int dist = 1; dist < 4; ++dist) {
+    if (warp < 4 - dist) {
+      const int j = warp, i = warp + dist;
+      double* T = Xb(j, i);
+      gemm16_warp<false>(Ab(i, j), Xb(j, j), T, 1.0, 0.0);                       // L_ij X_jj
+      for (int k = j + 1; k < i; ++k) {
+        __syncwarp();
+        gemm16_warp<false>(Ab(i, k), Xb(k, j), T, 1.0, 1.0);                     // + L_ik X_kj
+      }
+      __syncwarp();
+      gemm16_warp<false>(Xb(i, i), T, Xb(i, j), -1.0, 0.0);                      // X_ij = -X_ii T
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  gemm32<false>(A21, X11, X12, 1.0, 0.0);         // X12 (scratch) <- L21 X11
-  __syncthreads();
-  gemm32<false>(X22, X12, X21, -1.0, 0.0);        // X21 = -X22 L21 X11
-  __syncthreads();
-  for (int e = threadIdx.x; e < 32 * 32; e += kCholThreads) X12[(e >> 5) * kLd + (e & 31)] = 0.0;
+  for (int e = threadIdx.x; e < 6 * 256; e += kCholThreads) {                     // zero the scratch (upper blocks)
+    const int blk = e >> 8, r = (e >> 4) & 15, c = e & 15;
+    const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2), bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
+    Xb(bi, bj)[r * kLd + c] = 0.0;
+  }
   __syncthreads();
   return *sbad;
 }

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   extern __shared__ double sm[];
   __shared__ double sVinv[6 * kBlkObs];
   __shared__ double sG[3 * kBlkObs + 8];
+  __shared__ int sOff[kBlkObs];          // reduced offset of every slot's pose
   const int tid = threadIdx.x;
   const LmBlock blk = a.blocks[blockIdx.x];
   const int ldk = schur_ldk(blk.n_lms);
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
     const int n2 = rows * ldk;            // 2 * rows * ldk doubles = rows*ldk double2
     for (int e = tid; e < n2; e += kBlkObs) z[e] = make_double2(0.0, 0.0);
   }
+  for (int e = tid; e < blk.n_slots; e += kBlkObs) sOff[e] = a.pose_off[a.slot_pose[blk.slot_begin + e]];
   // V^-1 and b_p of the block's landmarks
   for (int l = tid; l < blk.n_lms; l += kBlkObs) {
     const int q = blk.lm_begin + l;
@@ -172,20 +174,25 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int kdim = (3 * blk.n_lms + 3) & ~3;
-  // slot pairs (sa, sb) with sb <= sa, dealt round-robin to the 4 warps
+  // slot pairs (sa, sb <= sa), dealt round-robin to the 4 warps
   int pidx = 0;
   for (int sa = 0; sa < blk.n_slots; ++sa)
    for (int sb = 0; sb <= sa; ++sb, ++pidx) {
     if ((pidx & 3) != warp) continue;
-    int oa = a.pose_off[a.slot_pose[blk.slot_begin + sa]];
-    int ob = a.pose_off[a.slot_pose[blk.slot_begin + sb]];
+    int oa = sOff[sa], ob = sOff[sb];
     // rows must belong to the pose with the larger reduced offset (lower triangle)
     const int ra = oa >= ob ? sa : sb, rb = oa >= ob ? sb : sa;
     if (oa < ob) { const int tmp = oa; oa = ob; ob = tmp; }
     const double* pa = Yt + (size_t)(kSlotRows * ra + g) * ldk + t;
     const double* pb = Wt + (size_t)(kSlotRows * rb + g) * ldk + t;
-    double c0 = 0.0, c1 = 0.0;
-    for (int k0 = 0; k0 < kdim; k0 += 4) dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int k0 = 0;
+    for (; k0 + 8 <= kdim; k0 += 8) {            // two independent accumulator chains
+      dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
+      dmma_8x8x4(d0, d1, pa[k0 + 4], pb[k0 + 4]);
+    }
+    if (k0 < kdim) dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
+    c0 += d0; c1 += d1;
     // C[g][2t], C[g][2t+1] = sum_K Y_ra[g][K] W_rb[2t(+1)][K]
     if (g < 6 && 2 * t < 6) {
       const bool diag = (sa == sb);
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
     const double* y = Yt + (size_t)(kSlotRows * sl + r) * ldk;
     double acc = 0.0;
     for (int k = 0; k < 3 * blk.n_lms; ++k) acc += y[k] * sG[k];
-    red_add(a.rhs + a.pose_off[a.slot_pose[blk.slot_begin + sl]] + r, -acc);
+    red_add(a.rhs + sOff[sl] + r, -acc);
   }
 }
 

@@ -15,13 +15,13 @@ __global__ void __launch_bounds__(kCholThreads, 1) micro(const double* A, double
     for (int e = tid; e < kNB * kNB; e += kCholThreads) sA[(e >> 6) * kLd + (e & 63)] = A[e];
     __syncthreads();
     long long t0 = clock64();
-    if (tid < 32) potrf32_warp(sA, scol, srcp);
+    if (tid < 32) potrf16_warp(sA, scol, srcp);
     __syncthreads();
     long long t1 = clock64();
-    if (tid < 32) trtri32_warp(sA, srcp, sX);
+    if (tid < 32) trtri16_warp(sA, srcp, sX);
     __syncthreads();
     long long t2 = clock64();
-    gemm32<true>(sA + 32 * kLd, sX, sX + 32 * kLd, 1.0, 0.0);
+    if (tid < 32) gemm16_warp<true>(sA + 16 * kLd, sX, sX + 16 * kLd, 1.0, 0.0);
     __syncthreads();
     long long t3 = clock64();
     if (tid == 0) { cyc[0] = t1 - t0; cyc[1] = t2 - t1; cyc[2] = t3 - t2; }
@@ -57,7 +57,7 @@ int main() {
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
   long long c[8]; std::vector<double> out(3 * n * n);
   cudaMemcpy(c, dc, 64, cudaMemcpyDeviceToHost); cudaMemcpy(out.data(), dout, 3 * n * n * 8, cudaMemcpyDeviceToHost);
-  printf("cycles: potrf32 %lld  trtri32 %lld  gemm32 %lld | tile_potrf_inv %lld  tile_mma 64^3 %lld\n", c[0], c[1], c[2], c[3], c[4]);
+  printf("cycles: potrf16 %lld  trtri16 %lld  gemm16 %lld | tile_potrf_inv %lld  tile_mma 64^3 %lld\n", c[0], c[1], c[2], c[3], c[4]);
   // check L L^T = A and X L = I
   double eL = 0, eX = 0;
   for (int i = 0; i < n; ++i) for (int j = 0; j <= i; ++j) {
