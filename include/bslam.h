@@ -215,6 +215,12 @@ BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS 
  * and of the scalar tail alone (second, 16-double all-reduce after retract). */
 BSLAM_API int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles,
                          void** scalars_dev_ptr, int32_t* n_pad);
+/* Compact all-reduce payload: only the structurally non-zero 64x64 tiles of S (before fill-in),
+ * then rhs and the scalars.  bslam_pack_reduced(s, 0) gathers it from the dense buffer after
+ * bslam_reduce, the host all-reduces bslam_packed_buffer, bslam_pack_reduced(s, 1) scatters it back
+ * before bslam_solve_reduced.  (The tile structures of all ranks must have been merged first.) */
+BSLAM_API int bslam_packed_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles);
+BSLAM_API int bslam_pack_reduced(bslam_solver* s, int unpack);
 /* Tile structure (64x64 tiles, (n_pad/64 + 1) x (n_pad/64) bytes, row-major) of
  * the reduced system as seen by THIS handle's residual blocks.  set == 0 copies it
  * out; set != 0 ORs `mask` into it -- with sharded landmarks the host ORs the

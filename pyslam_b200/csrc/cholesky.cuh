@@ -532,6 +532,21 @@ __global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S,
   }
 }
 
+// gather (unpack == 0) / scatter (unpack != 0) the listed tiles between S and a contiguous buffer
+__global__ void __launch_bounds__(256) pack_tiles_kernel(double* __restrict__ S, int ld, int nt, const int* __restrict__ tiles,
+                                                         double* __restrict__ pack, int unpack) {
+  const int id = tiles[blockIdx.x];
+  double* T = S + (size_t)(id / nt) * kNB * ld + (size_t)(id % nt) * kNB;
+  double* P = pack + (size_t)blockIdx.x * kNB * kNB;
+  for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
+    const int r = e >> 5, c2 = (e & 31) << 1;
+    double2* t2 = reinterpret_cast<double2*>(T + (size_t)r * ld + c2);
+    double2* p2 = reinterpret_cast<double2*>(P + 2 * (size_t)e);
+    if (unpack) *t2 = *p2;
+    else *p2 = *t2;
+  }
+}
+
 // identity on the padding diagonal so the padded factorisation is well defined
 __global__ void pad_diag_kernel(double* __restrict__ S, int ld, const int* __restrict__ pad_idx, int n_pads) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -226,123 +226,165 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
 __device__ __constant__ unsigned char kTriRow[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
 __device__ __constant__ unsigned char kTriCol[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
 
+BS_D void dmma_f64(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Persistent CTAs (grid = a few per SM) walk the landmark blocks with a stride; while a block is being
+// processed the per-observation inputs of the CTA's next block are already in flight.  Each thread leaves
+// its 27 camera values and 9 landmark values in a shared-memory row; the CTA then reduces them per slot
+// (observations grouped by cam_perm) and per landmark (contiguous observations).
+// (A variant doing both reductions as 0/1 selection-matrix products on the DMMA pipe was measured:
+//  same time, 25% more instructions -- see profiles/.)
 template <bool kSingleGroup>
 __global__ void __launch_bounds__(kBlkObs, 5)
 reproj_block_kernel(const ReprojArgs a) {
   __shared__ double sT[kBlkObs * kRow];
   __shared__ double sred[kBlkObs / 32];
+  __shared__ LmBlock sNext;
   const int tid = threadIdx.x;
-  const LmBlock blk = a.blocks[blockIdx.x];
   const int N = a.n_obs;
   double cost = 0.0;
+  int b = blockIdx.x;
+  if (b >= a.n_blocks) return;
+  LmBlock blk = a.blocks[b];
 
-  // Every global load of the block is issued up front (one DRAM round trip): the
-  // observation, its slot / landmark index, and -- cooperatively -- the poses of
-  // the block's slots and its (contiguous) landmark coordinates, staged in sT.
+  // per-observation inputs of the current block
   double ou = 0.0, ov = 0.0, od = 0.0;
   int sl = 255, ql = 0, gi = 0;
-  const int i = blk.obs_begin + tid;
   if (tid < blk.n_obs) {
+    const int i = blk.obs_begin + tid;
     ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
     sl = a.obs_slot[i];
     ql = a.obs_pt[i] - blk.lm_begin;
     if (!kSingleGroup) gi = a.obs_grp[i];
   }
-  double* sPose = sT;                               // [n_slots + 1][12]; last row: scratch for constant poses
-  double* sPts = sT + 12 * (kBlkObs + 1);           // [n_lms][3]
-  for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) {
-    const int s = e / 12;
-    sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + s] + (e - 12 * s)];
-  }
-  for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
-  __syncthreads();
-  double P[12], X[3];
-  if (tid < blk.n_obs) {
-    if (sl != 255) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
-    } else {                                        // constant pose: not a slot, read it directly
-      const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) X[k] = sPts[3 * ql + k];
-  }
-  __syncthreads();                                  // sT is reused for the per-observation rows below
 
-  if (tid < blk.n_obs) {
-    const bool pose_var = sl != 255;
-    const ReprojGroup& g = kSingleGroup ? a.g0 : a.groups[gi];
-    ReprojBlocks o;
-    reproj_blocks(g, P, X, ou, ov, od, o);
-    cost = o.cost;
+  for (;;) {
+    const int bn = b + gridDim.x;
+    const bool has_next = bn < a.n_blocks;
+    if (tid == 0 && has_next) sNext = a.blocks[bn];
+    // poses of the block's slots and its (contiguous) landmark coordinates, staged in sT
+    double* sPose = sT;                               // [n_slots][12]
+    double* sPts = sT + 12 * (kBlkObs + 1);           // [n_lms][3]
+    for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) {
+      const int s = e / 12;
+      sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + s] + (e - 12 * s)];
+    }
+    for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
+    __syncthreads();
+    // prefetch: the next block's per-observation inputs stay in flight during this block's arithmetic
+    double nu = 0.0, nv = 0.0, nd = 0.0;
+    int nsl = 255, nql = 0, ngi = 0;
+    LmBlock nblk = blk;
+    if (has_next) {
+      nblk = sNext;
+      if (tid < nblk.n_obs) {
+        const int i = nblk.obs_begin + tid;
+        nu = ld_stream(a.obs_u + i); nv = ld_stream(a.obs_v + i); nd = ld_stream(a.obs_d + i);
+        nsl = a.obs_slot[i];
+        nql = a.obs_pt[i] - nblk.lm_begin;
+        if (!kSingleGroup) ngi = a.obs_grp[i];
+      }
+    }
+    double P[12], X[3];
+    if (tid < blk.n_obs) {
+      if (sl != 255) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
+      } else {                                        // constant pose: not a slot, read it directly
+        const double* Pg = a.poses + 12 * (size_t)a.obs_pose[blk.obs_begin + tid];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) X[k] = sPts[3 * ql + k];
+    }
+    __syncthreads();                                  // sT is reused for the per-observation rows below
+
     double* row = sT + tid * kRow;
-    if (pose_var) {
-      // U_c lower triangle, rows 0-2: M; rows 3-5: [(M B)^T | B^T M B]
-      row[0] = o.M[0];
-      row[1] = o.M[1]; row[2] = o.M[3];
-      row[3] = o.M[2]; row[4] = o.M[4]; row[5] = o.M[5];
-      row[6] = o.MB[0]; row[7] = o.MB[3]; row[8] = o.MB[6]; row[9] = o.BMB[0];
-      row[10] = o.MB[1]; row[11] = o.MB[4]; row[12] = o.MB[7]; row[13] = o.BMB[1]; row[14] = o.BMB[3];
-      row[15] = o.MB[2]; row[16] = o.MB[5]; row[17] = o.MB[8]; row[18] = o.BMB[2]; row[19] = o.BMB[4]; row[20] = o.BMB[5];
-      // b_c = -[t; B^T t]
-      row[21] = -o.t[0]; row[22] = -o.t[1]; row[23] = -o.t[2];
-      row[24] = -(o.y * o.t[2] - o.z * o.t[1]);
-      row[25] = -(o.z * o.t[0] - o.x * o.t[2]);
-      row[26] = -(o.x * o.t[1] - o.y * o.t[0]);
-      // W = [M R; B^T M R], SoA planes
-      double* Wp = a.W + i;
-      if (!(a.dbg & 2)) {
+    if (tid < blk.n_obs) {
+      const int i = blk.obs_begin + tid;
+      const ReprojGroup& grp = kSingleGroup ? a.g0 : a.groups[gi];
+      ReprojBlocks o;
+      reproj_blocks(grp, P, X, ou, ov, od, o);
+      cost += o.cost;
+      if (sl != 255) {
+        // U_c lower triangle, rows 0-2: M; rows 3-5: [(M B)^T | B^T M B]
+        row[0] = o.M[0];
+        row[1] = o.M[1]; row[2] = o.M[3];
+        row[3] = o.M[2]; row[4] = o.M[4]; row[5] = o.M[5];
+        row[6] = o.MB[0]; row[7] = o.MB[3]; row[8] = o.MB[6]; row[9] = o.BMB[0];
+        row[10] = o.MB[1]; row[11] = o.MB[4]; row[12] = o.MB[7]; row[13] = o.BMB[1]; row[14] = o.BMB[3];
+        row[15] = o.MB[2]; row[16] = o.MB[5]; row[17] = o.MB[8]; row[18] = o.BMB[2]; row[19] = o.BMB[4]; row[20] = o.BMB[5];
+        // b_c = -[t; B^T t]
+        row[21] = -o.t[0]; row[22] = -o.t[1]; row[23] = -o.t[2];
+        row[24] = -(o.y * o.t[2] - o.z * o.t[1]);
+        row[25] = -(o.z * o.t[0] - o.x * o.t[2]);
+        row[26] = -(o.x * o.t[1] - o.y * o.t[0]);
+        // W = [M R; B^T M R], SoA planes
+        double* Wp = a.W + i;
+        if (!(a.dbg & 2)) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Wp[(size_t)k * N] = o.MR[k];
+          for (int k = 0; k < 9; ++k) Wp[(size_t)k * N] = o.MR[k];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        Wp[(size_t)(9 + j) * N] = o.y * o.MR[6 + j] - o.z * o.MR[3 + j];
-        Wp[(size_t)(12 + j) * N] = o.z * o.MR[j] - o.x * o.MR[6 + j];
-        Wp[(size_t)(15 + j) * N] = o.x * o.MR[3 + j] - o.y * o.MR[j];
+          for (int j = 0; j < 3; ++j) {
+            Wp[(size_t)(9 + j) * N] = o.y * o.MR[6 + j] - o.z * o.MR[3 + j];
+            Wp[(size_t)(12 + j) * N] = o.z * o.MR[j] - o.x * o.MR[6 + j];
+            Wp[(size_t)(15 + j) * N] = o.x * o.MR[3 + j] - o.y * o.MR[j];
+          }
+        }
       }
-      }
+      // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
+      row[27] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
+      row[28] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
+      row[29] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
+      row[30] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
+      row[31] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
+      row[32] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
+      row[33] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
+      row[34] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
+      row[35] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
     }
-    // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
-    row[27] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
-    row[28] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
-    row[29] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
-    row[30] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
-    row[31] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
-    row[32] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
-    row[33] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
-    row[34] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
-    row[35] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // camera side: one task per (slot, value); observations of a slot are contiguous in cam_perm order
-  if (!(a.dbg & 4)) {
-    const unsigned char* perm = a.cam_perm + blk.obs_begin;
-    const unsigned char* seg = a.seg_start + blk.seg_begin;
-    const int n_tasks = blk.n_slots * 27;
-    for (int t = tid; t < n_tasks; t += kBlkObs) {
-      const int s = t / 27, v = t - 27 * s;
-      double acc = 0.0;
-      for (int k = seg[s]; k < seg[s + 1]; ++k) acc += sT[perm[k] * kRow + v];
-      const int off = a.pose_off[a.slot_pose[blk.slot_begin + s]];
-      if (a.dbg & 1) { if (acc == 1.2345e-300) a.Vg[0] = acc; }
-      else if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
-      else red_add(a.rhs + off + (v - 21), acc);
+    if (!(a.dbg & 4)) {
+      // camera side: one task per (slot, value); observations of a slot are contiguous in cam_perm order
+      const unsigned char* perm = a.cam_perm + blk.obs_begin;
+      const unsigned char* seg = a.seg_start + blk.seg_begin;
+      const int n_ct = blk.n_slots * 27;
+      for (int task = tid; task < n_ct; task += kBlkObs) {
+        const int s = task / 27, v = task - 27 * s;
+        double acc0 = 0.0, acc1 = 0.0;
+        int k = seg[s];
+        const int k1 = seg[s + 1];
+        for (; k + 1 < k1; k += 2) {
+          acc0 += sT[perm[k] * kRow + v];
+          acc1 += sT[perm[k + 1] * kRow + v];
+        }
+        if (k < k1) acc0 += sT[perm[k] * kRow + v];
+        const double acc = acc0 + acc1;
+        const int off = a.pose_off[a.slot_pose[blk.slot_begin + s]];
+        if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
+        else red_add(a.rhs + off + (v - 21), acc);
+      }
+      // landmark side: one task per (landmark, value); a landmark's observations are contiguous
+      const int n_lt = blk.n_lms * 9;
+      for (int task = tid; task < n_lt; task += kBlkObs) {
+        const int l = task / 9, v = task - 9 * l;
+        const int q = blk.lm_begin + l;
+        const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
+        double acc = 0.0;
+        for (int k = k0; k < k1; ++k) acc += sT[k * kRow + 27 + v];
+        a.Vg[9 * (size_t)q + v] = acc;
+      }
     }
-  }
-  // landmark side: one task per (landmark, value); a landmark's observations are contiguous
-  if (!(a.dbg & 4)) {
-    const int n_tasks = blk.n_lms * 9;
-    for (int t = tid; t < n_tasks; t += kBlkObs) {
-      const int l = t / 9, v = t - 9 * l;
-      const int q = blk.lm_begin + l;
-      const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
-      double acc = 0.0;
-      for (int k = k0; k < k1; ++k) acc += sT[k * kRow + 27 + v];
-      a.Vg[9 * (size_t)q + v] = acc;
-    }
+    if (!has_next) break;
+    __syncthreads();                                  // everybody is done with sT / sSlot / sLm / sNext
+    b = bn; blk = nblk;
+    ou = nu; ov = nv; od = nd; sl = nsl; ql = nql; gi = ngi;
   }
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
 }

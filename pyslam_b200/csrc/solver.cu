@@ -143,6 +143,9 @@ struct bslam_solver {
   std::vector<bs::CholTask> h_tasks;
   DevBuf<int> d_dirty_tiles;                       // tiles (i*nt+j) that carry data: zeroed before every linearisation
   int n_dirty_tiles = 0;
+  DevBuf<int> d_nz_tiles;                          // structurally non-zero tiles BEFORE fill-in (what assembly/Schur write)
+  int n_nz_tiles = 0;
+  DevBuf<double> d_pack;                           // [n_nz_tiles * 4096 | rhs n_pad | scalars]: the multi-GPU all-reduce payload
 
   double* S() { return d_red.p; }
   double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
@@ -331,8 +334,9 @@ int do_linearize(bslam_solver* s) {
     LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
   record(s, 1);
   if (s->n_lmblocks > 0) {
-    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
-    else LAUNCH(s, bs::reproj_block_kernel<false>, s->n_lmblocks, bs::kBlkObs, 0, reproj_args(s));
+    const int grid = std::min(s->n_lmblocks, 148 * 5);      // persistent CTAs, 5 resident per SM
+    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, grid, bs::kBlkObs, 0, reproj_args(s));
+    else LAUNCH(s, bs::reproj_block_kernel<false>, grid, bs::kBlkObs, 0, reproj_args(s));
   }
   record(s, 2);
   if (s->n_obs > s->tail_begin)
@@ -473,6 +477,14 @@ int build_chol_plan(bslam_solver* s) {
     s->n_dirty_tiles = (int)dirty.size();
     if (dirty.empty()) dirty.push_back(0);
     CU(upload(s->d_dirty_tiles, dirty, st));
+    std::vector<int> nz;
+    for (int i = 0; i < nt; ++i)
+      for (int j = 0; j <= i; ++j)
+        if (s->tile_mask[(size_t)i * nt + j]) nz.push_back(i * nt + j);
+    s->n_nz_tiles = (int)nz.size();
+    if (nz.empty()) nz.push_back(0);
+    CU(upload(s->d_nz_tiles, nz, st));
+    CU(s->d_pack.alloc((size_t)s->n_nz_tiles * bs::kNB * bs::kNB + s->n_pad + BSLAM_N_SCALARS));
   }
   CU(upload(s->d_fill_mask, m, st));
   CU(upload(s->d_tasks, tasks, st));
@@ -1396,6 +1408,29 @@ int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles, voi
   if (n_doubles) *n_doubles = s->red_len();
   if (scalars_dev_ptr) *scalars_dev_ptr = s->scalars();
   if (n_pad) *n_pad = s->n_pad;
+  return BSLAM_OK;
+}
+
+int bslam_packed_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles) {
+  NEED(s && s->finalized, "bslam_packed_buffer: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  if (dev_ptr) *dev_ptr = s->d_pack.p;
+  if (n_doubles) *n_doubles = s->d_pack.n;
+  return BSLAM_OK;
+}
+
+int bslam_pack_reduced(bslam_solver* s, int unpack) {
+  NEED(s && s->finalized, "bslam_pack_reduced: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  const size_t tiles = (size_t)s->n_nz_tiles * bs::kNB * bs::kNB;
+  if (s->n_nz_tiles > 0)
+    LAUNCH(s, bs::pack_tiles_kernel, s->n_nz_tiles, 256, 0, s->S(), s->n_pad, s->nblk, s->d_nz_tiles.p, s->d_pack.p, unpack);
+  const size_t tail = (size_t)s->n_pad + BSLAM_N_SCALARS;      // rhs | scalars are contiguous in both buffers
+  if (unpack) CU(cudaMemcpyAsync(s->rhs(), s->d_pack.p + tiles, tail * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  else CU(cudaMemcpyAsync(s->d_pack.p + tiles, s->rhs(), tail * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+  CU(cudaGetLastError());
   return BSLAM_OK;
 }
 

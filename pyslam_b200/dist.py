@@ -6,7 +6,8 @@ ranks; the poses and the reduced camera system are replicated.  Per iteration:
 
     every rank : linearise its observations, eliminate its landmarks
                  -> partial [S | rhs | cost]                      (CUDA, local)
-    all ranks  : ONE all-reduce (sum, fp64) of that buffer         (NCCL)
+    all ranks  : ONE all-reduce (sum, fp64) of that buffer, packed to its
+                 structurally non-zero 64x64 tiles                 (NCCL)
     every rank : factorise S, solve dx_c (redundantly, bit-identical inputs),
                  back-substitute and retract its own landmarks, cost at the
                  new point                                         (CUDA, local)
@@ -75,8 +76,15 @@ class ShardedSolver:
         stream = eng.torch_stream()
         eng.linearize(fetch_cost=False)
         eng.reduce(lam)
-        with _on_stream(stream):
-            dist.all_reduce(eng.reduced_tensor(), group=self.group)
+        if hasattr(eng, 'pack_reduced'):
+            # only the structurally non-zero tiles of S (+ rhs + scalars) travel over NVLink
+            eng.pack_reduced(False)
+            with _on_stream(stream):
+                dist.all_reduce(eng.packed_tensor(), group=self.group)
+            eng.pack_reduced(True)
+        else:
+            with _on_stream(stream):
+                dist.all_reduce(eng.reduced_tensor(), group=self.group)
         eng.solve_reduced()
         eng.retract(eval_new_cost)
         with _on_stream(stream):

@@ -61,6 +61,8 @@ SIGNATURES = {
     'bslam_retract': (C.c_int, [_h, C.c_int]),
     'bslam_get_scalars': (C.c_int, [_h, _dp]),
     'bslam_reduced_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), _ip]),
+    'bslam_packed_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    'bslam_pack_reduced': (C.c_int, [_h, C.c_int]),
     'bslam_tile_structure': (C.c_int, [_h, _bp, C.c_size_t, C.c_int]),
     'bslam_set_shard': (C.c_int, [_h, C.c_int]),
     'bslam_stream': (C.c_void_p, [_h]),
@@ -320,6 +322,20 @@ class Engine:
     def merge_tile_structure(self, mask):
         m = np.ascontiguousarray(mask, dtype=np.uint8)
         self._ck(self._lib.bslam_tile_structure(self._h, _b(m), m.size, 1))
+
+    def pack_reduced(self, unpack=False):
+        self._ck(self._lib.bslam_pack_reduced(self._h, int(bool(unpack))))
+
+    def packed_tensor(self):
+        """torch.float64 tensor aliasing the compact all-reduce payload (non-zero tiles | rhs | scalars)."""
+        import torch
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.bslam_packed_buffer(self._h, C.byref(p), C.byref(n)))
+        key = ('pack', p.value, n.value)
+        if getattr(self, '_pcache_key', None) != key:
+            self._pcache = torch.as_tensor(_DevArray(p.value, n.value), device='cuda:%d' % self.device)
+            self._pcache_key = key
+        return self._pcache
 
     def set_shard(self, rank):
         self._ck(self._lib.bslam_set_shard(self._h, int(rank)))
