@@ -72,6 +72,9 @@ struct ReprojArgs {
   const int* __restrict__ slot_pose;
   const unsigned char* __restrict__ cam_perm;   // [N] local obs index, grouped by slot inside each block
   const unsigned char* __restrict__ seg_start;
+  const int* __restrict__ slot_off;             // pose_off[slot_pose[e]] per slot entry (static)
+  const double* __restrict__ slot_poses;        // [n_slot_entries][12], gathered per linearisation
+  int stage_len;                                // doubles per staging buffer (max over blocks of 12 n_slots + 3 n_lms)
   // tail processed by the generic kernel
   int tail_begin;
   int dbg;                                  // profiling aid (BSLAM_DBG): 1 no atomics, 2 no W stores, 4 no reductions
@@ -226,87 +229,125 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
 __device__ __constant__ unsigned char kTriRow[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
 __device__ __constant__ unsigned char kTriCol[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
 
-BS_D void dmma_f64(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
+// ---- cp.async helpers (LDGSTS): global -> shared without staging registers -------------------
+BS_D void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+BS_D void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+BS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+BS_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// poses of all slot entries, gathered once per linearisation: slot_poses[e] = poses[slot_pose[e]]
+// (removes the pose indirection from the block kernels: a block's poses become one contiguous range)
+__global__ void __launch_bounds__(256) gather_slot_poses_kernel(int n, const int* __restrict__ slot_pose,
+                                                                const double* __restrict__ poses,
+                                                                double* __restrict__ slot_poses) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < 12 * n) slot_poses[e] = poses[12 * (size_t)slot_pose[e / 12] + e % 12];
 }
 
-// Persistent CTAs (grid = a few per SM) walk the landmark blocks with a stride; while a block is being
-// processed the per-observation inputs of the CTA's next block are already in flight.  Each thread leaves
-// its 27 camera values and 9 landmark values in a shared-memory row; the CTA then reduces them per slot
-// (observations grouped by cam_perm) and per landmark (contiguous observations).
-// (A variant doing both reductions as 0/1 selection-matrix products on the DMMA pipe was measured:
-//  same time, 25% more instructions -- see profiles/.)
+// Software-pipelined persistent kernel.  A CTA walks landmark blocks b, b + grid, ...  While block i is
+// being processed, everything block i+1 needs is already in flight: its descriptor (cp.async, two blocks
+// ahead), its slot poses and landmark coordinates (cp.async into the other half of a double-buffered
+// staging area) and its per-observation inputs (registers).  No global load sits on the critical path of
+// a block; the five resident CTAs per SM then overlap arithmetic only.
+//   phase 1  one thread per observation: structured linearisation, W stores, 36 values -> shared row
+//   phase 2  warp-parallel reductions: a warp owns a slot (lanes = the 27 camera values) or three
+//            landmarks (lanes = 3 x 9 landmark values); one fp64 atomic per (slot, value) leaves the SM,
+//            V_p / b_p are plain stores.
 template <bool kSingleGroup>
 __global__ void __launch_bounds__(kBlkObs, 5)
 reproj_block_kernel(const ReprojArgs a) {
+  extern __shared__ double sStage[];                  // 2 x stage_len doubles: [slot poses | landmark points]
   __shared__ double sT[kBlkObs * kRow];
   __shared__ double sred[kBlkObs / 32];
-  __shared__ LmBlock sNext;
-  const int tid = threadIdx.x;
+  __shared__ __align__(16) LmBlock sDesc[3];          // descriptor ring
+  __shared__ unsigned char sPerm[kBlkObs], sSeg[kBlkObs + 1];
+  __shared__ int sOff[kBlkObs], sLmStart[kBlkObs + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.n_obs;
+  const int stride = gridDim.x;
   double cost = 0.0;
   int b = blockIdx.x;
   if (b >= a.n_blocks) return;
+
+  auto stage = [&](const LmBlock& d, double* dst) {    // async copy of a block's poses and points
+    const int np = 12 * d.n_slots, nq = 3 * d.n_lms;
+    const double* gp = a.slot_poses + 12 * (size_t)d.slot_begin;
+    const double* gq = a.pts + 3 * (size_t)d.lm_begin;
+    for (int e = tid; e < np; e += kBlkObs) cp_async8(dst + e, gp + e);
+    for (int e = tid; e < nq; e += kBlkObs) cp_async8(dst + np + e, gq + e);
+  };
+  auto fetch_desc = [&](int blk_id, int slot) {        // 32-byte descriptor, two 16-byte async copies
+    if (tid < 2 && blk_id < a.n_blocks)
+      cp_async16(reinterpret_cast<char*>(&sDesc[slot]) + 16 * tid, reinterpret_cast<const char*>(a.blocks + blk_id) + 16 * tid);
+  };
+
+  // ---- prologue: block b synchronously, descriptors of b + stride and b + 2 stride in flight
   LmBlock blk = a.blocks[b];
-
-  // per-observation inputs of the current block
+  fetch_desc(b + stride, 1);
+  fetch_desc(b + 2 * stride, 2);
+  stage(blk, sStage);
+  cp_async_commit();
   double ou = 0.0, ov = 0.0, od = 0.0;
-  int sl = 255, ql = 0, gi = 0;
-  if (tid < blk.n_obs) {
-    const int i = blk.obs_begin + tid;
-    ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
-    sl = a.obs_slot[i];
-    ql = a.obs_pt[i] - blk.lm_begin;
-    if (!kSingleGroup) gi = a.obs_grp[i];
-  }
+  int sl = 255, ql = 0, gi = 0, perm = 0, seg = 0, soff = 0, lms = 0;
+  auto load_inputs = [&](const LmBlock& d, double& u, double& v, double& dd, int& s_, int& q_, int& g_, int& pm, int& sg,
+                         int& so, int& lm) {
+    if (tid < d.n_obs) {
+      const int i = d.obs_begin + tid;
+      u = ld_stream(a.obs_u + i); v = ld_stream(a.obs_v + i); dd = ld_stream(a.obs_d + i);
+      s_ = a.obs_slot[i];
+      q_ = a.obs_pt[i] - d.lm_begin;
+      pm = a.cam_perm[i];
+      if (!kSingleGroup) g_ = a.obs_grp[i];
+    } else { s_ = 255; q_ = 0; pm = 0; }
+    if (tid <= d.n_slots) sg = a.seg_start[d.seg_begin + tid];
+    if (tid < d.n_slots) so = a.slot_off[d.slot_begin + tid];
+    if (tid <= d.n_lms) lm = a.lm_start[d.lm_begin + tid] - d.obs_begin;
+  };
+  load_inputs(blk, ou, ov, od, sl, ql, gi, perm, seg, soff, lms);
 
+  int it = 0;
   for (;;) {
-    const int bn = b + gridDim.x;
+    double* cur = sStage + (it & 1) * a.stage_len;
+    double* nxt = sStage + ((it + 1) & 1) * a.stage_len;
+    const int bn = b + stride;
     const bool has_next = bn < a.n_blocks;
-    if (tid == 0 && has_next) sNext = a.blocks[bn];
-    // poses of the block's slots and its (contiguous) landmark coordinates, staged in sT
-    double* sPose = sT;                               // [n_slots][12]
-    double* sPts = sT + 12 * (kBlkObs + 1);           // [n_lms][3]
-    for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) {
-      const int s = e / 12;
-      sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + s] + (e - 12 * s)];
-    }
-    for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
-    __syncthreads();
-    // prefetch: the next block's per-observation inputs stay in flight during this block's arithmetic
+    sPerm[tid] = (unsigned char)perm; sSeg[tid] = (unsigned char)seg; sOff[tid] = soff; sLmStart[tid] = lms;
+    if (tid == 0) { sSeg[kBlkObs] = (unsigned char)blk.n_obs; sLmStart[kBlkObs] = blk.n_obs; }   // used only if n_slots / n_lms == 128
+    cp_async_wait_all();
+    __syncthreads();                                   // staging of this block and the next descriptor have landed
+    // ---- everything the NEXT block needs goes in flight now
     double nu = 0.0, nv = 0.0, nd = 0.0;
-    int nsl = 255, nql = 0, ngi = 0;
+    int nsl = 255, nql = 0, ngi = 0, nperm = 0, nseg = 0, nsoff = 0, nlms = 0;
     LmBlock nblk = blk;
     if (has_next) {
-      nblk = sNext;
-      if (tid < nblk.n_obs) {
-        const int i = nblk.obs_begin + tid;
-        nu = ld_stream(a.obs_u + i); nv = ld_stream(a.obs_v + i); nd = ld_stream(a.obs_d + i);
-        nsl = a.obs_slot[i];
-        nql = a.obs_pt[i] - nblk.lm_begin;
-        if (!kSingleGroup) ngi = a.obs_grp[i];
-      }
+      nblk = sDesc[(it + 1) % 3];
+      stage(nblk, nxt);
+      load_inputs(nblk, nu, nv, nd, nsl, nql, ngi, nperm, nseg, nsoff, nlms);
     }
-    double P[12], X[3];
+    fetch_desc(b + 3 * stride, it % 3);                // slot of the current block's descriptor is free again
+    cp_async_commit();
+
+    // ---- phase 1
+    double* row = sT + tid * kRow;
     if (tid < blk.n_obs) {
+      const int i = blk.obs_begin + tid;
+      double P[12], X[3];
       if (sl != 255) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
-      } else {                                        // constant pose: not a slot, read it directly
-        const double* Pg = a.poses + 12 * (size_t)a.obs_pose[blk.obs_begin + tid];
+        for (int k = 0; k < 12; ++k) P[k] = cur[12 * sl + k];
+      } else {                                         // constant pose: not a slot, read it directly
+        const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
 #pragma unroll
         for (int k = 0; k < 12; ++k) P[k] = Pg[k];
       }
 #pragma unroll
-      for (int k = 0; k < 3; ++k) X[k] = sPts[3 * ql + k];
-    }
-    __syncthreads();                                  // sT is reused for the per-observation rows below
-
-    double* row = sT + tid * kRow;
-    if (tid < blk.n_obs) {
-      const int i = blk.obs_begin + tid;
+      for (int k = 0; k < 3; ++k) X[k] = cur[12 * blk.n_slots + 3 * ql + k];
       const ReprojGroup& grp = kSingleGroup ? a.g0 : a.groups[gi];
       ReprojBlocks o;
       reproj_blocks(grp, P, X, ou, ov, od, o);
@@ -350,42 +391,44 @@ reproj_block_kernel(const ReprojArgs a) {
     }
     __syncthreads();
 
+    // ---- phase 2
     if (!(a.dbg & 4)) {
-      // camera side: one task per (slot, value); observations of a slot are contiguous in cam_perm order
-      const unsigned char* perm = a.cam_perm + blk.obs_begin;
-      const unsigned char* seg = a.seg_start + blk.seg_begin;
-      const int n_ct = blk.n_slots * 27;
-      for (int task = tid; task < n_ct; task += kBlkObs) {
-        const int s = task / 27, v = task - 27 * s;
-        double acc0 = 0.0, acc1 = 0.0;
-        int k = seg[s];
-        const int k1 = seg[s + 1];
-        for (; k + 1 < k1; k += 2) {
-          acc0 += sT[perm[k] * kRow + v];
-          acc1 += sT[perm[k + 1] * kRow + v];
+      // camera side: a warp owns a slot, lane = value index (27 of 32 lanes busy)
+      if (lane < 27) {
+        for (int s_ = warp; s_ < blk.n_slots; s_ += kBlkObs / 32) {
+          double acc0 = 0.0, acc1 = 0.0;
+          int k = sSeg[s_];
+          const int k1 = sSeg[s_ + 1];
+          for (; k + 1 < k1; k += 2) {
+            acc0 += sT[sPerm[k] * kRow + lane];
+            acc1 += sT[sPerm[k + 1] * kRow + lane];
+          }
+          if (k < k1) acc0 += sT[sPerm[k] * kRow + lane];
+          const double acc = acc0 + acc1;
+          const int off = sOff[s_];
+          if (lane < 21) red_add(a.S + (size_t)(off + kTriRow[lane]) * a.ldS + off + kTriCol[lane], acc);
+          else red_add(a.rhs + off + (lane - 21), acc);
         }
-        if (k < k1) acc0 += sT[perm[k] * kRow + v];
-        const double acc = acc0 + acc1;
-        const int off = a.pose_off[a.slot_pose[blk.slot_begin + s]];
-        if (v < 21) red_add(a.S + (size_t)(off + kTriRow[v]) * a.ldS + off + kTriCol[v], acc);
-        else red_add(a.rhs + off + (v - 21), acc);
-      }
-      // landmark side: one task per (landmark, value); a landmark's observations are contiguous
-      const int n_lt = blk.n_lms * 9;
-      for (int task = tid; task < n_lt; task += kBlkObs) {
-        const int l = task / 9, v = task - 9 * l;
-        const int q = blk.lm_begin + l;
-        const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
-        double acc = 0.0;
-        for (int k = k0; k < k1; ++k) acc += sT[k * kRow + 27 + v];
-        a.Vg[9 * (size_t)q + v] = acc;
+        // landmark side: a warp owns three landmarks at a time, lane = 9 * (landmark in group) + value
+        const int sub = lane / 9, v = lane - 9 * sub;
+        for (int l0 = 3 * warp; l0 < blk.n_lms; l0 += 3 * (kBlkObs / 32)) {
+          const int l = l0 + sub;
+          if (l < blk.n_lms) {
+            double acc = 0.0;
+            const int k1 = sLmStart[l + 1];
+            for (int k = sLmStart[l]; k < k1; ++k) acc += sT[k * kRow + 27 + v];
+            a.Vg[9 * (size_t)(blk.lm_begin + l) + v] = acc;
+          }
+        }
       }
     }
     if (!has_next) break;
-    __syncthreads();                                  // everybody is done with sT / sSlot / sLm / sNext
-    b = bn; blk = nblk;
+    __syncthreads();                                   // everybody is done with sT and the side arrays
+    b = bn; blk = nblk; ++it;
     ou = nu; ov = nv; od = nd; sl = nsl; ql = nql; gi = ngi;
+    perm = nperm; seg = nseg; soff = nsoff; lms = nlms;
   }
+  cp_async_wait_all();
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
 }
 

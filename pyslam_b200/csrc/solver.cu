@@ -115,6 +115,9 @@ struct bslam_solver {
   int n_lmblocks = 0, tail_begin = 0, n_regular = 0;
   size_t schur_smem = 0;
   DevBuf<unsigned char> d_obs_slot;
+  DevBuf<int> d_slot_off;
+  DevBuf<double> d_slot_poses;
+  int n_slot_entries = 0, stage_len = 0;
   DevBuf<bs::LmBlock> d_blocks;
   DevBuf<int> d_slot_pose;
   DevBuf<unsigned char> d_cam_perm, d_seg_start;
@@ -248,6 +251,7 @@ bs::ReprojArgs reproj_args(bslam_solver* s) {
   a.n_blocks = s->n_lmblocks;
   a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p;
   a.cam_perm = s->d_cam_perm.p; a.seg_start = s->d_seg_start.p;
+  a.slot_off = s->d_slot_off.p; a.slot_poses = s->d_slot_poses.p; a.stage_len = s->stage_len;
   a.tail_begin = s->tail_begin;
   { const char* e = getenv("BSLAM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.W = s->d_W.p; a.Vg = s->d_Vg.p;
@@ -334,9 +338,12 @@ int do_linearize(bslam_solver* s) {
     LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
   record(s, 1);
   if (s->n_lmblocks > 0) {
+    LAUNCH(s, bs::gather_slot_poses_kernel, cdiv(12LL * s->n_slot_entries, 256), 256, 0, s->n_slot_entries, s->d_slot_pose.p,
+           s->d_se3.p, s->d_slot_poses.p);
     const int grid = std::min(s->n_lmblocks, 148 * 5);      // persistent CTAs, 5 resident per SM
-    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, grid, bs::kBlkObs, 0, reproj_args(s));
-    else LAUNCH(s, bs::reproj_block_kernel<false>, grid, bs::kBlkObs, 0, reproj_args(s));
+    const size_t smem = 2 * (size_t)s->stage_len * sizeof(double);
+    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, grid, bs::kBlkObs, smem, reproj_args(s));
+    else LAUNCH(s, bs::reproj_block_kernel<false>, grid, bs::kBlkObs, smem, reproj_args(s));
   }
   record(s, 2);
   if (s->n_obs > s->tail_begin)
@@ -1195,6 +1202,12 @@ int bslam_finalize(bslam_solver* s) {
   }
   s->schur_smem = schur_smem;
   s->n_regular = n_regular;
+  std::vector<int> slot_off(slot_pose.size());
+  for (size_t k = 0; k < slot_pose.size(); ++k) slot_off[k] = s->se3_off[slot_pose[k]];
+  s->n_slot_entries = (int)slot_pose.size();
+  s->stage_len = 2;
+  for (const auto& b : blocks) s->stage_len = std::max(s->stage_len, 12 * b.n_slots + 3 * b.n_lms);
+  s->stage_len = (s->stage_len + 1) & ~1;
   s->n_lmblocks = (int)blocks.size();
   s->tail_begin = lm_start[n_regular];
   if (slot_pose.empty()) slot_pose.push_back(0);
@@ -1244,6 +1257,8 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_cam_perm, cam_perm, st));
   CU(upload(s->d_seg_start, seg_start, st));
   CU(upload(s->d_obs_slot, obs_slot, st));
+  CU(upload(s->d_slot_off, slot_off, st));
+  CU(s->d_slot_poses.alloc(12 * slot_pose.size()));
   if (s->schur_smem > 0)   // static + dynamic shared memory may exceed the 48 KB default
     CU(cudaFuncSetAttribute(bs::schur_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->schur_smem));
   CU(upload(s->d_groups, s->groups, st));
