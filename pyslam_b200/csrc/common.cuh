@@ -41,10 +41,33 @@ BS_D double ld_stream(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+BS_D unsigned ld_stream(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+BS_D double2 ld_stream2(const double* p) {     // 16-byte aligned pair
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 BS_D int ld_stream(const int* p) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+
+// ---- layout of W = J_T^T w J_p (6x3 per observation, row-major k = 3r + c) ----------------------
+// Observations are grouped in tiles of 32; inside a tile the 18 values are stored as nine planes of
+// (k, k+1) pairs:  W[tile][k/2][obs % 32][k % 2].  A warp that owns 32 consecutive observations
+// moves a plane with one 512-byte, 16-byte-per-lane access (STG.128 / LDG.128) at an immediate
+// offset from one base pointer, instead of 18 strided 8-byte accesses.
+constexpr int kWTile = 32;
+constexpr int kWTileLen = 18 * kWTile;      // doubles per tile
+BS_HD size_t w_index(int i, int k) {
+  return (size_t)(i >> 5) * kWTileLen + (size_t)(k >> 1) * (2 * kWTile) + ((i & 31) << 1) + (k & 1);
+}
+BS_HD size_t w_pair_base(int i) { return (size_t)(i >> 5) * kWTileLen + ((i & 31) << 1); }   // + 64 * (k/2)
+BS_HD size_t w_alloc_len(int n_obs) { return (size_t)((n_obs + kWTile - 1) / kWTile) * kWTileLen; }
 
 }  // namespace bs

@@ -86,8 +86,9 @@ struct CovLmArgs {
   size_t D;
   const int* __restrict__ obs_pose;
   const int* __restrict__ lm_start;
+  const int* __restrict__ lm_obs;    // [N] CSR position -> observation index
   const int* __restrict__ pose_off;
-  const double* __restrict__ W;      // [18][N]
+  const double* __restrict__ W;      // tiled, see w_index()
   const double* __restrict__ Vinv;   // [n_lm][6]
   double* __restrict__ cov;          // [D][D]
 };
@@ -100,9 +101,8 @@ BS_D double sym6(const double* v, int a, int b) {
 // B_p[a][off_j + r] = sum_c Vinv_p[a][c] W_j[r][c]
 BS_D double cov_B(const CovLmArgs& A, int p, int j, int a, int r) {
   const double* vi = A.Vinv + 6 * (size_t)p;
-  const double* Wj = A.W + j;
-  const size_t N = (size_t)A.n_obs;
-  return sym6(vi, a, 0) * Wj[(3 * r) * N] + sym6(vi, a, 1) * Wj[(3 * r + 1) * N] + sym6(vi, a, 2) * Wj[(3 * r + 2) * N];
+  return sym6(vi, a, 0) * A.W[w_index(j, 3 * r)] + sym6(vi, a, 1) * A.W[w_index(j, 3 * r + 1)] +
+         sym6(vi, a, 2) * A.W[w_index(j, 3 * r + 2)];
 }
 
 // Sigma_pc = -B_p Sigma_cc : grid (n_pad columns / 128, 3 * n_lm rows)
@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(128) cov_lm_pose_kernel(const CovLmArgs A) {
   const int p = blockIdx.y / 3, a = blockIdx.y % 3;
   if (col >= A.n_pad) return;
   double s = 0.0;
-  for (int j = A.lm_start[p]; j < A.lm_start[p + 1]; ++j) {
+  for (int jj = A.lm_start[p]; jj < A.lm_start[p + 1]; ++jj) {
+    const int j = A.lm_obs[jj];
     const int off = A.pose_off[A.obs_pose[j]];
     if (off < 0) continue;
     for (int r = 0; r < 6; ++r) s += cov_B(A, p, j, a, r) * A.cov[(size_t)(off + r) * A.D + col];
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(128) cov_lm_lm_kernel(const CovLmArgs A) {
   if (p2 >= A.n_lm) return;
   const size_t row = (size_t)A.n_pad + 3 * (size_t)p + a;
   double out[3] = {0.0, 0.0, 0.0};
-  for (int j = A.lm_start[p2]; j < A.lm_start[p2 + 1]; ++j) {
+  for (int jj = A.lm_start[p2]; jj < A.lm_start[p2 + 1]; ++jj) {
+    const int j = A.lm_obs[jj];
     const int off = A.pose_off[A.obs_pose[j]];
     if (off < 0) continue;
     for (int r = 0; r < 6; ++r) {

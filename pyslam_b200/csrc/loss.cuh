@@ -43,4 +43,17 @@ BS_D double loss_weight(const Loss& L, double x) {
   }
 }
 
+// Compile-time loss kind (kKind >= 0) or the run-time switch above (kKind < 0): the block kernels are
+// instantiated per kind so that the common single-group case carries no switch and no dead branches.
+template <int kKind>
+BS_D double loss_rho_t(const Loss& L, double x) {
+  if constexpr (kKind < 0) return loss_rho(L, x);
+  else { Loss c; c.kind = kKind; c.k = L.k; return loss_rho(c, x); }
+}
+template <int kKind>
+BS_D double loss_weight_t(const Loss& L, double x) {
+  if constexpr (kKind < 0) return loss_weight(L, x);
+  else { Loss c; c.kind = kKind; c.k = L.k; return loss_weight(c, x); }
+}
+
 }  // namespace bs

@@ -42,16 +42,16 @@ struct ReprojGroup {     // constants shared by a batch of blocks
   Loss loss;
 };
 
-struct LmBlock {         // a run of whole landmarks
+struct LmBlock {         // a run of whole landmarks; its observations are stored SLOT-MAJOR (grouped by pose)
   int obs_begin, n_obs;  // n_obs <= kBlkObs
   int lm_begin, n_lms;
-  int slot_begin, n_slots;   // into slot_pose[] / (slot_begin + block index) into seg_start[]
-  int seg_begin;             // into seg_start[]: n_slots + 1 entries (local positions in cam_perm order)
+  int slot_begin, n_slots;   // into slot_pose[] / slot_off[] / slot_poses[]
+  int seg_begin;             // into seg_start[]: n_slots + 1 entries (first observation of every slot, block-local)
   int pad;
 };
 
 struct ReprojArgs {
-  int n_obs;                      // all observations (SoA stride of W)
+  int n_obs;                      // all observations
   int n_lm;                       // points with index < n_lm are eliminated landmarks
   const double* __restrict__ obs_u;
   const double* __restrict__ obs_v;
@@ -61,24 +61,23 @@ struct ReprojArgs {
   const int* __restrict__ obs_grp;          // nullptr when there is a single group
   const ReprojGroup* __restrict__ groups;
   ReprojGroup g0;                           // groups[0] by value (constant bank) for the single-group fast path
-  const unsigned char* __restrict__ obs_slot;   // [N] slot of the observation inside its block (255: constant pose)
+  const unsigned* __restrict__ obs_code;    // [N] slot (bits 0-7, 255: constant pose) | block-local landmark (8-15) | group (16-31)
   const double* __restrict__ poses;         // [K][12]
   const int* __restrict__ pose_off;         // reduced offset of the pose or -1 (constant)
   const double* __restrict__ pts;           // [P][3]
-  const int* __restrict__ lm_start;         // [n_lm+1]
+  const int* __restrict__ lm_start;         // [n_lm+1] CSR over landmarks
+  const int* __restrict__ lm_obs;           // [N] CSR position -> observation index (identity in the tail)
   // landmark blocks
   int n_blocks;
   const LmBlock* __restrict__ blocks;
-  const int* __restrict__ slot_pose;
-  const unsigned char* __restrict__ cam_perm;   // [N] local obs index, grouped by slot inside each block
+  const unsigned char* __restrict__ lm_obs_local;   // [N] CSR position -> block-local observation index
   const unsigned char* __restrict__ seg_start;
   const int* __restrict__ slot_off;             // pose_off[slot_pose[e]] per slot entry (static)
   const double* __restrict__ slot_poses;        // [n_slot_entries][12], gathered per linearisation
   int stage_len;                                // doubles per staging buffer (max over blocks of 12 n_slots + 3 n_lms)
   // tail processed by the generic kernel
   int tail_begin;
-  int dbg;                                  // profiling aid (BSLAM_DBG): 1 no atomics, 2 no W stores, 4 no reductions
-  double* __restrict__ W;                   // [18][N]
+  double* __restrict__ W;                   // tiled, see w_index()
   double* __restrict__ Vg;                  // [n_lm][9]
   double* __restrict__ S;                   // [n_pad][ldS]
   int ldS;
@@ -89,7 +88,8 @@ struct ReprojArgs {
 constexpr int kBlkObs = 128;      // observations per landmark block = threads per CTA
 constexpr int kMaxTrack = 64;     // longer tracks go through the generic (atomic) kernels
 constexpr int kSchurCap = 768;    // n_slots * ldk cap of a multi-landmark block (96 KB of Schur operands)
-constexpr int kRow = 37;          // 27 camera + 9 landmark values + 1 pad (odd stride: conflict-free rows)
+constexpr int kRow = 38;          // 27 camera + 9 landmark values + 2 pad: 16-byte aligned rows whose 128-bit
+                                  // stores are bank-conflict free (row stride = 12 banks mod 32)
 
 // Residual and the two Jacobians of one observation.
 struct ReprojLin {
@@ -162,6 +162,7 @@ struct ReprojBlocks {
   double cost;
 };
 
+template <int kLoss>
 BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, const double* __restrict__ X,
                         double u, double v, double d, ReprojBlocks& o) {
   const double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9];
@@ -180,8 +181,8 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
   for (int k = 0; k < 3; ++k) {
     const double s0 = g.S[3 * k], s1 = g.S[3 * k + 1], s2 = g.S[3 * k + 2];
     const double r = s0 * e0 + s1 * e1 + s2 * e2;
-    const double w = loss_weight(g.loss, r);
-    cost += loss_rho(g.loss, r);
+    const double w = loss_weight_t<kLoss>(g.loss, r);
+    cost += loss_rho_t<kLoss>(g.loss, r);
     const double ws0 = w * s0, ws1 = w * s1, ws2 = w * s2;
     q00 = fma(ws0, s0, q00); q01 = fma(ws0, s1, q01); q02 = fma(ws0, s2, q02);
     q11 = fma(ws1, s1, q11); q12 = fma(ws1, s2, q12); q22 = fma(ws2, s2, q22);
@@ -225,10 +226,6 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
       o.MR[3 * i + j] = Mr[3 * i] * P[j] + Mr[3 * i + 1] * P[3 + j] + Mr[3 * i + 2] * P[6 + j];
 }
 
-// value index 0..20 -> (row, col) of the lower triangle of a 6x6 block, row-major
-__device__ __constant__ unsigned char kTriRow[21] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5};
-__device__ __constant__ unsigned char kTriCol[21] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5};
-
 // ---- cp.async helpers (LDGSTS): global -> shared without staging registers -------------------
 BS_D void cp_async8(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -253,38 +250,63 @@ __global__ void __launch_bounds__(256) gather_slot_poses_kernel(int n, const int
 // Software-pipelined persistent kernel.  A CTA walks landmark blocks b, b + grid, ...  While block i is
 // being processed, everything block i+1 needs is already in flight: its descriptor (cp.async, two blocks
 // ahead), its slot poses and landmark coordinates (cp.async into the other half of a double-buffered
-// staging area) and its per-observation inputs (registers).  No global load sits on the critical path of
-// a block; the five resident CTAs per SM then overlap arithmetic only.
-//   phase 1  one thread per observation: structured linearisation, W stores, 36 values -> shared row
-//   phase 2  warp-parallel reductions: a warp owns a slot (lanes = the 27 camera values) or three
-//            landmarks (lanes = 3 x 9 landmark values); one fp64 atomic per (slot, value) leaves the SM,
+// staging area) and its per-observation inputs (registers, untouched until the next round so that no
+// load is waited for early).
+//   phase 1  one thread per observation (slot-major order, so the pose reads of a warp are shared-memory
+//            broadcasts): structured linearisation, nine 16-byte W stores into the tiled layout, 36 values
+//            -> a shared row (eighteen 16-byte stores)
+//   phase 2  warp-parallel reductions: a warp owns a slot (lanes = the 27 camera values, the slot's rows
+//            are contiguous) or three landmarks (lanes = 3 x 9 landmark values, rows gathered through the
+//            block's landmark -> observation list); one fp64 atomic per (slot, value) leaves the SM,
 //            V_p / b_p are plain stores.
-template <bool kSingleGroup>
+// kLoss >= 0: single group with that loss kind (compile time); kLoss < 0: per-observation groups.
+template <int kLoss>
 __global__ void __launch_bounds__(kBlkObs, 5)
 reproj_block_kernel(const ReprojArgs a) {
-  extern __shared__ double sStage[];                  // 2 x stage_len doubles: [slot poses | landmark points]
-  __shared__ double sT[kBlkObs * kRow];
+  extern __shared__ __align__(16) double sStage[];    // 2 x stage_len doubles: [slot poses | landmark points]
+  __shared__ __align__(16) double sT[kBlkObs * kRow];
   __shared__ double sred[kBlkObs / 32];
   __shared__ __align__(16) LmBlock sDesc[3];          // descriptor ring
-  __shared__ unsigned char sPerm[kBlkObs], sSeg[kBlkObs + 1];
-  __shared__ int sOff[kBlkObs], sLmStart[kBlkObs + 1];
+  __shared__ unsigned char sLmObs[kBlkObs], sSeg[kBlkObs + 4], sLmStart[kBlkObs + 4];
+  __shared__ int sOff[kBlkObs];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = a.n_obs;
   const int stride = gridDim.x;
   double cost = 0.0;
   int b = blockIdx.x;
   if (b >= a.n_blocks) return;
+  // lane -> position of its camera value inside the pose's diagonal block of S (lower triangle, row-major)
+  int tri_off;
+  {
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= lane) ++r;
+    tri_off = lane < 21 ? r * a.ldS + (lane - r * (r + 1) / 2) : 0;
+  }
+  const int lm_sub = lane / 9, lm_v = lane - 9 * lm_sub;    // landmark-side role of the lane (lanes 27..31 idle)
 
   auto stage = [&](const LmBlock& d, double* dst) {    // async copy of a block's poses and points
-    const int np = 12 * d.n_slots, nq = 3 * d.n_lms;
+    const int np2 = 6 * d.n_slots, nq = 3 * d.n_lms;
     const double* gp = a.slot_poses + 12 * (size_t)d.slot_begin;
     const double* gq = a.pts + 3 * (size_t)d.lm_begin;
-    for (int e = tid; e < np; e += kBlkObs) cp_async8(dst + e, gp + e);
-    for (int e = tid; e < nq; e += kBlkObs) cp_async8(dst + np + e, gq + e);
+    for (int e = tid; e < np2; e += kBlkObs) cp_async16(dst + 2 * e, gp + 2 * e);
+    for (int e = tid; e < nq; e += kBlkObs) cp_async8(dst + 2 * np2 + e, gq + e);
   };
   auto fetch_desc = [&](int blk_id, int slot) {        // 32-byte descriptor, two 16-byte async copies
     if (tid < 2 && blk_id < a.n_blocks)
       cp_async16(reinterpret_cast<char*>(&sDesc[slot]) + 16 * tid, reinterpret_cast<const char*>(a.blocks + blk_id) + 16 * tid);
+  };
+  // per-observation inputs and the block's side tables, as loaded (nothing derived: deriving would wait)
+  struct Inputs { double u, v, d; unsigned code; int lmobs, lmstart, seg, soff; };
+  auto load_inputs = [&](const LmBlock& d, Inputs& in) {
+    in.u = in.v = in.d = 0.0; in.code = 255u; in.lmobs = 0; in.lmstart = 0; in.seg = 0; in.soff = 0;
+    if (tid < d.n_obs) {
+      const int i = d.obs_begin + tid;
+      in.u = ld_stream(a.obs_u + i); in.v = ld_stream(a.obs_v + i); in.d = ld_stream(a.obs_d + i);
+      in.code = ld_stream(a.obs_code + i);
+      in.lmobs = a.lm_obs_local[i];
+    }
+    if (tid <= d.n_slots) in.seg = a.seg_start[d.seg_begin + tid];
+    if (tid < d.n_slots) in.soff = a.slot_off[d.slot_begin + tid];
+    if (tid <= d.n_lms) in.lmstart = a.lm_start[d.lm_begin + tid];
   };
 
   // ---- prologue: block b synchronously, descriptors of b + stride and b + 2 stride in flight
@@ -293,23 +315,8 @@ reproj_block_kernel(const ReprojArgs a) {
   fetch_desc(b + 2 * stride, 2);
   stage(blk, sStage);
   cp_async_commit();
-  double ou = 0.0, ov = 0.0, od = 0.0;
-  int sl = 255, ql = 0, gi = 0, perm = 0, seg = 0, soff = 0, lms = 0;
-  auto load_inputs = [&](const LmBlock& d, double& u, double& v, double& dd, int& s_, int& q_, int& g_, int& pm, int& sg,
-                         int& so, int& lm) {
-    if (tid < d.n_obs) {
-      const int i = d.obs_begin + tid;
-      u = ld_stream(a.obs_u + i); v = ld_stream(a.obs_v + i); dd = ld_stream(a.obs_d + i);
-      s_ = a.obs_slot[i];
-      q_ = a.obs_pt[i] - d.lm_begin;
-      pm = a.cam_perm[i];
-      if (!kSingleGroup) g_ = a.obs_grp[i];
-    } else { s_ = 255; q_ = 0; pm = 0; }
-    if (tid <= d.n_slots) sg = a.seg_start[d.seg_begin + tid];
-    if (tid < d.n_slots) so = a.slot_off[d.slot_begin + tid];
-    if (tid <= d.n_lms) lm = a.lm_start[d.lm_begin + tid] - d.obs_begin;
-  };
-  load_inputs(blk, ou, ov, od, sl, ql, gi, perm, seg, soff, lms);
+  Inputs in;
+  load_inputs(blk, in);
 
   int it = 0;
   for (;;) {
@@ -317,30 +324,31 @@ reproj_block_kernel(const ReprojArgs a) {
     double* nxt = sStage + ((it + 1) & 1) * a.stage_len;
     const int bn = b + stride;
     const bool has_next = bn < a.n_blocks;
-    sPerm[tid] = (unsigned char)perm; sSeg[tid] = (unsigned char)seg; sOff[tid] = soff; sLmStart[tid] = lms;
-    if (tid == 0) { sSeg[kBlkObs] = (unsigned char)blk.n_obs; sLmStart[kBlkObs] = blk.n_obs; }   // used only if n_slots / n_lms == 128
+    sLmObs[tid] = (unsigned char)in.lmobs; sSeg[tid] = (unsigned char)in.seg; sOff[tid] = in.soff;
+    sLmStart[tid] = (unsigned char)(in.lmstart - blk.obs_begin);
+    if (tid == 0) { sSeg[kBlkObs] = (unsigned char)blk.n_obs; sLmStart[kBlkObs] = (unsigned char)blk.n_obs; }   // n_slots / n_lms == 128
     cp_async_wait_all();
     __syncthreads();                                   // staging of this block and the next descriptor have landed
     // ---- everything the NEXT block needs goes in flight now
-    double nu = 0.0, nv = 0.0, nd = 0.0;
-    int nsl = 255, nql = 0, ngi = 0, nperm = 0, nseg = 0, nsoff = 0, nlms = 0;
+    Inputs nin = in;
     LmBlock nblk = blk;
     if (has_next) {
       nblk = sDesc[(it + 1) % 3];
       stage(nblk, nxt);
-      load_inputs(nblk, nu, nv, nd, nsl, nql, ngi, nperm, nseg, nsoff, nlms);
+      load_inputs(nblk, nin);
     }
     fetch_desc(b + 3 * stride, it % 3);                // slot of the current block's descriptor is free again
     cp_async_commit();
 
     // ---- phase 1
-    double* row = sT + tid * kRow;
     if (tid < blk.n_obs) {
       const int i = blk.obs_begin + tid;
+      const int sl = in.code & 255, ql = (in.code >> 8) & 255;
       double P[12], X[3];
       if (sl != 255) {
+        const double2* Ps = reinterpret_cast<const double2*>(cur + 12 * sl);
 #pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = cur[12 * sl + k];
+        for (int k = 0; k < 6; ++k) { const double2 t = Ps[k]; P[2 * k] = t.x; P[2 * k + 1] = t.y; }
       } else {                                         // constant pose: not a slot, read it directly
         const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
 #pragma unroll
@@ -348,85 +356,92 @@ reproj_block_kernel(const ReprojArgs a) {
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) X[k] = cur[12 * blk.n_slots + 3 * ql + k];
-      const ReprojGroup& grp = kSingleGroup ? a.g0 : a.groups[gi];
+      const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[in.code >> 16];
       ReprojBlocks o;
-      reproj_blocks(grp, P, X, ou, ov, od, o);
+      reproj_blocks<kLoss>(grp, P, X, in.u, in.v, in.d, o);
       cost += o.cost;
+      double2* row = reinterpret_cast<double2*>(sT + tid * kRow);
       if (sl != 255) {
-        // U_c lower triangle, rows 0-2: M; rows 3-5: [(M B)^T | B^T M B]
-        row[0] = o.M[0];
-        row[1] = o.M[1]; row[2] = o.M[3];
-        row[3] = o.M[2]; row[4] = o.M[4]; row[5] = o.M[5];
-        row[6] = o.MB[0]; row[7] = o.MB[3]; row[8] = o.MB[6]; row[9] = o.BMB[0];
-        row[10] = o.MB[1]; row[11] = o.MB[4]; row[12] = o.MB[7]; row[13] = o.BMB[1]; row[14] = o.BMB[3];
-        row[15] = o.MB[2]; row[16] = o.MB[5]; row[17] = o.MB[8]; row[18] = o.BMB[2]; row[19] = o.BMB[4]; row[20] = o.BMB[5];
-        // b_c = -[t; B^T t]
-        row[21] = -o.t[0]; row[22] = -o.t[1]; row[23] = -o.t[2];
-        row[24] = -(o.y * o.t[2] - o.z * o.t[1]);
-        row[25] = -(o.z * o.t[0] - o.x * o.t[2]);
-        row[26] = -(o.x * o.t[1] - o.y * o.t[0]);
-        // W = [M R; B^T M R], SoA planes
-        double* Wp = a.W + i;
-        if (!(a.dbg & 2)) {
+        // U_c lower triangle (row-major), rows 0-2: M; rows 3-5: [(M B)^T | B^T M B];  then b_c = -[t; B^T t]
+        const double bc3 = -(o.y * o.t[2] - o.z * o.t[1]);
+        const double bc4 = -(o.z * o.t[0] - o.x * o.t[2]);
+        const double bc5 = -(o.x * o.t[1] - o.y * o.t[0]);
+        row[0] = make_double2(o.M[0], o.M[1]);
+        row[1] = make_double2(o.M[3], o.M[2]);
+        row[2] = make_double2(o.M[4], o.M[5]);
+        row[3] = make_double2(o.MB[0], o.MB[3]);
+        row[4] = make_double2(o.MB[6], o.BMB[0]);
+        row[5] = make_double2(o.MB[1], o.MB[4]);
+        row[6] = make_double2(o.MB[7], o.BMB[1]);
+        row[7] = make_double2(o.BMB[3], o.MB[2]);
+        row[8] = make_double2(o.MB[5], o.MB[8]);
+        row[9] = make_double2(o.BMB[2], o.BMB[4]);
+        row[10] = make_double2(o.BMB[5], -o.t[0]);
+        row[11] = make_double2(-o.t[1], -o.t[2]);
+        row[12] = make_double2(bc3, bc4);
+        // W = [M R; B^T M R] as nine (k, k+1) pairs, 512 bytes apart
+        double2* Wp = reinterpret_cast<double2*>(a.W + w_pair_base(i));
+        double w[18];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) Wp[(size_t)k * N] = o.MR[k];
+        for (int k = 0; k < 9; ++k) w[k] = o.MR[k];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            Wp[(size_t)(9 + j) * N] = o.y * o.MR[6 + j] - o.z * o.MR[3 + j];
-            Wp[(size_t)(12 + j) * N] = o.z * o.MR[j] - o.x * o.MR[6 + j];
-            Wp[(size_t)(15 + j) * N] = o.x * o.MR[3 + j] - o.y * o.MR[j];
-          }
+        for (int j = 0; j < 3; ++j) {
+          w[9 + j] = o.y * o.MR[6 + j] - o.z * o.MR[3 + j];
+          w[12 + j] = o.z * o.MR[j] - o.x * o.MR[6 + j];
+          w[15 + j] = o.x * o.MR[3 + j] - o.y * o.MR[j];
         }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Wp[kWTile * k] = make_double2(w[2 * k], w[2 * k + 1]);
+        // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
+        row[13] = make_double2(bc5, P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6]);
+      } else {
+        row[13] = make_double2(0.0, P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6]);
       }
-      // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
-      row[27] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
-      row[28] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
-      row[29] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
-      row[30] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
-      row[31] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
-      row[32] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
-      row[33] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
-      row[34] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
-      row[35] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
+      row[14] = make_double2(P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7], P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8]);
+      row[15] = make_double2(P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7], P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8]);
+      row[16] = make_double2(P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8], -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]));
+      row[17] = make_double2(-(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]), -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]));
     }
     __syncthreads();
 
     // ---- phase 2
-    if (!(a.dbg & 4)) {
-      // camera side: a warp owns a slot, lane = value index (27 of 32 lanes busy)
-      if (lane < 27) {
-        for (int s_ = warp; s_ < blk.n_slots; s_ += kBlkObs / 32) {
-          double acc0 = 0.0, acc1 = 0.0;
-          int k = sSeg[s_];
-          const int k1 = sSeg[s_ + 1];
-          for (; k + 1 < k1; k += 2) {
-            acc0 += sT[sPerm[k] * kRow + lane];
-            acc1 += sT[sPerm[k + 1] * kRow + lane];
-          }
-          if (k < k1) acc0 += sT[sPerm[k] * kRow + lane];
-          const double acc = acc0 + acc1;
-          const int off = sOff[s_];
-          if (lane < 21) red_add(a.S + (size_t)(off + kTriRow[lane]) * a.ldS + off + kTriCol[lane], acc);
-          else red_add(a.rhs + off + (lane - 21), acc);
+    if (lane < 27) {
+      // camera side: a warp owns a slot, lane = value index; the slot's rows are contiguous
+      for (int s_ = warp; s_ < blk.n_slots; s_ += kBlkObs / 32) {
+        int k = sSeg[s_];
+        const int k1 = sSeg[s_ + 1];
+        const double* p = sT + k * kRow + lane;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        for (; k + 4 <= k1; k += 4, p += 4 * kRow) {
+          acc0 += p[0]; acc1 += p[kRow]; acc2 += p[2 * kRow]; acc3 += p[3 * kRow];
         }
-        // landmark side: a warp owns three landmarks at a time, lane = 9 * (landmark in group) + value
-        const int sub = lane / 9, v = lane - 9 * sub;
-        for (int l0 = 3 * warp; l0 < blk.n_lms; l0 += 3 * (kBlkObs / 32)) {
-          const int l = l0 + sub;
-          if (l < blk.n_lms) {
-            double acc = 0.0;
-            const int k1 = sLmStart[l + 1];
-            for (int k = sLmStart[l]; k < k1; ++k) acc += sT[k * kRow + 27 + v];
-            a.Vg[9 * (size_t)(blk.lm_begin + l) + v] = acc;
+        for (; k < k1; ++k, p += kRow) acc0 += p[0];
+        const double acc = (acc0 + acc1) + (acc2 + acc3);
+        const int off = sOff[s_];
+        if (lane < 21) red_add(a.S + (size_t)off * (a.ldS + 1) + tri_off, acc);
+        else red_add(a.rhs + off + (lane - 21), acc);
+      }
+      // landmark side: a warp owns three landmarks at a time, lane = 9 * (landmark in group) + value
+      const double* q = sT + 27 + lm_v;
+      for (int l0 = 3 * warp; l0 < blk.n_lms; l0 += 3 * (kBlkObs / 32)) {
+        const int l = l0 + lm_sub;
+        if (l < blk.n_lms) {
+          int k = sLmStart[l];
+          const int k1 = sLmStart[l + 1];
+          double acc0 = 0.0, acc1 = 0.0;
+          for (; k + 2 <= k1; k += 2) {
+            acc0 += q[sLmObs[k] * kRow];
+            acc1 += q[sLmObs[k + 1] * kRow];
           }
+          if (k < k1) acc0 += q[sLmObs[k] * kRow];
+          a.Vg[9 * (size_t)(blk.lm_begin + l) + lm_v] = acc0 + acc1;
         }
       }
     }
     if (!has_next) break;
     __syncthreads();                                   // everybody is done with sT and the side arrays
     b = bn; blk = nblk; ++it;
-    ou = nu; ov = nv; od = nd; sl = nsl; ql = nql; gi = ngi;
-    perm = nperm; seg = nseg; soff = nsoff; lms = nlms;
+    in = nin;
   }
   cp_async_wait_all();
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
@@ -480,12 +495,11 @@ reproj_generic_kernel(const ReprojArgs a) {
           red_add(vg + 6 + r, -(L.Jp[r] * wr[0] + L.Jp[3 + r] * wr[1] + L.Jp[6 + r] * wr[2]));
       }
       if (poff >= 0 && pt_var) {
-        double* Wp = a.W + i;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            Wp[(size_t)(3 * r + c) * N] = w[0] * L.JT[r] * L.Jp[c] + w[1] * L.JT[6 + r] * L.Jp[3 + c] +
+            a.W[w_index(i, 3 * r + c)] = w[0] * L.JT[r] * L.Jp[c] + w[1] * L.JT[6 + r] * L.Jp[3 + c] +
                                           w[2] * L.JT[12 + r] * L.Jp[6 + c];
       }
     }

@@ -45,13 +45,14 @@ struct SchurArgs {
   int n_blocks;
   const LmBlock* __restrict__ blocks;
   const int* __restrict__ slot_pose;
-  const unsigned char* __restrict__ obs_slot;   // [N] slot of the observation inside its block (255: constant pose)
+  const unsigned* __restrict__ obs_code;        // [N] slot (bits 0-7, 255: constant pose) | block-local landmark (8-15)
   double* __restrict__ Vinv_out;
   const int* __restrict__ obs_pose;
   const int* __restrict__ obs_pt;
-  const int* __restrict__ lm_start;   // [n_lm+1] observation range of each landmark
+  const int* __restrict__ lm_start;   // [n_lm+1] CSR over landmarks
+  const int* __restrict__ lm_obs;     // [N] CSR position -> observation index
   const int* __restrict__ pose_off;
-  const double* __restrict__ W;       // [18][N] (SoA planes)
+  const double* __restrict__ W;       // tiled, see w_index()
   const double* __restrict__ Vg;      // [n_lm][9]
   const double* __restrict__ Vinv;    // [n_lm][6]
   double* __restrict__ S;
@@ -70,12 +71,10 @@ __global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
   if (oi < 0) return;
   const double* vi = a.Vinv + 6 * (size_t)q;
   const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-  const size_t N = (size_t)a.n_obs;
-  const double* Wi = a.W + i;
   double Y[18];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
-    const double w0 = Wi[(3 * r) * N], w1 = Wi[(3 * r + 1) * N], w2 = Wi[(3 * r + 2) * N];
+    const double w0 = a.W[w_index(i, 3 * r)], w1 = a.W[w_index(i, 3 * r + 1)], w2 = a.W[w_index(i, 3 * r + 2)];
     Y[3 * r + 0] = w0 * m00 + w1 * m01 + w2 * m02;
     Y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
     Y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
@@ -86,13 +85,13 @@ __global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
   for (int r = 0; r < 6; ++r) red_add(a.rhs + oi + r, -(Y[3 * r] * g0 + Y[3 * r + 1] * g1 + Y[3 * r + 2] * g2));
 
   const int j0 = a.lm_start[q], j1 = a.lm_start[q + 1];
-  for (int j = j0; j < j1; ++j) {
+  for (int jj = j0; jj < j1; ++jj) {
+    const int j = a.lm_obs[jj];
     const int oj = a.pose_off[a.obs_pose[j]];
     if (oj < 0 || oj > oi) continue;
-    const double* Wj = a.W + j;
     double wj[18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k) wj[k] = Wj[k * N];
+    for (int k = 0; k < 18; ++k) wj[k] = a.W[w_index(j, k)];
     double* Sd = a.S + (size_t)oi * a.ldS + oj;
     const bool diag = (oj == oi);
 #pragma unroll
@@ -130,7 +129,6 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   const int rows = kSlotRows * blk.n_slots + 2;     // +2: the last slot's fragment rows 6-7
   double* Yt = sm;
   double* Wt = sm + (size_t)rows * ldk;
-  const size_t N = (size_t)a.n_obs;
 
   // zero the operands (pairs (slot, landmark) without an observation contribute nothing)
   {
@@ -152,17 +150,23 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
   __syncthreads();
   if (tid < blk.n_obs) {
     const int i = blk.obs_begin + tid;
-    const int sl = a.obs_slot[i];
+    const unsigned code = a.obs_code[i];
+    const int sl = code & 255;
     if (sl != 255) {
-      const int l = a.obs_pt[i] - blk.lm_begin;
+      const int l = (code >> 8) & 255;
       const double* vi = sVinv + 6 * l;
       const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
       double* yr = Yt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
       double* wr = Wt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
-      const double* Wi = a.W + i;
+      double w18[18];
+      {
+        const double* Wp = a.W + w_pair_base(i);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
+      }
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        const double w0 = Wi[(3 * r) * N], w1 = Wi[(3 * r + 1) * N], w2 = Wi[(3 * r + 2) * N];
+        const double w0 = w18[3 * r], w1 = w18[3 * r + 1], w2 = w18[3 * r + 2];
         wr[r * ldk] = w0; wr[r * ldk + 1] = w1; wr[r * ldk + 2] = w2;
         yr[r * ldk] = w0 * m00 + w1 * m01 + w2 * m02;
         yr[r * ldk + 1] = w0 * m01 + w1 * m11 + w2 * m12;
@@ -218,6 +222,7 @@ struct BacksubArgs {
   int lm_off;                         // landmark slice of dx starts here
   const int* __restrict__ obs_pose;
   const int* __restrict__ lm_start;
+  const int* __restrict__ lm_obs;
   const int* __restrict__ pose_off;
   const double* __restrict__ W;
   const double* __restrict__ Vg;
@@ -231,18 +236,17 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
   if (q >= a.n_lm) return;
   const double* g = a.Vg + 9 * (size_t)q + 6;
   double s0 = g[0], s1 = g[1], s2 = g[2];
-  for (int j = a.lm_start[q]; j < a.lm_start[q + 1]; ++j) {
+  for (int jj = a.lm_start[q]; jj < a.lm_start[q + 1]; ++jj) {
+    const int j = a.lm_obs[jj];
     const int oj = a.pose_off[a.obs_pose[j]];
     if (oj < 0) continue;
-    const double* Wj = a.W + j;
-    const size_t N = (size_t)a.n_obs;
     const double* d = a.dx + oj;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       const double dr = d[r];
-      s0 -= Wj[(3 * r) * N] * dr;
-      s1 -= Wj[(3 * r + 1) * N] * dr;
-      s2 -= Wj[(3 * r + 2) * N] * dr;
+      s0 -= a.W[w_index(j, 3 * r)] * dr;
+      s1 -= a.W[w_index(j, 3 * r + 1)] * dr;
+      s2 -= a.W[w_index(j, 3 * r + 2)] * dr;
     }
   }
   const double* vi = a.Vinv + 6 * (size_t)q;
@@ -263,14 +267,13 @@ struct FinishArgs {
   int n_blocks;
   const LmBlock* __restrict__ blocks;
   const int* __restrict__ slot_pose;
-  const unsigned char* __restrict__ obs_slot;
+  const int* __restrict__ slot_off;
+  const unsigned* __restrict__ obs_code;
+  const unsigned char* __restrict__ lm_obs_local;
   const int* __restrict__ obs_pose;
-  const int* __restrict__ obs_pt;
-  const int* __restrict__ obs_grp;
   const ReprojGroup* __restrict__ groups;
   ReprojGroup g0;
   const int* __restrict__ lm_start;
-  const int* __restrict__ pose_off;
   const double* __restrict__ obs_u;
   const double* __restrict__ obs_v;
   const double* __restrict__ obs_d;
@@ -283,41 +286,49 @@ struct FinishArgs {
   double* __restrict__ scalars;
 };
 
-template <bool kSingleGroup>
+// One CTA per landmark block, one thread per observation.  All global loads are issued up front
+// (W as nine 16-byte loads per thread, the slot tables through precomputed offsets), so the only
+// dependent chain is slot -> pose index -> pose.
+template <int kLoss>
 __global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) {
-  __shared__ double sPose[12 * (kBlkObs + 1)];
+  __shared__ __align__(16) double sPose[12 * kBlkObs];
   __shared__ double sDx[6 * kBlkObs];
   __shared__ double sPts[3 * kBlkObs];
   __shared__ double sAcc[3 * kBlkObs];
   __shared__ double sred[2 * (kBlkObs / 32)];
+  __shared__ unsigned char sLmObs[kBlkObs];
   const int tid = threadIdx.x;
   const LmBlock blk = a.blocks[blockIdx.x];
-  const size_t N = (size_t)a.n_obs;
   const int i = blk.obs_begin + tid;
   double w18[18];
   double ou = 0.0, ov = 0.0, od = 0.0;
-  int sl = 255, ql = 0, gi = 0;
+  unsigned code = 255u;
   if (tid < blk.n_obs) {
-    sl = a.obs_slot[i];
-    ql = a.obs_pt[i] - blk.lm_begin;
-    if (sl != 255) {
+    code = ld_stream(a.obs_code + i);
+    sLmObs[tid] = a.lm_obs_local[i];
+    const double* Wp = a.W + w_pair_base(i);
 #pragma unroll
-      for (int k = 0; k < 18; ++k) w18[k] = ld_stream(a.W + k * N + i);
-    }
-    if (a.eval_cost) {
-      ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
-      if (!kSingleGroup) gi = a.obs_grp[i];
-    }
+    for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
+    if (a.eval_cost) { ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i); }
   }
-  for (int e = tid; e < blk.n_slots; e += kBlkObs) {
-    const int pose = a.slot_pose[blk.slot_begin + e];
-    const int off = a.pose_off[pose];
+  const int sl = code & 255, ql = (code >> 8) & 255;
+  // per landmark: b_p, V^-1, CSR range, current point
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0, vi[6] = {0, 0, 0, 0, 0, 0}, p0 = 0.0, p1 = 0.0, p2 = 0.0;
+  int k0 = 0, k1 = 0;
+  if (tid < blk.n_lms) {
+    const int q = blk.lm_begin + tid;
+    const double* g = a.Vg + 9 * (size_t)q + 6;
+    g0 = g[0]; g1 = g[1]; g2 = g[2];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) sDx[6 * e + k] = a.dx[off + k];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) sPose[12 * e + k] = a.poses[12 * (size_t)pose + k];
+    for (int k = 0; k < 6; ++k) vi[k] = a.Vinv[6 * (size_t)q + k];
+    k0 = a.lm_start[q] - blk.obs_begin; k1 = a.lm_start[q + 1] - blk.obs_begin;
+    const double* P = a.pts + 3 * (size_t)q;
+    p0 = P[0]; p1 = P[1]; p2 = P[2];
   }
-  for (int e = tid; e < 3 * blk.n_lms; e += kBlkObs) sPts[e] = a.pts[3 * (size_t)blk.lm_begin + e];
+  // slot tables: dx_c through the static offsets, the retracted poses through the pose index
+  for (int e = tid; e < 6 * blk.n_slots; e += kBlkObs) sDx[e] = a.dx[a.slot_off[blk.slot_begin + e / 6] + e % 6];
+  if (a.eval_cost)
+    for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + e / 12] + e % 12];
   __syncthreads();
   if (tid < blk.n_obs) {
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
@@ -334,18 +345,15 @@ __global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) 
   double dx2 = 0.0;
   if (tid < blk.n_lms) {
     const int q = blk.lm_begin + tid;
-    const double* g = a.Vg + 9 * (size_t)q + 6;
-    double s0 = g[0], s1 = g[1], s2 = g[2];
-    const int k0 = a.lm_start[q] - blk.obs_begin, k1 = a.lm_start[q + 1] - blk.obs_begin;
-    for (int k = k0; k < k1; ++k) { s0 -= sAcc[3 * k]; s1 -= sAcc[3 * k + 1]; s2 -= sAcc[3 * k + 2]; }
-    const double* vi = a.Vinv + 6 * (size_t)q;
+    double s0 = g0, s1 = g1, s2 = g2;
+    for (int k = k0; k < k1; ++k) { const int o = sLmObs[k]; s0 -= sAcc[3 * o]; s1 -= sAcc[3 * o + 1]; s2 -= sAcc[3 * o + 2]; }
     const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
     const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
     const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
     double* o = a.dx + a.lm_off + 3 * (size_t)q;
     o[0] = d0; o[1] = d1; o[2] = d2;
     dx2 = d0 * d0 + d1 * d1 + d2 * d2;
-    const double p0 = sPts[3 * tid] + d0, p1 = sPts[3 * tid + 1] + d1, p2 = sPts[3 * tid + 2] + d2;
+    p0 += d0; p1 += d1; p2 += d2;
     sPts[3 * tid] = p0; sPts[3 * tid + 1] = p1; sPts[3 * tid + 2] = p2;
     double* P = a.pts + 3 * (size_t)q;
     P[0] = p0; P[1] = p1; P[2] = p2;
@@ -353,11 +361,12 @@ __global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) 
   __syncthreads();
   double cost = 0.0;
   if (a.eval_cost && tid < blk.n_obs) {
-    const ReprojGroup& g = kSingleGroup ? a.g0 : a.groups[gi];
+    const ReprojGroup& g = kLoss >= 0 ? a.g0 : a.groups[code >> 16];
     double P[12];
     if (sl != 255) {
+      const double2* Ps = reinterpret_cast<const double2*>(sPose + 12 * sl);
 #pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = sPose[12 * sl + k];
+      for (int k = 0; k < 6; ++k) { const double2 t = Ps[k]; P[2 * k] = t.x; P[2 * k + 1] = t.y; }
     } else {
       const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
 #pragma unroll
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) 
     double r[3];
     reproj_residual_only(g, P, sPts + 3 * ql, ou, ov, od, r);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cost += loss_rho(g.loss, r[k]);
+    for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(g.loss, r[k]);
   }
   // two block sums -> two atomics
   cost = warp_sum(cost);

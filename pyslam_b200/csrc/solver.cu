@@ -114,13 +114,14 @@ struct bslam_solver {
   // landmark blocks of the fast reprojection / Schur kernels
   int n_lmblocks = 0, tail_begin = 0, n_regular = 0;
   size_t schur_smem = 0;
-  DevBuf<unsigned char> d_obs_slot;
-  DevBuf<int> d_slot_off;
+  DevBuf<unsigned> d_obs_code;                       // slot | block-local landmark << 8 | group << 16
+  DevBuf<int> d_slot_off, d_lm_obs;                  // d_lm_obs: CSR position (landmark order) -> observation index
+  int loss_kind = -1;                                // loss kind of the single reprojection group, -1: several groups
   DevBuf<double> d_slot_poses;
   int n_slot_entries = 0, stage_len = 0;
   DevBuf<bs::LmBlock> d_blocks;
   DevBuf<int> d_slot_pose;
-  DevBuf<unsigned char> d_cam_perm, d_seg_start;
+  DevBuf<unsigned char> d_lm_obs_local, d_seg_start;
   DevBuf<bs::ReprojGroup> d_groups;
   DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_Linv;
   DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
@@ -243,17 +244,16 @@ bs::ReprojArgs reproj_args(bslam_solver* s) {
   a.obs_grp = s->groups.size() > 1 ? s->d_ogrp.p : nullptr;
   a.groups = s->d_groups.p;
   if (!s->groups.empty()) a.g0 = s->groups[0];
-  a.obs_slot = s->d_obs_slot.p;
+  a.obs_code = s->d_obs_code.p;
   a.poses = s->d_se3.p;
   a.pose_off = s->d_se3_off.p;
   a.pts = s->d_pts.p;
-  a.lm_start = s->d_lm_start.p;
+  a.lm_start = s->d_lm_start.p; a.lm_obs = s->d_lm_obs.p;
   a.n_blocks = s->n_lmblocks;
-  a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p;
-  a.cam_perm = s->d_cam_perm.p; a.seg_start = s->d_seg_start.p;
+  a.blocks = s->d_blocks.p;
+  a.lm_obs_local = s->d_lm_obs_local.p; a.seg_start = s->d_seg_start.p;
   a.slot_off = s->d_slot_off.p; a.slot_poses = s->d_slot_poses.p; a.stage_len = s->stage_len;
   a.tail_begin = s->tail_begin;
-  { const char* e = getenv("BSLAM_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.W = s->d_W.p; a.Vg = s->d_Vg.p;
   a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
   return a;
@@ -342,8 +342,16 @@ int do_linearize(bslam_solver* s) {
            s->d_se3.p, s->d_slot_poses.p);
     const int grid = std::min(s->n_lmblocks, 148 * 5);      // persistent CTAs, 5 resident per SM
     const size_t smem = 2 * (size_t)s->stage_len * sizeof(double);
-    if (s->groups.size() == 1) LAUNCH(s, bs::reproj_block_kernel<true>, grid, bs::kBlkObs, smem, reproj_args(s));
-    else LAUNCH(s, bs::reproj_block_kernel<false>, grid, bs::kBlkObs, smem, reproj_args(s));
+    const bs::ReprojArgs ra = reproj_args(s);
+    switch (s->loss_kind) {
+      case 0: LAUNCH(s, bs::reproj_block_kernel<0>, grid, bs::kBlkObs, smem, ra); break;
+      case 1: LAUNCH(s, bs::reproj_block_kernel<1>, grid, bs::kBlkObs, smem, ra); break;
+      case 2: LAUNCH(s, bs::reproj_block_kernel<2>, grid, bs::kBlkObs, smem, ra); break;
+      case 3: LAUNCH(s, bs::reproj_block_kernel<3>, grid, bs::kBlkObs, smem, ra); break;
+      case 4: LAUNCH(s, bs::reproj_block_kernel<4>, grid, bs::kBlkObs, smem, ra); break;
+      case 5: LAUNCH(s, bs::reproj_block_kernel<5>, grid, bs::kBlkObs, smem, ra); break;
+      default: LAUNCH(s, bs::reproj_block_kernel<-1>, grid, bs::kBlkObs, smem, ra); break;
+    }
   }
   record(s, 2);
   if (s->n_obs > s->tail_begin)
@@ -375,9 +383,9 @@ int do_reduce(bslam_solver* s, double lambda) {
   if (s->n_lm > 0) {
     bs::SchurArgs a;
     a.n_obs = s->n_obs; a.n_lm = s->n_lm; a.obs_begin = s->tail_begin; a.lambda = lambda;
-    a.n_blocks = s->n_lmblocks; a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_slot = s->d_obs_slot.p;
+    a.n_blocks = s->n_lmblocks; a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_code = s->d_obs_code.p;
     a.Vinv_out = s->d_Vinv.p;
-    a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.lm_start = s->d_lm_start.p;
+    a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.lm_start = s->d_lm_start.p; a.lm_obs = s->d_lm_obs.p;
     a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
@@ -535,7 +543,7 @@ int do_solve_reduced(bslam_solver* s) {
   if (s->n_lm > s->n_regular) {      // regular landmarks are back-substituted by lm_finish_kernel (do_retract)
     bs::BacksubArgs a;
     a.n_lm = s->n_lm; a.q_begin = s->n_regular; a.n_obs = s->n_obs; a.lm_off = s->n_pad;
-    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.lm_obs = s->d_lm_obs.p; a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p; a.dx = s->d_dx.p;
     LAUNCH(s, bs::backsub_kernel, cdiv(s->n_lm - s->n_regular, 128), 128, 0, a);
   }
@@ -562,15 +570,23 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
   if (s->n_lmblocks > 0) {
     bs::FinishArgs a;
     a.n_obs = s->n_obs; a.lm_off = s->n_pad; a.eval_cost = eval_new_cost; a.n_blocks = s->n_lmblocks;
-    a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_slot = s->d_obs_slot.p;
-    a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.obs_grp = s->d_ogrp.p; a.groups = s->d_groups.p;
+    a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.slot_off = s->d_slot_off.p; a.obs_code = s->d_obs_code.p;
+    a.lm_obs_local = s->d_lm_obs_local.p;
+    a.obs_pose = s->d_opose.p; a.groups = s->d_groups.p;
     if (!s->groups.empty()) a.g0 = s->groups[0];
-    a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.lm_start = s->d_lm_start.p;
     a.obs_u = s->d_ou.p; a.obs_v = s->d_ov.p; a.obs_d = s->d_od.p;
     a.poses = s->d_se3.p; a.pts = s->d_pts.p; a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.dx = s->d_dx.p; a.scalars = s->scalars();
-    if (s->groups.size() == 1) LAUNCH(s, bs::lm_finish_kernel<true>, s->n_lmblocks, bs::kBlkObs, 0, a);
-    else LAUNCH(s, bs::lm_finish_kernel<false>, s->n_lmblocks, bs::kBlkObs, 0, a);
+    switch (s->loss_kind) {
+      case 0: LAUNCH(s, bs::lm_finish_kernel<0>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 1: LAUNCH(s, bs::lm_finish_kernel<1>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 2: LAUNCH(s, bs::lm_finish_kernel<2>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 3: LAUNCH(s, bs::lm_finish_kernel<3>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 4: LAUNCH(s, bs::lm_finish_kernel<4>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 5: LAUNCH(s, bs::lm_finish_kernel<5>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      default: LAUNCH(s, bs::lm_finish_kernel<-1>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+    }
   }
   // tail: landmarks with long tracks (already back-substituted), then everything that is not a landmark block
   if (s->n_lm > s->n_regular) {
@@ -1158,13 +1174,23 @@ int bslam_finalize(bslam_solver* s) {
   for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
 
   // ---- landmark blocks: whole landmarks, <= kBlkObs observations, bounded Schur operands ----
+  // Inside a block the observations are re-ordered SLOT-MAJOR (grouped by pose, constant poses last):
+  // a warp of the block kernels then reads one or two poses (shared-memory broadcasts) and the camera-side
+  // reduction runs over contiguous rows.  lm_obs / lm_obs_local map the landmark-ordered CSR positions
+  // (lm_start) to the observations' new places.
+  const std::vector<int> opose_lm = opose;      // landmark-sorted order (build_tile_mask below)
   std::vector<bs::LmBlock> blocks;
-  std::vector<int> slot_pose;
-  std::vector<unsigned char> cam_perm(N, 0), seg_start, obs_slot(N, 255);
+  std::vector<int> slot_pose, lm_obs(N);
+  std::vector<unsigned char> lm_obs_local(N, 0), seg_start;
+  std::vector<unsigned> obs_code(N, 255u);
+  std::iota(lm_obs.begin(), lm_obs.end(), 0);
   size_t schur_smem = 0;
   {
     int q = 0;
     std::vector<int> cur;                       // distinct variable poses of the block under construction
+    std::vector<int> slot_of, new_pos;
+    std::vector<double> tu, tv, td;
+    std::vector<int> tpose, tpt, tgrp;
     while (q < n_regular) {
       bs::LmBlock b{};
       b.obs_begin = lm_start[q]; b.lm_begin = q;
@@ -1183,23 +1209,43 @@ int bslam_finalize(bslam_solver* s) {
       b.slot_begin = (int)slot_pose.size(); b.seg_begin = (int)seg_start.size();
       slot_pose.insert(slot_pose.end(), cur.begin(), cur.end());
       b.n_slots = (int)cur.size();
+      slot_of.assign(b.n_obs, 255);
       for (int k = 0; k < b.n_obs; ++k) {
         const int pose = opose[b.obs_begin + k];
         if (s->se3_off[pose] < 0) continue;
-        obs_slot[b.obs_begin + k] = (unsigned char)(std::find(cur.begin(), cur.end(), pose) - cur.begin());
+        slot_of[k] = (int)(std::find(cur.begin(), cur.end(), pose) - cur.begin());
       }
+      // new position of every observation (k = landmark-ordered position inside the block)
+      new_pos.assign(b.n_obs, 0);
       int pos = 0;
       for (int sl = 0; sl < b.n_slots; ++sl) {
         seg_start.push_back((unsigned char)pos);
         for (int k = 0; k < b.n_obs; ++k)
-          if (obs_slot[b.obs_begin + k] == sl) cam_perm[b.obs_begin + pos++] = (unsigned char)k;
+          if (slot_of[k] == sl) new_pos[k] = pos++;
       }
       seg_start.push_back((unsigned char)pos);
+      for (int k = 0; k < b.n_obs; ++k)
+        if (slot_of[k] == 255) new_pos[k] = pos++;
+      tu.resize(b.n_obs); tv.resize(b.n_obs); td.resize(b.n_obs); tpose.resize(b.n_obs); tpt.resize(b.n_obs); tgrp.resize(b.n_obs);
+      for (int k = 0; k < b.n_obs; ++k) {
+        const int src = b.obs_begin + k, dst = new_pos[k];
+        tu[dst] = ou[src]; tv[dst] = ov[src]; td[dst] = od[src];
+        tpose[dst] = opose[src]; tpt[dst] = opt[src]; tgrp[dst] = ogrp[src];
+        obs_code[b.obs_begin + dst] = (unsigned)slot_of[k] | ((unsigned)(opt[src] - b.lm_begin) << 8) | ((unsigned)ogrp[src] << 16);
+        lm_obs[src] = b.obs_begin + dst;
+        lm_obs_local[src] = (unsigned char)dst;
+      }
+      for (int k = 0; k < b.n_obs; ++k) {
+        const int dst = b.obs_begin + k;
+        ou[dst] = tu[k]; ov[dst] = tv[k]; od[dst] = td[k]; opose[dst] = tpose[k]; opt[dst] = tpt[k]; ogrp[dst] = tgrp[k];
+      }
       schur_smem = std::max(schur_smem, (size_t)16 * (bs::kSlotRows * b.n_slots + 2) * bs::schur_ldk(b.n_lms));
       blocks.push_back(b);
       q = q1;
     }
   }
+  s->loss_kind = s->groups.size() == 1 ? s->groups[0].loss.kind : -1;
+  NEED(s->groups.size() < 65536, "too many reprojection groups (%zu)", s->groups.size());
   s->schur_smem = schur_smem;
   s->n_regular = n_regular;
   std::vector<int> slot_off(slot_pose.size());
@@ -1254,9 +1300,10 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_lm_start, lm_start, st));
   CU(upload(s->d_blocks, blocks, st));
   CU(upload(s->d_slot_pose, slot_pose, st));
-  CU(upload(s->d_cam_perm, cam_perm, st));
+  CU(upload(s->d_lm_obs, lm_obs, st));
+  CU(upload(s->d_lm_obs_local, lm_obs_local, st));
   CU(upload(s->d_seg_start, seg_start, st));
-  CU(upload(s->d_obs_slot, obs_slot, st));
+  CU(upload(s->d_obs_code, obs_code, st));
   CU(upload(s->d_slot_off, slot_off, st));
   CU(s->d_slot_poses.alloc(12 * slot_pose.size()));
   if (s->schur_smem > 0)   // static + dynamic shared memory may exceed the 48 KB default
@@ -1280,7 +1327,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_dn_col_index, s->dn_col_index, st));
   CU(s->d_dn_J.alloc((size_t)s->dn_j_ptr.back()));
   CU(s->d_dn_e.alloc((size_t)s->dn_row_ptr.back()));
-  CU(s->d_W.alloc(18 * (size_t)N));
+  CU(s->d_W.alloc(bs::w_alloc_len(N)));
   CU(s->d_Vg.alloc(9 * (size_t)s->n_lm));
   CU(s->d_Vinv.alloc(6 * (size_t)s->n_lm));
   CU(s->d_red.alloc(s->red_len()));
@@ -1292,7 +1339,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
   if (N > 0) CU(cudaMemsetAsync(s->d_W.p, 0, s->d_W.n * sizeof(double), st));
   CU(cudaStreamSynchronize(st));
-  build_tile_mask(s, opose, lm_start);
+  build_tile_mask(s, opose_lm, lm_start);
   s->finalized = true;
   s->dn_uploaded = false;
   return BSLAM_OK;
@@ -1521,7 +1568,7 @@ int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
   NEED(s->dim <= 20000, "bslam_get_normal_equations: D = %d too large for a dense export", s->dim);
   CU(cudaSetDevice(s->device));
   const int D = s->dim, n = s->n_red, ld = s->n_pad, N = s->n_obs;
-  std::vector<double> Sd((size_t)ld * ld), W(18 * (size_t)N), Vg(9 * (size_t)s->n_lm);
+  std::vector<double> Sd((size_t)ld * ld), W(bs::w_alloc_len(N)), Vg(9 * (size_t)s->n_lm);
   std::vector<int> opose(N), opt(N);
   CU(cudaMemcpyAsync(Sd.data(), s->S(), Sd.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (n) CU(cudaMemcpyAsync(b, s->rhs(), n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1549,8 +1596,8 @@ int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
     const int o = n + 3 * opt[k];
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 3; ++c) {
-        H[(size_t)(po + r) * D + o + c] += W[(size_t)(3 * r + c) * N + k];
-        H[(size_t)(o + c) * D + po + r] += W[(size_t)(3 * r + c) * N + k];
+        H[(size_t)(po + r) * D + o + c] += W[bs::w_index(k, 3 * r + c)];
+        H[(size_t)(o + c) * D + po + r] += W[bs::w_index(k, 3 * r + c)];
       }
   }
   return BSLAM_OK;
@@ -1579,7 +1626,7 @@ int bslam_covariance(bslam_solver* s, double* cov) {
   if (s->n_lm > 0) {
     bs::CovLmArgs a;
     a.n_lm = s->n_lm; a.n_obs = s->n_obs; a.n_pad = s->n_pad; a.D = D;
-    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.pose_off = s->d_se3_off.p;
+    a.obs_pose = s->d_opose.p; a.lm_start = s->d_lm_start.p; a.lm_obs = s->d_lm_obs.p; a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vinv = s->d_Vinv.p; a.cov = d_cov.p;
     LAUNCH(s, bs::cov_lm_pose_kernel, dim3(cdiv(s->n_pad, 128), 3 * s->n_lm), 128, 0, a);
     LAUNCH(s, bs::cov_lm_lm_kernel, dim3(cdiv(s->n_lm, 128), 3 * s->n_lm), 128, 0, a);
