@@ -30,9 +30,18 @@
 
 namespace bs {
 
-constexpr int kNB = 64;           // tile edge
-constexpr int kLd = 68;           // smem leading dimension (doubles): rows shift by 8 banks
+#ifndef BSLAM_TILE
+#define BSLAM_TILE 32
+#endif
+constexpr int kNB = BSLAM_TILE;   // tile edge (32 or 64).  The factorisation of sparse (trajectory-like) reduced
+                                  // systems is bound by the latency of the pivot chain along the elimination tree's
+                                  // critical path, not by flops: 32-wide supernodes/separators halve that chain.
+constexpr int kLd = kNB + 4;      // smem leading dimension (doubles): rows shift by 8 banks
 constexpr int kCholThreads = 256;
+constexpr int kNB16 = kNB / 16;   // 16x16 blocks per tile edge
+static_assert(kNB == 32 || kNB == 64, "tile edge must be 32 or 64");
+constexpr int kAccMI = kNB / 32;  // 8-row MMA blocks per warp   (warp w: rows (kNB/4) * (w / 2) ...)
+constexpr int kAccNJ = kNB / 16;  // 8-col MMA blocks per warp   (        cols (kNB/2) * (w % 2) ...)
 
 struct CholTask {
   int i, j;        // tile row / column (i == nt: right-hand-side row)
@@ -88,37 +97,37 @@ BS_D void post_flag(int* flag, int epoch) {
   if (threadIdx.x == 0) st_release(flag, epoch);
 }
 
-// 64x64 accumulator of the CTA: 8 warps, warp w owns rows 16*(w/2).., cols 32*(w%2)..
+// kNB x kNB accumulator of the CTA: 8 warps, warp w owns rows (kNB/4)*(w/2).., cols (kNB/2)*(w%2)..
 // m8n8k4 lane mapping: a = A[g][t], b = B[g][t] (B^T operand), c = C[g][2t..2t+1],
 // g = lane/4, t = lane%4.
 struct TileAcc {
-  double c[2][4][2];
+  double c[kAccMI][kAccNJ][2];
 };
 
 BS_D void acc_zero(TileAcc& acc) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kAccMI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc.c[i][j][0] = acc.c[i][j][1] = 0.0;
+    for (int j = 0; j < kAccNJ; ++j) acc.c[i][j][0] = acc.c[i][j][1] = 0.0;
 }
 
-// acc += A(64x64) * B(64x64)^T, both in shared memory (leading dimension kLd)
+// acc += A(kNB x kNB) * B(kNB x kNB)^T, both in shared memory (leading dimension kLd)
 BS_D void tile_mma_abt(const double* __restrict__ sA, const double* __restrict__ sB, TileAcc& acc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const double* pa = sA + (16 * (warp >> 1) + g) * kLd + t;
-  const double* pb = sB + (32 * (warp & 1) + g) * kLd + t;
+  const double* pa = sA + ((kNB / 4) * (warp >> 1) + g) * kLd + t;
+  const double* pb = sB + ((kNB / 2) * (warp & 1) + g) * kLd + t;
 #pragma unroll 4
   for (int k0 = 0; k0 < kNB; k0 += 4) {
-    double a[2], b[4];
+    double a[kAccMI], b[kAccNJ];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) a[i] = pa[8 * i * kLd + k0];
+    for (int i = 0; i < kAccMI; ++i) a[i] = pa[8 * i * kLd + k0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = pb[8 * j * kLd + k0];
+    for (int j = 0; j < kAccNJ; ++j) b[j] = pb[8 * j * kLd + k0];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kAccMI; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dmma_8x8x4(acc.c[i][j][0], acc.c[i][j][1], a[i], b[j]);
+      for (int j = 0; j < kAccNJ; ++j) dmma_8x8x4(acc.c[i][j][0], acc.c[i][j][1], a[i], b[j]);
   }
 }
 
@@ -126,7 +135,7 @@ BS_D void tile_mma_abt(const double* __restrict__ sA, const double* __restrict__
 // L2-coherent loads (ld.global.cg): the data may have been produced by another CTA of this launch.
 BS_D void tile_load(double* __restrict__ s, const double* __restrict__ gsrc, int ld, int nrows) {
   for (int e = threadIdx.x; e < kNB * kNB / 2; e += kCholThreads) {
-    const int r = e >> 5, c2 = (e & 31) << 1;
+    const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
     double2 v = make_double2(0.0, 0.0);
     if (r < nrows) v = __ldcg(reinterpret_cast<const double2*>(gsrc + (size_t)r * ld + c2));
     s[r * kLd + c2] = v.x;
@@ -139,11 +148,11 @@ template <typename F>
 BS_D void acc_foreach(F f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int m0 = 16 * (warp >> 1), n0 = 32 * (warp & 1);
+  const int m0 = (kNB / 4) * (warp >> 1), n0 = (kNB / 2) * (warp & 1);
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < kAccMI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) f(i, j, m0 + 8 * i + g, n0 + 8 * j + 2 * t);
+    for (int j = 0; j < kAccNJ; ++j) f(i, j, m0 + 8 * i + g, n0 + 8 * j + 2 * t);
 }
 
 // ---- 32x32 building blocks of the diagonal-tile factorisation -------------------
@@ -337,7 +346,7 @@ BS_D void gemm16_warp(const double* __restrict__ A, const double* __restrict__ B
     }
 }
 
-// Factorise the 64x64 tile in sA (lower triangle) in place and build X = L^-1 in sX (lower
+// Factorise the kNB x kNB tile in sA (lower triangle) in place and build X = L^-1 in sX (lower
 // triangular, zeros above the diagonal), blocked by 16: per block column a register-resident
 // potrf16 + trtri16 on warp 0, then the panel and trailing updates as one 16x16 DMMA product
 // per warp; the off-diagonal blocks of X follow by block back-substitution.  Returns #bad pivots.
@@ -348,7 +357,7 @@ BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double
   auto Xb = [&](int i, int j) { return sX + (16 * i) * kLd + 16 * j; };
   if (threadIdx.x == 0) *sbad = 0;
   __syncthreads();
-  for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < kNB16; ++b) {
     if (warp == 0) {
       const int bad = potrf16_warp(Ab(b, b), scol, srcp + 16 * b);
       __syncwarp();
@@ -356,22 +365,22 @@ BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double
       if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
     }
     __syncthreads();
-    if (b == 3) break;
+    if (b == kNB16 - 1) break;
     // panel: L_ib = A_ib X_bb^T
-    if (warp < 3 - b) gemm16_warp<true>(Ab(b + 1 + warp, b), Xb(b, b), Ab(b + 1 + warp, b), 1.0, 0.0);
+    if (warp < kNB16 - 1 - b) gemm16_warp<true>(Ab(b + 1 + warp, b), Xb(b, b), Ab(b + 1 + warp, b), 1.0, 0.0);
     __syncthreads();
-    // trailing update: A_ij -= L_ib L_jb^T for b < j <= i <= 3  (at most 6 blocks, one per warp)
+    // trailing update: A_ij -= L_ib L_jb^T for b < j <= i < kNB16  (at most 6 blocks, one per warp)
     {
       int w = 0;
-      for (int i = b + 1; i < 4; ++i)
+      for (int i = b + 1; i < kNB16; ++i)
         for (int j = b + 1; j <= i; ++j, ++w)
           if (w == warp) gemm16_warp<true>(Ab(i, b), Ab(j, b), Ab(i, j), -1.0, 1.0);
     }
     __syncthreads();
   }
   // off-diagonal blocks of X by distance from the diagonal; the mirror block (j, i) is scratch
-  for (int dist = 1; dist < 4; ++dist) {
-    if (warp < 4 - dist) {
+  for (int dist = 1; dist < kNB16; ++dist) {
+    if (warp < kNB16 - dist) {
       const int j = warp, i = warp + dist;
       double* T = Xb(j, i);
       gemm16_warp<false>(Ab(i, j), Xb(j, j), T, 1.0, 0.0);                       // L_ij X_jj
@@ -384,10 +393,9 @@ BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double
     }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < 6 * 256; e += kCholThreads) {                     // zero the scratch (upper blocks)
-    const int blk = e >> 8, r = (e >> 4) & 15, c = e & 15;
-    const int bi = blk < 3 ? 0 : (blk < 5 ? 1 : 2), bj = blk < 3 ? blk + 1 : (blk < 5 ? blk - 1 : 3);
-    Xb(bi, bj)[r * kLd + c] = 0.0;
+  for (int e = threadIdx.x; e < kNB * kNB; e += kCholThreads) {                   // zero the scratch (upper blocks)
+    const int r = e / kNB, c = e % kNB;
+    if ((c >> 4) > (r >> 4)) sX[r * kLd + c] = 0.0;
   }
   __syncthreads();
   return *sbad;
@@ -402,7 +410,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
   double* sB = smem + kNB * kLd;
   double* scol = smem + 2 * kNB * kLd;      // 64
   double* srcp = scol + 64;                 // 64
-  double* sred = srcp + 64;                 // 4 * 64
+  double* sred = srcp + 64;                 // kCholThreads
   __shared__ int s_ticket, s_bad;
   const int tid = threadIdx.x;
   const int nt = p.nt;
@@ -451,7 +459,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         if (bad && tid == 0) red_add(scalars + 3 /*CHOL_FAIL*/, (double)bad);
         double* Lk = Linv + (size_t)tj * kNB * kNB;
         for (int e = tid; e < kNB * kNB; e += kCholThreads) {
-          const int r = e >> 6, c = e & 63;
+          const int r = e / kNB, c = e % kNB;
           if (c <= r) Cij[(size_t)r * ld + c] = sA[r * kLd + c];
           Lk[e] = sB[r * kLd + c];
         }
@@ -471,44 +479,53 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
     } else {
       // ------------------------------------------------ backward substitution, column k
       const int k = nt - 1 - (tk - p.n_tile_tasks);
-      const int c = tid & 63, grp = tid >> 6;        // 4 row groups of 16
+      constexpr int kG = kCholThreads / kNB, kR = kNB / kG;      // row groups, rows per group
+      const int c = tid % kNB, grp = tid / kNB;
       // X_kk rows of this thread, prefetched: x_k[c] = sum_r X_kk[r][c] v[r]
       wait_flag(p.ready + k * nt + k, p.epoch);
-      double xr[16];
+      double xr[kR];
       {
-        const double* X = Linv + (size_t)k * kNB * kNB + (size_t)(16 * grp) * kNB + c;
+        const double* X = Linv + (size_t)k * kNB * kNB + (size_t)(kR * grp) * kNB + c;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) xr[r] = __ldcg(X + (size_t)r * kNB);
+        for (int r = 0; r < kR; ++r) xr[r] = __ldcg(X + (size_t)r * kNB);
       }
       double part = 0.0;
       for (int q = p.bwd_ptr[k]; q < p.bwd_ptr[k + 1]; ++q) {
         const int i = p.bwd_rows[q];
         wait_flag(p.ready + i * nt + k, p.epoch);
-        double lr[16];
-        const double* L = S + (size_t)(i * kNB + 16 * grp) * ld + (size_t)k * kNB + c;
+        double lr[kR];
+        const double* L = S + (size_t)(i * kNB + kR * grp) * ld + (size_t)k * kNB + c;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) lr[r] = __ldcg(L + (size_t)r * ld);
+        for (int r = 0; r < kR; ++r) lr[r] = __ldcg(L + (size_t)r * ld);
         wait_flag(p.xready + i, p.epoch);
-        const double* xi = x + (size_t)i * kNB + 16 * grp;
+        const double* xi = x + (size_t)i * kNB + kR * grp;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) part = fma(lr[r], __ldcg(xi + r), part);
+        for (int r = 0; r < kR; ++r) part = fma(lr[r], __ldcg(xi + r), part);
       }
       wait_flag(p.ready + nt * nt + k, p.epoch);     // y_k (row 0 of the right-hand-side tile)
       if (p.trace && tid == 0) t1 = gtime();
-      sred[grp * 64 + c] = part;
+      sred[grp * kNB + c] = part;
       __syncthreads();
       if (grp == 0) {
         const double y = __ldcg(S + (size_t)nt * kNB * ld + (size_t)k * kNB + c);
-        scol[c] = y - (sred[c] + sred[64 + c] + sred[128 + c] + sred[192 + c]);
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kG; ++q) sum += sred[q * kNB + c];
+        scol[c] = y - sum;
       }
       __syncthreads();
       double v = 0.0;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v = fma(xr[r], scol[16 * grp + r], v);
+      for (int r = 0; r < kR; ++r) v = fma(xr[r], scol[kR * grp + r], v);
       __syncthreads();
-      sred[grp * 64 + c] = v;
+      sred[grp * kNB + c] = v;
       __syncthreads();
-      if (grp == 0) x[(size_t)k * kNB + c] = sred[c] + sred[64 + c] + sred[128 + c] + sred[192 + c];
+      if (grp == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < kG; ++q) sum += sred[q * kNB + c];
+        x[(size_t)k * kNB + c] = sum;
+      }
       post_flag(p.xready + k, p.epoch);
     }
     if (p.trace && tid == 0) {
@@ -520,14 +537,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
   }
 }
 
-constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + 4 * 64) * sizeof(double);
+constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + kCholThreads) * sizeof(double);
 
 // zero the listed 64x64 tiles (tile id = i * nt + j) of S
 __global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S, int ld, int nt, const int* __restrict__ tiles) {
   const int id = tiles[blockIdx.x];
   double* T = S + (size_t)(id / nt) * kNB * ld + (size_t)(id % nt) * kNB;
   for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
-    const int r = e >> 5, c2 = (e & 31) << 1;
+    const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
     *reinterpret_cast<double2*>(T + (size_t)r * ld + c2) = make_double2(0.0, 0.0);
   }
 }
@@ -539,7 +556,7 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(double* __restrict__ S,
   double* T = S + (size_t)(id / nt) * kNB * ld + (size_t)(id % nt) * kNB;
   double* P = pack + (size_t)blockIdx.x * kNB * kNB;
   for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
-    const int r = e >> 5, c2 = (e & 31) << 1;
+    const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
     double2* t2 = reinterpret_cast<double2*>(T + (size_t)r * ld + c2);
     double2* p2 = reinterpret_cast<double2*>(P + 2 * (size_t)e);
     if (unpack) *t2 = *p2;

@@ -12,7 +12,7 @@ namespace bs {
 // shared tile <- global tile, transposed: s[c][r] = g[r][c]
 BS_D void tile_load_t(double* __restrict__ s, const double* __restrict__ gsrc, int ld) {
   for (int e = threadIdx.x; e < kNB * kNB; e += kCholThreads) {
-    const int r = e >> 6, c = e & 63;
+    const int r = e / kNB, c = e % kNB;
     s[c * kLd + r] = __ldcg(gsrc + (size_t)r * ld + c);
   }
 }
