@@ -346,6 +346,50 @@ BS_D void gemm16_warp(const double* __restrict__ A, const double* __restrict__ B
     }
 }
 
+// Cholesky AND inverse of the 16x16 block at `s` in one pass of ONE warp.  Lanes 0..15 hold the rows of A
+// (as potrf16_warp); lanes 16..31, idle there, hold the columns of X = L^-1 as right-hand sides e_c of
+// L x = e_c: the column-j update  v[c] -= l * L[c][j]  is the same instruction for both halves (l = L[row][j]
+// for a row of A, l = x_j = b[j] / L_jj for a column of X), so the inverse costs no extra latency on the
+// pivot chain.  X goes to sX (lower triangular, zeros above the diagonal); 1/L_jj to srcp.
+BS_D int potrf16_inv_warp(double* __restrict__ s, double* __restrict__ sX, double* __restrict__ scol,
+                          double* __restrict__ srcp) {
+  const int lane = threadIdx.x & 31, row = lane & 15;
+  const bool hi = lane >= 16;
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = hi ? (c == row ? 1.0 : 0.0) : s[row * kLd + c];
+  int bad = 0;
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double r = fast_rsqrt(d);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (!(d > 0.0)) ++bad;
+    const double l = (lane == j) ? d * r : a[j] * r;
+    a[j] = l;
+    if (lane == j) srcp[j] = r;
+    double dn = 0.0, rn = 0.0;
+    if (j + 1 < 16) {
+      dn = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
+      rn = fast_rsqrt(dn);
+    }
+    double* sc = scol + (j & 1) * 16;
+    if (!hi) sc[row] = l;
+    __syncwarp();
+#pragma unroll
+    for (int c = j + 1; c < 16; ++c) a[c] = fma(-l, sc[c], a[c]);
+    d = dn;
+    r = rn;
+  }
+  if (!hi) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s[row * kLd + c] = (c <= row) ? a[c] : 0.0;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) sX[c * kLd + row] = a[c];       // X[c][row]
+  }
+  return bad;
+}
+
 // Factorise the kNB x kNB tile in sA (lower triangle) in place and build X = L^-1 in sX (lower
 // triangular, zeros above the diagonal), blocked by 16: per block column a register-resident
 // potrf16 + trtri16 on warp 0, then the panel and trailing updates as one 16x16 DMMA product
@@ -357,11 +401,36 @@ BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double
   auto Xb = [&](int i, int j) { return sX + (16 * i) * kLd + 16 * j; };
   if (threadIdx.x == 0) *sbad = 0;
   __syncthreads();
+  if constexpr (kNB16 == 2) {
+    // 32x32: everything on the pivot chain runs on warp 0; warp 1 forms T = L10 X00 beside the trailing
+    // update, warp 2 clears the upper block of X.  The upper block (0,1) of A is scratch (never stored).
+    const int lane = threadIdx.x & 31;
+    double* T = Ab(0, 1);
+    if (warp == 0) {
+      const int bad = potrf16_inv_warp(Ab(0, 0), Xb(0, 0), scol, srcp);
+      if (lane == 0 && bad) *sbad += bad;
+      __syncwarp();
+      gemm16_warp<true>(Ab(1, 0), Xb(0, 0), Ab(1, 0), 1.0, 0.0);               // L10 = A10 X00^T
+    } else if (warp == 2) {
+      for (int e = lane; e < 256; e += 32) Xb(0, 1)[(e >> 4) * kLd + (e & 15)] = 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      gemm16_warp<true>(Ab(1, 0), Ab(1, 0), Ab(1, 1), -1.0, 1.0);              // A11 -= L10 L10^T
+      __syncwarp();
+      const int bad = potrf16_inv_warp(Ab(1, 1), Xb(1, 1), scol, srcp + 16);
+      if (lane == 0 && bad) *sbad += bad;
+    } else if (warp == 1) {
+      gemm16_warp<false>(Ab(1, 0), Xb(0, 0), T, 1.0, 0.0);                     // T = L10 X00
+    }
+    __syncthreads();
+    if (warp == 0) gemm16_warp<false>(Xb(1, 1), T, Xb(1, 0), -1.0, 0.0);       // X10 = -X11 T
+    __syncthreads();
+    return *sbad;
+  } else {
   for (int b = 0; b < kNB16; ++b) {
     if (warp == 0) {
-      const int bad = potrf16_warp(Ab(b, b), scol, srcp + 16 * b);
-      __syncwarp();
-      trtri16_warp(Ab(b, b), srcp + 16 * b, Xb(b, b));
+      const int bad = potrf16_inv_warp(Ab(b, b), Xb(b, b), scol, srcp + 16 * b);
       if ((threadIdx.x & 31) == 0 && bad) *sbad += bad;
     }
     __syncthreads();
@@ -399,6 +468,7 @@ BS_D int tile_potrf_inv(double* __restrict__ sA, double* __restrict__ sX, double
   }
   __syncthreads();
   return *sbad;
+  }
 }
 
 // ---- the persistent kernel ---------------------------------------------------------

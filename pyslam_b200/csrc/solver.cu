@@ -474,6 +474,30 @@ int build_chol_plan(bslam_solver* s) {
       t.kend = (int)klist.size();
       tasks.push_back(t);
     }
+  // Ticket order = dependency LEVEL (longest chain of producer tiles below the task), not column order:
+  // with nested dissection the leaves of all subtrees sit at scattered column indices, and a CTA that
+  // holds an early ticket for a task high in the tree would only spin while ready leaves wait for a CTA.
+  // Any topological order keeps the no-deadlock argument (a waiting CTA waits on earlier tickets only).
+  {
+    std::vector<int> tix((size_t)(nt + 1) * nt, -1), level(tasks.size(), 0), order(tasks.size());
+    for (size_t t = 0; t < tasks.size(); ++t) tix[(size_t)tasks[t].i * nt + tasks[t].j] = (int)t;
+    for (size_t t = 0; t < tasks.size(); ++t) {          // column-major: producers come first
+      const bs::CholTask& T = tasks[t];
+      int lv = 0;
+      for (int kk = T.kbeg; kk < T.kend; ++kk) {
+        const int k = klist[kk];
+        lv = std::max(lv, level[tix[(size_t)T.i * nt + k]] + 1);
+        lv = std::max(lv, level[tix[(size_t)T.j * nt + k]] + 1);
+      }
+      if (T.i != T.j) lv = std::max(lv, level[tix[(size_t)T.j * nt + T.j]] + 1);
+      level[t] = lv;
+    }
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
+    std::vector<bs::CholTask> sorted(tasks.size());
+    for (size_t t = 0; t < tasks.size(); ++t) sorted[t] = tasks[order[t]];
+    tasks.swap(sorted);
+  }
   for (int k = 0; k < nt; ++k) {
     for (int i = nt - 1; i > k; --i)
       if (at(i, k)) bwd_rows.push_back(i);
