@@ -57,8 +57,8 @@ struct CholPlan {
   const int* bwd_rows;   // rows i > k with a non-zero tile (i,k), descending
   int* ready;            // [(nt+1)*nt] epoch flags: tile final
   int* xready;           // [nt]       epoch flags: x_k final
-  int* ticket;
-  int epoch;
+  int* ticket;           // [0] ticket counter, [1] epoch of the last completed launch, [2] CTAs finished
+                         // (the last CTA to finish resets [0], [2] and advances [1]: no memsets between launches)
   long long* trace;      // optional [n_tasks][4]: start, dependencies satisfied, end (globaltimer ns), SM id
 };
 
@@ -481,9 +481,12 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
   double* scol = smem + 2 * kNB * kLd;      // 64
   double* srcp = scol + 64;                 // 64
   double* sred = srcp + 64;                 // kCholThreads
-  __shared__ int s_ticket, s_bad;
+  __shared__ int s_ticket, s_bad, s_epoch;
   const int tid = threadIdx.x;
   const int nt = p.nt;
+  if (tid == 0) s_epoch = ld_acquire(p.ticket + 1) + 1;
+  __syncthreads();
+  const int epoch = s_epoch;        // flags equal to this value are "ready" in this launch
 
   for (;;) {
     __syncthreads();
@@ -503,9 +506,10 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       acc_zero(acc);
       for (int kk = task.kbeg; kk < task.kend; ++kk) {
         const int k = p.klist[kk];
-        if (tid == 0) {
-          while (ld_acquire(p.ready + ti * nt + k) != p.epoch) __nanosleep(20);
-          while (ld_acquire(p.ready + tj * nt + k) != p.epoch) __nanosleep(20);
+        if (tid == 0) {                    // the two producers are polled by two warps at once
+          while (ld_acquire(p.ready + ti * nt + k) != epoch) __nanosleep(20);
+        } else if (tid == 32) {
+          while (ld_acquire(p.ready + tj * nt + k) != epoch) __nanosleep(20);
         }
         __syncthreads();   // also protects sA/sB of the previous round
         tile_load(sA, S + (size_t)ti * kNB * ld + (size_t)k * kNB, ld, rows_i);
@@ -534,7 +538,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
           Lk[e] = sB[r * kLd + c];
         }
       } else {
-        wait_flag(p.ready + tj * nt + tj, p.epoch);
+        wait_flag(p.ready + tj * nt + tj, epoch);
         if (p.trace && tid == 0) t1 = gtime();
         tile_load(sB, Linv + (size_t)tj * kNB * kNB, kNB, kNB);
         __syncthreads();
@@ -545,14 +549,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
             *reinterpret_cast<double2*>(Cij + (size_t)r * ld + c) = make_double2(acc.c[i][j][0], acc.c[i][j][1]);
         });
       }
-      post_flag(p.ready + ti * nt + tj, p.epoch);
+      post_flag(p.ready + ti * nt + tj, epoch);
     } else {
       // ------------------------------------------------ backward substitution, column k
       const int k = nt - 1 - (tk - p.n_tile_tasks);
       constexpr int kG = kCholThreads / kNB, kR = kNB / kG;      // row groups, rows per group
       const int c = tid % kNB, grp = tid / kNB;
       // X_kk rows of this thread, prefetched: x_k[c] = sum_r X_kk[r][c] v[r]
-      wait_flag(p.ready + k * nt + k, p.epoch);
+      wait_flag(p.ready + k * nt + k, epoch);
       double xr[kR];
       {
         const double* X = Linv + (size_t)k * kNB * kNB + (size_t)(kR * grp) * kNB + c;
@@ -562,17 +566,17 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       double part = 0.0;
       for (int q = p.bwd_ptr[k]; q < p.bwd_ptr[k + 1]; ++q) {
         const int i = p.bwd_rows[q];
-        wait_flag(p.ready + i * nt + k, p.epoch);
+        wait_flag(p.ready + i * nt + k, epoch);
         double lr[kR];
         const double* L = S + (size_t)(i * kNB + kR * grp) * ld + (size_t)k * kNB + c;
 #pragma unroll
         for (int r = 0; r < kR; ++r) lr[r] = __ldcg(L + (size_t)r * ld);
-        wait_flag(p.xready + i, p.epoch);
+        wait_flag(p.xready + i, epoch);
         const double* xi = x + (size_t)i * kNB + kR * grp;
 #pragma unroll
         for (int r = 0; r < kR; ++r) part = fma(lr[r], __ldcg(xi + r), part);
       }
-      wait_flag(p.ready + nt * nt + k, p.epoch);     // y_k (row 0 of the right-hand-side tile)
+      wait_flag(p.ready + nt * nt + k, epoch);     // y_k (row 0 of the right-hand-side tile)
       if (p.trace && tid == 0) t1 = gtime();
       sred[grp * kNB + c] = part;
       __syncthreads();
@@ -596,13 +600,23 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         for (int q = 0; q < kG; ++q) sum += sred[q * kNB + c];
         x[(size_t)k * kNB + c] = sum;
       }
-      post_flag(p.xready + k, p.epoch);
+      post_flag(p.xready + k, epoch);
     }
     if (p.trace && tid == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
       long long* tr = p.trace + 4 * (size_t)tk;
       tr[0] = t0; tr[1] = t1; tr[2] = gtime(); tr[3] = smid;
+    }
+  }
+  // the last CTA out re-arms the control block for the next launch
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.ticket + 2, 1) == (int)gridDim.x - 1) {
+      p.ticket[0] = 0;
+      p.ticket[2] = 0;
+      __threadfence();
+      st_release(p.ticket + 1, epoch);
     }
   }
 }
@@ -617,6 +631,42 @@ __global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S,
     const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
     *reinterpret_cast<double2*>(T + (size_t)r * ld + c2) = make_double2(0.0, 0.0);
   }
+}
+
+// Everything a linearisation needs cleared or refreshed, in ONE launch (each dependent launch inside the
+// iteration's CUDA graph costs 2-3 us of latency):
+//   blocks [0, n_tiles)   zero the structurally non-zero tiles; diagonal tiles get 1.0 on padding entries
+//   remaining blocks      zero rhs | scalars, zero the V/b_p accumulators of long-track landmarks,
+//                         gather the slot poses  slot_poses[e] = poses[slot_pose[e]]
+struct PrepareArgs {
+  double* S; int ld, nt, n_tiles;
+  const int* tiles;
+  const unsigned char* used;        // [n_pad] 1: a real unknown, 0: padding
+  double* rhs; int n_rhs;           // rhs | scalars, contiguous
+  double* vg_tail; int n_vg_tail;
+  int n_slot_entries;
+  const int* slot_pose;
+  const double* poses;
+  double* slot_poses;
+};
+__global__ void __launch_bounds__(256) prepare_kernel(const PrepareArgs a) {
+  if ((int)blockIdx.x < a.n_tiles) {
+    const int id = a.tiles[blockIdx.x];
+    const int ti = id / a.nt, tj = id % a.nt;
+    double* T = a.S + (size_t)ti * kNB * a.ld + (size_t)tj * kNB;
+    for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
+      const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
+      double2 v = make_double2(0.0, 0.0);
+      if (ti == tj && (r >> 1) == (c2 >> 1) && !a.used[ti * kNB + r]) { if (r & 1) v.y = 1.0; else v.x = 1.0; }
+      *reinterpret_cast<double2*>(T + (size_t)r * a.ld + c2) = v;
+    }
+    return;
+  }
+  const int nb = gridDim.x - a.n_tiles;
+  const int t0 = (blockIdx.x - a.n_tiles) * 256 + threadIdx.x, stride = nb * 256;
+  for (int e = t0; e < a.n_rhs; e += stride) a.rhs[e] = 0.0;
+  for (int e = t0; e < a.n_vg_tail; e += stride) a.vg_tail[e] = 0.0;
+  for (int e = t0; e < 12 * a.n_slot_entries; e += stride) a.slot_poses[e] = a.poses[12 * (size_t)a.slot_pose[e / 12] + e % 12];
 }
 
 // gather (unpack == 0) / scatter (unpack != 0) the listed tiles between S and a contiguous buffer

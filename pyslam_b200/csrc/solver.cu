@@ -102,6 +102,7 @@ struct bslam_solver {
   // ---- layout ----
   int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0, n_pads = 0;
   DevBuf<int> d_pad_idx;
+  DevBuf<unsigned char> d_used;                      // [n_pad] 1: real unknown, 0: padding entry of the reduced system
   std::vector<int> pt_perm, pt_iperm;               // user -> internal, internal -> user
   std::vector<int> se3_off, se2_off, vec_off, pt_off_user, vec_entry_off, pt_red_entry_off;
 
@@ -329,17 +330,19 @@ int do_linearize(bslam_solver* s) {
   if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
   // zero only what the iteration dirties: the structurally non-zero tiles (after fill-in), rhs, scalars;
   // the rest of S was zeroed at finalize and is never written
-  if (s->n_dirty_tiles > 0)
-    LAUNCH(s, bs::zero_tiles_kernel, s->n_dirty_tiles, 256, 0, s->S(), s->n_pad, s->nblk, s->d_dirty_tiles.p);
-  CU(cudaMemsetAsync(s->rhs(), 0, (s->n_pad + BSLAM_N_SCALARS) * sizeof(double), s->stream));
-  if (s->n_lm > s->n_regular)
-    CU(cudaMemsetAsync(s->d_Vg.p + 9 * (size_t)s->n_regular, 0, 9 * (size_t)(s->n_lm - s->n_regular) * sizeof(double), s->stream));
-  if (s->n_pads > 0)
-    LAUNCH(s, bs::pad_diag_kernel, cdiv(s->n_pads, 128), 128, 0, s->S(), s->n_pad, s->d_pad_idx.p, s->n_pads);
+  {
+    bs::PrepareArgs a;
+    a.S = s->S(); a.ld = s->n_pad; a.nt = s->nblk; a.n_tiles = s->n_dirty_tiles; a.tiles = s->d_dirty_tiles.p;
+    a.used = s->d_used.p;
+    a.rhs = s->rhs(); a.n_rhs = s->n_pad + BSLAM_N_SCALARS;
+    a.vg_tail = s->d_Vg.p + 9 * (size_t)s->n_regular; a.n_vg_tail = 9 * (s->n_lm - s->n_regular);
+    a.n_slot_entries = s->n_lmblocks > 0 ? s->n_slot_entries : 0;
+    a.slot_pose = s->d_slot_pose.p; a.poses = s->d_se3.p; a.slot_poses = s->d_slot_poses.p;
+    const int work = std::max(std::max(a.n_rhs, a.n_vg_tail), 12 * a.n_slot_entries);
+    LAUNCH(s, bs::prepare_kernel, s->n_dirty_tiles + std::max(1, std::min(cdiv(work, 256), 148)), 256, 0, a);
+  }
   record(s, 1);
   if (s->n_lmblocks > 0) {
-    LAUNCH(s, bs::gather_slot_poses_kernel, cdiv(12LL * s->n_slot_entries, 256), 256, 0, s->n_slot_entries, s->d_slot_pose.p,
-           s->d_se3.p, s->d_slot_poses.p);
     const int grid = std::min(s->n_lmblocks, 148 * 5);      // persistent CTAs, 5 resident per SM
     const size_t smem = 2 * (size_t)s->stage_len * sizeof(double);
     const bs::ReprojArgs ra = reproj_args(s);
@@ -492,6 +495,13 @@ int build_chol_plan(bslam_solver* s) {
       if (T.i != T.j) lv = std::max(lv, level[tix[(size_t)T.j * nt + T.j]] + 1);
       level[t] = lv;
     }
+    // inside a task, consume the producer tiles in the order they become available (lowest level first), so
+    // that only one accumulation step is left when the last producer arrives
+    for (size_t t = 0; t < tasks.size(); ++t) {
+      const bs::CholTask& T = tasks[t];
+      auto key = [&](int k) { return std::max(level[tix[(size_t)T.i * nt + k]], level[tix[(size_t)T.j * nt + k]]); };
+      std::stable_sort(klist.begin() + T.kbeg, klist.begin() + T.kend, [&](int x, int y) { return key(x) < key(y); });
+    }
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
     std::vector<bs::CholTask> sorted(tasks.size());
@@ -532,7 +542,8 @@ int build_chol_plan(bslam_solver* s) {
   CU(upload(s->d_bwd_rows, bwd_rows, st));
   CU(s->d_ready.alloc((size_t)(nt + 1) * nt));
   CU(s->d_xready.alloc(nt));
-  CU(s->d_ticket.alloc(1));
+  CU(s->d_ticket.alloc(4));                     // [ticket, epoch of the last completed launch, CTAs done]
+  CU(cudaMemsetAsync(s->d_ticket.p, 0, 4 * sizeof(int), st));
   CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), st));
   CU(cudaMemsetAsync(s->d_xready.p, 0, s->d_xready.n * sizeof(int), st));
   s->chol_epoch = 0;
@@ -555,11 +566,8 @@ int do_solve_reduced(bslam_solver* s) {
   p.n_tile_tasks = s->n_tile_tasks;
   p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
-  p.epoch = 1;
   p.trace = s->d_trace.p;
-  CU(cudaMemsetAsync(s->d_ticket.p, 0, sizeof(int), s->stream));
-  CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), s->stream));
-  CU(cudaMemsetAsync(s->d_xready.p, 0, s->d_xready.n * sizeof(int), s->stream));
+  // no per-launch memsets: the flags carry the launch epoch, which the kernel advances itself
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
          s->d_dx.p, s->scalars(), p);
   record(s, 5);
@@ -1315,6 +1323,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(s->d_stage.alloc(3 * (size_t)s->n_pt));
   CU(upload(s->d_pt_perm, s->pt_perm, st));
   CU(upload(s->d_pad_idx, pad_idx, st));
+  CU(upload(s->d_used, used, st));
   CU(upload(s->d_se3_off, s->se3_off, st));
   CU(upload(s->d_se2_off, s->se2_off, st));
   CU(upload(s->d_vec_entry_off, s->vec_entry_off, st));
