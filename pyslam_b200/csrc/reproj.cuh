@@ -87,7 +87,7 @@ struct ReprojArgs {
 
 constexpr int kBlkObs = 128;      // observations per landmark block = threads per CTA
 constexpr int kMaxTrack = 64;     // longer tracks go through the generic (atomic) kernels
-constexpr int kSchurCap = 768;    // n_slots * ldk cap of a multi-landmark block (96 KB of Schur operands)
+
 constexpr int kRow = 38;          // 27 camera + 9 landmark values + 2 pad: 16-byte aligned rows whose 128-bit
                                   // stores are bank-conflict free (row stride = 12 banks mod 32)
 

@@ -58,6 +58,13 @@ struct SchurArgs {
   double* __restrict__ S;
   int ldS;
   double* __restrict__ rhs;
+  // static structure of the block kernel (built at finalize)
+  const int* __restrict__ slot_off;         // reduced offset per slot entry
+  const int* __restrict__ pair_ptr;         // [n_blocks + 1] into pairs[]
+  const int* __restrict__ combo_ptr;        // [n_blocks + 1] into combos[]
+  const struct SchurPair* __restrict__ pairs;
+  const unsigned* __restrict__ combos;      // runs: row observation | col observation << 8 | length << 16 (block-local)
+  int max_lms, max_pairs;                   // shared-memory carve-up
 };
 
 // One thread per observation i: Y_i = W_i V^-1, then for every observation j of
@@ -107,36 +114,54 @@ __global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
 
 
 // ---- fast path: one CTA per landmark block, Schur products on the fp64 tensor cores ----
-// For the block's landmarks l and pose slots a the CTA builds two zero-padded operand
-// matrices in shared memory (8 rows per slot, K = 3*l + c):
-//     Yt[8a + r][K] = (W_{l,a} V_l^-1)[r][c]      Wt[8a + r][K] = W_{l,a}[r][c]
-// so that for every slot pair   S(a,b) -= sum_K Yt[8a+.][K] Wt[8b+.][K]   is a
-// chain of mma.sync.m8n8k4.f64; one fp64 atomic per output element leaves the CTA
-// (instead of one per landmark and element).  b_c -= Y b_p rides along as a mat-vec.
-constexpr int kSlotRows = 6;        // rows per slot; MMA fragments read 8 rows, rows 6-7 only feed discarded outputs
-BS_HD int schur_ldk(int n_lms) {              // row stride: >= 3*n_lms (+pad), = 4 mod 16 -> conflict-free fragments
-  return ((3 * n_lms + 3 + 11) / 16) * 16 + 4;
+// A landmark l seen by the poses (slots) a, b of its block contributes  S(a,b) -= Y_{l,a} W_{l,b}^T  with
+// Y = W V_l^-1 (6x3).  The list of all such (observation of a, observation of b) "combos" is static: it is
+// built once at finalize, grouped by slot pair, so a warp that owns a slot pair walks its combos and chains
+// ONE mma.sync.m8n8k4.f64 per combo (rows = the 6 rows of Y, columns = the 6 rows of W, K = 3 of 4) into a
+// register accumulator; one fp64 atomic per element of the 6x6 block leaves the SM per slot pair.
+// b_c -= Y b_p rides along for free on the diagonal pairs: column 6 of the W operand holds b_p.
+// Operands live in shared memory in MMA-fragment order, so a fragment load is one conflict-free LDS.64
+// at  lane offset + observation * stride:
+//     sY[o][3 r + c]           (stride 18; the K = 3 lane reads the next row's entry, times a zero of W)
+//     sW[o][4 r + c], c = 3: 0, r = 6: b_p                     (stride 30: conflict-free 16-byte stores)
+// Combos of a slot pair are stored as RUNS (row observation o, col observation o', length n) meaning the
+// combos (o, o'), (o+1, o'+1), ...: the observations of a slot are sorted by landmark, so the landmarks two
+// poses share are usually consecutive in both lists and a pair is one run; the fragment addresses of a run
+// advance by constant strides, i.e. the inner loop is two LDS.64 at immediate offsets and one DMMA per combo.
+struct SchurPair { unsigned slots_n; int rbeg; };   // row slot | col slot << 8 | #runs << 16;  first run (block-relative)
+constexpr int kYS = 18, kWS = 30;
+BS_HD size_t schur_smem_bytes(int max_lms, int max_pairs, int max_combos) {
+  return sizeof(double) * ((size_t)kBlkObs * kYS + 8 + (size_t)kBlkObs * kWS + 8 + 9 * (size_t)max_lms) +
+         sizeof(SchurPair) * (size_t)max_pairs + sizeof(unsigned) * (size_t)max_combos;
 }
 
-__global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a) {
-  extern __shared__ double sm[];
-  __shared__ double sVinv[6 * kBlkObs];
-  __shared__ double sG[3 * kBlkObs + 8];
+__global__ void __launch_bounds__(kBlkObs, 4) schur_block_kernel(const SchurArgs a) {
+  extern __shared__ __align__(16) double sm[];
   __shared__ int sOff[kBlkObs];          // reduced offset of every slot's pose
-  const int tid = threadIdx.x;
+  double* sY = sm;
+  double* sW = sY + kBlkObs * kYS + 8;
+  double* sVinv = sW + kBlkObs * kWS + 8;
+  double* sG = sVinv + 6 * a.max_lms;
+  SchurPair* sPair = reinterpret_cast<SchurPair*>(sG + 3 * a.max_lms);
+  unsigned* sRun = reinterpret_cast<unsigned*>(sPair + a.max_pairs);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const LmBlock blk = a.blocks[blockIdx.x];
-  const int ldk = schur_ldk(blk.n_lms);
-  const int rows = kSlotRows * blk.n_slots + 2;     // +2: the last slot's fragment rows 6-7
-  double* Yt = sm;
-  double* Wt = sm + (size_t)rows * ldk;
+  const int p0 = a.pair_ptr[blockIdx.x], n_pairs = a.pair_ptr[blockIdx.x + 1] - p0;
+  const int c0g = a.combo_ptr[blockIdx.x], n_combos = a.combo_ptr[blockIdx.x + 1] - c0g;
 
-  // zero the operands (pairs (slot, landmark) without an observation contribute nothing)
-  {
-    double2* z = reinterpret_cast<double2*>(sm);
-    const int n2 = rows * ldk;            // 2 * rows * ldk doubles = rows*ldk double2
-    for (int e = tid; e < n2; e += kBlkObs) z[e] = make_double2(0.0, 0.0);
+  // ---- everything this block reads from global memory is requested up front
+  unsigned code = 255u;
+  double w18[18];
+  if (tid < blk.n_obs) {
+    const int i = blk.obs_begin + tid;
+    code = ld_stream(a.obs_code + i);
+    const double* Wp = a.W + w_pair_base(i);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
   }
-  for (int e = tid; e < blk.n_slots; e += kBlkObs) sOff[e] = a.pose_off[a.slot_pose[blk.slot_begin + e]];
+  for (int e = tid; e < blk.n_slots; e += kBlkObs) sOff[e] = a.slot_off[blk.slot_begin + e];
+  for (int e = tid; e < n_pairs; e += kBlkObs) sPair[e] = a.pairs[p0 + e];
+  for (int e = tid; e < n_combos; e += kBlkObs) sRun[e] = a.combos[c0g + e];
   // V^-1 and b_p of the block's landmarks
   for (int l = tid; l < blk.n_lms; l += kBlkObs) {
     const int q = blk.lm_begin + l;
@@ -147,71 +172,80 @@ __global__ void __launch_bounds__(kBlkObs) schur_block_kernel(const SchurArgs a)
 #pragma unroll
     for (int k = 0; k < 3; ++k) sG[3 * l + k] = a.Vg[9 * (size_t)q + 6 + k];
   }
+  if (tid < 8) sY[kBlkObs * kYS + tid] = 0.0;
   __syncthreads();
-  if (tid < blk.n_obs) {
-    const int i = blk.obs_begin + tid;
-    const unsigned code = a.obs_code[i];
+  {
     const int sl = code & 255;
     if (sl != 255) {
       const int l = (code >> 8) & 255;
       const double* vi = sVinv + 6 * l;
       const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-      double* yr = Yt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
-      double* wr = Wt + (size_t)(kSlotRows * sl) * ldk + 3 * l;
-      double w18[18];
-      {
-        const double* Wp = a.W + w_pair_base(i);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
-      }
+      double y[18];
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         const double w0 = w18[3 * r], w1 = w18[3 * r + 1], w2 = w18[3 * r + 2];
-        wr[r * ldk] = w0; wr[r * ldk + 1] = w1; wr[r * ldk + 2] = w2;
-        yr[r * ldk] = w0 * m00 + w1 * m01 + w2 * m02;
-        yr[r * ldk + 1] = w0 * m01 + w1 * m11 + w2 * m12;
-        yr[r * ldk + 2] = w0 * m02 + w1 * m12 + w2 * m22;
+        y[3 * r] = w0 * m00 + w1 * m01 + w2 * m02;
+        y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
+        y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
       }
+      double2* yr = reinterpret_cast<double2*>(sY + tid * kYS);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) yr[k] = make_double2(y[2 * k], y[2 * k + 1]);
+      double2* wr = reinterpret_cast<double2*>(sW + tid * kWS);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        wr[2 * r] = make_double2(w18[3 * r], w18[3 * r + 1]);
+        wr[2 * r + 1] = make_double2(w18[3 * r + 2], 0.0);
+      }
+      wr[12] = make_double2(sG[3 * l], sG[3 * l + 1]);
+      wr[13] = make_double2(sG[3 * l + 2], 0.0);
+    } else {
+      sY[tid * kYS] = 0.0;        // read (times zero) by the K = 3 lane of the previous row
     }
   }
   __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
+
+  // ---- slot pairs, dealt round-robin to the warps (sorted by decreasing length at finalize)
   const int g = lane >> 2, t = lane & 3;
-  const int kdim = (3 * blk.n_lms + 3) & ~3;
-  // slot pairs (sa, sb <= sa), dealt round-robin to the 4 warps
-  int pidx = 0;
-  for (int sa = 0; sa < blk.n_slots; ++sa)
-   for (int sb = 0; sb <= sa; ++sb, ++pidx) {
-    if ((pidx & 3) != warp) continue;
-    int oa = sOff[sa], ob = sOff[sb];
-    // rows must belong to the pose with the larger reduced offset (lower triangle)
-    const int ra = oa >= ob ? sa : sb, rb = oa >= ob ? sb : sa;
-    if (oa < ob) { const int tmp = oa; oa = ob; ob = tmp; }
-    const double* pa = Yt + (size_t)(kSlotRows * ra + g) * ldk + t;
-    const double* pb = Wt + (size_t)(kSlotRows * rb + g) * ldk + t;
+  const char* pY = reinterpret_cast<const char*>(sY + 3 * g + t);      // rows 6-7: discarded outputs
+  const char* pW = reinterpret_cast<const char*>(sW + lane);           // 4 n + t == lane
+  const int lane_S = g * a.ldS + 2 * t;
+  for (int p = warp; p < n_pairs; p += kBlkObs / 32) {
+    const SchurPair P = sPair[p];
+    const int n_runs = P.slots_n >> 16;
+    const unsigned* rl = sRun + P.rbeg;
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    int k0 = 0;
-    for (; k0 + 8 <= kdim; k0 += 8) {            // two independent accumulator chains
-      dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
-      dmma_8x8x4(d0, d1, pa[k0 + 4], pb[k0 + 4]);
+    for (int r = 0; r < n_runs; ++r) {
+      const unsigned run = rl[r];
+      const double* ya = reinterpret_cast<const double*>(pY + (run & 255u) * (kYS * 8));
+      const double* wb = reinterpret_cast<const double*>(pW + ((run >> 8) & 255u) * (kWS * 8));
+      int n = run >> 16;
+      for (; n >= 4; n -= 4, ya += 4 * kYS, wb += 4 * kWS) {       // two independent accumulator chains
+        dmma_8x8x4(c0, c1, ya[0], wb[0]);
+        dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
+        dmma_8x8x4(c0, c1, ya[2 * kYS], wb[2 * kWS]);
+        dmma_8x8x4(d0, d1, ya[3 * kYS], wb[3 * kWS]);
+      }
+      if (n & 2) {
+        dmma_8x8x4(c0, c1, ya[0], wb[0]);
+        dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
+        ya += 2 * kYS; wb += 2 * kWS;
+      }
+      if (n & 1) dmma_8x8x4(c0, c1, ya[0], wb[0]);
     }
-    if (k0 < kdim) dmma_8x8x4(c0, c1, pa[k0], pb[k0]);
     c0 += d0; c1 += d1;
-    // C[g][2t], C[g][2t+1] = sum_K Y_ra[g][K] W_rb[2t(+1)][K]
-    if (g < 6 && 2 * t < 6) {
-      const bool diag = (sa == sb);
-      double* Sd = a.S + (size_t)(oa + g) * a.ldS + ob + 2 * t;
-      if (!diag || 2 * t <= g) red_add(Sd, -c0);
-      if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
+    // C[g][2t], C[g][2t+1] = sum Y_row[g][.] W_col[2t(+1)][.]
+    const int oa = sOff[P.slots_n & 255u], ob = sOff[(P.slots_n >> 8) & 255u];
+    const bool diag = oa == ob;
+    if (g < 6) {
+      if (t < 3) {
+        double* Sd = a.S + ((size_t)oa * a.ldS + ob + lane_S);
+        if (!diag || 2 * t <= g) red_add(Sd, -c0);
+        if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
+      } else if (diag) {
+        red_add(a.rhs + oa + g, -c0);             // column 6: Y b_p
+      }
     }
-  }
-  // right-hand side: b_c(slot) -= Y b_p
-  for (int e = tid; e < 6 * blk.n_slots; e += kBlkObs) {
-    const int sl = e / 6, r = e - 6 * sl;
-    const double* y = Yt + (size_t)(kSlotRows * sl + r) * ldk;
-    double acc = 0.0;
-    for (int k = 0; k < 3 * blk.n_lms; ++k) acc += y[k] * sG[k];
-    red_add(a.rhs + sOff[sl] + r, -acc);
   }
 }
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/bslam.h"
@@ -115,6 +116,10 @@ struct bslam_solver {
   // landmark blocks of the fast reprojection / Schur kernels
   int n_lmblocks = 0, tail_begin = 0, n_regular = 0;
   size_t schur_smem = 0;
+  int schur_max_lms = 1, schur_max_pairs = 1;
+  DevBuf<bs::SchurPair> d_sch_pairs;
+  DevBuf<unsigned> d_sch_combos;
+  DevBuf<int> d_sch_pair_ptr, d_sch_combo_ptr;
   DevBuf<unsigned> d_obs_code;                       // slot | block-local landmark << 8 | group << 16
   DevBuf<int> d_slot_off, d_lm_obs;                  // d_lm_obs: CSR position (landmark order) -> observation index
   int loss_kind = -1;                                // loss kind of the single reprojection group, -1: several groups
@@ -392,6 +397,9 @@ int do_reduce(bslam_solver* s, double lambda) {
     a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
+    a.slot_off = s->d_slot_off.p; a.pair_ptr = s->d_sch_pair_ptr.p; a.combo_ptr = s->d_sch_combo_ptr.p;
+    a.pairs = s->d_sch_pairs.p; a.combos = s->d_sch_combos.p;
+    a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs;
     if (s->n_lmblocks > 0) LAUNCH(s, bs::schur_block_kernel, s->n_lmblocks, bs::kBlkObs, s->schur_smem, a);
     if (s->n_lm > s->n_regular) {
       LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm - s->n_regular, 256), 256, 0, s->n_regular, s->n_lm, s->d_Vg.p,
@@ -985,6 +993,16 @@ int bslam_finalize(bslam_solver* s) {
     n_obs_of[s->ob_pt[i]]++;
     first_pose[s->ob_pt[i]] = std::min(first_pose[s->ob_pt[i]], s->ob_pose[i]);
   }
+  // a landmark observed twice by the same pose goes through the generic (atomic) kernels: the block
+  // kernels assume at most one observation per (pose, landmark)
+  std::vector<uint8_t> dup_obs(s->n_pt, 0);
+  {
+    std::vector<std::pair<int, int>> pp(N);
+    for (int i = 0; i < N; ++i) pp[i] = {s->ob_pt[i], s->ob_pose[i]};
+    std::sort(pp.begin(), pp.end());
+    for (int i = 1; i < N; ++i)
+      if (pp[i] == pp[i - 1]) dup_obs[pp[i].first] = 1;
+  }
   std::vector<int> regular, big, rest;
   for (int p = 0; p < s->n_pt; ++p) {
     bool elim = false;
@@ -997,7 +1015,7 @@ int bslam_finalize(bslam_solver* s) {
       elim = by_reproj[p] != 0;
     }
     if (!elim) rest.push_back(p);
-    else if (n_obs_of[p] <= bs::kMaxTrack) regular.push_back(p);
+    else if (n_obs_of[p] <= bs::kMaxTrack && !dup_obs[p]) regular.push_back(p);
     else big.push_back(p);
   }
   std::stable_sort(regular.begin(), regular.end(), [&](int a, int b) { return first_pose[a] < first_pose[b]; });
@@ -1216,7 +1234,10 @@ int bslam_finalize(bslam_solver* s) {
   std::vector<unsigned char> lm_obs_local(N, 0), seg_start;
   std::vector<unsigned> obs_code(N, 255u);
   std::iota(lm_obs.begin(), lm_obs.end(), 0);
-  size_t schur_smem = 0;
+  std::vector<bs::SchurPair> sch_pairs;
+  std::vector<unsigned> sch_combos;             // runs of combos, see schur.cuh
+  std::vector<int> sch_pair_ptr(1, 0), sch_combo_ptr(1, 0);
+  int max_pairs = 1, max_combos = 4, max_lms = 1;
   {
     int q = 0;
     std::vector<int> cur;                       // distinct variable poses of the block under construction
@@ -1233,7 +1254,6 @@ int bslam_finalize(bslam_solver* s) {
         for (int k = lm_start[q1]; k < lm_start[q1 + 1]; ++k)
           if (s->se3_off[opose[k]] >= 0 && std::find(trial.begin(), trial.end(), opose[k]) == trial.end())
             trial.push_back(opose[k]);
-        if (q1 > q && (int)trial.size() * bs::schur_ldk(q1 + 1 - q) > bs::kSchurCap) break;
         cur.swap(trial);
         ++q1;
       }
@@ -1271,14 +1291,59 @@ int bslam_finalize(bslam_solver* s) {
         const int dst = b.obs_begin + k;
         ou[dst] = tu[k]; ov[dst] = tv[k]; od[dst] = td[k]; opose[dst] = tpose[k]; opt[dst] = tpt[k]; ogrp[dst] = tgrp[k];
       }
-      schur_smem = std::max(schur_smem, (size_t)16 * (bs::kSlotRows * b.n_slots + 2) * bs::schur_ldk(b.n_lms));
+      // Schur combos of the block: for every landmark and every unordered pair of its (variable-pose)
+      // observations, (row observation, col observation) with the row pose the one at the larger reduced
+      // offset (lower triangle); grouped by slot pair, longest pairs first (balanced round-robin over warps)
+      {
+        std::map<std::pair<int, int>, std::vector<unsigned short>> by_pair;
+        for (int l = 0; l < b.n_lms; ++l) {
+          const int k0 = lm_start[b.lm_begin + l] - b.obs_begin, k1 = lm_start[b.lm_begin + l + 1] - b.obs_begin;
+          for (int x = k0; x < k1; ++x) {
+            if (slot_of[x] == 255) continue;
+            for (int y = k0; y <= x; ++y) {
+              if (slot_of[y] == 255) continue;
+              int ro = x, co = y;
+              if (s->se3_off[cur[slot_of[ro]]] < s->se3_off[cur[slot_of[co]]]) std::swap(ro, co);
+              by_pair[{slot_of[ro], slot_of[co]}].push_back((unsigned short)(new_pos[ro] | (new_pos[co] << 8)));
+            }
+          }
+        }
+        std::vector<std::pair<std::pair<int, int>, std::vector<unsigned short>>> pv(by_pair.begin(), by_pair.end());
+        std::stable_sort(pv.begin(), pv.end(), [](const auto& x, const auto& y) { return x.second.size() > y.second.size(); });
+        const int cb0 = (int)sch_combos.size();
+        for (auto& e : pv) {
+          // combos -> runs of (row + i, col + i)
+          std::vector<unsigned short>& cl = e.second;
+          std::sort(cl.begin(), cl.end(), [](unsigned short x, unsigned short y) { return (x & 255) != (y & 255) ? (x & 255) < (y & 255) : x < y; });
+          const int rb0 = (int)sch_combos.size();
+          for (size_t k = 0; k < cl.size();) {
+            size_t k2 = k + 1;
+            while (k2 < cl.size() && (cl[k2] & 255) == (cl[k] & 255) + (k2 - k) && (cl[k2] >> 8) == (cl[k] >> 8) + (k2 - k)) ++k2;
+            sch_combos.push_back((unsigned)cl[k] | ((unsigned)(k2 - k) << 16));
+            k = k2;
+          }
+          bs::SchurPair P;
+          P.slots_n = (unsigned)e.first.first | ((unsigned)e.first.second << 8) | ((unsigned)(sch_combos.size() - rb0) << 16);
+          P.rbeg = rb0 - cb0;
+          sch_pairs.push_back(P);
+        }
+        sch_pair_ptr.push_back((int)sch_pairs.size());
+        sch_combo_ptr.push_back((int)sch_combos.size());
+        max_pairs = std::max(max_pairs, (int)pv.size());
+        max_combos = std::max(max_combos, (int)sch_combos.size() - cb0);
+        max_lms = std::max(max_lms, b.n_lms);
+      }
       blocks.push_back(b);
       q = q1;
     }
   }
   s->loss_kind = s->groups.size() == 1 ? s->groups[0].loss.kind : -1;
   NEED(s->groups.size() < 65536, "too many reprojection groups (%zu)", s->groups.size());
-  s->schur_smem = schur_smem;
+  s->schur_smem = blocks.empty() ? 0 : bs::schur_smem_bytes(max_lms, max_pairs, max_combos);
+  s->schur_max_lms = max_lms; s->schur_max_pairs = max_pairs;
+  NEED(s->schur_smem <= 200 * 1024, "landmark block structure needs %zu bytes of shared memory", s->schur_smem);
+  if (sch_pairs.empty()) sch_pairs.push_back(bs::SchurPair{0u, 0});
+  if (sch_combos.empty()) sch_combos.push_back(0);
   s->n_regular = n_regular;
   std::vector<int> slot_off(slot_pose.size());
   for (size_t k = 0; k < slot_pose.size(); ++k) slot_off[k] = s->se3_off[slot_pose[k]];
@@ -1337,8 +1402,25 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_lm_obs_local, lm_obs_local, st));
   CU(upload(s->d_seg_start, seg_start, st));
   CU(upload(s->d_obs_code, obs_code, st));
+  CU(upload(s->d_sch_pairs, sch_pairs, st));
+  CU(upload(s->d_sch_combos, sch_combos, st));
+  CU(upload(s->d_sch_pair_ptr, sch_pair_ptr, st));
+  CU(upload(s->d_sch_combo_ptr, sch_combo_ptr, st));
   CU(upload(s->d_slot_off, slot_off, st));
   CU(s->d_slot_poses.alloc(12 * slot_pose.size()));
+  {                        // blocks with many poses: staging (dynamic) + rows (static) may exceed the 48 KB default
+    const void* fn = nullptr;
+    switch (s->loss_kind) {
+      case 0: fn = (const void*)bs::reproj_block_kernel<0>; break;
+      case 1: fn = (const void*)bs::reproj_block_kernel<1>; break;
+      case 2: fn = (const void*)bs::reproj_block_kernel<2>; break;
+      case 3: fn = (const void*)bs::reproj_block_kernel<3>; break;
+      case 4: fn = (const void*)bs::reproj_block_kernel<4>; break;
+      case 5: fn = (const void*)bs::reproj_block_kernel<5>; break;
+      default: fn = (const void*)bs::reproj_block_kernel<-1>; break;
+    }
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (size_t)s->stage_len * sizeof(double))));
+  }
   if (s->schur_smem > 0)   // static + dynamic shared memory may exceed the 48 KB default
     CU(cudaFuncSetAttribute(bs::schur_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->schur_smem));
   CU(upload(s->d_groups, s->groups, st));
