@@ -504,6 +504,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       const int rows_i = (ti == nt) ? 1 : kNB;
       TileAcc acc;
       acc_zero(acc);
+      // the task's own tile of S is final before the kernel starts: fetch it now, off the dependency chain
+      double* Cij = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
+      TileAcc own;
+      acc_foreach([&](int i, int j, int r, int c) {
+        double2 v = make_double2(0.0, 0.0);
+        if (r < rows_i) v = __ldcg(reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c));
+        own.c[i][j][0] = v.x; own.c[i][j][1] = v.y;
+      });
       for (int kk = task.kbeg; kk < task.kend; ++kk) {
         const int k = p.klist[kk];
         if (tid == 0) {                    // the two producers are polled by two warps at once
@@ -520,12 +528,9 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       __syncthreads();
       if (p.trace && tid == 0) t1 = gtime();
       // C = S_ij - acc  -> sA
-      double* Cij = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
       acc_foreach([&](int i, int j, int r, int c) {
-        double2 v = make_double2(0.0, 0.0);
-        if (r < rows_i) v = *reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c);
-        sA[r * kLd + c] = v.x - acc.c[i][j][0];
-        sA[r * kLd + c + 1] = v.y - acc.c[i][j][1];
+        sA[r * kLd + c] = own.c[i][j][0] - acc.c[i][j][0];
+        sA[r * kLd + c + 1] = own.c[i][j][1] - acc.c[i][j][1];
       });
       __syncthreads();
       if (ti == tj) {

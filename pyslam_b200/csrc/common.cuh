@@ -15,6 +15,19 @@ constexpr double kSmallAngle = 1e-8;   // np.isclose(x, 0.) with default toleran
 // fire-and-forget fp64 reduction into global memory (RED.E.ADD.F64)
 BS_D void red_add(double* addr, double v) { atomicAdd(addr, v); }
 
+// 1/a to within an ulp or two: hardware seed (MUFU.RCP64H) + two Newton steps, ~8 instructions instead of
+// the ~25-instruction IEEE division sequence with its slow-path branch.  a must be finite and non-zero.
+BS_D double fast_rcp(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+  }
+  return y;
+}
+
 BS_D double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,10 +36,10 @@ BS_D double loss_weight(const Loss& L, double x) {
   switch (L.kind) {
     case kL2: return 1.0;
     case kL1: { const double a = fabs(x); return a <= kSmallAngle ? nan("") : 1.0 / a; }
-    case kCauchy: { const double q = x / L.k; return 1.0 / (1.0 + q * q); }
-    case kHuber: { const double a = fabs(x); return a <= L.k ? 1.0 : L.k / a; }
+    case kCauchy: { const double q = x / L.k; return fast_rcp(1.0 + q * q); }
+    case kHuber: { const double a = fabs(x); return a <= L.k ? 1.0 : L.k * fast_rcp(a); }
     case kTukey: { if (fabs(x) <= L.k) { const double q = x / L.k; return 1.0 - q * q; } return 0.0; }
-    default: return (L.k + 1.0) / (L.k + x * x);
+    default: return (L.k + 1.0) * fast_rcp(L.k + x * x);
   }
 }
 

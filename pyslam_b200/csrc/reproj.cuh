@@ -103,7 +103,7 @@ BS_D void reproj_residual_only(const ReprojGroup& g, const double* __restrict__ 
   const double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9];
   const double y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10];
   const double z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
-  const double iz = 1.0 / z;
+  const double iz = fast_rcp(z);
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
   const double e2 = g.fu * g.b * iz - d;
@@ -116,7 +116,7 @@ BS_D void reproj_linearize_one(const ReprojGroup& g, const double* __restrict__ 
   const double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9];
   const double y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10];
   const double z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
-  const double iz = 1.0 / z;
+  const double iz = fast_rcp(z);
   const double iz2 = iz * iz;
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
@@ -169,7 +169,7 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
   const double y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10];
   const double z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
   o.x = x; o.y = y; o.z = z;
-  const double iz = 1.0 / z;
+  const double iz = fast_rcp(z);
   const double iz2 = iz * iz;
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
@@ -260,8 +260,12 @@ __global__ void __launch_bounds__(256) gather_slot_poses_kernel(int n, const int
 //            block's landmark -> observation list); one fp64 atomic per (slot, value) leaves the SM,
 //            V_p / b_p are plain stores.
 // kLoss >= 0: single group with that loss kind (compile time); kLoss < 0: per-observation groups.
+#ifndef BSLAM_REPROJ_CTAS
+#define BSLAM_REPROJ_CTAS 5
+#endif
+constexpr int kReprojCtas = BSLAM_REPROJ_CTAS;     // resident CTAs per SM (register budget = 65536 / (128 * this))
 template <int kLoss>
-__global__ void __launch_bounds__(kBlkObs, 5)
+__global__ void __launch_bounds__(kBlkObs, kReprojCtas)
 reproj_block_kernel(const ReprojArgs a) {
   extern __shared__ __align__(16) double sStage[];    // 2 x stage_len doubles: [slot poses | landmark points]
   __shared__ __align__(16) double sT[kBlkObs * kRow];

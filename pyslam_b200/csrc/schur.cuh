@@ -64,7 +64,8 @@ struct SchurArgs {
   const int* __restrict__ combo_ptr;        // [n_blocks + 1] into combos[]
   const struct SchurPair* __restrict__ pairs;
   const unsigned* __restrict__ combos;      // runs: row observation | col observation << 8 | length << 16 (block-local)
-  int max_lms, max_pairs;                   // shared-memory carve-up
+  const struct SchurDesc* __restrict__ descs;  // [n_blocks]
+  int max_lms, max_pairs, max_runs;         // shared-memory carve-up
 };
 
 // One thread per observation i: Y_i = W_i V^-1, then for every observation j of
@@ -130,123 +131,199 @@ __global__ void __launch_bounds__(128) schur_generic_kernel(const SchurArgs a) {
 // advance by constant strides, i.e. the inner loop is two LDS.64 at immediate offsets and one DMMA per combo.
 struct SchurPair { unsigned slots_n; int rbeg; };   // row slot | col slot << 8 | #runs << 16;  first run (block-relative)
 constexpr int kYS = 18, kWS = 30;
-BS_HD size_t schur_smem_bytes(int max_lms, int max_pairs, int max_combos) {
-  return sizeof(double) * ((size_t)kBlkObs * kYS + 8 + (size_t)kBlkObs * kWS + 8 + 9 * (size_t)max_lms) +
-         sizeof(SchurPair) * (size_t)max_pairs + sizeof(unsigned) * (size_t)max_combos;
+
+// Per-block descriptor of the Schur kernel (48 bytes: three 16-byte cp.async copies into a ring).
+struct SchurDesc {
+  int obs_begin, n_obs, lm_begin, n_lms;
+  int slot_begin, n_slots, pair_begin, n_pairs;
+  int run_begin, n_runs, pad0, pad1;
+};
+
+#ifndef BSLAM_SCHUR_CTAS
+#define BSLAM_SCHUR_CTAS 4
+#endif
+constexpr int kSchurCtas = BSLAM_SCHUR_CTAS;
+// small per-block tables, double-buffered: [slot offsets (int) | pairs | runs]
+BS_HD size_t schur_tab_bytes(int max_pairs, int max_runs) {
+  return ((sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)max_pairs + sizeof(unsigned) * (size_t)max_runs) + 15) & ~(size_t)15;
+}
+BS_HD size_t schur_smem_bytes(int max_lms, int max_pairs, int max_runs) {
+  return sizeof(double) * ((size_t)kBlkObs * kYS + 8 + (size_t)kBlkObs * kWS + 8 + 10 * (size_t)max_lms) +
+         2 * schur_tab_bytes(max_pairs, max_runs);
 }
 
-__global__ void __launch_bounds__(kBlkObs, 4) schur_block_kernel(const SchurArgs a) {
+// Persistent, software-pipelined: a CTA walks blocks b, b + grid, ...  The W tile, the observation codes and
+// the landmark blocks V_p | b_p of block i+1 are requested (into the registers block i has just finished
+// with) before the MMA phase of block i starts, and its small tables arrive by cp.async, so no global
+// load is waited for on the critical path of a block.
+__global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const SchurArgs a) {
   extern __shared__ __align__(16) double sm[];
-  __shared__ int sOff[kBlkObs];          // reduced offset of every slot's pose
+  __shared__ __align__(16) SchurDesc sDesc[3];
   double* sY = sm;
   double* sW = sY + kBlkObs * kYS + 8;
-  double* sVinv = sW + kBlkObs * kWS + 8;
-  double* sG = sVinv + 6 * a.max_lms;
-  SchurPair* sPair = reinterpret_cast<SchurPair*>(sG + 3 * a.max_lms);
-  unsigned* sRun = reinterpret_cast<unsigned*>(sPair + a.max_pairs);
+  double* sVinv = sW + kBlkObs * kWS + 8;           // [6 max_lms]
+  double* sG = sVinv + 6 * a.max_lms;               // [4 max_lms] (padded to pairs)
+  char* sTab = reinterpret_cast<char*>(sG + 4 * a.max_lms);
+  const size_t tab_bytes = schur_tab_bytes(a.max_pairs, a.max_runs);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const LmBlock blk = a.blocks[blockIdx.x];
-  const int p0 = a.pair_ptr[blockIdx.x], n_pairs = a.pair_ptr[blockIdx.x + 1] - p0;
-  const int c0g = a.combo_ptr[blockIdx.x], n_combos = a.combo_ptr[blockIdx.x + 1] - c0g;
+  const int stride = gridDim.x;
+  int b = blockIdx.x;
+  if (b >= a.n_blocks) return;
 
-  // ---- everything this block reads from global memory is requested up front
+  auto tab_off = [&](int buf) { return reinterpret_cast<int*>(sTab + buf * tab_bytes); };
+  auto tab_pair = [&](int buf) { return reinterpret_cast<SchurPair*>(sTab + buf * tab_bytes + sizeof(int) * kBlkObs); };
+  auto tab_run = [&](int buf) {
+    return reinterpret_cast<unsigned*>(sTab + buf * tab_bytes + sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)a.max_pairs);
+  };
+  auto cp_async4 = [&](void* dst, const void* src) {
+    const unsigned s_ = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_), "l"(src) : "memory");
+  };
+  auto fetch_desc = [&](int blk_id, int slot) {
+    if (tid < 3 && blk_id < a.n_blocks)
+      cp_async16(reinterpret_cast<char*>(&sDesc[slot]) + 16 * tid, reinterpret_cast<const char*>(a.descs + blk_id) + 16 * tid);
+  };
+  auto stage_tables = [&](const SchurDesc& d, int buf) {
+    int* so = tab_off(buf); SchurPair* sp = tab_pair(buf); unsigned* sr = tab_run(buf);
+    for (int e = tid; e < d.n_slots; e += kBlkObs) cp_async4(so + e, a.slot_off + d.slot_begin + e);
+    for (int e = tid; e < d.n_pairs; e += kBlkObs) cp_async8(sp + e, a.pairs + d.pair_begin + e);
+    for (int e = tid; e < d.n_runs; e += kBlkObs) cp_async4(sr + e, a.combos + d.run_begin + e);
+  };
   unsigned code = 255u;
   double w18[18];
-  if (tid < blk.n_obs) {
-    const int i = blk.obs_begin + tid;
-    code = ld_stream(a.obs_code + i);
-    const double* Wp = a.W + w_pair_base(i);
+  double vg[9];
+  auto load_inputs = [&](const SchurDesc& d) {
+    code = 255u;
+    if (tid < d.n_obs) {
+      const int i = d.obs_begin + tid;
+      code = ld_stream(a.obs_code + i);
+      const double* Wp = a.W + w_pair_base(i);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
-  }
-  for (int e = tid; e < blk.n_slots; e += kBlkObs) sOff[e] = a.slot_off[blk.slot_begin + e];
-  for (int e = tid; e < n_pairs; e += kBlkObs) sPair[e] = a.pairs[p0 + e];
-  for (int e = tid; e < n_combos; e += kBlkObs) sRun[e] = a.combos[c0g + e];
-  // V^-1 and b_p of the block's landmarks
-  for (int l = tid; l < blk.n_lms; l += kBlkObs) {
-    const int q = blk.lm_begin + l;
-    double vi[6];
-    sym3_inverse(a.Vg + 9 * (size_t)q, a.lambda, vi);
+      for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
+    }
+    if (tid < d.n_lms) {
+      const double* v = a.Vg + 9 * (size_t)(d.lm_begin + tid);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) { sVinv[6 * l + k] = vi[k]; a.Vinv_out[6 * (size_t)q + k] = vi[k]; }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sG[3 * l + k] = a.Vg[9 * (size_t)q + 6 + k];
-  }
+      for (int k = 0; k < 9; ++k) vg[k] = ld_stream(v + k);
+    }
+  };
+
+  // ---- prologue
+  if (tid < 3) reinterpret_cast<int4*>(&sDesc[0])[tid] = reinterpret_cast<const int4*>(a.descs + b)[tid];
   if (tid < 8) sY[kBlkObs * kYS + tid] = 0.0;
   __syncthreads();
-  {
-    const int sl = code & 255;
-    if (sl != 255) {
-      const int l = (code >> 8) & 255;
-      const double* vi = sVinv + 6 * l;
-      const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-      double y[18];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const double w0 = w18[3 * r], w1 = w18[3 * r + 1], w2 = w18[3 * r + 2];
-        y[3 * r] = w0 * m00 + w1 * m01 + w2 * m02;
-        y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
-        y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
-      }
-      double2* yr = reinterpret_cast<double2*>(sY + tid * kYS);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) yr[k] = make_double2(y[2 * k], y[2 * k + 1]);
-      double2* wr = reinterpret_cast<double2*>(sW + tid * kWS);
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        wr[2 * r] = make_double2(w18[3 * r], w18[3 * r + 1]);
-        wr[2 * r + 1] = make_double2(w18[3 * r + 2], 0.0);
-      }
-      wr[12] = make_double2(sG[3 * l], sG[3 * l + 1]);
-      wr[13] = make_double2(sG[3 * l + 2], 0.0);
-    } else {
-      sY[tid * kYS] = 0.0;        // read (times zero) by the K = 3 lane of the previous row
-    }
-  }
-  __syncthreads();
+  SchurDesc blk = sDesc[0];
+  fetch_desc(b + stride, 1);
+  fetch_desc(b + 2 * stride, 2);
+  stage_tables(blk, 0);
+  cp_async_commit();
+  load_inputs(blk);
 
-  // ---- slot pairs, dealt round-robin to the warps (sorted by decreasing length at finalize)
   const int g = lane >> 2, t = lane & 3;
   const char* pY = reinterpret_cast<const char*>(sY + 3 * g + t);      // rows 6-7: discarded outputs
   const char* pW = reinterpret_cast<const char*>(sW + lane);           // 4 n + t == lane
   const int lane_S = g * a.ldS + 2 * t;
-  for (int p = warp; p < n_pairs; p += kBlkObs / 32) {
-    const SchurPair P = sPair[p];
-    const int n_runs = P.slots_n >> 16;
-    const unsigned* rl = sRun + P.rbeg;
-    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    for (int r = 0; r < n_runs; ++r) {
-      const unsigned run = rl[r];
-      const double* ya = reinterpret_cast<const double*>(pY + (run & 255u) * (kYS * 8));
-      const double* wb = reinterpret_cast<const double*>(pW + ((run >> 8) & 255u) * (kWS * 8));
-      int n = run >> 16;
-      for (; n >= 4; n -= 4, ya += 4 * kYS, wb += 4 * kWS) {       // two independent accumulator chains
-        dmma_8x8x4(c0, c1, ya[0], wb[0]);
-        dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
-        dmma_8x8x4(c0, c1, ya[2 * kYS], wb[2 * kWS]);
-        dmma_8x8x4(d0, d1, ya[3 * kYS], wb[3 * kWS]);
-      }
-      if (n & 2) {
-        dmma_8x8x4(c0, c1, ya[0], wb[0]);
-        dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
-        ya += 2 * kYS; wb += 2 * kWS;
-      }
-      if (n & 1) dmma_8x8x4(c0, c1, ya[0], wb[0]);
+  int it = 0;
+  for (;;) {
+    const int buf = it & 1;
+    const int bn = b + stride;
+    const bool has_next = bn < a.n_blocks;
+    // ---- phase A1: V^-1 and b_p of the block's landmarks (one thread each; blocks hold <= 128 landmarks)
+    if (tid < blk.n_lms) {
+      double vi[6];
+      sym3_inverse(vg, a.lambda, vi);
+      const int q = blk.lm_begin + tid;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { sVinv[6 * tid + k] = vi[k]; a.Vinv_out[6 * (size_t)q + k] = vi[k]; }
+      sG[4 * tid] = vg[6]; sG[4 * tid + 1] = vg[7]; sG[4 * tid + 2] = vg[8]; sG[4 * tid + 3] = 0.0;
     }
-    c0 += d0; c1 += d1;
-    // C[g][2t], C[g][2t+1] = sum Y_row[g][.] W_col[2t(+1)][.]
-    const int oa = sOff[P.slots_n & 255u], ob = sOff[(P.slots_n >> 8) & 255u];
-    const bool diag = oa == ob;
-    if (g < 6) {
-      if (t < 3) {
-        double* Sd = a.S + ((size_t)oa * a.ldS + ob + lane_S);
-        if (!diag || 2 * t <= g) red_add(Sd, -c0);
-        if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
-      } else if (diag) {
-        red_add(a.rhs + oa + g, -c0);             // column 6: Y b_p
+    cp_async_wait_all();
+    __syncthreads();               // V^-1 visible; tables of this block and the next descriptor have landed;
+                                   // the MMA phase of the previous block is over (sY / sW are free)
+    // ---- phase A2: operands of this block
+    {
+      const int sl = code & 255;
+      if (sl != 255) {
+        const int l = (code >> 8) & 255;
+        const double* vi = sVinv + 6 * l;
+        const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
+        double2* yr = reinterpret_cast<double2*>(sY + tid * kYS);
+        double2* wr = reinterpret_cast<double2*>(sW + tid * kWS);
+        double y[18];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double w0 = w18[3 * r], w1 = w18[3 * r + 1], w2 = w18[3 * r + 2];
+          y[3 * r] = w0 * m00 + w1 * m01 + w2 * m02;
+          y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
+          y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
+          wr[2 * r] = make_double2(w0, w1);
+          wr[2 * r + 1] = make_double2(w2, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) yr[k] = make_double2(y[2 * k], y[2 * k + 1]);
+        const double2* gl = reinterpret_cast<const double2*>(sG + 4 * l);
+        wr[12] = gl[0];
+        wr[13] = gl[1];
+      } else {
+        sY[tid * kYS] = 0.0;        // read (times zero) by the K = 3 lane of the previous row
       }
     }
+    // ---- everything the NEXT block needs goes in flight now (registers of this block are free)
+    SchurDesc nblk = blk;
+    if (has_next) {
+      nblk = sDesc[(it + 1) % 3];
+      load_inputs(nblk);
+      stage_tables(nblk, buf ^ 1);
+    }
+    fetch_desc(b + 3 * stride, it % 3);
+    cp_async_commit();
+    __syncthreads();               // operands complete
+
+    // ---- phase B: slot pairs, dealt round-robin to the warps (sorted by decreasing length at finalize)
+    const int* sOff = tab_off(buf);
+    const SchurPair* sPair = tab_pair(buf);
+    const unsigned* sRun = tab_run(buf);
+    for (int p = warp; p < blk.n_pairs; p += kBlkObs / 32) {
+      const SchurPair P = sPair[p];
+      const int n_runs = P.slots_n >> 16;
+      const unsigned* rl = sRun + P.rbeg;
+      double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+      for (int r = 0; r < n_runs; ++r) {
+        const unsigned run = rl[r];
+        const double* ya = reinterpret_cast<const double*>(pY + (run & 255u) * (kYS * 8));
+        const double* wb = reinterpret_cast<const double*>(pW + ((run >> 8) & 255u) * (kWS * 8));
+        int n = run >> 16;
+        for (; n >= 4; n -= 4, ya += 4 * kYS, wb += 4 * kWS) {       // two independent accumulator chains
+          dmma_8x8x4(c0, c1, ya[0], wb[0]);
+          dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
+          dmma_8x8x4(c0, c1, ya[2 * kYS], wb[2 * kWS]);
+          dmma_8x8x4(d0, d1, ya[3 * kYS], wb[3 * kWS]);
+        }
+        if (n & 2) {
+          dmma_8x8x4(c0, c1, ya[0], wb[0]);
+          dmma_8x8x4(d0, d1, ya[kYS], wb[kWS]);
+          ya += 2 * kYS; wb += 2 * kWS;
+        }
+        if (n & 1) dmma_8x8x4(c0, c1, ya[0], wb[0]);
+      }
+      c0 += d0; c1 += d1;
+      // C[g][2t], C[g][2t+1] = sum Y_row[g][.] W_col[2t(+1)][.]
+      const int oa = sOff[P.slots_n & 255u], ob = sOff[(P.slots_n >> 8) & 255u];
+      const bool diag = oa == ob;
+      if (g < 6) {
+        if (t < 3) {
+          double* Sd = a.S + ((size_t)oa * a.ldS + ob + lane_S);
+          if (!diag || 2 * t <= g) red_add(Sd, -c0);
+          if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
+        } else if (diag) {
+          red_add(a.rhs + oa + g, -c0);             // column 6: Y b_p
+        }
+      }
+    }
+    if (!has_next) break;
+    b = bn; blk = nblk; ++it;
   }
+  cp_async_wait_all();
 }
 
 struct BacksubArgs {
@@ -323,8 +400,11 @@ struct FinishArgs {
 // One CTA per landmark block, one thread per observation.  All global loads are issued up front
 // (W as nine 16-byte loads per thread, the slot tables through precomputed offsets), so the only
 // dependent chain is slot -> pose index -> pose.
+#ifndef BSLAM_FINISH_CTAS
+#define BSLAM_FINISH_CTAS 5
+#endif
 template <int kLoss>
-__global__ void __launch_bounds__(kBlkObs) lm_finish_kernel(const FinishArgs a) {
+__global__ void __launch_bounds__(kBlkObs, BSLAM_FINISH_CTAS) lm_finish_kernel(const FinishArgs a) {
   __shared__ __align__(16) double sPose[12 * kBlkObs];
   __shared__ double sDx[6 * kBlkObs];
   __shared__ double sPts[3 * kBlkObs];

@@ -116,7 +116,9 @@ struct bslam_solver {
   // landmark blocks of the fast reprojection / Schur kernels
   int n_lmblocks = 0, tail_begin = 0, n_regular = 0;
   size_t schur_smem = 0;
-  int schur_max_lms = 1, schur_max_pairs = 1;
+  int schur_grid = 0;
+  int schur_max_lms = 1, schur_max_pairs = 1, schur_max_runs = 1;
+  DevBuf<bs::SchurDesc> d_sch_descs;
   DevBuf<bs::SchurPair> d_sch_pairs;
   DevBuf<unsigned> d_sch_combos;
   DevBuf<int> d_sch_pair_ptr, d_sch_combo_ptr;
@@ -348,7 +350,7 @@ int do_linearize(bslam_solver* s) {
   }
   record(s, 1);
   if (s->n_lmblocks > 0) {
-    const int grid = std::min(s->n_lmblocks, 148 * 5);      // persistent CTAs, 5 resident per SM
+    const int grid = std::min(s->n_lmblocks, 148 * bs::kReprojCtas);      // persistent CTAs, all resident
     const size_t smem = 2 * (size_t)s->stage_len * sizeof(double);
     const bs::ReprojArgs ra = reproj_args(s);
     switch (s->loss_kind) {
@@ -399,8 +401,11 @@ int do_reduce(bslam_solver* s, double lambda) {
     a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
     a.slot_off = s->d_slot_off.p; a.pair_ptr = s->d_sch_pair_ptr.p; a.combo_ptr = s->d_sch_combo_ptr.p;
     a.pairs = s->d_sch_pairs.p; a.combos = s->d_sch_combos.p;
-    a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs;
-    if (s->n_lmblocks > 0) LAUNCH(s, bs::schur_block_kernel, s->n_lmblocks, bs::kBlkObs, s->schur_smem, a);
+    a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs; a.max_runs = s->schur_max_runs;
+    a.descs = s->d_sch_descs.p;
+    if (s->n_lmblocks > 0) {
+      LAUNCH(s, bs::schur_block_kernel, std::min(s->n_lmblocks, s->schur_grid), bs::kBlkObs, s->schur_smem, a);
+    }
     if (s->n_lm > s->n_regular) {
       LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm - s->n_regular, 256), 256, 0, s->n_regular, s->n_lm, s->d_Vg.p,
              lambda, s->d_Vinv.p);
@@ -1234,6 +1239,7 @@ int bslam_finalize(bslam_solver* s) {
   std::vector<unsigned char> lm_obs_local(N, 0), seg_start;
   std::vector<unsigned> obs_code(N, 255u);
   std::iota(lm_obs.begin(), lm_obs.end(), 0);
+  std::vector<bs::SchurDesc> sch_descs;
   std::vector<bs::SchurPair> sch_pairs;
   std::vector<unsigned> sch_combos;             // runs of combos, see schur.cuh
   std::vector<int> sch_pair_ptr(1, 0), sch_combo_ptr(1, 0);
@@ -1327,6 +1333,14 @@ int bslam_finalize(bslam_solver* s) {
           P.rbeg = rb0 - cb0;
           sch_pairs.push_back(P);
         }
+        {
+          bs::SchurDesc sd{};
+          sd.obs_begin = b.obs_begin; sd.n_obs = b.n_obs; sd.lm_begin = b.lm_begin; sd.n_lms = b.n_lms;
+          sd.slot_begin = b.slot_begin; sd.n_slots = b.n_slots;
+          sd.pair_begin = sch_pair_ptr.back(); sd.n_pairs = (int)sch_pairs.size() - sd.pair_begin;
+          sd.run_begin = cb0; sd.n_runs = (int)sch_combos.size() - cb0;
+          sch_descs.push_back(sd);
+        }
         sch_pair_ptr.push_back((int)sch_pairs.size());
         sch_combo_ptr.push_back((int)sch_combos.size());
         max_pairs = std::max(max_pairs, (int)pv.size());
@@ -1340,7 +1354,8 @@ int bslam_finalize(bslam_solver* s) {
   s->loss_kind = s->groups.size() == 1 ? s->groups[0].loss.kind : -1;
   NEED(s->groups.size() < 65536, "too many reprojection groups (%zu)", s->groups.size());
   s->schur_smem = blocks.empty() ? 0 : bs::schur_smem_bytes(max_lms, max_pairs, max_combos);
-  s->schur_max_lms = max_lms; s->schur_max_pairs = max_pairs;
+  s->schur_max_lms = max_lms; s->schur_max_pairs = max_pairs; s->schur_max_runs = max_combos;
+  if (sch_descs.empty()) sch_descs.push_back(bs::SchurDesc{});
   NEED(s->schur_smem <= 200 * 1024, "landmark block structure needs %zu bytes of shared memory", s->schur_smem);
   if (sch_pairs.empty()) sch_pairs.push_back(bs::SchurPair{0u, 0});
   if (sch_combos.empty()) sch_combos.push_back(0);
@@ -1402,6 +1417,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_lm_obs_local, lm_obs_local, st));
   CU(upload(s->d_seg_start, seg_start, st));
   CU(upload(s->d_obs_code, obs_code, st));
+  CU(upload(s->d_sch_descs, sch_descs, st));
   CU(upload(s->d_sch_pairs, sch_pairs, st));
   CU(upload(s->d_sch_combos, sch_combos, st));
   CU(upload(s->d_sch_pair_ptr, sch_pair_ptr, st));
@@ -1423,6 +1439,13 @@ int bslam_finalize(bslam_solver* s) {
   }
   if (s->schur_smem > 0)   // static + dynamic shared memory may exceed the 48 KB default
     CU(cudaFuncSetAttribute(bs::schur_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->schur_smem));
+  {
+    int per_sm = 1, sms = 148;
+    if (s->schur_smem > 0)
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bs::schur_block_kernel, bs::kBlkObs, s->schur_smem));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    s->schur_grid = std::max(1, per_sm) * sms;       // persistent CTAs, all resident
+  }
   CU(upload(s->d_groups, s->groups, st));
   for (auto* b : s->edges) {
     CU(upload(b->d_i1, b->i1, st));

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbslam.so')
+# BSLAM_LIB: developer override used to A/B kernel build variants (tools/variants.sh)
+LIB_PATH = os.environ.get('BSLAM_LIB') or os.path.join(_HERE, 'libbslam.so')
 
 N_SCALARS = 16
 N_TIMINGS = 16
