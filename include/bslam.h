@@ -85,6 +85,9 @@ typedef struct bslam_solver bslam_solver;
 
 /* Library/ABI version (major*10000 + minor*100 + patch). */
 BSLAM_API int bslam_version(void);
+/* Edge of the square tiles the reduced camera system is stored and factorised in (32): the unit of
+ * bslam_tile_structure masks and of the packed multi-GPU payload. */
+BSLAM_API int bslam_tile_edge(void);
 
 /* Create a solver bound to CUDA device `device`.  Replaces `Problem.__init__`
  * (pyslam/problem.py:43-69).  Fails with BSLAM_E_CUDA when no usable GPU exists:

@@ -682,7 +682,9 @@ int fetch_scalars(bslam_solver* s) {
 
 extern "C" {
 
-int bslam_version(void) { return 100; }
+int bslam_version(void) { return 101; }
+
+int bslam_tile_edge(void) { return bs::kNB; }
 
 const char* bslam_last_error(const bslam_solver* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
 

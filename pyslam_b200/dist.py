@@ -7,7 +7,7 @@ ranks; the poses and the reduced camera system are replicated.  Per iteration:
     every rank : linearise its observations, eliminate its landmarks
                  -> partial [S | rhs | cost]                      (CUDA, local)
     all ranks  : ONE all-reduce (sum, fp64) of that buffer, packed to its
-                 structurally non-zero 64x64 tiles                 (NCCL)
+                 structurally non-zero 32x32 tiles                 (NCCL)
     every rank : factorise S, solve dx_c (redundantly, bit-identical inputs),
                  back-substitute and retract its own landmarks, cost at the
                  new point                                         (CUDA, local)

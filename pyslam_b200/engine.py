@@ -33,6 +33,7 @@ _h = C.c_void_p
 # name -> (restype, argtypes); must list every symbol declared in include/bslam.h
 SIGNATURES = {
     'bslam_version': (C.c_int, []),
+    'bslam_tile_edge': (C.c_int, []),
     'bslam_create': (C.c_int, [C.POINTER(_h), C.c_int]),
     'bslam_destroy': (None, [_h]),
     'bslam_last_error': (C.c_char_p, [_h]),
@@ -313,9 +314,9 @@ class Engine:
         return p.value, n.value, ps.value, npad.value
 
     def tile_structure(self):
-        """uint8 mask [(nt+1), nt] of the non-zero 64x64 tiles of the reduced system."""
+        """uint8 mask [(nt+1), nt] of the non-zero tiles (bslam_tile_edge() wide) of the reduced system."""
         _, _, _, npad = self.reduced_buffer()
-        nt = npad // 64
+        nt = npad // self._lib.bslam_tile_edge()
         m = np.zeros((nt + 1, nt), np.uint8)
         self._ck(self._lib.bslam_tile_structure(self._h, _b(m), m.size, 0))
         return m
