@@ -24,6 +24,40 @@ __global__ void __launch_bounds__(128) retract_poses_kernel(int n, double* __res
   Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
 }
 
+// SE3 poses of a bundle-adjustment problem, one launch: threads [0, n) retract the pose table; threads
+// [n, n + n_slot_entries) retract the per-slot copies the landmark-block kernels read (slot_poses holds the
+// poses gathered at linearisation time, so the copies never read the table while it is being rewritten) and
+// gather dx_c per slot; all threads also reduce ||dx_c||^2 over the first n_red entries of dx.
+__global__ void __launch_bounds__(128) retract_se3_slots_kernel(int n, double* __restrict__ poses, const int* __restrict__ off,
+                                                                const double* __restrict__ dx, int n_slot_entries,
+                                                                const int* __restrict__ slot_off, double* __restrict__ slot_poses,
+                                                                double* __restrict__ slot_dx, int n_red, double* __restrict__ dx_norm2) {
+  using Gr = Group<3>;
+  __shared__ double sred[4];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int o = off[i];
+    if (o >= 0) {
+      double xi[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xi[k] = dx[o + k];
+      double* p = poses + 12 * (size_t)i;
+      Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
+    }
+  } else if (i < n + n_slot_entries) {
+    const int e = i - n;
+    const int o = slot_off[e];
+    double xi[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { xi[k] = dx[o + k]; slot_dx[6 * (size_t)e + k] = xi[k]; }
+    double* p = slot_poses + 12 * (size_t)e;
+    Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
+  }
+  double s = 0.0;
+  for (int k = i; k < n_red; k += gridDim.x * blockDim.x) s += dx[k] * dx[k];
+  block_sum_to(s, dx_norm2, sred);
+}
+
 // entry e of a flat parameter array moves by dx[off[e]] (off < 0: constant)
 __global__ void __launch_bounds__(256) retract_flat_kernel(int n, double* __restrict__ vals,
                                                            const int* __restrict__ off,

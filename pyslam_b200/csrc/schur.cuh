@@ -370,15 +370,15 @@ __global__ void __launch_bounds__(128) backsub_kernel(const BacksubArgs a) {
 // ---- fused tail of the iteration for the landmark blocks ------------------------------
 // back-substitution dx_p = V^-1 (b_p - W^T dx_c), retraction p <- p + dx_p, ||dx_p||^2 and the
 // cost at the new point (pyslam/problem.py:155-156, 189-190, 400-409) in one pass over W and
-// the observations.  The poses must already be retracted (retract_poses_kernel).
+// the observations.  The poses must already be retracted (retract_poses_kernel) and gathered
+// per slot together with dx_c (retract_se3_slots_kernel).
 struct FinishArgs {
   int n_obs;
   int lm_off;
   int eval_cost;
   int n_blocks;
+  int max_slots;                        // shared-memory carve-up of the slot tables
   const LmBlock* __restrict__ blocks;
-  const int* __restrict__ slot_pose;
-  const int* __restrict__ slot_off;
   const unsigned* __restrict__ obs_code;
   const unsigned char* __restrict__ lm_obs_local;
   const int* __restrict__ obs_pose;
@@ -388,7 +388,9 @@ struct FinishArgs {
   const double* __restrict__ obs_u;
   const double* __restrict__ obs_v;
   const double* __restrict__ obs_d;
-  const double* __restrict__ poses;     // retracted
+  const double* __restrict__ poses;       // retracted
+  const double* __restrict__ slot_poses;  // [n_slot_entries][12] retracted poses per slot entry
+  const double* __restrict__ slot_dx;     // [n_slot_entries][6]  dx_c per slot entry
   double* __restrict__ pts;
   const double* __restrict__ W;
   const double* __restrict__ Vg;
@@ -397,101 +399,168 @@ struct FinishArgs {
   double* __restrict__ scalars;
 };
 
-// One CTA per landmark block, one thread per observation.  All global loads are issued up front
-// (W as nine 16-byte loads per thread, the slot tables through precomputed offsets), so the only
-// dependent chain is slot -> pose index -> pose.
 #ifndef BSLAM_FINISH_CTAS
-#define BSLAM_FINISH_CTAS 5
+#define BSLAM_FINISH_CTAS 4
 #endif
+constexpr int kFinishCtas = BSLAM_FINISH_CTAS;
+BS_HD size_t finish_smem_bytes(int max_slots) { return 2 * sizeof(double) * 18 * (size_t)max_slots; }
+
+// Persistent, software-pipelined like the assembly kernel: the W tile, the observations and the landmark
+// data of block i+1 are requested into the registers block i has just finished with, the slot tables arrive
+// by cp.async into the other half of a double buffer.  One atomic per CTA for the cost and for ||dx_p||^2.
 template <int kLoss>
-__global__ void __launch_bounds__(kBlkObs, BSLAM_FINISH_CTAS) lm_finish_kernel(const FinishArgs a) {
-  __shared__ __align__(16) double sPose[12 * kBlkObs];
-  __shared__ double sDx[6 * kBlkObs];
+__global__ void __launch_bounds__(kBlkObs, kFinishCtas) lm_finish_kernel(const FinishArgs a) {
+  extern __shared__ __align__(16) double sSlot[];      // 2 x [12 max_slots poses | 6 max_slots dx_c]
   __shared__ double sPts[3 * kBlkObs];
   __shared__ double sAcc[3 * kBlkObs];
   __shared__ double sred[2 * (kBlkObs / 32)];
+  __shared__ __align__(16) LmBlock sDesc[3];
   __shared__ unsigned char sLmObs[kBlkObs];
   const int tid = threadIdx.x;
-  const LmBlock blk = a.blocks[blockIdx.x];
-  const int i = blk.obs_begin + tid;
+  const int stride = gridDim.x;
+  int b = blockIdx.x;
+  if (b >= a.n_blocks) return;
+  const int tab = 18 * a.max_slots;
+
+  auto fetch_desc = [&](int blk_id, int slot) {
+    if (tid < 2 && blk_id < a.n_blocks)
+      cp_async16(reinterpret_cast<char*>(&sDesc[slot]) + 16 * tid, reinterpret_cast<const char*>(a.blocks + blk_id) + 16 * tid);
+  };
+  auto stage_slots = [&](const LmBlock& d, int buf) {
+    double* dp = sSlot + buf * tab;
+    double* dd = dp + 12 * a.max_slots;
+    const double* gp = a.slot_poses + 12 * (size_t)d.slot_begin;
+    const double* gd = a.slot_dx + 6 * (size_t)d.slot_begin;
+    if (a.eval_cost)
+      for (int e = tid; e < 6 * d.n_slots; e += kBlkObs) cp_async16(dp + 2 * e, gp + 2 * e);
+    for (int e = tid; e < 3 * d.n_slots; e += kBlkObs) cp_async16(dd + 2 * e, gd + 2 * e);
+  };
+  // registers that carry a block's inputs
   double w18[18];
-  double ou = 0.0, ov = 0.0, od = 0.0;
   unsigned code = 255u;
-  if (tid < blk.n_obs) {
-    code = ld_stream(a.obs_code + i);
-    sLmObs[tid] = a.lm_obs_local[i];
-    const double* Wp = a.W + w_pair_base(i);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
-    if (a.eval_cost) { ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i); }
-  }
-  const int sl = code & 255, ql = (code >> 8) & 255;
-  // per landmark: b_p, V^-1, CSR range, current point
+  int lmobs = 0;
+  double ou = 0.0, ov = 0.0, od = 0.0;
   double g0 = 0.0, g1 = 0.0, g2 = 0.0, vi[6] = {0, 0, 0, 0, 0, 0}, p0 = 0.0, p1 = 0.0, p2 = 0.0;
   int k0 = 0, k1 = 0;
-  if (tid < blk.n_lms) {
-    const int q = blk.lm_begin + tid;
-    const double* g = a.Vg + 9 * (size_t)q + 6;
-    g0 = g[0]; g1 = g[1]; g2 = g[2];
+  auto load_obs = [&](const LmBlock& d) {
+    code = 255u;
+    if (tid < d.n_obs) {
+      const int i = d.obs_begin + tid;
+      code = ld_stream(a.obs_code + i);
+      lmobs = a.lm_obs_local[i];
+      const double* Wp = a.W + w_pair_base(i);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) vi[k] = a.Vinv[6 * (size_t)q + k];
-    k0 = a.lm_start[q] - blk.obs_begin; k1 = a.lm_start[q + 1] - blk.obs_begin;
-    const double* P = a.pts + 3 * (size_t)q;
-    p0 = P[0]; p1 = P[1]; p2 = P[2];
-  }
-  // slot tables: dx_c through the static offsets, the retracted poses through the pose index
-  for (int e = tid; e < 6 * blk.n_slots; e += kBlkObs) sDx[e] = a.dx[a.slot_off[blk.slot_begin + e / 6] + e % 6];
-  if (a.eval_cost)
-    for (int e = tid; e < 12 * blk.n_slots; e += kBlkObs) sPose[e] = a.poses[12 * (size_t)a.slot_pose[blk.slot_begin + e / 12] + e % 12];
-  __syncthreads();
-  if (tid < blk.n_obs) {
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-    if (sl != 255) {
+      for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
+    }
+  };
+  auto load_uvd = [&](const LmBlock& d) {
+    if (a.eval_cost && tid < d.n_obs) {
+      const int i = d.obs_begin + tid;
+      ou = ld_stream(a.obs_u + i); ov = ld_stream(a.obs_v + i); od = ld_stream(a.obs_d + i);
+    }
+  };
+  auto load_lm = [&](const LmBlock& d) {
+    if (tid < d.n_lms) {
+      const int q = d.lm_begin + tid;
+      const double* g = a.Vg + 9 * (size_t)q + 6;
+      g0 = ld_stream(g); g1 = ld_stream(g + 1); g2 = ld_stream(g + 2);
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const double d = sDx[6 * sl + r];
-        c0 = fma(w18[3 * r], d, c0); c1 = fma(w18[3 * r + 1], d, c1); c2 = fma(w18[3 * r + 2], d, c2);
+      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * (size_t)q + k);
+      k0 = a.lm_start[q]; k1 = a.lm_start[q + 1];
+      const double* P = a.pts + 3 * (size_t)q;
+      p0 = P[0]; p1 = P[1]; p2 = P[2];
+    }
+  };
+
+  // ---- prologue
+  LmBlock blk = a.blocks[b];
+  fetch_desc(b + stride, 1);
+  fetch_desc(b + 2 * stride, 2);
+  stage_slots(blk, 0);
+  cp_async_commit();
+  load_obs(blk);
+  load_uvd(blk);
+  load_lm(blk);
+
+  double cost = 0.0, dx2 = 0.0;
+  int it = 0;
+  for (;;) {
+    const int buf = it & 1;
+    const int bn = b + stride;
+    const bool has_next = bn < a.n_blocks;
+    const double* sPose = sSlot + buf * tab;
+    const double* sDx = sPose + 12 * a.max_slots;
+    sLmObs[tid] = (unsigned char)lmobs;
+    cp_async_wait_all();
+    __syncthreads();                 // slot tables of this block, next descriptor; previous block fully done
+    LmBlock nblk = blk;
+    if (has_next) nblk = sDesc[(it + 1) % 3];
+    const int sl = code & 255, ql = (code >> 8) & 255, grp_id = code >> 16;
+    const int i = blk.obs_begin + tid;
+    // ---- W^T dx_c per observation
+    if (tid < blk.n_obs) {
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      if (sl != 255) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double d = sDx[6 * sl + r];
+          c0 = fma(w18[3 * r], d, c0); c1 = fma(w18[3 * r + 1], d, c1); c2 = fma(w18[3 * r + 2], d, c2);
+        }
       }
+      sAcc[3 * tid] = c0; sAcc[3 * tid + 1] = c1; sAcc[3 * tid + 2] = c2;
     }
-    sAcc[3 * tid] = c0; sAcc[3 * tid + 1] = c1; sAcc[3 * tid + 2] = c2;
-  }
-  __syncthreads();
-  double dx2 = 0.0;
-  if (tid < blk.n_lms) {
-    const int q = blk.lm_begin + tid;
-    double s0 = g0, s1 = g1, s2 = g2;
-    for (int k = k0; k < k1; ++k) { const int o = sLmObs[k]; s0 -= sAcc[3 * o]; s1 -= sAcc[3 * o + 1]; s2 -= sAcc[3 * o + 2]; }
-    const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
-    const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
-    const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
-    double* o = a.dx + a.lm_off + 3 * (size_t)q;
-    o[0] = d0; o[1] = d1; o[2] = d2;
-    dx2 = d0 * d0 + d1 * d1 + d2 * d2;
-    p0 += d0; p1 += d1; p2 += d2;
-    sPts[3 * tid] = p0; sPts[3 * tid + 1] = p1; sPts[3 * tid + 2] = p2;
-    double* P = a.pts + 3 * (size_t)q;
-    P[0] = p0; P[1] = p1; P[2] = p2;
-  }
-  __syncthreads();
-  double cost = 0.0;
-  if (a.eval_cost && tid < blk.n_obs) {
-    const ReprojGroup& g = kLoss >= 0 ? a.g0 : a.groups[code >> 16];
-    double P[12];
-    if (sl != 255) {
-      const double2* Ps = reinterpret_cast<const double2*>(sPose + 12 * sl);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { const double2 t = Ps[k]; P[2 * k] = t.x; P[2 * k + 1] = t.y; }
-    } else {
-      const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+    if (has_next) load_obs(nblk);    // W / code / landmark map of the next block (code, sl, ql of this block are copies)
+    __syncthreads();
+    // ---- per landmark: back-substitution, retraction
+    if (tid < blk.n_lms) {
+      const int q = blk.lm_begin + tid;
+      double s0 = g0, s1 = g1, s2 = g2;
+      for (int k = k0 - blk.obs_begin; k < k1 - blk.obs_begin; ++k) {
+        const int o = sLmObs[k];
+        s0 -= sAcc[3 * o]; s1 -= sAcc[3 * o + 1]; s2 -= sAcc[3 * o + 2];
+      }
+      const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
+      const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
+      const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
+      double* o = a.dx + a.lm_off + 3 * (size_t)q;
+      o[0] = d0; o[1] = d1; o[2] = d2;
+      dx2 += d0 * d0 + d1 * d1 + d2 * d2;
+      const double n0 = p0 + d0, n1 = p1 + d1, n2 = p2 + d2;
+      sPts[3 * tid] = n0; sPts[3 * tid + 1] = n1; sPts[3 * tid + 2] = n2;
+      double* P = a.pts + 3 * (size_t)q;
+      P[0] = n0; P[1] = n1; P[2] = n2;
     }
-    double r[3];
-    reproj_residual_only(g, P, sPts + 3 * ql, ou, ov, od, r);
+    if (has_next) load_lm(nblk);
+    __syncthreads();
+    // ---- cost at the new point
+    if (a.eval_cost && tid < blk.n_obs) {
+      const ReprojGroup& g = kLoss >= 0 ? a.g0 : a.groups[grp_id];
+      double P[12];
+      if (sl != 255) {
+        const double2* Ps = reinterpret_cast<const double2*>(sPose + 12 * sl);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(g.loss, r[k]);
+        for (int k = 0; k < 6; ++k) { const double2 t = Ps[k]; P[2 * k] = t.x; P[2 * k + 1] = t.y; }
+      } else {
+        const double* Pg = a.poses + 12 * (size_t)a.obs_pose[i];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+      }
+      double r[3];
+      reproj_residual_only(g, P, sPts + 3 * ql, ou, ov, od, r);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(g.loss, r[k]);
+    }
+    if (has_next) {
+      load_uvd(nblk);
+      stage_slots(nblk, buf ^ 1);
+    }
+    fetch_desc(b + 3 * stride, it % 3);
+    cp_async_commit();
+    if (!has_next) break;
+    b = bn; blk = nblk; ++it;
   }
-  // two block sums -> two atomics
+  cp_async_wait_all();
+  // two block sums -> two atomics per CTA
   cost = warp_sum(cost);
   dx2 = warp_sum(dx2);
   const int lane = tid & 31, warp = tid >> 5;

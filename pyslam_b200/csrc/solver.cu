@@ -125,7 +125,8 @@ struct bslam_solver {
   DevBuf<unsigned> d_obs_code;                       // slot | block-local landmark << 8 | group << 16
   DevBuf<int> d_slot_off, d_lm_obs;                  // d_lm_obs: CSR position (landmark order) -> observation index
   int loss_kind = -1;                                // loss kind of the single reprojection group, -1: several groups
-  DevBuf<double> d_slot_poses;
+  DevBuf<double> d_slot_poses, d_slot_dx;
+  int max_slots = 1;
   int n_slot_entries = 0, stage_len = 0;
   DevBuf<bs::LmBlock> d_blocks;
   DevBuf<int> d_slot_pose;
@@ -346,7 +347,7 @@ int do_linearize(bslam_solver* s) {
     a.n_slot_entries = s->n_lmblocks > 0 ? s->n_slot_entries : 0;
     a.slot_pose = s->d_slot_pose.p; a.poses = s->d_se3.p; a.slot_poses = s->d_slot_poses.p;
     const int work = std::max(std::max(a.n_rhs, a.n_vg_tail), 12 * a.n_slot_entries);
-    LAUNCH(s, bs::prepare_kernel, s->n_dirty_tiles + std::max(1, std::min(cdiv(work, 256), 148)), 256, 0, a);
+    LAUNCH(s, bs::prepare_kernel, s->n_dirty_tiles + std::max(1, cdiv(work, 256)), 256, 0, a);   // one element per thread: all gathers in flight at once
   }
   record(s, 1);
   if (s->n_lmblocks > 0) {
@@ -599,7 +600,13 @@ int do_solve_reduced(bslam_solver* s) {
 
 int do_retract(bslam_solver* s, int eval_new_cost) {
   const double* dx = s->d_dx.p;
-  if (s->n_se3 > 0) LAUNCH(s, bs::retract_poses_kernel<3>, cdiv(s->n_se3, 128), 128, 0, s->n_se3, s->d_se3.p, s->d_se3_off.p, dx);
+  // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
+  const int n_red_here = s->shard_rank == 0 ? s->n_red : 0;
+  if (s->n_se3 > 0) {
+    const int n_slots = s->n_lmblocks > 0 ? s->n_slot_entries : 0;
+    LAUNCH(s, bs::retract_se3_slots_kernel, cdiv(s->n_se3 + n_slots, 128), 128, 0, s->n_se3, s->d_se3.p, s->d_se3_off.p, dx, n_slots,
+           s->d_slot_off.p, s->d_slot_poses.p, s->d_slot_dx.p, n_red_here, s->scalars() + BSLAM_S_DX_NORM2);
+  }
   if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
   if (s->n_vec_entries > 0)
     LAUNCH(s, bs::retract_flat_kernel, cdiv(s->n_vec_entries, 256), 256, 0, s->n_vec_entries, s->d_vec.p, s->d_vec_entry_off.p, dx);
@@ -607,15 +614,16 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
     const int n3 = 3 * (s->n_pt - s->n_lm);
     LAUNCH(s, bs::retract_flat_kernel, cdiv(n3, 256), 256, 0, n3, s->d_pts.p + 3 * (size_t)s->n_lm, s->d_ptred_entry_off.p, dx);
   }
-  // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
-  if (s->n_red > 0 && s->shard_rank == 0)
+  if (s->n_se3 == 0 && n_red_here > 0)
     LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(s->n_red, 256), 148), 256, 0, s->n_red, dx, s->scalars() + BSLAM_S_DX_NORM2);
   record(s, 8);
   // landmark blocks: back-substitution + retraction + ||dx_p||^2 + cost at the new point, fused
   if (s->n_lmblocks > 0) {
     bs::FinishArgs a;
     a.n_obs = s->n_obs; a.lm_off = s->n_pad; a.eval_cost = eval_new_cost; a.n_blocks = s->n_lmblocks;
-    a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.slot_off = s->d_slot_off.p; a.obs_code = s->d_obs_code.p;
+    a.max_slots = s->max_slots;
+    a.blocks = s->d_blocks.p; a.obs_code = s->d_obs_code.p;
+    a.slot_poses = s->d_slot_poses.p; a.slot_dx = s->d_slot_dx.p;
     a.lm_obs_local = s->d_lm_obs_local.p;
     a.obs_pose = s->d_opose.p; a.groups = s->d_groups.p;
     if (!s->groups.empty()) a.g0 = s->groups[0];
@@ -623,14 +631,16 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
     a.obs_u = s->d_ou.p; a.obs_v = s->d_ov.p; a.obs_d = s->d_od.p;
     a.poses = s->d_se3.p; a.pts = s->d_pts.p; a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.dx = s->d_dx.p; a.scalars = s->scalars();
+    const int fgrid = std::min(s->n_lmblocks, 148 * bs::kFinishCtas);      // persistent CTAs, all resident
+    const size_t fsmem = bs::finish_smem_bytes(s->max_slots);
     switch (s->loss_kind) {
-      case 0: LAUNCH(s, bs::lm_finish_kernel<0>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      case 1: LAUNCH(s, bs::lm_finish_kernel<1>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      case 2: LAUNCH(s, bs::lm_finish_kernel<2>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      case 3: LAUNCH(s, bs::lm_finish_kernel<3>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      case 4: LAUNCH(s, bs::lm_finish_kernel<4>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      case 5: LAUNCH(s, bs::lm_finish_kernel<5>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
-      default: LAUNCH(s, bs::lm_finish_kernel<-1>, s->n_lmblocks, bs::kBlkObs, 0, a); break;
+      case 0: LAUNCH(s, bs::lm_finish_kernel<0>, fgrid, bs::kBlkObs, fsmem, a); break;
+      case 1: LAUNCH(s, bs::lm_finish_kernel<1>, fgrid, bs::kBlkObs, fsmem, a); break;
+      case 2: LAUNCH(s, bs::lm_finish_kernel<2>, fgrid, bs::kBlkObs, fsmem, a); break;
+      case 3: LAUNCH(s, bs::lm_finish_kernel<3>, fgrid, bs::kBlkObs, fsmem, a); break;
+      case 4: LAUNCH(s, bs::lm_finish_kernel<4>, fgrid, bs::kBlkObs, fsmem, a); break;
+      case 5: LAUNCH(s, bs::lm_finish_kernel<5>, fgrid, bs::kBlkObs, fsmem, a); break;
+      default: LAUNCH(s, bs::lm_finish_kernel<-1>, fgrid, bs::kBlkObs, fsmem, a); break;
     }
   }
   // tail: landmarks with long tracks (already back-substituted), then everything that is not a landmark block
@@ -1366,7 +1376,9 @@ int bslam_finalize(bslam_solver* s) {
   for (size_t k = 0; k < slot_pose.size(); ++k) slot_off[k] = s->se3_off[slot_pose[k]];
   s->n_slot_entries = (int)slot_pose.size();
   s->stage_len = 2;
+  s->max_slots = 1;
   for (const auto& b : blocks) s->stage_len = std::max(s->stage_len, 12 * b.n_slots + 3 * b.n_lms);
+  for (const auto& b : blocks) s->max_slots = std::max(s->max_slots, b.n_slots);
   s->stage_len = (s->stage_len + 1) & ~1;
   s->n_lmblocks = (int)blocks.size();
   s->tail_begin = lm_start[n_regular];
@@ -1426,6 +1438,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_sch_combo_ptr, sch_combo_ptr, st));
   CU(upload(s->d_slot_off, slot_off, st));
   CU(s->d_slot_poses.alloc(12 * slot_pose.size()));
+  CU(s->d_slot_dx.alloc(6 * slot_pose.size()));
   {                        // blocks with many poses: staging (dynamic) + rows (static) may exceed the 48 KB default
     const void* fn = nullptr;
     switch (s->loss_kind) {
