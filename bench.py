@@ -177,20 +177,18 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers (pinned) ----
     pin_Rt = torch.from_numpy(Rt0.copy()).pin_memory()
     pin_pts = torch.from_numpy(np.ascontiguousarray(d['pts0'])).pin_memory()
-    out_Rt = torch.empty_like(pin_Rt).pin_memory()
-    out_pts = torch.empty_like(pin_pts).pin_memory()
     h2d = pin_Rt.numel() * 8 + pin_pts.numel() * 8
-    d2h = out_Rt.numel() * 8 + out_pts.numel() * 8 + 16 * 8
-    np_Rt, np_pts, np_oRt, np_opts = pin_Rt.numpy(), pin_pts.numpy(), out_Rt.numpy(), out_pts.numpy()
+    d2h = pin_Rt.numel() * 8 + pin_pts.numel() * 8 + 16 * 8
+    np_Rt, np_pts = pin_Rt.numpy(), pin_pts.numpy()
 
     def e2e_step():
+        # host parameters -> device, one iteration, updated parameters -> the same (pinned) host buffers,
+        # which are the inputs of the next step
         eng.set_poses_se3(np_Rt)
         eng.set_points(np_pts)
         r = solver.iterate(0., True)
-        eng.get_poses_se3(np_oRt)
-        eng.get_points(np_opts)
-        np_Rt[...] = np_oRt          # next step starts from the updated host copy
-        np_pts[...] = np_opts
+        eng.get_poses_se3(np_Rt)
+        eng.get_points(np_pts)
         return r
 
     for _ in range(max(1, min(args.warmup, 3))):
