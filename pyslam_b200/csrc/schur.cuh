@@ -143,20 +143,23 @@ struct SchurDesc {
 #define BSLAM_SCHUR_CTAS 4
 #endif
 constexpr int kSchurCtas = BSLAM_SCHUR_CTAS;
-// small per-block tables, double-buffered: [slot offsets (int) | pairs | runs]
-BS_HD size_t schur_tab_bytes(int max_pairs, int max_runs) {
-  return ((sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)max_pairs + sizeof(unsigned) * (size_t)max_runs) + 15) & ~(size_t)15;
+constexpr int kSchurThreads = 2 * kBlkObs;     // two threads per observation (three rows of W / Y each), 8 MMA warps
+// small per-block tables, double-buffered: [slot offsets (int) | pairs | runs | V_p, b_p of the landmarks]
+BS_HD size_t schur_tab_bytes(int max_lms, int max_pairs, int max_runs) {
+  return ((sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)max_pairs + sizeof(unsigned) * (size_t)max_runs +
+           sizeof(double) * 9 * (size_t)max_lms + 7) & ~(size_t)7) + 8;
 }
 BS_HD size_t schur_smem_bytes(int max_lms, int max_pairs, int max_runs) {
   return sizeof(double) * ((size_t)kBlkObs * kYS + 8 + (size_t)kBlkObs * kWS + 8 + 10 * (size_t)max_lms) +
-         2 * schur_tab_bytes(max_pairs, max_runs);
+         2 * ((schur_tab_bytes(max_lms, max_pairs, max_runs) + 15) & ~(size_t)15);
 }
 
-// Persistent, software-pipelined: a CTA walks blocks b, b + grid, ...  The W tile, the observation codes and
-// the landmark blocks V_p | b_p of block i+1 are requested (into the registers block i has just finished
-// with) before the MMA phase of block i starts, and its small tables arrive by cp.async, so no global
-// load is waited for on the critical path of a block.
-__global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const SchurArgs a) {
+// Persistent, software-pipelined: a CTA walks blocks b, b + grid, ...  The W tile and the observation codes
+// of block i+1 are requested (into the registers block i has just finished with) before the MMA phase of
+// block i starts; its small tables and landmark blocks V_p | b_p arrive by cp.async.  256 threads: the
+// operand phase uses two threads per observation (register budget 64 -> 32 resident warps per SM, which is
+// what the latency-bound MMA phase needs), the MMA phase deals the slot pairs to 8 warps.
+__global__ void __launch_bounds__(kSchurThreads, kSchurCtas) schur_block_kernel(const SchurArgs a) {
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(16) SchurDesc sDesc[3];
   double* sY = sm;
@@ -164,8 +167,9 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
   double* sVinv = sW + kBlkObs * kWS + 8;           // [6 max_lms]
   double* sG = sVinv + 6 * a.max_lms;               // [4 max_lms] (padded to pairs)
   char* sTab = reinterpret_cast<char*>(sG + 4 * a.max_lms);
-  const size_t tab_bytes = schur_tab_bytes(a.max_pairs, a.max_runs);
+  const size_t tab_bytes = (schur_tab_bytes(a.max_lms, a.max_pairs, a.max_runs) + 15) & ~(size_t)15;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ob = tid & (kBlkObs - 1), half = tid >> 7;      // observation of the block, rows 3 half .. 3 half + 2
   const int stride = gridDim.x;
   int b = blockIdx.x;
   if (b >= a.n_blocks) return;
@@ -174,6 +178,10 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
   auto tab_pair = [&](int buf) { return reinterpret_cast<SchurPair*>(sTab + buf * tab_bytes + sizeof(int) * kBlkObs); };
   auto tab_run = [&](int buf) {
     return reinterpret_cast<unsigned*>(sTab + buf * tab_bytes + sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)a.max_pairs);
+  };
+  auto tab_vg = [&](int buf) {
+    const size_t o = sizeof(int) * kBlkObs + sizeof(SchurPair) * (size_t)a.max_pairs + sizeof(unsigned) * (size_t)a.max_runs;
+    return reinterpret_cast<double*>(sTab + buf * tab_bytes + ((o + 7) & ~(size_t)7));
   };
   auto cp_async4 = [&](void* dst, const void* src) {
     const unsigned s_ = (unsigned)__cvta_generic_to_shared(dst);
@@ -184,27 +192,22 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
       cp_async16(reinterpret_cast<char*>(&sDesc[slot]) + 16 * tid, reinterpret_cast<const char*>(a.descs + blk_id) + 16 * tid);
   };
   auto stage_tables = [&](const SchurDesc& d, int buf) {
-    int* so = tab_off(buf); SchurPair* sp = tab_pair(buf); unsigned* sr = tab_run(buf);
-    for (int e = tid; e < d.n_slots; e += kBlkObs) cp_async4(so + e, a.slot_off + d.slot_begin + e);
-    for (int e = tid; e < d.n_pairs; e += kBlkObs) cp_async8(sp + e, a.pairs + d.pair_begin + e);
-    for (int e = tid; e < d.n_runs; e += kBlkObs) cp_async4(sr + e, a.combos + d.run_begin + e);
+    int* so = tab_off(buf); SchurPair* sp = tab_pair(buf); unsigned* sr = tab_run(buf); double* sv = tab_vg(buf);
+    for (int e = tid; e < d.n_slots; e += kSchurThreads) cp_async4(so + e, a.slot_off + d.slot_begin + e);
+    for (int e = tid; e < d.n_pairs; e += kSchurThreads) cp_async8(sp + e, a.pairs + d.pair_begin + e);
+    for (int e = tid; e < d.n_runs; e += kSchurThreads) cp_async4(sr + e, a.combos + d.run_begin + e);
+    for (int e = tid; e < 9 * d.n_lms; e += kSchurThreads) cp_async8(sv + e, a.Vg + 9 * (size_t)d.lm_begin + e);
   };
   unsigned code = 255u;
-  double w18[18];
-  double vg[9];
+  double w10[10];                 // W values k = 8 half .. 8 half + 9 (five (k, k+1) pairs; k = 9 half .. 9 half + 8 are used)
   auto load_inputs = [&](const SchurDesc& d) {
     code = 255u;
-    if (tid < d.n_obs) {
-      const int i = d.obs_begin + tid;
+    if (ob < d.n_obs) {
+      const int i = d.obs_begin + ob;
       code = ld_stream(a.obs_code + i);
-      const double* Wp = a.W + w_pair_base(i);
+      const double* Wp = a.W + w_pair_base(i) + 2 * kWTile * (4 * half);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w18[2 * k] = t.x; w18[2 * k + 1] = t.y; }
-    }
-    if (tid < d.n_lms) {
-      const double* v = a.Vg + 9 * (size_t)(d.lm_begin + tid);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) vg[k] = ld_stream(v + k);
+      for (int k = 0; k < 5; ++k) { const double2 t = ld_stream2(Wp + 2 * kWTile * k); w10[2 * k] = t.x; w10[2 * k + 1] = t.y; }
     }
   };
 
@@ -228,8 +231,12 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
     const int buf = it & 1;
     const int bn = b + stride;
     const bool has_next = bn < a.n_blocks;
+    cp_async_wait_all();
+    __syncthreads();               // tables / V_p of this block and the next descriptor have landed;
+                                   // the MMA phase of the previous block is over (sY / sW / sVinv are free)
     // ---- phase A1: V^-1 and b_p of the block's landmarks (one thread each; blocks hold <= 128 landmarks)
     if (tid < blk.n_lms) {
+      const double* vg = tab_vg(buf) + 9 * tid;
       double vi[6];
       sym3_inverse(vg, a.lambda, vi);
       const int q = blk.lm_begin + tid;
@@ -237,35 +244,35 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
       for (int k = 0; k < 6; ++k) { sVinv[6 * tid + k] = vi[k]; a.Vinv_out[6 * (size_t)q + k] = vi[k]; }
       sG[4 * tid] = vg[6]; sG[4 * tid + 1] = vg[7]; sG[4 * tid + 2] = vg[8]; sG[4 * tid + 3] = 0.0;
     }
-    cp_async_wait_all();
-    __syncthreads();               // V^-1 visible; tables of this block and the next descriptor have landed;
-                                   // the MMA phase of the previous block is over (sY / sW are free)
-    // ---- phase A2: operands of this block
+    __syncthreads();
+    // ---- phase A2: operands of this block, rows 3 half .. 3 half + 2 of W and Y
     {
       const int sl = code & 255;
       if (sl != 255) {
         const int l = (code >> 8) & 255;
         const double* vi = sVinv + 6 * l;
         const double m00 = vi[0], m01 = vi[1], m02 = vi[2], m11 = vi[3], m12 = vi[4], m22 = vi[5];
-        double2* yr = reinterpret_cast<double2*>(sY + tid * kYS);
-        double2* wr = reinterpret_cast<double2*>(sW + tid * kWS);
-        double y[18];
+        double* yr = sY + ob * kYS + 9 * half;
+        double2* wr = reinterpret_cast<double2*>(sW + ob * kWS + 12 * half);
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double w0 = w18[3 * r], w1 = w18[3 * r + 1], w2 = w18[3 * r + 2];
-          y[3 * r] = w0 * m00 + w1 * m01 + w2 * m02;
-          y[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
-          y[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
+        for (int r = 0; r < 3; ++r) {
+          // k = 9 half + 3 r + c  ->  w10 index k - 8 half = half + 3 r + c
+          const double w0 = half ? w10[1 + 3 * r] : w10[3 * r];
+          const double w1 = half ? w10[2 + 3 * r] : w10[3 * r + 1];
+          const double w2 = half ? w10[3 + 3 * r] : w10[3 * r + 2];
+          yr[3 * r] = w0 * m00 + w1 * m01 + w2 * m02;
+          yr[3 * r + 1] = w0 * m01 + w1 * m11 + w2 * m12;
+          yr[3 * r + 2] = w0 * m02 + w1 * m12 + w2 * m22;
           wr[2 * r] = make_double2(w0, w1);
           wr[2 * r + 1] = make_double2(w2, 0.0);
         }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) yr[k] = make_double2(y[2 * k], y[2 * k + 1]);
-        const double2* gl = reinterpret_cast<const double2*>(sG + 4 * l);
-        wr[12] = gl[0];
-        wr[13] = gl[1];
-      } else {
-        sY[tid * kYS] = 0.0;        // read (times zero) by the K = 3 lane of the previous row
+        if (half) {
+          const double2* gl = reinterpret_cast<const double2*>(sG + 4 * l);
+          wr[6] = gl[0];           // operand row 6: b_p
+          wr[7] = gl[1];
+        }
+      } else if (!half) {
+        sY[ob * kYS] = 0.0;        // read (times zero) by the K = 3 lane of the previous row
       }
     }
     // ---- everything the NEXT block needs goes in flight now (registers of this block are free)
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
     const int* sOff = tab_off(buf);
     const SchurPair* sPair = tab_pair(buf);
     const unsigned* sRun = tab_run(buf);
-    for (int p = warp; p < blk.n_pairs; p += kBlkObs / 32) {
+    for (int p = warp; p < blk.n_pairs; p += kSchurThreads / 32) {
       const SchurPair P = sPair[p];
       const int n_runs = P.slots_n >> 16;
       const unsigned* rl = sRun + P.rbeg;
@@ -308,11 +315,11 @@ __global__ void __launch_bounds__(kBlkObs, kSchurCtas) schur_block_kernel(const 
       }
       c0 += d0; c1 += d1;
       // C[g][2t], C[g][2t+1] = sum Y_row[g][.] W_col[2t(+1)][.]
-      const int oa = sOff[P.slots_n & 255u], ob = sOff[(P.slots_n >> 8) & 255u];
-      const bool diag = oa == ob;
+      const int oa = sOff[P.slots_n & 255u], ob_ = sOff[(P.slots_n >> 8) & 255u];
+      const bool diag = oa == ob_;
       if (g < 6) {
         if (t < 3) {
-          double* Sd = a.S + ((size_t)oa * a.ldS + ob + lane_S);
+          double* Sd = a.S + ((size_t)oa * a.ldS + ob_ + lane_S);
           if (!diag || 2 * t <= g) red_add(Sd, -c0);
           if (!diag || 2 * t + 1 <= g) red_add(Sd + 1, -c1);
         } else if (diag) {

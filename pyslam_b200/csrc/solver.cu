@@ -405,7 +405,7 @@ int do_reduce(bslam_solver* s, double lambda) {
     a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs; a.max_runs = s->schur_max_runs;
     a.descs = s->d_sch_descs.p;
     if (s->n_lmblocks > 0) {
-      LAUNCH(s, bs::schur_block_kernel, std::min(s->n_lmblocks, s->schur_grid), bs::kBlkObs, s->schur_smem, a);
+      LAUNCH(s, bs::schur_block_kernel, std::min(s->n_lmblocks, s->schur_grid), bs::kSchurThreads, s->schur_smem, a);
     }
     if (s->n_lm > s->n_regular) {
       LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm - s->n_regular, 256), 256, 0, s->n_regular, s->n_lm, s->d_Vg.p,
@@ -1457,7 +1457,7 @@ int bslam_finalize(bslam_solver* s) {
   {
     int per_sm = 1, sms = 148;
     if (s->schur_smem > 0)
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bs::schur_block_kernel, bs::kBlkObs, s->schur_smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bs::schur_block_kernel, bs::kSchurThreads, s->schur_smem));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     s->schur_grid = std::max(1, per_sm) * sms;       // persistent CTAs, all resident
   }
