@@ -303,6 +303,46 @@ def test_random_visibility_blocks():
         assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
 
 
+def _check_ba_against_oracle(d, n_iters=2):
+    from oracle import gn_oracle as O
+    ba = B.oracle_ba_arrays(d)
+    pr = B.product_ba_problem(d, bulk=True)
+    Ho, bo, co = O.ba_linearize(ba)
+    H, b, cost = normal_equations_ref_order(pr)
+    assert rel_err(H, Ho.toarray()) < TOL_LIN
+    assert rel_err(b, bo) < TOL_LIN
+    assert abs(cost - co) < TOL_LIN * co
+    low = pr._low
+    for it in range(n_iters):
+        ref = O.ba_iteration(ba)
+        cost_lin, cost_new, dx_norm = pr._engine.iterate(0., True)
+        dx = pr._engine.get_update(low.dim)[low.ref_from_internal]
+        assert rel_err(dx, ref['dx']) < 1e-6, 'iteration %d' % it
+        assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
+
+
+def test_duplicate_observations_of_a_landmark_by_one_pose():
+    """Two reprojection blocks on the same (pose, landmark) pair: legal in the reference (two rows of the
+    Jacobian), outside the block kernels' one-observation-per-(slot, landmark) layout -> generic path."""
+    from oracle import gn_oracle as O
+    from pyslam_b200 import synthetic
+    rng = np.random.default_rng(11)
+    d = synthetic.stereo_ba(12, 150, track=5, seed=9)
+    dup = rng.choice(len(d['pose_idx']), size=40, replace=False)
+    d['pose_idx'] = np.concatenate([d['pose_idx'], d['pose_idx'][dup]]).astype(np.int32)
+    d['pt_idx'] = np.concatenate([d['pt_idx'], d['pt_idx'][dup]]).astype(np.int32)
+    d['obs'] = np.vstack([d['obs'], d['obs'][dup] + 0.3 * rng.standard_normal((40, 3))])
+    _check_ba_against_oracle(d)
+
+
+def test_short_tracks_many_landmarks_per_block():
+    """Tracks of 2 observations: 64 landmarks per landmark block (the per-block landmark tables of the
+    Schur / back-substitution kernels are sized by the largest block)."""
+    from pyslam_b200 import synthetic
+    d = synthetic.stereo_ba(30, 900, track=2, seed=13)
+    _check_ba_against_oracle(d)
+
+
 def test_mixed_groups_losses_and_stiffness():
     """Reprojection blocks with different losses and per-block stiffness in one
     problem (several constant groups inside one kernel launch)."""
