@@ -46,7 +46,13 @@ constexpr int kAccNJ = kNB / 16;  // 8-col MMA blocks per warp   (        cols (
 struct CholTask {
   int i, j;        // tile row / column (i == nt: right-hand-side row)
   int kbeg, kend;  // range in klist: columns k < j with L_ik and L_jk both non-zero
+  int early;       // off-diagonal (i, j): e + 1 = also publish C_ij = S_ij - sum L_ik L_jk^T (before the triangular
+                   //                    solve) into early slot e of row i
+                   // diagonal (i, i): take the LAST `early` (0..kEarly) producer columns of klist through early C tiles
+  int pad;
 };
+
+constexpr int kEarly = 2;   // early C tiles per diagonal task (a separator has two children in the nested-dissection tree)
 
 struct CholPlan {
   int nt;
@@ -57,6 +63,12 @@ struct CholPlan {
   const int* bwd_rows;   // rows i > k with a non-zero tile (i,k), descending
   int* ready;            // [(nt+1)*nt] epoch flags: tile final
   int* xready;           // [nt]       epoch flags: x_k final
+  int* cready;           // [kEarly nt] epoch flags: early C tile (slot e of row i) published
+  double* cscr;          // [kEarly nt][kNB*kNB] early C tiles.  The critical chain of the factorisation is
+                         //   diag(k) -> off(i,k): L_ik = C_ik X_kk^T -> diag(i): acc += L_ik L_ik^T
+                         // with a global-memory hop (store, fence, flag, poll, load) after each arrow.  C_ik is known
+                         // long before X_kk, so the diagonal task i forms L_ik itself from the early C_ik and X_kk
+                         // as soon as diag(k) posts: one hop and one tile task leave the chain per tree level.
   int* ticket;           // [0] ticket counter, [1] epoch of the last completed launch, [2] CTAs finished
                          // (the last CTA to finish resets [0], [2] and advances [1]: no memsets between launches)
   long long* trace;      // optional [n_tasks][4]: start, dependencies satisfied, end (globaltimer ns), SM id
@@ -512,7 +524,9 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         if (r < rows_i) v = __ldcg(reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c));
         own.c[i][j][0] = v.x; own.c[i][j][1] = v.y;
       });
-      for (int kk = task.kbeg; kk < task.kend; ++kk) {
+      const int n_early = (ti == tj) ? task.early : 0;
+      const int kend_l = task.kend - n_early;
+      for (int kk = task.kbeg; kk < kend_l; ++kk) {
         const int k = p.klist[kk];
         if (tid == 0) {                    // the two producers are polled by two warps at once
           while (ld_acquire(p.ready + ti * nt + k) != epoch) __nanosleep(20);
@@ -525,6 +539,29 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         __syncthreads();
         tile_mma_abt(sA, ti != tj ? sB : sA, acc);
       }
+      for (int e = 0; e < n_early; ++e) {
+        // last (critical) producer columns k: L_ik = C_ik X_kk^T formed here from the early C tile
+        const int k = p.klist[kend_l + e];
+        if (tid == 0) {
+          while (ld_acquire(p.cready + kEarly * ti + e) != epoch) __nanosleep(20);
+        } else if (tid == 32) {
+          while (ld_acquire(p.ready + k * nt + k) != epoch) __nanosleep(20);
+        }
+        __syncthreads();
+        tile_load(sA, p.cscr + (size_t)(kEarly * ti + e) * kNB * kNB, kNB, kNB);
+        tile_load(sB, Linv + (size_t)k * kNB * kNB, kNB, kNB);
+        __syncthreads();
+        TileAcc t_acc;
+        acc_zero(t_acc);
+        tile_mma_abt(sA, sB, t_acc);
+        __syncthreads();
+        acc_foreach([&](int i, int j, int r, int c) {
+          sA[r * kLd + c] = t_acc.c[i][j][0];
+          sA[r * kLd + c + 1] = t_acc.c[i][j][1];
+        });
+        __syncthreads();
+        tile_mma_abt(sA, sA, acc);
+      }
       __syncthreads();
       if (p.trace && tid == 0) t1 = gtime();
       // C = S_ij - acc  -> sA
@@ -533,6 +570,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         sA[r * kLd + c + 1] = own.c[i][j][1] - acc.c[i][j][1];
       });
       __syncthreads();
+      if (ti != tj && task.early) {          // publish the early C tile for the diagonal task of row ti
+        double* Cs = p.cscr + (size_t)(kEarly * ti + task.early - 1) * kNB * kNB;
+        for (int e = tid; e < kNB * kNB / 2; e += kCholThreads) {
+          const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
+          *reinterpret_cast<double2*>(Cs + r * kNB + c2) = make_double2(sA[r * kLd + c2], sA[r * kLd + c2 + 1]);
+        }
+        post_flag(p.cready + kEarly * ti + task.early - 1, epoch);
+      }
       if (ti == tj) {
         const int bad = tile_potrf_inv(sA, sB, scol, srcp, &s_bad);
         if (bad && tid == 0) red_add(scalars + 3 /*CHOL_FAIL*/, (double)bad);

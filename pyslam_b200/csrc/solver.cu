@@ -150,7 +150,8 @@ struct bslam_solver {
   bool plan_valid = false;
   int chol_epoch = 0, chol_grid = 0, n_tile_tasks = 0;
   DevBuf<bs::CholTask> d_tasks;
-  DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_ticket;
+  DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_cready, d_ticket;
+  DevBuf<double> d_cscr;                           // early C tiles of the diagonal tasks (CholPlan::cscr)
   DevBuf<unsigned char> d_fill_mask;               // tile mask after symbolic fill-in
   DevBuf<long long> d_trace;                       // debug: per-task timestamps (bslam_debug_chol_trace)
   std::vector<bs::CholTask> h_tasks;
@@ -484,7 +485,7 @@ int build_chol_plan(bslam_solver* s) {
   for (int j = 0; j < nt; ++j)
     for (int i = j; i <= nt; ++i) {
       if (!at(i, j)) continue;
-      bs::CholTask t;
+      bs::CholTask t{};
       t.i = i; t.j = j; t.kbeg = (int)klist.size();
       for (int k = 0; k < j; ++k)
         if (at(i, k) && at(j, k)) klist.push_back(k);
@@ -515,6 +516,15 @@ int build_chol_plan(bslam_solver* s) {
       const bs::CholTask& T = tasks[t];
       auto key = [&](int k) { return std::max(level[tix[(size_t)T.i * nt + k]], level[tix[(size_t)T.j * nt + k]]); };
       std::stable_sort(klist.begin() + T.kbeg, klist.begin() + T.kend, [&](int x, int y) { return key(x) < key(y); });
+    }
+    // early C tiles: the diagonal task of row i takes its last (critical) producer column k straight from
+    // C_ik and X_kk; the off-diagonal task (i, k) publishes C_ik for it (see CholPlan::cscr)
+    for (size_t t = 0; t < tasks.size(); ++t) {
+      bs::CholTask& T = tasks[t];
+      if (T.i != T.j) continue;
+      T.early = std::min(bs::kEarly, T.kend - T.kbeg);
+      for (int e = 0; e < T.early; ++e)
+        tasks[tix[(size_t)T.i * nt + klist[T.kend - T.early + e]]].early = e + 1;
     }
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
@@ -556,6 +566,9 @@ int build_chol_plan(bslam_solver* s) {
   CU(upload(s->d_bwd_rows, bwd_rows, st));
   CU(s->d_ready.alloc((size_t)(nt + 1) * nt));
   CU(s->d_xready.alloc(nt));
+  CU(s->d_cready.alloc((size_t)bs::kEarly * nt));
+  CU(s->d_cscr.alloc((size_t)bs::kEarly * nt * bs::kNB * bs::kNB));
+  CU(cudaMemsetAsync(s->d_cready.p, 0, s->d_cready.n * sizeof(int), st));
   CU(s->d_ticket.alloc(4));                     // [ticket, epoch of the last completed launch, CTAs done]
   CU(cudaMemsetAsync(s->d_ticket.p, 0, 4 * sizeof(int), st));
   CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), st));
@@ -580,6 +593,7 @@ int do_solve_reduced(bslam_solver* s) {
   p.n_tile_tasks = s->n_tile_tasks;
   p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
+  p.cready = s->d_cready.p; p.cscr = s->d_cscr.p;
   p.trace = s->d_trace.p;
   // no per-launch memsets: the flags carry the launch epoch, which the kernel advances itself
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
