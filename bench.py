@@ -43,15 +43,56 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region.  The region is a few tens of milliseconds, far
+    below nvidia-smi's sampling period, so NVML is polled in-process from a thread (~1 kHz); nvidia-smi -lms
+    is the fallback when pynvml is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu):
-        self.gpu, self.proc, self.path = gpu, None, None
+        self.gpu, self.proc, self.path, self.thread = gpu, None, None, None
+        self.samples, self.reasons, self.max_mhz, self.stop_flag = [], set(), None, False
+
+    def _nvml_loop(self, nv, h):
+        bits = []
+        for name, attr in (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown'), ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown'),
+                           ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown'), ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap')):
+            v = getattr(nv, attr, None) or getattr(nv, attr.replace('ClocksEventReason', 'ClocksThrottleReason'), None)
+            if v is not None:
+                bits.append((name, v))
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for name, bit in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
@@ -63,6 +104,13 @@ class ClockSampler:
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                           samples=len(self.samples), source='NVML polled in-process during the timed region')
+            return out
         if self.proc is None:
             return out
         time.sleep(0.15)
@@ -86,7 +134,8 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source='nvidia-smi -lms 100')
         return out
 
 
@@ -343,7 +392,7 @@ def run_reference(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     a = ap.parse_args()
