@@ -167,82 +167,6 @@ BS_D void acc_foreach(F f) {
     for (int j = 0; j < kAccNJ; ++j) f(i, j, m0 + 8 * i + g, n0 + 8 * j + 2 * t);
 }
 
-// ---- 32x32 building blocks of the diagonal-tile factorisation -------------------
-
-// In-place Cholesky of the 32x32 block at `s` (leading dimension kLd) by ONE warp:
-// lane = row, the row lives in registers, the current column is exchanged through
-// `scol`.  Writes 1/L_jj to `srcp`.  Returns the number of non-positive pivots.
-BS_D int potrf32_warp(double* __restrict__ s, double* __restrict__ scol, double* __restrict__ srcp) {
-  const int lane = threadIdx.x & 31;
-  double a[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = s[lane * kLd + c];
-  int bad = 0;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const double d = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(d > 0.0)) ++bad;
-    const double r = rsqrt(d);
-    const double l = (lane == j) ? d * r : a[j] * r;
-    a[j] = l;
-    scol[lane] = l;
-    if (lane == j) srcp[j] = r;
-    __syncwarp();
-#pragma unroll
-    for (int c = j + 1; c < 32; ++c) a[c] = fma(-l, scol[c], a[c]);
-    __syncwarp();
-  }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) s[lane * kLd + c] = (c <= lane) ? a[c] : 0.0;
-  return bad;
-}
-
-// X = L^-1 for the 32x32 lower-triangular block at `sL` (reciprocal diagonal in
-// srcp) by ONE warp: lane = column of X, forward substitution down the rows.
-BS_D void trtri32_warp(const double* __restrict__ sL, const double* __restrict__ srcp, double* __restrict__ sX) {
-  const int lane = threadIdx.x & 31;
-  double x[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int m = 0; m < i; ++m) {
-      const double l = sL[i * kLd + m];
-      if ((m & 3) == 0) s0 = fma(-l, x[m], s0);
-      else if ((m & 3) == 1) s1 = fma(-l, x[m], s1);
-      else if ((m & 3) == 2) s2 = fma(-l, x[m], s2);
-      else s3 = fma(-l, x[m], s3);
-    }
-    x[i] = ((s0 + s1) + (s2 + s3)) * srcp[i];
-  }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) sX[i * kLd + lane] = x[i];
-}
-
-// C(32x32) = alpha * A(32x32) * op(B)(32x32) + beta * C, all in shared memory
-// (leading dimension kLd), 8 warps: warp w computes the 8x8 output blocks 2w, 2w+1.
-// kTransB: op(B) = B^T (C[m][n] = sum_c A[m][c] B[n][c]); else op(B) = B.
-template <bool kTransB>
-BS_D void gemm32(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, double alpha,
-                 double beta) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int blk = 2 * warp + q, bm = 8 * (blk >> 2), bn = 8 * (blk & 3);
-    double c0 = 0.0, c1 = 0.0;
-#pragma unroll
-    for (int k0 = 0; k0 < 32; k0 += 4) {
-      const double a = A[(bm + g) * kLd + k0 + t];
-      const double b = kTransB ? B[(bn + g) * kLd + k0 + t] : B[(k0 + t) * kLd + bn + g];
-      dmma_8x8x4(c0, c1, a, b);
-    }
-    double* p = C + (bm + g) * kLd + bn + 2 * t;
-    p[0] = alpha * c0 + (beta != 0.0 ? beta * p[0] : 0.0);
-    p[1] = alpha * c1 + (beta != 0.0 ? beta * p[1] : 0.0);
-  }
-}
-
 // 1/sqrt(d) to full double precision: hardware approximation (MUFU.RSQ64H, ~2^-22) + two
 // Newton steps; ~2x shorter dependency chain than the library rsqrt() on the pivot critical path.
 BS_D double fast_rsqrt(double d) {
@@ -257,65 +181,6 @@ BS_D double fast_rsqrt(double d) {
 }
 
 // ---- 16x16 building blocks (one warp each) ------------------------------------------------
-// In-place Cholesky of the 16x16 block at `s` (lanes 0..15 = rows, the row lives in registers).
-// The next pivot is formed and its rsqrt started BEFORE the trailing update of the current column,
-// so the per-pivot critical chain is mul -> fma -> shfl -> rsqrt only.  `scol` holds 2 x 16 doubles
-// (double-buffered column broadcast); 1/L_jj goes to srcp.  Returns #non-positive pivots.
-BS_D int potrf16_warp(double* __restrict__ s, double* __restrict__ scol, double* __restrict__ srcp) {
-  const int lane = threadIdx.x & 31, row = lane & 15;
-  double a[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) a[c] = s[row * kLd + c];
-  int bad = 0;
-  double d = __shfl_sync(0xffffffffu, a[0], 0);
-  double r = fast_rsqrt(d);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (!(d > 0.0)) ++bad;
-    const double l = (row == j) ? d * r : a[j] * r;
-    a[j] = l;
-    if (lane == j) srcp[j] = r;
-    double dn = 0.0, rn = 0.0;
-    if (j + 1 < 16) {
-      dn = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
-      rn = fast_rsqrt(dn);
-    }
-    double* sc = scol + (j & 1) * 16;
-    if (lane < 16) sc[row] = l;
-    __syncwarp();
-#pragma unroll
-    for (int c = j + 1; c < 16; ++c) a[c] = fma(-l, sc[c], a[c]);
-    d = dn;
-    r = rn;
-  }
-  if (lane < 16) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) s[row * kLd + c] = (c <= row) ? a[c] : 0.0;
-  }
-  return bad;
-}
-
-// X = L^-1 of the 16x16 lower-triangular block at sL (lanes 0..15 = columns of X).
-BS_D void trtri16_warp(const double* __restrict__ sL, const double* __restrict__ srcp, double* __restrict__ sX) {
-  const int lane = threadIdx.x & 31, col = lane & 15;
-  double x[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    double s0 = (i == col) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-    for (int m = 0; m < i; ++m) {
-      const double l = sL[i * kLd + m];
-      if (m & 1) s1 = fma(-l, x[m], s1);
-      else s0 = fma(-l, x[m], s0);
-    }
-    x[i] = (s0 + s1) * srcp[i];
-  }
-  if (lane < 16) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sX[i * kLd + col] = x[i];
-  }
-}
-
 // C(16x16) = alpha * A(16x16) * op(B) + beta * C by ONE warp (DMMA), shared memory, leading
 // dimension kLd.  Safe when C aliases A or B: every operand is read before anything is stored.
 template <bool kTransB>
@@ -673,16 +538,6 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
 
 constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + kCholThreads) * sizeof(double);
 
-// zero the listed 64x64 tiles (tile id = i * nt + j) of S
-__global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S, int ld, int nt, const int* __restrict__ tiles) {
-  const int id = tiles[blockIdx.x];
-  double* T = S + (size_t)(id / nt) * kNB * ld + (size_t)(id % nt) * kNB;
-  for (int e = threadIdx.x; e < kNB * kNB / 2; e += 256) {
-    const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
-    *reinterpret_cast<double2*>(T + (size_t)r * ld + c2) = make_double2(0.0, 0.0);
-  }
-}
-
 // Everything a linearisation needs cleared or refreshed, in ONE launch (each dependent launch inside the
 // iteration's CUDA graph costs 2-3 us of latency):
 //   blocks [0, n_tiles)   zero the structurally non-zero tiles; diagonal tiles get 1.0 on padding entries
@@ -732,12 +587,6 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(double* __restrict__ S,
     if (unpack) *t2 = *p2;
     else *p2 = *t2;
   }
-}
-
-// identity on the padding diagonal so the padded factorisation is well defined
-__global__ void pad_diag_kernel(double* __restrict__ S, int ld, const int* __restrict__ pad_idx, int n_pads) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n_pads) S[(size_t)pad_idx[k] * ld + pad_idx[k]] = 1.0;
 }
 
 // S_ii *= (1 + lambda) for i < n  (LM damping lambda * diag(H); extension)

@@ -238,15 +238,6 @@ BS_D void cp_async16(void* smem_dst, const void* gsrc) {
 BS_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 BS_D void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// poses of all slot entries, gathered once per linearisation: slot_poses[e] = poses[slot_pose[e]]
-// (removes the pose indirection from the block kernels: a block's poses become one contiguous range)
-__global__ void __launch_bounds__(256) gather_slot_poses_kernel(int n, const int* __restrict__ slot_pose,
-                                                                const double* __restrict__ poses,
-                                                                double* __restrict__ slot_poses) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < 12 * n) slot_poses[e] = poses[12 * (size_t)slot_pose[e / 12] + e % 12];
-}
-
 // Software-pipelined persistent kernel.  A CTA walks landmark blocks b, b + grid, ...  While block i is
 // being processed, everything block i+1 needs is already in flight: its descriptor (cp.async, two blocks
 // ahead), its slot poses and landmark coordinates (cp.async into the other half of a double-buffered

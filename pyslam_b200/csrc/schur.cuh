@@ -60,8 +60,6 @@ struct SchurArgs {
   double* __restrict__ rhs;
   // static structure of the block kernel (built at finalize)
   const int* __restrict__ slot_off;         // reduced offset per slot entry
-  const int* __restrict__ pair_ptr;         // [n_blocks + 1] into pairs[]
-  const int* __restrict__ combo_ptr;        // [n_blocks + 1] into combos[]
   const struct SchurPair* __restrict__ pairs;
   const unsigned* __restrict__ combos;      // runs: row observation | col observation << 8 | length << 16 (block-local)
   const struct SchurDesc* __restrict__ descs;  // [n_blocks]

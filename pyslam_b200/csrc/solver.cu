@@ -101,8 +101,7 @@ struct bslam_solver {
   double dn_cost = 0.0;
 
   // ---- layout ----
-  int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0, n_pads = 0;
-  DevBuf<int> d_pad_idx;
+  int n_lm = 0, n_red = 0, n_pad = 0, nblk = 0, dim = 0, n_obs = 0;
   DevBuf<unsigned char> d_used;                      // [n_pad] 1: real unknown, 0: padding entry of the reduced system
   std::vector<int> pt_perm, pt_iperm;               // user -> internal, internal -> user
   std::vector<int> se3_off, se2_off, vec_off, pt_off_user, vec_entry_off, pt_red_entry_off;
@@ -121,7 +120,6 @@ struct bslam_solver {
   DevBuf<bs::SchurDesc> d_sch_descs;
   DevBuf<bs::SchurPair> d_sch_pairs;
   DevBuf<unsigned> d_sch_combos;
-  DevBuf<int> d_sch_pair_ptr, d_sch_combo_ptr;
   DevBuf<unsigned> d_obs_code;                       // slot | block-local landmark << 8 | group << 16
   DevBuf<int> d_slot_off, d_lm_obs;                  // d_lm_obs: CSR position (landmark order) -> observation index
   int loss_kind = -1;                                // loss kind of the single reprojection group, -1: several groups
@@ -401,7 +399,7 @@ int do_reduce(bslam_solver* s, double lambda) {
     a.pose_off = s->d_se3_off.p;
     a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
-    a.slot_off = s->d_slot_off.p; a.pair_ptr = s->d_sch_pair_ptr.p; a.combo_ptr = s->d_sch_combo_ptr.p;
+    a.slot_off = s->d_slot_off.p;
     a.pairs = s->d_sch_pairs.p; a.combos = s->d_sch_combos.p;
     a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs; a.max_runs = s->schur_max_runs;
     a.descs = s->d_sch_descs.p;
@@ -1230,10 +1228,6 @@ int bslam_finalize(bslam_solver* s) {
                                                                                                             : s->pt_off_user[it.idx];
     mark_used(off, it.dof);
   }
-  std::vector<int> pad_idx;
-  for (int i = 0; i < s->n_pad; ++i)
-    if (!used[i]) pad_idx.push_back(i);
-  s->n_pads = (int)pad_idx.size();
   for (int q = 0; q < s->n_lm; ++q) s->pt_off_user[s->pt_iperm[q]] = s->n_red + 3 * q;
   s->dim = s->n_red + 3 * s->n_lm;
 
@@ -1268,7 +1262,6 @@ int bslam_finalize(bslam_solver* s) {
   std::vector<bs::SchurDesc> sch_descs;
   std::vector<bs::SchurPair> sch_pairs;
   std::vector<unsigned> sch_combos;             // runs of combos, see schur.cuh
-  std::vector<int> sch_pair_ptr(1, 0), sch_combo_ptr(1, 0);
   int max_pairs = 1, max_combos = 4, max_lms = 1;
   {
     int q = 0;
@@ -1342,7 +1335,7 @@ int bslam_finalize(bslam_solver* s) {
         }
         std::vector<std::pair<std::pair<int, int>, std::vector<unsigned short>>> pv(by_pair.begin(), by_pair.end());
         std::stable_sort(pv.begin(), pv.end(), [](const auto& x, const auto& y) { return x.second.size() > y.second.size(); });
-        const int cb0 = (int)sch_combos.size();
+        const int cb0 = (int)sch_combos.size(), pb0 = (int)sch_pairs.size();
         for (auto& e : pv) {
           // combos -> runs of (row + i, col + i)
           std::vector<unsigned short>& cl = e.second;
@@ -1363,12 +1356,10 @@ int bslam_finalize(bslam_solver* s) {
           bs::SchurDesc sd{};
           sd.obs_begin = b.obs_begin; sd.n_obs = b.n_obs; sd.lm_begin = b.lm_begin; sd.n_lms = b.n_lms;
           sd.slot_begin = b.slot_begin; sd.n_slots = b.n_slots;
-          sd.pair_begin = sch_pair_ptr.back(); sd.n_pairs = (int)sch_pairs.size() - sd.pair_begin;
+          sd.pair_begin = pb0; sd.n_pairs = (int)sch_pairs.size() - pb0;
           sd.run_begin = cb0; sd.n_runs = (int)sch_combos.size() - cb0;
           sch_descs.push_back(sd);
         }
-        sch_pair_ptr.push_back((int)sch_pairs.size());
-        sch_combo_ptr.push_back((int)sch_combos.size());
         max_pairs = std::max(max_pairs, (int)pv.size());
         max_combos = std::max(max_combos, (int)sch_combos.size() - cb0);
         max_lms = std::max(max_lms, b.n_lms);
@@ -1430,7 +1421,6 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_vec, s->h_vec, st));
   CU(s->d_stage.alloc(3 * (size_t)s->n_pt));
   CU(upload(s->d_pt_perm, s->pt_perm, st));
-  CU(upload(s->d_pad_idx, pad_idx, st));
   CU(upload(s->d_used, used, st));
   CU(upload(s->d_se3_off, s->se3_off, st));
   CU(upload(s->d_se2_off, s->se2_off, st));
@@ -1448,8 +1438,6 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_sch_descs, sch_descs, st));
   CU(upload(s->d_sch_pairs, sch_pairs, st));
   CU(upload(s->d_sch_combos, sch_combos, st));
-  CU(upload(s->d_sch_pair_ptr, sch_pair_ptr, st));
-  CU(upload(s->d_sch_combo_ptr, sch_combo_ptr, st));
   CU(upload(s->d_slot_off, slot_off, st));
   CU(s->d_slot_poses.alloc(12 * slot_pose.size()));
   CU(s->d_slot_dx.alloc(6 * slot_pose.size()));
