@@ -218,13 +218,20 @@ BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS 
  * and of the scalar tail alone (second, 16-double all-reduce after retract). */
 BSLAM_API int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles,
                          void** scalars_dev_ptr, int32_t* n_pad);
-/* Compact all-reduce payload: only the structurally non-zero 64x64 tiles of S (before fill-in),
+/* Compact all-reduce payload: only the structurally non-zero tiles of S (before fill-in),
  * then rhs and the scalars.  bslam_pack_reduced(s, 0) gathers it from the dense buffer after
  * bslam_reduce, the host all-reduces bslam_packed_buffer, bslam_pack_reduced(s, 1) scatters it back
  * before bslam_solve_reduced.  (The tile structures of all ranks must have been merged first.) */
 BSLAM_API int bslam_packed_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles);
 BSLAM_API int bslam_pack_reduced(bslam_solver* s, int unpack);
-/* Tile structure (64x64 tiles, (n_pad/64 + 1) x (n_pad/64) bytes, row-major) of
+/* The two halves of a sharded iteration as single calls (each recorded once as a CUDA graph and replayed):
+ *   bslam_iterate_pre  = bslam_linearize + bslam_reduce(lambda) + bslam_pack_reduced(0)
+ *   [the host all-reduces bslam_packed_buffer over the ranks]
+ *   bslam_iterate_post = bslam_pack_reduced(1) + bslam_solve_reduced + bslam_retract(eval_new_cost)
+ * Neither synchronises; read the scalars with bslam_get_scalars after the ranks' scalar all-reduce. */
+BSLAM_API int bslam_iterate_pre(bslam_solver* s, double lambda);
+BSLAM_API int bslam_iterate_post(bslam_solver* s, int eval_new_cost);
+/* Tile structure (tiles of bslam_tile_edge(), (nt + 1) x nt bytes with nt = n_pad / edge, row-major) of
  * the reduced system as seen by THIS handle's residual blocks.  set == 0 copies it
  * out; set != 0 ORs `mask` into it -- with sharded landmarks the host ORs the
  * masks of all ranks (all-reduce MAX) once after bslam_finalize, because the

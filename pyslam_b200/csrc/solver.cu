@@ -138,6 +138,11 @@ struct bslam_solver {
 
   // ---- CUDA graph of one whole iteration (single GPU, built-in blocks only) ----
   cudaGraphExec_t graph_exec = nullptr;
+  // the two halves of a SHARDED iteration (multi-GPU: the host all-reduces the packed payload in between)
+  cudaGraphExec_t graph_pre = nullptr, graph_post = nullptr;
+  double graph_pre_lambda = -1.0;
+  int graph_post_eval = -1;
+  int64_t graph_pre_launches = 0, graph_post_launches = 0;
   double graph_lambda = -1.0;
   int graph_eval = -1;
   int64_t graph_launches = 0;
@@ -170,6 +175,8 @@ struct bslam_solver {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph_pre) cudaGraphExecDestroy(graph_pre);
+    if (graph_post) cudaGraphExecDestroy(graph_post);
     if (h_scalars) cudaFreeHost(h_scalars);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -236,6 +243,9 @@ __global__ void permute_rows_kernel(int n, int width, const double* __restrict__
 
 void drop_graph(bslam_solver* s) {
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph_pre) cudaGraphExecDestroy(s->graph_pre);
+  if (s->graph_post) cudaGraphExecDestroy(s->graph_post);
+  s->graph_pre = s->graph_post = nullptr;
   s->graph_exec = nullptr;
 }
 
@@ -699,6 +709,31 @@ int fetch_scalars(bslam_solver* s) {
 }
 
 }  // namespace
+
+// Record `body` (kernel launches and async copies on the handle's stream) as a CUDA graph once, replay it after.
+template <typename F>
+int run_graphed(bslam_solver* s, cudaGraphExec_t* exec, int64_t* n_launches, F body) {
+  if (!*exec) {
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = s->launches;
+    CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    const cudaError_t ee = cudaStreamEndCapture(s->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ee != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      return fail(s, BSLAM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ee));
+    }
+    const cudaError_t ce = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { *exec = nullptr; return fail(s, BSLAM_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+    *n_launches = s->launches - l0;
+    s->launches = l0;
+  }
+  CU(cudaGraphLaunch(*exec, s->stream));
+  s->launches += *n_launches;
+  return BSLAM_OK;
+}
 
 // =============================================================== C ABI ====
 
@@ -1637,10 +1672,16 @@ int bslam_packed_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles) {
   return BSLAM_OK;
 }
 
+static int do_pack(bslam_solver* s, int unpack);
+
 int bslam_pack_reduced(bslam_solver* s, int unpack) {
   NEED(s && s->finalized, "bslam_pack_reduced: solver not finalized");
   CU(cudaSetDevice(s->device));
   if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  return do_pack(s, unpack);
+}
+
+static int do_pack(bslam_solver* s, int unpack) {
   const size_t tiles = (size_t)s->n_nz_tiles * bs::kNB * bs::kNB;
   if (s->n_nz_tiles > 0)
     LAUNCH(s, bs::pack_tiles_kernel, s->n_nz_tiles, 256, 0, s->S(), s->n_pad, s->nblk, s->d_nz_tiles.p, s->d_pack.p, unpack);
@@ -1649,6 +1690,45 @@ int bslam_pack_reduced(bslam_solver* s, int unpack) {
   else CU(cudaMemcpyAsync(s->d_pack.p + tiles, s->rhs(), tail * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   CU(cudaGetLastError());
   return BSLAM_OK;
+}
+
+int bslam_iterate_pre(bslam_solver* s, double lambda) {
+  NEED(s && s->finalized, "bslam_iterate_pre: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_iterate_pre: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+  auto body = [&]() {
+    int r = do_linearize(s);
+    if (!r) r = do_reduce(s, lambda);
+    if (!r) r = do_pack(s, 0);
+    return r;
+  };
+  if (s->use_graph && !s->timing && s->dn_blocks == 0) {
+    if (s->graph_pre && s->graph_pre_lambda != lambda) { cudaGraphExecDestroy(s->graph_pre); s->graph_pre = nullptr; }
+    s->graph_pre_lambda = lambda;
+    return run_graphed(s, &s->graph_pre, &s->graph_pre_launches, body);
+  }
+  return body();
+}
+
+int bslam_iterate_post(bslam_solver* s, int eval_new_cost) {
+  NEED(s && s->finalized, "bslam_iterate_post: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+  auto body = [&]() {
+    int r = do_pack(s, 1);
+    if (!r) r = do_solve_reduced(s);
+    if (!r) r = do_retract(s, eval_new_cost);
+    return r;
+  };
+  if (s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr) {
+    if (s->graph_post && s->graph_post_eval != eval_new_cost) { cudaGraphExecDestroy(s->graph_post); s->graph_post = nullptr; }
+    s->graph_post_eval = eval_new_cost;
+    return run_graphed(s, &s->graph_post, &s->graph_post_launches, body);
+  }
+  return body();
 }
 
 int bslam_set_shard(bslam_solver* s, int rank) {

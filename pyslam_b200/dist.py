@@ -74,19 +74,26 @@ class ShardedSolver:
             return eng.iterate(lam, eval_new_cost)
         import torch.distributed as dist
         stream = eng.torch_stream()
-        eng.linearize(fetch_cost=False)
-        eng.reduce(lam)
-        if hasattr(eng, 'pack_reduced'):
-            # only the structurally non-zero tiles of S (+ rhs + scalars) travel over NVLink
-            eng.pack_reduced(False)
+        if hasattr(eng, 'iterate_pre'):
+            # two graph replays around the NCCL all-reduce of the packed non-zero tiles of S (+ rhs + scalars)
+            eng.iterate_pre(lam)
             with _on_stream(stream):
                 dist.all_reduce(eng.packed_tensor(), group=self.group)
-            eng.pack_reduced(True)
+            eng.iterate_post(eval_new_cost)
         else:
-            with _on_stream(stream):
-                dist.all_reduce(eng.reduced_tensor(), group=self.group)
-        eng.solve_reduced()
-        eng.retract(eval_new_cost)
+            eng.linearize(fetch_cost=False)
+            eng.reduce(lam)
+            if hasattr(eng, 'pack_reduced'):
+                # only the structurally non-zero tiles of S (+ rhs + scalars) travel over NVLink
+                eng.pack_reduced(False)
+                with _on_stream(stream):
+                    dist.all_reduce(eng.packed_tensor(), group=self.group)
+                eng.pack_reduced(True)
+            else:
+                with _on_stream(stream):
+                    dist.all_reduce(eng.reduced_tensor(), group=self.group)
+            eng.solve_reduced()
+            eng.retract(eval_new_cost)
         with _on_stream(stream):
             dist.all_reduce(eng.scalars_tensor()[1:3], group=self.group)      # COST_NEW, DX_NORM2
         s = eng.scalars()

@@ -64,6 +64,8 @@ SIGNATURES = {
     'bslam_get_scalars': (C.c_int, [_h, _dp]),
     'bslam_reduced_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), _ip]),
     'bslam_packed_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    'bslam_iterate_pre': (C.c_int, [_h, C.c_double]),
+    'bslam_iterate_post': (C.c_int, [_h, C.c_int]),
     'bslam_pack_reduced': (C.c_int, [_h, C.c_int]),
     'bslam_tile_structure': (C.c_int, [_h, _bp, C.c_size_t, C.c_int]),
     'bslam_set_shard': (C.c_int, [_h, C.c_int]),
@@ -324,6 +326,14 @@ class Engine:
     def merge_tile_structure(self, mask):
         m = np.ascontiguousarray(mask, dtype=np.uint8)
         self._ck(self._lib.bslam_tile_structure(self._h, _b(m), m.size, 1))
+
+    def iterate_pre(self, lam=0.):
+        """linearize + reduce + pack of a sharded iteration (one CUDA graph)."""
+        self._ck(self._lib.bslam_iterate_pre(self._h, float(lam)))
+
+    def iterate_post(self, eval_new_cost=True):
+        """unpack + reduced solve + retract of a sharded iteration (one CUDA graph)."""
+        self._ck(self._lib.bslam_iterate_post(self._h, int(bool(eval_new_cost))))
 
     def pack_reduced(self, unpack=False):
         self._ck(self._lib.bslam_pack_reduced(self._h, int(bool(unpack))))
