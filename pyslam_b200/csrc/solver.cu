@@ -1226,6 +1226,62 @@ int bslam_finalize(bslam_solver* s) {
       todo.push_back({useL ? rest : left, false});
     }
   }
+  // Alternative: minimum-degree ordering.  Nested dissection of the table order is right for trajectory-like
+  // (banded) graphs, where minimum degree would eat the chain from its ends (a sequential factorisation); for
+  // graphs with long-range couplings (loop closures, random visibility) the bisection separators get wide and
+  // dense and minimum degree gives a shallower elimination tree.  The tile Cholesky is bound by the LENGTH OF
+  // THE CHAIN of dependent diagonal tiles, so both orders are scored by the height of their elimination tree
+  // (symbolic elimination on the supernode graph) and the shallower one wins; ties go to fewer filled tiles.
+  if (n_sn > 2 && n_sn <= 768) {
+    auto score = [&](const std::vector<int>& order, int& height, long long& fill) {
+      std::vector<int> pos(n_sn);
+      for (int i = 0; i < n_sn; ++i) pos[order[i]] = i;
+      std::vector<uint8_t> m((size_t)n_sn * n_sn, 0);
+      for (int u = 0; u < n_sn; ++u)
+        for (int v : adj[u]) {
+          const int hi = std::max(pos[u], pos[v]), lo = std::min(pos[u], pos[v]);
+          m[(size_t)hi * n_sn + lo] = 1;
+        }
+      std::vector<int> rows, h(n_sn, 1);
+      fill = 0; height = 1;
+      for (int k = 0; k < n_sn; ++k) {
+        rows.clear();
+        for (int i = k + 1; i < n_sn; ++i)
+          if (m[(size_t)i * n_sn + k]) rows.push_back(i);
+        fill += (long long)rows.size();
+        for (int a2 : rows) {
+          h[a2] = std::max(h[a2], h[k] + 1);
+          for (int b2 : rows)
+            if (a2 > b2) m[(size_t)a2 * n_sn + b2] = 1;
+        }
+        height = std::max(height, h[k]);
+      }
+    };
+    std::vector<int> md_order;
+    {
+      std::vector<std::vector<int>> nb(adj);
+      std::vector<uint8_t> alive(n_sn, 1);
+      for (int step = 0; step < n_sn; ++step) {
+        int best = -1;
+        for (int i = 0; i < n_sn; ++i)
+          if (alive[i] && (best < 0 || nb[i].size() < nb[best].size())) best = i;
+        md_order.push_back(best);
+        alive[best] = 0;
+        const std::vector<int> ns = nb[best];
+        for (int a2 : ns) {
+          std::vector<int>& na = nb[a2];
+          na.erase(std::remove(na.begin(), na.end(), best), na.end());
+          for (int b2 : ns)
+            if (b2 != a2 && std::find(na.begin(), na.end(), b2) == na.end()) na.push_back(b2);
+        }
+      }
+    }
+    int h_nd = 0, h_md = 0;
+    long long f_nd = 0, f_md = 0;
+    score(sn_order, h_nd, f_nd);
+    score(md_order, h_md, f_md);
+    if (h_md < h_nd || (h_md == h_nd && f_md < f_nd)) sn_order.swap(md_order);
+  }
   // offsets
   s->se3_off.assign(s->n_se3, -1);
   s->se2_off.assign(s->n_se2, -1);
