@@ -1210,7 +1210,10 @@ int bslam_finalize(bslam_solver* s) {
         for (int v : adj[u])
           if (side[v] == 1) { sepR.push_back(u); break; }
       for (int u : w.nodes) side[u] = 0;
-      const bool useL = sepL.size() <= sepR.size();
+      // the smaller separator; on ties the one that leaves the more balanced parts (for a chain this picks the
+      // middle node of three and saves one level of the elimination tree)
+      const size_t restL = std::max(left.size() - sepL.size(), right.size()), restR = std::max(left.size(), right.size() - sepR.size());
+      const bool useL = sepL.size() != sepR.size() ? sepL.size() < sepR.size() : restL <= restR;
       std::vector<int>& sep = useL ? sepL : sepR;
       if (sep.size() * 2 >= w.nodes.size()) {      // no useful separator: keep the table order
         sn_order.insert(sn_order.end(), w.nodes.begin(), w.nodes.end());
