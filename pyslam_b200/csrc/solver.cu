@@ -1229,12 +1229,12 @@ int bslam_finalize(bslam_solver* s) {
       todo.push_back({useL ? rest : left, false});
     }
   }
-  // Alternative: minimum-degree ordering.  Nested dissection of the table order is right for trajectory-like
-  // (banded) graphs, where minimum degree would eat the chain from its ends (a sequential factorisation); for
-  // graphs with long-range couplings (loop closures, random visibility) the bisection separators get wide and
-  // dense and minimum degree gives a shallower elimination tree.  The tile Cholesky is bound by the LENGTH OF
-  // THE CHAIN of dependent diagonal tiles, so both orders are scored by the height of their elimination tree
-  // (symbolic elimination on the supernode graph) and the shallower one wins; ties go to fewer filled tiles.
+  // Alternatives: greedy elimination orders.  Nested dissection of the table order is right for trajectory-like
+  // (banded) graphs, where plain minimum degree would eat the chain from its ends (a sequential factorisation);
+  // for graphs with long-range couplings (loop closures, random visibility) the bisection separators get wide
+  // and dense and a greedy order gives a shallower elimination tree.  The tile Cholesky is bound by the LENGTH
+  // OF THE CHAIN of dependent diagonal tiles, so the candidates are scored by the height of their elimination
+  // tree (symbolic elimination on the supernode graph) and the shallowest wins; ties go to fewer filled tiles.
   if (n_sn > 2 && n_sn <= 768) {
     auto score = [&](const std::vector<int>& order, int& height, long long& fill) {
       std::vector<int> pos(n_sn);
@@ -1260,30 +1260,45 @@ int bslam_finalize(bslam_solver* s) {
         height = std::max(height, h[k]);
       }
     };
-    std::vector<int> md_order;
-    {
+    // greedy elimination orders: key (degree) = minimum degree; key (height of the vertex's subtree so far,
+    // degree) = eliminate the shallowest vertices first, which keeps the elimination tree bushy
+    auto greedy = [&](bool height_first) {
+      std::vector<int> order;
       std::vector<std::vector<int>> nb(adj);
       std::vector<uint8_t> alive(n_sn, 1);
+      std::vector<int> h(n_sn, 1);
       for (int step = 0; step < n_sn; ++step) {
         int best = -1;
-        for (int i = 0; i < n_sn; ++i)
-          if (alive[i] && (best < 0 || nb[i].size() < nb[best].size())) best = i;
-        md_order.push_back(best);
+        for (int i = 0; i < n_sn; ++i) {
+          if (!alive[i]) continue;
+          if (best < 0) { best = i; continue; }
+          const bool better = height_first ? (h[i] != h[best] ? h[i] < h[best] : nb[i].size() < nb[best].size())
+                                           : nb[i].size() < nb[best].size();
+          if (better) best = i;
+        }
+        order.push_back(best);
         alive[best] = 0;
         const std::vector<int> ns = nb[best];
         for (int a2 : ns) {
           std::vector<int>& na = nb[a2];
           na.erase(std::remove(na.begin(), na.end(), best), na.end());
+          h[a2] = std::max(h[a2], h[best] + 1);
           for (int b2 : ns)
             if (b2 != a2 && std::find(na.begin(), na.end(), b2) == na.end()) na.push_back(b2);
         }
       }
+      return order;
+    };
+    int h_best = 0;
+    long long f_best = 0;
+    score(sn_order, h_best, f_best);
+    for (int mode = 0; mode < 2; ++mode) {
+      std::vector<int> cand = greedy(mode == 1);
+      int h_c = 0;
+      long long f_c = 0;
+      score(cand, h_c, f_c);
+      if (h_c < h_best || (h_c == h_best && f_c < f_best)) { sn_order.swap(cand); h_best = h_c; f_best = f_c; }
     }
-    int h_nd = 0, h_md = 0;
-    long long f_nd = 0, f_md = 0;
-    score(sn_order, h_nd, f_nd);
-    score(md_order, h_md, f_md);
-    if (h_md < h_nd || (h_md == h_nd && f_md < f_nd)) sn_order.swap(md_order);
   }
   // offsets
   s->se3_off.assign(s->n_se3, -1);
