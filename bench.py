@@ -13,9 +13,9 @@ new point -- what `Problem.solve_one_iter()` + the update does in the
 reference (pyslam/problem.py:143-156,182-194).
 
 Prints ONE JSON line (see the keys at the bottom).  `value` is measured with
-the problem resident in HBM; `e2e` goes through the C-ABI calls with HOST
-buffers (pinned): every step uploads the parameters, iterates and downloads the
-updated parameters.
+the problem resident in HBM; `e2e` goes through the C-ABI with HOST buffers
+(pinned): every step uploads the parameters, iterates and downloads the updated
+parameters (`bslam_iterate_host`, one call and one synchronisation per step).
 """
 import argparse
 import json
@@ -233,6 +233,8 @@ def run_ours(args):
     def e2e_step():
         # host parameters -> device, one iteration, updated parameters -> the same (pinned) host buffers,
         # which are the inputs of the next step
+        if world == 1:
+            return eng.iterate_host(np_Rt, np_pts, 0., True)      # one C-ABI call, one synchronisation
         eng.set_poses_se3(np_Rt)
         eng.set_points(np_pts)
         r = solver.iterate(0., True)

@@ -204,6 +204,13 @@ BSLAM_API int bslam_eval_cost(bslam_solver* s, double* cost);
  * (extension, not in the reference).  Any out pointer may be NULL. */
 BSLAM_API int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost,
                   double* cost_lin, double* cost_new, double* dx_norm);
+/* The same iteration for a caller whose parameters live in HOST memory, as the reference's param_dict does
+ * (pyslam/problem.py:143-156): upload the SE3 pose table (n x 12) and the point table (n x 3, user order),
+ * iterate, download the updated tables, with ONE stream synchronisation for the whole step.  Pinned buffers
+ * make the copies asynchronous; in == out is allowed; any pointer may be NULL (that transfer is skipped). */
+BSLAM_API int bslam_iterate_host(bslam_solver* s, double lambda, int eval_new_cost,
+                       const double* Rt_in, const double* xyz_in, double* Rt_out, double* xyz_out,
+                       double* cost_lin, double* cost_new, double* dx_norm);
 
 /* The same iteration in separately callable phases (parity tests, multi-GPU). */
 BSLAM_API int bslam_linearize(bslam_solver* s, double* cost_lin);          /* no Schur yet          */

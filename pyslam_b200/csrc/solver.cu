@@ -686,8 +686,15 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
   return BSLAM_OK;
 }
 
+int sync_and_timings(bslam_solver* s);
+
 int fetch_scalars(bslam_solver* s) {
   CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return sync_and_timings(s);
+}
+
+// wait for the handle's stream; with timing enabled, turn the recorded events into per-phase milliseconds
+int sync_and_timings(bslam_solver* s) {
   CU(cudaStreamSynchronize(s->stream));
   if (s->timing) {
     auto el = [&](int a, int b) {
@@ -1679,53 +1686,79 @@ int bslam_get_scalars(bslam_solver* s, double* out) {
   return BSLAM_OK;
 }
 
+// One full iteration enqueued on the handle's stream, scalars copied to the pinned host mirror, NO synchronisation.
+static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
+  int rc;
+  const bool graphable = s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr;
+  if (graphable) {
+    // the whole iteration (6 kernels + the scalar read-back) is one graph launch
+    if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+    if (s->graph_exec && (s->graph_lambda != lambda || s->graph_eval != eval_new_cost)) {
+      cudaGraphExecDestroy(s->graph_exec);
+      s->graph_exec = nullptr;
+    }
+    s->graph_lambda = lambda;
+    s->graph_eval = eval_new_cost;
+    return run_graphed(s, &s->graph_exec, &s->graph_launches, [&]() {
+      int r = do_linearize(s);
+      if (!r) r = do_reduce(s, lambda);
+      if (!r) r = do_solve_reduced(s);
+      if (!r) r = do_retract(s, eval_new_cost);
+      if (!r && cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost,
+                                s->stream) != cudaSuccess)
+        r = fail(s, BSLAM_E_CUDA, "scalar read-back could not be captured");
+      return r;
+    });
+  }
+  if ((rc = do_linearize(s))) return rc;
+  if ((rc = do_reduce(s, lambda))) return rc;
+  if ((rc = do_solve_reduced(s))) return rc;
+  if ((rc = do_retract(s, eval_new_cost))) return rc;
+  CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  return BSLAM_OK;
+}
+
+static int iterate_finish(bslam_solver* s, double* cost_lin, double* cost_new, double* dx_norm) {
+  int rc;
+  if ((rc = sync_and_timings(s))) return rc;       // one synchronisation (the scalar read-back is already enqueued)
+  if (cost_lin) *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
+  if (cost_new) *cost_new = s->h_scalars[BSLAM_S_COST_NEW];
+  if (dx_norm) *dx_norm = std::sqrt(s->h_scalars[BSLAM_S_DX_NORM2]);
+  return BSLAM_OK;
+}
+
 int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost, double* cost_lin, double* cost_new, double* dx_norm) {
   NEED(s && s->finalized, "bslam_iterate: solver not finalized");
   NEED(lambda >= 0.0, "bslam_iterate: lambda must be >= 0");
   CU(cudaSetDevice(s->device));
   int rc;
-  const bool graphable = s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr;
-  if (graphable) {
-    // the whole iteration (~15 kernels + memsets + the scalar read-back) is one graph launch
-    if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
-    if (s->graph_exec && (s->graph_lambda != lambda || s->graph_eval != eval_new_cost)) drop_graph(s);
-    if (!s->graph_exec) {
-      cudaGraph_t graph = nullptr;
-      const int64_t l0 = s->launches;
-      CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-      rc = do_linearize(s);
-      if (!rc) rc = do_reduce(s, lambda);
-      if (!rc) rc = do_solve_reduced(s);
-      if (!rc) rc = do_retract(s, eval_new_cost);
-      cudaError_t ce = cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
-      cudaError_t ee = cudaStreamEndCapture(s->stream, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess || ee != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        return fail(s, BSLAM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : ee));
-      }
-      ce = cudaGraphInstantiate(&s->graph_exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) { s->graph_exec = nullptr; return fail(s, BSLAM_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
-      s->graph_launches = s->launches - l0;
-      s->launches = l0;
-      s->graph_lambda = lambda;
-      s->graph_eval = eval_new_cost;
-    }
-    CU(cudaGraphLaunch(s->graph_exec, s->stream));
-    s->launches += s->graph_launches;
-    CU(cudaStreamSynchronize(s->stream));
-  } else {
-    if ((rc = do_linearize(s))) return rc;
-    if ((rc = do_reduce(s, lambda))) return rc;
-    if ((rc = do_solve_reduced(s))) return rc;
-    if ((rc = do_retract(s, eval_new_cost))) return rc;
-    if ((rc = fetch_scalars(s))) return rc;
+  if ((rc = iterate_enqueue(s, lambda, eval_new_cost))) return rc;
+  return iterate_finish(s, cost_lin, cost_new, dx_norm);
+}
+
+int bslam_iterate_host(bslam_solver* s, double lambda, int eval_new_cost, const double* Rt_in, const double* xyz_in,
+                       double* Rt_out, double* xyz_out, double* cost_lin, double* cost_new, double* dx_norm) {
+  NEED(s && s->finalized, "bslam_iterate_host: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_iterate_host: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  int rc;
+  // host parameters -> device (stream-ordered; the point table is permuted to the internal order on the device)
+  if (Rt_in && s->n_se3 > 0)
+    CU(cudaMemcpyAsync(s->d_se3.p, Rt_in, (size_t)s->n_se3 * 12 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  if (xyz_in && s->n_pt > 0) {
+    CU(cudaMemcpyAsync(s->d_stage.p, xyz_in, (size_t)s->n_pt * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    LAUNCH(s, permute_rows_kernel, cdiv(3LL * s->n_pt, 256), 256, 0, s->n_pt, 3, s->d_stage.p, s->d_pts.p, s->d_pt_perm.p, 1);
   }
-  if (cost_lin) *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
-  if (cost_new) *cost_new = s->h_scalars[BSLAM_S_COST_NEW];
-  if (dx_norm) *dx_norm = std::sqrt(s->h_scalars[BSLAM_S_DX_NORM2]);
-  return BSLAM_OK;
+  if ((rc = iterate_enqueue(s, lambda, eval_new_cost))) return rc;
+  // updated parameters -> host, then ONE synchronisation for the whole step
+  if (Rt_out && s->n_se3 > 0)
+    CU(cudaMemcpyAsync(Rt_out, s->d_se3.p, (size_t)s->n_se3 * 12 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  if (xyz_out && s->n_pt > 0) {
+    LAUNCH(s, permute_rows_kernel, cdiv(3LL * s->n_pt, 256), 256, 0, s->n_pt, 3, s->d_pts.p, s->d_stage.p, s->d_pt_perm.p, 0);
+    CU(cudaMemcpyAsync(xyz_out, s->d_stage.p, (size_t)s->n_pt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  }
+  CU(cudaGetLastError());
+  return iterate_finish(s, cost_lin, cost_new, dx_norm);
 }
 
 int bslam_reduced_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles, void** scalars_dev_ptr, int32_t* n_pad) {

@@ -57,6 +57,7 @@ SIGNATURES = {
     'bslam_get_layout': (C.c_int, [_h, _ip, _ip, _ip, _ip, _ip, _ip]),
     'bslam_eval_cost': (C.c_int, [_h, _dp]),
     'bslam_iterate': (C.c_int, [_h, C.c_double, C.c_int, _dp, _dp, _dp]),
+    'bslam_iterate_host': (C.c_int, [_h, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     'bslam_linearize': (C.c_int, [_h, _dp]),
     'bslam_reduce': (C.c_int, [_h, C.c_double]),
     'bslam_solve_reduced': (C.c_int, [_h]),
@@ -289,6 +290,18 @@ class Engine:
         """(cost at linearisation point, cost at x [+] dx, ||dx||)."""
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._ck(self._lib.bslam_iterate(self._h, float(lam), int(bool(eval_new_cost)), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def iterate_host(self, Rt, xyz, lam=0., eval_new_cost=True):
+        """One iteration on HOST parameter tables (float64, C-contiguous; pinned memory makes the copies
+        asynchronous): `Rt` (n_se3 x 12) and `xyz` (n_pt x 3) are uploaded, updated in place and read back
+        with a single synchronisation.  Returns (cost at the linearisation point, cost at x [+] dx, ||dx||)."""
+        for arr in (Rt, xyz):
+            if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags['C_CONTIGUOUS']):
+                raise EngineError('iterate_host needs C-contiguous float64 arrays (it writes the result in place)')
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.bslam_iterate_host(self._h, float(lam), int(bool(eval_new_cost)), _d(Rt), _d(xyz), _d(Rt), _d(xyz),
+                                              C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
     def linearize(self, fetch_cost=True):

@@ -343,6 +343,29 @@ def test_short_tracks_many_landmarks_per_block():
     _check_ba_against_oracle(d)
 
 
+def test_iterate_host_equals_separate_calls():
+    """bslam_iterate_host (upload + iterate + download, one synchronisation) against set / iterate / get on a
+    second handle.  The two handles sum their fp64 atomics in different orders, so the trajectories agree to
+    rounding amplified by the solve, not bit for bit."""
+    from pyslam_b200 import synthetic
+    d = synthetic.stereo_ba(12, 300, track=5, seed=21)
+    pr1 = B.product_ba_problem(d, bulk=True); pr1._ensure_lowered()
+    pr2 = B.product_ba_problem(d, bulk=True); pr2._ensure_lowered()
+    e1, e2 = pr1._engine, pr2._engine
+    Rt = np.ascontiguousarray(np.concatenate([d['R0'].reshape(-1, 9), d['t0']], axis=1))
+    pts = np.ascontiguousarray(d['pts0'], dtype=np.float64)
+    Rt2, pts2 = Rt.copy(), pts.copy()
+    for it in range(3):
+        e1.set_poses_se3(Rt); e1.set_points(pts)
+        r1 = e1.iterate(0., True)
+        e1.get_poses_se3(Rt); e1.get_points(pts)
+        r2 = e2.iterate_host(Rt2, pts2, 0., True)
+        np.testing.assert_allclose(r2, r1, rtol=1e-8)
+        np.testing.assert_allclose(Rt2, Rt, rtol=0, atol=1e-8)
+        np.testing.assert_allclose(pts2, pts, rtol=0, atol=1e-8)
+    assert r1[1] < r1[0]
+
+
 def test_mixed_groups_losses_and_stiffness():
     """Reprojection blocks with different losses and per-block stiffness in one
     problem (several constant groups inside one kernel launch)."""
