@@ -3,24 +3,29 @@
 // schur.cuh this replaces `splinalg.spsolve(precision, information)`
 // (pyslam/problem.py:186).
 //
-// Layout: S is n_pad x n_pad row-major (n_pad = 64 * nt, identity on the padding
-// diagonal, lower triangle referenced); the right-hand side is stored as row
+// Layout: S is n_pad x n_pad row-major (n_pad = kNB * nt, kNB = 32, identity on the
+// padding diagonal, lower triangle referenced); the right-hand side is stored as row
 // n_pad of the same buffer, i.e. it is tile-row `nt` of a (nt+1) x nt grid of
-// 64x64 tiles.  Carrying b as an extra row makes the forward substitution part
+// kNB x kNB tiles.  Carrying b as an extra row makes the forward substitution part
 // of the factorisation:  [L; y^T] [L^T] = [S; b^T].
 //
-// Schedule: left-looking, one task per non-zero tile (i,j) of L, dispatched in
-// column-major order through an atomic ticket; the structure (which tiles are
-// non-zero after fill-in) is computed once on the host from the co-visibility
-// graph, so banded / sparse camera systems skip their zero tiles.
-//     C   = S_ij - sum_{k<j} L_ik L_jk^T       fp64 tensor-core MMAs (DMMA m8n8k4),
-//                                              waiting per k on the producers' flags
-//     i==j: L_jj = chol(C), X_jj = L_jj^-1      (two 32x32 register-resident warp
-//                                              factorisations + DMMA for the rest)
+// Schedule: left-looking, one task per non-zero tile (i,j) of L, dispatched through an
+// atomic ticket in DEPENDENCY-LEVEL order (solver.cu: build_chol_plan); the structure
+// (which tiles are non-zero after fill-in) is computed once on the host from the
+// co-visibility graph, so banded / sparse camera systems skip their zero tiles.
+//     C   = S_ij - sum_{k<j} L_ik L_jk^T       fp64 tensor-core MMAs (DMMA m8n8k4), producers
+//                                              consumed in readiness order, waiting on their flags
+//     i==j: L_jj = chol(C), X_jj = L_jj^-1      (two 16x16 register-resident warp factorisations
+//                                              whose idle half-warp forms the inverse in the same
+//                                              pivot loop + DMMA for the off-diagonal block)
 //     i>j : L_ij = C X_jj^T                      DMMA
 // followed by nt backward-substitution tasks x_k = X_kk^T (y_k - sum_{i>k} L_ik^T x_i).
-// Dependencies are epoch flags in global memory (st.release / ld.acquire at gpu
-// scope); all CTAs are co-resident and take tickets in increasing order, so a
+// The run time is the latency of the chain diag(k) -> L_ik -> diag(i) along the elimination
+// tree, not flops: diagonal tasks therefore take their (up to two) critical producers
+// through early-published C_ik tiles and form L_ik themselves (CholPlan::cscr).
+// Dependencies are flags in global memory (st.release / ld.acquire at gpu scope) compared
+// against a launch epoch the kernel advances itself (no memsets between launches); all
+// CTAs are co-resident and take tickets in increasing order of a topological order, so a
 // waiting CTA always waits on a ticket held by a running CTA (no deadlock).
 //
 // tcgen05 has no fp64 kind: DMMA (mma.sync.m8n8k4.f64) is the tensor path an

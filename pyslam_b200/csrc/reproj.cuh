@@ -8,28 +8,30 @@
 //   sqrt(loss.weight) row scaling, cost  pyslam/problem.py:349-360
 //   HT.HT^T, -HT.e for these blocks      pyslam/problem.py:329-333
 //
-// Data layout (all fp64, device resident, built once by Solver::finalize):
-//   observations sorted by landmark, SoA:  obs_u/obs_v/obs_d[N], obs_pose[N], obs_pt[N]
+// Data layout (all fp64, device resident, built once by bslam_finalize):
 //   poses   [K][12] = R row-major | t      (K small: L1/L2 resident)
 //   points  [P][3], landmarks to be eliminated first (index < n_lm), ordered by the
 //           first pose that sees them so that neighbouring landmarks share cameras
 //   "landmark blocks": runs of whole landmarks with <= 128 observations; per block the
-//           distinct variable poses ("slots"), a per-observation slot id and the
-//           block's observations grouped by slot (cam_perm / seg_start)
+//           distinct variable poses ("slots"), seg_start (first observation of every slot)
+//   observations, SoA: obs_u/obs_v/obs_d[N], obs_code[N] (slot | block-local landmark | group),
+//           obs_pose[N], obs_pt[N]; SLOT-MAJOR inside each block (grouped by pose);
+//           lm_start (CSR over landmarks) + lm_obs / lm_obs_local give the landmark order
 // Outputs per launch:
-//   W   [18][N]   J_T^T w J_p (6x3 row-major index k = 3r+c), SoA planes of N doubles
+//   W   tiled (common.cuh: w_index)  J_T^T w J_p (6x3 row-major index k = 3r+c) per observation
 //   Vg  [n_lm][9] V_p (xx,xy,xz,yy,yz,zz) | b_p   -- landmark blocks
 //   S   lower triangle of the dense reduced matrix: U_c added at the pose's offset
 //   rhs b_c = -J_T^T w r
 //   scalars[COST_LIN] += sum rho(r)
 //
-// reproj_block_kernel (the fast path): one CTA per landmark block, one thread per
-// observation.  Each thread leaves its 27 camera values (U_c lower triangle, b_c)
+// reproj_block_kernel (the fast path): persistent CTAs walking landmark blocks, one thread
+// per observation.  Each thread leaves its 27 camera values (U_c lower triangle, b_c)
 // and 9 landmark values (V_p, b_p) in a shared-memory row; the CTA then reduces
 // them per slot / per landmark, so HBM sees one fp64 atomic per (slot, value) and
 // a plain store per landmark value instead of 36 atomics per observation.
-// reproj_generic_kernel: same arithmetic with global atomics for the tail
-// (landmarks with more than 128 observations, observations of constant points).
+// reproj_generic_kernel: same arithmetic with global atomics for the tail (landmarks with
+// more than 64 observations or two observations by one pose, observations of points that
+// are not eliminated).
 #pragma once
 #include "common.cuh"
 #include "loss.cuh"

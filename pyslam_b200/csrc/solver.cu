@@ -1101,11 +1101,12 @@ int bslam_finalize(bslam_solver* s) {
 
   // ---- reduced-system layout ----------------------------------------------------------
   // The non-eliminated parameter blocks (SE3 poses, SE2 poses, vectors, remaining points,
-  // in table order) are packed into "supernodes" of <= 64 tangent dimensions; every
-  // supernode starts on a 64x64 tile boundary of the reduced matrix (unused entries are
-  // padding: identity diagonal, zero right-hand side).  The supernodes are then ordered by
-  // nested dissection of their coupling graph, so that the tile Cholesky's dependency DAG
-  // is a bushy tree instead of a chain (trajectory-like problems are banded in table order).
+  // in table order) are packed into "supernodes" of <= kNB (32) tangent dimensions; every
+  // supernode starts on a tile boundary of the reduced matrix (unused entries are padding:
+  // identity diagonal, zero right-hand side).  The supernodes are then ordered by nested
+  // dissection of their coupling graph -- or a greedy elimination order when that gives a
+  // shallower elimination tree, see below -- so that the tile Cholesky's dependency DAG is a
+  // bushy tree instead of a chain (trajectory-like problems are banded in table order).
   struct Item { int kind, idx, dof; };
   std::vector<Item> items;
   for (int i = 0; i < s->n_se3; ++i) if (!s->se3_const[i]) items.push_back({0, i, 6});
