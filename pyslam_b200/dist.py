@@ -5,12 +5,12 @@ the observations that reference them -- are partitioned contiguously over the
 ranks; the poses and the reduced camera system are replicated.  Per iteration:
 
     every rank : linearise its observations, eliminate its landmarks
-                 -> partial [S | rhs | cost]                      (CUDA, local)
+                 -> partial [S | rhs | cost]     (bslam_iterate_pre: one CUDA graph)
     all ranks  : ONE all-reduce (sum, fp64) of that buffer, packed to its
                  structurally non-zero 32x32 tiles                 (NCCL)
     every rank : factorise S, solve dx_c (redundantly, bit-identical inputs),
                  back-substitute and retract its own landmarks, cost at the
-                 new point                                         (CUDA, local)
+                 new point                      (bslam_iterate_post: one CUDA graph)
     all ranks  : all-reduce of two scalars (new cost, ||dx_p||^2)
 
 The reference has no distributed path at all; this is the
@@ -74,26 +74,11 @@ class ShardedSolver:
             return eng.iterate(lam, eval_new_cost)
         import torch.distributed as dist
         stream = eng.torch_stream()
-        if hasattr(eng, 'iterate_pre'):
-            # two graph replays around the NCCL all-reduce of the packed non-zero tiles of S (+ rhs + scalars)
-            eng.iterate_pre(lam)
-            with _on_stream(stream):
-                dist.all_reduce(eng.packed_tensor(), group=self.group)
-            eng.iterate_post(eval_new_cost)
-        else:
-            eng.linearize(fetch_cost=False)
-            eng.reduce(lam)
-            if hasattr(eng, 'pack_reduced'):
-                # only the structurally non-zero tiles of S (+ rhs + scalars) travel over NVLink
-                eng.pack_reduced(False)
-                with _on_stream(stream):
-                    dist.all_reduce(eng.packed_tensor(), group=self.group)
-                eng.pack_reduced(True)
-            else:
-                with _on_stream(stream):
-                    dist.all_reduce(eng.reduced_tensor(), group=self.group)
-            eng.solve_reduced()
-            eng.retract(eval_new_cost)
+        # two graph replays around the NCCL all-reduce of the packed non-zero tiles of S (+ rhs + scalars)
+        eng.iterate_pre(lam)
+        with _on_stream(stream):
+            dist.all_reduce(eng.packed_tensor(), group=self.group)
+        eng.iterate_post(eval_new_cost)
         with _on_stream(stream):
             dist.all_reduce(eng.scalars_tensor()[1:3], group=self.group)      # COST_NEW, DX_NORM2
         s = eng.scalars()

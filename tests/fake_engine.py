@@ -291,6 +291,19 @@ class FakeEngine:
     def reduced_tensor(self):
         return self._buf
 
+    # the product engine's sharded-iteration surface (bslam_iterate_pre / bslam_packed_buffer / bslam_iterate_post):
+    # here the dense buffer doubles as the "packed" payload
+    def iterate_pre(self, lam=0.):
+        self.linearize(fetch_cost=False)
+        self.reduce(lam)
+
+    def packed_tensor(self):
+        return self._buf
+
+    def iterate_post(self, eval_new_cost=True):
+        self.solve_reduced()
+        self.retract(eval_new_cost)
+
     def scalars_tensor(self):
         import torch
         if getattr(self, '_buf', None) is None:
