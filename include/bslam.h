@@ -79,6 +79,7 @@ typedef struct bslam_solver bslam_solver;
 #define BSLAM_T_RETRACT    6   /* exp / retract + ||dx||                            */
 #define BSLAM_T_COST       7   /* cost at the new point                             */
 #define BSLAM_T_TOTAL      8
+#define BSLAM_T_FUSED      9   /* fused_panel_kernel alone (linearise + eliminate the panels) */
 #define BSLAM_N_TIMINGS   16
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -175,6 +176,17 @@ BSLAM_API int bslam_upload_dense_values(bslam_solver* s, const double* e, size_t
 
 BSLAM_API int bslam_clear_blocks(bslam_solver* s);
 
+/* How bslam_finalize lowers the reprojection blocks for bslam_iterate* (call before bslam_finalize):
+ *   0  landmark-block kernels only: W = J_T^T w J_p is materialised (144 B per observation);
+ *   1  (default) dense landmark panels -- runs of <= 64 landmarks seen by <= 8 poses whose
+ *      (pose, landmark) grid is at least half full -- are linearised AND eliminated by one fused
+ *      kernel that never writes W; everything else as in mode 0;
+ *   2  every run of landmarks that fits a panel takes the fused kernel (tests).
+ * The result of an iteration is the same up to rounding in all modes. */
+BSLAM_API int bslam_set_fused(bslam_solver* s, int mode);
+/* Number of panels / of landmarks inside panels chosen by the last bslam_finalize. */
+BSLAM_API int bslam_get_fused(bslam_solver* s, int32_t* n_panels, int32_t* n_landmarks);
+
 /* Lower the problem: orders observations by landmark, decides which points are
  * eliminated by the Schur complement, lays out the reduced system, allocates
  * device memory.  Replaces `_get_update_partition_dict` (problem.py:252-277)
@@ -218,6 +230,11 @@ BSLAM_API int bslam_reduce(bslam_solver* s, double lambda);                /* da
 BSLAM_API int bslam_solve_reduced(bslam_solver* s);                        /* Cholesky + substitution + landmark back-substitution */
 BSLAM_API int bslam_retract(bslam_solver* s, int eval_new_cost);           /* x <- x [+] dx (+ cost) */
 BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS */);   /* syncs */
+/* Exactly what bslam_iterate runs before the reduced solve (fused panels included): linearise + damping +
+ * landmark elimination.  bslam_get_reduced_system then returns the Schur complement the iteration
+ * factorises; bslam_solve_reduced and bslam_retract_iterate complete the iteration. */
+BSLAM_API int bslam_linearize_reduce(bslam_solver* s, double lambda);
+BSLAM_API int bslam_retract_iterate(bslam_solver* s, int eval_new_cost);
 
 /* Multi-GPU plumbing: device address/length (in doubles) of the contiguous
  * [S (n_pad x n_pad) | rhs (n_pad) | scalars (BSLAM_N_SCALARS)] buffer that the

@@ -1,0 +1,505 @@
+// panel.cuh -- fused linearisation + landmark elimination for DENSE landmark panels:
+// the product path of bundle adjustment.  W = J_T^T w J_p is never written to HBM.
+//
+// Replaces, for the reprojection blocks of a panel, in ONE kernel per iteration
+//   ReprojectionResidual.evaluate / StereoCamera.project   pyslam/residuals/reprojection_residual.py:13-37,
+//                                                           pyslam/sensors/stereo_camera.py:100-134
+//   sqrt(loss.weight) scaling, cost                         pyslam/problem.py:349-360
+//   HT.HT^T, -HT.e                                          pyslam/problem.py:329-333
+//   the landmark part of spsolve(H, g)                      pyslam/problem.py:186   (Schur complement)
+// and, in panel_finish_kernel, the landmark part of the update + the cost at x [+] dx
+//   (pyslam/problem.py:155-156, 189-190, 400-409).
+//
+// A PANEL is a run of <= 64 consecutive landmarks (internal order: sorted by the first pose that
+// sees them) together with the <= 8 distinct poses ("rows") that observe them; its observations are
+// stored as a padded grid  cell = (row, landmark)  [n_rows][64]  with a 64-bit presence mask per row
+// (bslam_finalize builds panels only where the grid is well filled; everything else takes the
+// landmark-block kernels of reproj.cuh / schur.cuh).  A CTA of 8 warps walks panels:
+//
+//   P1  warp = row, lane = two landmarks: structured linearisation (reproj_blocks), cost;
+//       camera values U_c, b_c (27) summed over the row by a register butterfly (no shared memory)
+//       -> one fp64 atomic per value; landmark values V_p, b_p (9) -> shared partials;
+//       W (6x3) -> shared memory, already in the operand layout of P4.
+//   P2  thread = landmark: V_p = sum of partials, (V_p + lambda diag)^-1 -> HBM (back-substitution),
+//       Cholesky V = L L^T, c = L^-1 b_p.
+//   P3  Z = W L^-T in place (so that W V^-1 W'^T = Z Z'^T and W V^-1 b_p = Z c).
+//   P4  S -= Zbig Zbig^T, rhs -= Zbig c: a symmetric rank-192 update of the panel's
+//       (6 n_var + 1)-row operand [Z_0; ...; Z_{n_var-1}; c] on 8x8x4 fp64 tensor-core tiles
+//       (mma.sync.m8n8k4.f64 = DMMA; tcgen05 has no fp64 kind), K = 4 packs landmark/coordinate
+//       pairs without padding, lower-triangular tiles only, one fp64 atomic per element.
+//
+// Algorithmic HBM bytes per iteration: 32 B per observation (u, v, d + padding of the grid) read,
+// 24 B per landmark read, 120 B per landmark written (V_p | b_p | V^-1), 432 B per pose of atomics
+// -> SURVEY 8(d)'s fused figure 32 N + 432 K + 120 L.  The kernel is bound by the fp64 pipe
+// (DFMA + DMMA share it on sm_100a), not by HBM: see DESIGN.md section 3.
+#pragma once
+#include "cholesky.cuh"
+#include "common.cuh"
+#include "reproj.cuh"
+#include "schur.cuh"
+
+namespace bs {
+
+constexpr int kPanelLm = 64;        // landmarks per panel (two per lane)
+constexpr int kPanelRows = 8;       // poses per panel = warps per CTA
+constexpr int kPanelThreads = 32 * kPanelRows;
+constexpr int kZGroup = 76;         // doubles per group of 4 landmarks of one row: 6 x 12 + 4 (bank shift)
+constexpr int kZRow = (kPanelLm / 4) * kZGroup;
+constexpr int kCGroup = 12;
+
+struct PanelRow {
+  int pose;                 // index into the SE3 table
+  int off;                  // reduced offset of the pose, -1: constant
+  unsigned mask_lo, mask_hi;  // landmark j of the panel is observed by this pose
+};
+struct Panel {
+  int lm_begin, n_lms;      // landmarks [lm_begin, lm_begin + n_lms)
+  int row_begin, n_rows;    // rows [row_begin, row_begin + n_rows): the variable poses first
+  int n_var;                // number of variable rows
+  int pad0, pad1, pad2;
+};
+
+struct PanelArgs {
+  int n_panels;
+  const Panel* __restrict__ panels;
+  const PanelRow* __restrict__ rows;
+  const double* __restrict__ pu;            // [n_rows_total][64] observations of the cells (0 where absent)
+  const double* __restrict__ pv;
+  const double* __restrict__ pd;
+  const unsigned short* __restrict__ pgrp;  // group per cell (kLoss < 0 only)
+  const ReprojGroup* __restrict__ groups;
+  ReprojGroup g0;
+  const double* __restrict__ poses;         // [K][12] at the linearisation point
+  const double* __restrict__ poses_new;     // finish: retracted poses
+  const double* __restrict__ pts_in;        // [P][3]
+  double* __restrict__ pts;                 // finish: updated in place (same buffer as pts_in)
+  double lambda;
+  double* __restrict__ Vg;                  // [n_lm][9] V_p | b_p
+  double* __restrict__ Vinv;                // [n_lm][6]
+  double* __restrict__ S;
+  int ldS;
+  double* __restrict__ rhs;
+  double* __restrict__ scalars;
+  const double* __restrict__ dx_red;        // finish: reduced update (dx_c at the poses' offsets)
+  double* __restrict__ dx_lm;               // finish: landmark part of the update vector
+  int eval_cost;
+  int max_var;                              // shared-memory carve-up (rows of Z)
+};
+
+BS_HD size_t panel_smem_bytes(int max_var) {
+  return sizeof(double) * ((size_t)max_var * kZRow + (kPanelLm / 4) * kCGroup + 4 * 9 * kPanelLm + 6 * kPanelLm + 3 * kPanelLm) +
+         sizeof(int) * 64 + sizeof(PanelRow) * kPanelRows;
+}
+
+// Sum over the 32 lanes of 32 values per lane; on return v[0] of lane L holds the total of value L.
+// 31 exchanges instead of 32 x 5 for a plain xor reduction of every value.
+BS_D void warp_transpose_sum32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+}
+
+// index t of the lower-triangular tile list (row-major) -> (I, J)
+BS_D void tile_ij(int t, int& I, int& J) {
+  int i = 0;
+  while ((i + 1) * (i + 2) / 2 <= t) ++i;
+  I = i;
+  J = t - i * (i + 1) / 2;
+}
+
+template <int kLoss>
+__global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const PanelArgs a) {
+  extern __shared__ __align__(16) double psm[];
+  __shared__ double sred[kPanelThreads / 32];
+  double* sZ = psm;                                           // [max_var][16 groups][76]
+  double* sC = sZ + (size_t)a.max_var * kZRow;                // [16 groups][12]
+  double* sVp = sC + (kPanelLm / 4) * kCGroup;                // [4][9][64]
+  double* sL = sVp + 4 * 9 * kPanelLm;                        // [6][64]: 1/l00, l10, 1/l11, l20, l21, 1/l22
+  double* sPts = sL + 6 * kPanelLm;                           // [64][3]
+  int* sIdx = reinterpret_cast<int*>(sPts + 3 * kPanelLm);    // operand row -> index in S / rhs
+  PanelRow* sRows = reinterpret_cast<PanelRow*>(sIdx + 64);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double cost = 0.0;
+  // lane -> position of its camera value inside the pose's diagonal block of S (lower triangle, row-major)
+  int tri_off;
+  {
+    int r = 0;
+    while ((r + 1) * (r + 2) / 2 <= lane) ++r;
+    tri_off = lane < 21 ? r * a.ldS + (lane - r * (r + 1) / 2) : 0;
+  }
+  const double damp = 1.0 + a.lambda;
+
+  for (int pn = blockIdx.x; pn < a.n_panels; pn += gridDim.x) {
+    const Panel pan = a.panels[pn];
+    if (tid < pan.n_rows) sRows[tid] = a.rows[pan.row_begin + tid];
+    if (tid < 3 * kPanelLm) sPts[tid] = tid < 3 * pan.n_lms ? a.pts_in[3 * (size_t)pan.lm_begin + tid] : 0.0;
+    __syncthreads();        // header visible; the tile phase of the previous panel is over
+
+    // ---------------------------------------------------------------- P1: one row per warp
+    double vp[2][9];
+#pragma unroll
+    for (int s_ = 0; s_ < 2; ++s_)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) vp[s_][k] = 0.0;
+    if (warp < pan.n_rows) {
+      const PanelRow row = sRows[warp];
+      const bool isvar = warp < pan.n_var;
+      double P[12];
+      {
+        const double* Pg = a.poses + 12 * (size_t)row.pose;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+      }
+      double U[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) U[k] = 0.0;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int j = lane + 32 * sub;
+        const bool present = (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) != 0;
+        double* zc = sZ + warp * kZRow + (j >> 2) * kZGroup + 3 * (j & 3);
+        if (present) {
+          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + j;
+          const double u = ld_stream(a.pu + cell), v = ld_stream(a.pv + cell), d = ld_stream(a.pd + cell);
+          const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[cell]];
+          double X[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) X[k] = sPts[3 * j + k];
+          ReprojBlocks o;
+          reproj_blocks<kLoss>(grp, P, X, u, v, d, o);
+          cost += o.cost;
+          // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
+          vp[sub][0] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
+          vp[sub][1] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
+          vp[sub][2] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
+          vp[sub][3] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
+          vp[sub][4] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
+          vp[sub][5] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
+          vp[sub][6] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
+          vp[sub][7] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
+          vp[sub][8] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
+          if (isvar) {
+            // U_c lower triangle (row-major): rows 0-2 M; rows 3-5 [(M B)^T | B^T M B]; then b_c = -[t; B^T t]
+            U[0] += o.M[0]; U[1] += o.M[1]; U[2] += o.M[3]; U[3] += o.M[2]; U[4] += o.M[4]; U[5] += o.M[5];
+            U[6] += o.MB[0]; U[7] += o.MB[3]; U[8] += o.MB[6]; U[9] += o.BMB[0];
+            U[10] += o.MB[1]; U[11] += o.MB[4]; U[12] += o.MB[7]; U[13] += o.BMB[1]; U[14] += o.BMB[3];
+            U[15] += o.MB[2]; U[16] += o.MB[5]; U[17] += o.MB[8]; U[18] += o.BMB[2]; U[19] += o.BMB[4]; U[20] += o.BMB[5];
+            U[21] -= o.t[0]; U[22] -= o.t[1]; U[23] -= o.t[2];
+            U[24] -= o.y * o.t[2] - o.z * o.t[1];
+            U[25] -= o.z * o.t[0] - o.x * o.t[2];
+            U[26] -= o.x * o.t[1] - o.y * o.t[0];
+            // W = [M R; B^T M R], element (r, c) at zc[12 r + c]
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              zc[c] = o.MR[c];
+              zc[12 + c] = o.MR[3 + c];
+              zc[24 + c] = o.MR[6 + c];
+              zc[36 + c] = o.y * o.MR[6 + c] - o.z * o.MR[3 + c];
+              zc[48 + c] = o.z * o.MR[c] - o.x * o.MR[6 + c];
+              zc[60 + c] = o.x * o.MR[3 + c] - o.y * o.MR[c];
+            }
+          }
+        } else if (isvar) {
+#pragma unroll
+          for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) zc[12 * r + c] = 0.0;
+        }
+      }
+      if (isvar) {
+        if (a.lambda > 0.0) { U[0] *= damp; U[2] *= damp; U[5] *= damp; U[9] *= damp; U[14] *= damp; U[20] *= damp; }
+        warp_transpose_sum32(U, lane);
+        if (lane < 21) red_add(a.S + (size_t)row.off * (a.ldS + 1) + tri_off, U[0]);
+        else if (lane < 27) red_add(a.rhs + row.off + (lane - 21), U[0]);
+      }
+    }
+    // landmark partials: rows 0-3 store, rows 4-7 add after the barrier
+    if (warp < 4) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sVp[(warp * 9 + k) * kPanelLm + lane + 32 * sub] = vp[sub][k];
+    }
+    __syncthreads();
+    if (warp >= 4 && warp < pan.n_rows) {
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sVp[((warp - 4) * 9 + k) * kPanelLm + lane + 32 * sub] += vp[sub][k];
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- P2: one landmark per thread
+    if (tid < kPanelLm) {
+      const int j = tid;
+      double V[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        V[k] = (sVp[k * kPanelLm + j] + sVp[(9 + k) * kPanelLm + j]) + (sVp[(18 + k) * kPanelLm + j] + sVp[(27 + k) * kPanelLm + j]);
+      double i00 = 1.0, l10 = 0.0, i11 = 1.0, l20 = 0.0, l21 = 0.0, i22 = 1.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
+      if (j < pan.n_lms) {
+        const size_t q = (size_t)pan.lm_begin + j;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a.Vg[9 * q + k] = V[k];
+        double vi[6];
+        sym3_inverse(V, a.lambda, vi);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.Vinv[6 * q + k] = vi[k];
+        // (V + lambda diag V) = L L^T
+        const double v00 = V[0] * damp, v11 = V[3] * damp, v22 = V[5] * damp;
+        i00 = fast_rsqrt(v00);
+        l10 = V[1] * i00; l20 = V[2] * i00;
+        i11 = fast_rsqrt(v11 - l10 * l10);
+        l21 = (V[4] - l20 * l10) * i11;
+        i22 = fast_rsqrt(v22 - l20 * l20 - l21 * l21);
+        c0 = V[6] * i00;
+        c1 = (V[7] - l10 * c0) * i11;
+        c2 = (V[8] - l20 * c0 - l21 * c1) * i22;
+      }
+      sL[j] = i00; sL[kPanelLm + j] = l10; sL[2 * kPanelLm + j] = i11;
+      sL[3 * kPanelLm + j] = l20; sL[4 * kPanelLm + j] = l21; sL[5 * kPanelLm + j] = i22;
+      double* cc = sC + (j >> 2) * kCGroup + 3 * (j & 3);
+      cc[0] = c0; cc[1] = c1; cc[2] = c2;
+    } else if (tid < kPanelLm + 64) {
+      const int zr = tid - kPanelLm;
+      int idx = -1;
+      if (zr < 6 * pan.n_var) idx = sRows[zr / 6].off + zr % 6;
+      else if (zr == 6 * pan.n_var) idx = -2;         // the row of c: its products go to the right-hand side
+      sIdx[zr] = idx;
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- P3: Z = W L^-T in place
+    if (warp < pan.n_var) {
+      const PanelRow row = sRows[warp];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int j = lane + 32 * sub;
+        if (!((((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u))) continue;
+        double* zc = sZ + warp * kZRow + (j >> 2) * kZGroup + 3 * (j & 3);
+        const double i00 = sL[j], l10 = sL[kPanelLm + j], i11 = sL[2 * kPanelLm + j];
+        const double l20 = sL[3 * kPanelLm + j], l21 = sL[4 * kPanelLm + j], i22 = sL[5 * kPanelLm + j];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double w0 = zc[12 * r], w1 = zc[12 * r + 1], w2 = zc[12 * r + 2];
+          const double z0 = w0 * i00;
+          const double z1 = (w1 - z0 * l10) * i11;
+          const double z2 = (w2 - z0 * l20 - z1 * l21) * i22;
+          zc[12 * r] = z0; zc[12 * r + 1] = z1; zc[12 * r + 2] = z2;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- P4: S -= Zbig Zbig^T on DMMA tiles
+    {
+      const int n_zr = 6 * pan.n_var + 1;
+      const int T = (n_zr + 7) >> 3;
+      const int ntiles = T * (T + 1) / 2;
+      const int ng = (pan.n_lms + 3) >> 2;
+      auto zptr = [&](int x, const double*& p, int& stride) {
+        if (x < 6 * pan.n_var) { p = sZ + (x / 6) * kZRow + (x % 6) * 12 + t; stride = kZGroup; }
+        else { p = sC + t; stride = kCGroup; }
+      };
+      auto emit = [&](int I, int J, double c0, double c1) {
+        const int x = 8 * I + g;
+        const int ix = sIdx[x];
+        if (ix == -1) return;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int y = 8 * J + 2 * t + h;
+          if (y > x) continue;
+          const int iy = sIdx[y];
+          if (iy < 0) continue;
+          const double c = h ? c1 : c0;
+          if (ix == -2) red_add(a.rhs + iy, -c);
+          else {
+            const int hi = max(ix, iy), lo = min(ix, iy);
+            red_add(a.S + (size_t)hi * a.ldS + lo, -c);
+          }
+        }
+      };
+      for (int p2 = 2 * warp; p2 < ntiles; p2 += 2 * kPanelRows) {
+        int I0, J0, I1, J1;
+        tile_ij(p2, I0, J0);
+        const bool two = p2 + 1 < ntiles;
+        if (two) tile_ij(p2 + 1, I1, J1);
+        else { I1 = I0; J1 = J0; }
+        const double *pa0, *pb0, *pa1, *pb1;
+        int sa0, sb0, sa1, sb1;
+        zptr(8 * I0 + g, pa0, sa0); zptr(8 * J0 + g, pb0, sb0);
+        zptr(8 * I1 + g, pa1, sa1); zptr(8 * J1 + g, pb1, sb1);
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        if (I0 == I1) {          // the two tiles share their row operand
+          for (int G = 0; G < ng; ++G) {
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+              const double av = pa0[G * sa0 + 4 * s_];
+              const double b0 = pb0[G * sb0 + 4 * s_], b1 = pb1[G * sb1 + 4 * s_];
+              dmma_8x8x4(c00, c01, av, b0);
+              dmma_8x8x4(c10, c11, av, b1);
+            }
+          }
+        } else {
+          for (int G = 0; G < ng; ++G) {
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+              const double a0 = pa0[G * sa0 + 4 * s_], b0 = pb0[G * sb0 + 4 * s_];
+              const double a1 = pa1[G * sa1 + 4 * s_], b1 = pb1[G * sb1 + 4 * s_];
+              dmma_8x8x4(c00, c01, a0, b0);
+              dmma_8x8x4(c10, c11, a1, b1);
+            }
+          }
+        }
+        emit(I0, J0, c00, c01);
+        if (two) emit(I1, J1, c10, c11);
+      }
+    }
+  }
+  block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
+}
+
+// ---- the tail of the iteration for panels -------------------------------------------------------
+// dx_p = V^-1 (b_p - sum_a W_a^T dx_a) with W_a^T dx_a = (M R)^T (d rho + B d phi) RECOMPUTED from the
+// observation, the pose and the point at the linearisation point (poses = table before retraction,
+// pts = not yet updated) -- ~250 flop per observation instead of a 144-byte read of W; then
+// p <- p + dx_p, ||dx_p||^2, and the cost at the new point with the retracted poses.
+BS_HD size_t panel_finish_smem_bytes() {
+  return sizeof(double) * (kPanelRows * 3 * kPanelLm + 3 * kPanelLm + 3 * kPanelLm) + sizeof(PanelRow) * kPanelRows;
+}
+
+template <int kLoss>
+__global__ void __launch_bounds__(kPanelThreads, 2) panel_finish_kernel(const PanelArgs a) {
+  extern __shared__ __align__(16) double psm[];
+  __shared__ double sred[2 * (kPanelThreads / 32)];
+  double* sAcc = psm;                                  // [8 rows][3][64]
+  double* sPts = sAcc + kPanelRows * 3 * kPanelLm;     // [64][3] old
+  double* sNew = sPts + 3 * kPanelLm;                  // [64][3] new
+  PanelRow* sRows = reinterpret_cast<PanelRow*>(sNew + 3 * kPanelLm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double cost = 0.0, dx2 = 0.0;
+
+  for (int pn = blockIdx.x; pn < a.n_panels; pn += gridDim.x) {
+    const Panel pan = a.panels[pn];
+    if (tid < pan.n_rows) sRows[tid] = a.rows[pan.row_begin + tid];
+    if (tid < 3 * kPanelLm) sPts[tid] = tid < 3 * pan.n_lms ? a.pts_in[3 * (size_t)pan.lm_begin + tid] : 0.0;
+    // landmark data of thread j, requested early
+    double bp[3] = {0, 0, 0}, vi[6] = {0, 0, 0, 0, 0, 0};
+    if (tid < pan.n_lms) {
+      const size_t q = (size_t)pan.lm_begin + tid;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) bp[k] = ld_stream(a.Vg + 9 * q + 6 + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * q + k);
+    }
+    __syncthreads();
+
+    // ---- F1: W^T dx_c per cell
+    PanelRow row{0, -1, 0u, 0u};
+    double ou[2] = {0, 0}, ov[2] = {0, 0}, od[2] = {0, 0};
+    int grp_id[2] = {0, 0};
+    if (warp < pan.n_rows) {
+      row = sRows[warp];
+      const bool isvar = row.off >= 0;
+      double P[12], dxa[6];
+      if (isvar) {
+        const double* Pg = a.poses + 12 * (size_t)row.pose;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dxa[k] = a.dx_red[row.off + k];
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int j = lane + 32 * sub;
+        const bool present = (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) != 0;
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+        if (present) {
+          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + j;
+          ou[sub] = ld_stream(a.pu + cell); ov[sub] = ld_stream(a.pv + cell); od[sub] = ld_stream(a.pd + cell);
+          if (kLoss < 0) grp_id[sub] = a.pgrp[cell];
+          if (isvar) {
+            const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[grp_id[sub]];
+            double X[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) X[k] = sPts[3 * j + k];
+            ReprojBlocks o;
+            reproj_blocks<kLoss>(grp, P, X, ou[sub], ov[sub], od[sub], o);
+            // e = d rho + B d phi,  B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
+            const double e0 = dxa[0] + o.z * dxa[4] - o.y * dxa[5];
+            const double e1 = dxa[1] - o.z * dxa[3] + o.x * dxa[5];
+            const double e2 = dxa[2] + o.y * dxa[3] - o.x * dxa[4];
+            c0 = o.MR[0] * e0 + o.MR[3] * e1 + o.MR[6] * e2;
+            c1 = o.MR[1] * e0 + o.MR[4] * e1 + o.MR[7] * e2;
+            c2 = o.MR[2] * e0 + o.MR[5] * e1 + o.MR[8] * e2;
+          }
+        }
+        sAcc[(warp * 3 + 0) * kPanelLm + j] = c0;
+        sAcc[(warp * 3 + 1) * kPanelLm + j] = c1;
+        sAcc[(warp * 3 + 2) * kPanelLm + j] = c2;
+      }
+    }
+    __syncthreads();
+
+    // ---- F2: back-substitution and retraction, one landmark per thread
+    if (tid < pan.n_lms) {
+      const int j = tid;
+      double s0 = bp[0], s1 = bp[1], s2 = bp[2];
+      for (int r = 0; r < pan.n_rows; ++r) {
+        s0 -= sAcc[(r * 3 + 0) * kPanelLm + j];
+        s1 -= sAcc[(r * 3 + 1) * kPanelLm + j];
+        s2 -= sAcc[(r * 3 + 2) * kPanelLm + j];
+      }
+      const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
+      const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
+      const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
+      const size_t q = (size_t)pan.lm_begin + j;
+      a.dx_lm[3 * q] = d0; a.dx_lm[3 * q + 1] = d1; a.dx_lm[3 * q + 2] = d2;
+      dx2 += d0 * d0 + d1 * d1 + d2 * d2;
+      const double n0 = sPts[3 * j] + d0, n1 = sPts[3 * j + 1] + d1, n2 = sPts[3 * j + 2] + d2;
+      sNew[3 * j] = n0; sNew[3 * j + 1] = n1; sNew[3 * j + 2] = n2;
+      a.pts[3 * q] = n0; a.pts[3 * q + 1] = n1; a.pts[3 * q + 2] = n2;
+    }
+    __syncthreads();
+
+    // ---- F3: cost at the new point
+    if (a.eval_cost && warp < pan.n_rows) {
+      double P[12];
+      const double* Pg = a.poses_new + 12 * (size_t)row.pose;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int j = lane + 32 * sub;
+        if (!((((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u))) continue;
+        const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[grp_id[sub]];
+        double r[3];
+        reproj_residual_only(grp, P, sNew + 3 * j, ou[sub], ov[sub], od[sub], r);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, r[k]);
+      }
+    }
+    // the next panel's header writes sPts / sRows: every read of them above precedes the last barrier
+  }
+  cost = warp_sum(cost);
+  dx2 = warp_sum(dx2);
+  if (lane == 0) { sred[warp] = cost; sred[kPanelThreads / 32 + warp] = dx2; }
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0, d = 0.0;
+#pragma unroll
+    for (int w = 0; w < kPanelThreads / 32; ++w) { c += sred[w]; d += sred[kPanelThreads / 32 + w]; }
+    if (a.eval_cost) red_add(a.scalars + 1 /*COST_NEW*/, c);
+    red_add(a.scalars + 2 /*DX_NORM2*/, d);
+  }
+}
+
+}  // namespace bs

@@ -27,21 +27,26 @@ __global__ void __launch_bounds__(128) retract_poses_kernel(int n, double* __res
 // SE3 poses of a bundle-adjustment problem, one launch: threads [0, n) retract the pose table; threads
 // [n, n + n_slot_entries) retract the per-slot copies the landmark-block kernels read (slot_poses holds the
 // poses gathered at linearisation time, so the copies never read the table while it is being rewritten) and
-// gather dx_c per slot; all threads also reduce ||dx_c||^2 over the first n_red entries of dx.
+// gather dx_c per slot; `prev` (optional) receives the pose table as it was; all threads also reduce ||dx_c||^2 over the first n_red entries of dx.
 __global__ void __launch_bounds__(128) retract_se3_slots_kernel(int n, double* __restrict__ poses, const int* __restrict__ off,
                                                                 const double* __restrict__ dx, int n_slot_entries,
                                                                 const int* __restrict__ slot_off, double* __restrict__ slot_poses,
-                                                                double* __restrict__ slot_dx, int n_red, double* __restrict__ dx_norm2) {
+                                                                double* __restrict__ slot_dx, int n_red, double* __restrict__ dx_norm2,
+                                                                double* __restrict__ prev) {
   using Gr = Group<3>;
   __shared__ double sred[4];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const int o = off[i];
+    double* p = poses + 12 * (size_t)i;
+    if (prev) {             // the panel finish kernel re-linearises at the poses before the update
+#pragma unroll
+      for (int k = 0; k < 12; ++k) prev[12 * (size_t)i + k] = p[k];
+    }
     if (o >= 0) {
       double xi[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) xi[k] = dx[o + k];
-      double* p = poses + 12 * (size_t)i;
       Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
     }
   } else if (i < n + n_slot_entries) {

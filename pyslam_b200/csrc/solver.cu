@@ -22,6 +22,7 @@
 #include "reproj.cuh"
 #include "retract.cuh"
 #include "schur.cuh"
+#include "panel.cuh"
 
 namespace {
 
@@ -76,7 +77,7 @@ struct bslam_solver {
   bool finalized = false;
   int64_t launches = 0;
   bool timing = false;
-  cudaEvent_t ev[12] = {};
+  cudaEvent_t ev[14] = {};
   double timings[BSLAM_N_TIMINGS] = {};
   int shard_rank = 0;
 
@@ -131,6 +132,17 @@ struct bslam_solver {
   DevBuf<unsigned char> d_lm_obs_local, d_seg_start;
   DevBuf<bs::ReprojGroup> d_groups;
   DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_Linv;
+  // dense landmark panels (panel.cuh): fused linearise + eliminate, W never materialised.  Landmarks
+  // [0, n_fused) belong to panels; the landmark blocks [0, nb_fused) cover the same landmarks for the
+  // step-wise / inspection API (bslam_linearize, bslam_reduce, bslam_get_normal_equations, bslam_covariance),
+  // which keeps the materialised-W kernels.  bslam_iterate uses the panels and blocks [nb_fused, n_lmblocks).
+  int fused_mode = 1;                                // 0: off, 1: well-filled panels only, 2: every panel that fits
+  int n_panels = 0, n_fused = 0, nb_fused = 0, panel_max_var = 1, panel_grid = 1, finish_grid = 1;
+  int n_panel_rows = 0;
+  DevBuf<bs::Panel> d_panels;
+  DevBuf<bs::PanelRow> d_prows;
+  DevBuf<double> d_pu, d_pv, d_pd, d_se3_prev;
+  DevBuf<unsigned short> d_pgrp;
   DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
   DevBuf<long long> d_dn_j_ptr;
   DevBuf<double> d_dn_J, d_dn_e;
@@ -336,15 +348,48 @@ void launch_cost(bslam_solver* s, int slot) {
     const int grid = std::min(cdiv(s->n_obs, 256), 148 * 8);
     LAUNCH(s, bs::reproj_cost_kernel, grid, 256, 0, reproj_args(s), slot, 0);
   }
-  for (auto* b : s->edges) launch_edges<true>(s, b, slot);
-  launch_photos<true>(s, slot);
+  if (s->shard_rank == 0) {      // not sharded: counted once across GPUs
+    for (auto* b : s->edges) launch_edges<true>(s, b, slot);
+    launch_photos<true>(s, slot);
+  }
 }
 
-int do_linearize(bslam_solver* s) {
+// W (144 bytes per observation) exists only for the materialised-W kernels: observations outside the panels
+// and the step-wise / inspection API.  Allocated on first use.
+int ensure_W(bslam_solver* s) {
+  if (s->d_W.p || s->n_obs == 0) return BSLAM_OK;
+  CU(s->d_W.alloc(bs::w_alloc_len(s->n_obs)));
+  CU(cudaMemsetAsync(s->d_W.p, 0, s->d_W.n * sizeof(double), s->stream));
+  return BSLAM_OK;
+}
+
+bs::PanelArgs panel_args(bslam_solver* s, double lambda) {
+  bs::PanelArgs a{};
+  a.n_panels = s->n_panels;
+  a.panels = s->d_panels.p; a.rows = s->d_prows.p;
+  a.pu = s->d_pu.p; a.pv = s->d_pv.p; a.pd = s->d_pd.p; a.pgrp = s->d_pgrp.p;
+  a.groups = s->d_groups.p;
+  if (!s->groups.empty()) a.g0 = s->groups[0];
+  a.poses = s->d_se3.p; a.poses_new = s->d_se3.p; a.pts_in = s->d_pts.p; a.pts = s->d_pts.p;
+  a.lambda = lambda;
+  a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
+  a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
+  a.dx_red = s->d_dx.p; a.dx_lm = s->d_dx.p + s->n_pad;
+  a.eval_cost = 0;
+  a.max_var = s->panel_max_var;
+  return a;
+}
+
+// `panels`: the landmarks of the dense panels are linearised AND eliminated by fused_panel_kernel in
+// do_reduce; only the remaining landmark blocks are linearised here.
+int do_linearize(bslam_solver* s, bool panels) {
   NEED(s->finalized, "bslam_finalize has not been called");
   NEED(s->dn_blocks == 0 || s->dn_uploaded, "dense blocks declared but bslam_upload_dense_values not called");
   record(s, 0);
   if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  const int b0 = panels ? s->nb_fused : 0;                 // first landmark block handled by the block kernels
+  const int nb = s->n_lmblocks - b0;
+  if (nb > 0 || s->n_obs > s->tail_begin) { int rc = ensure_W(s); if (rc) return rc; }
   // zero only what the iteration dirties: the structurally non-zero tiles (after fill-in), rhs, scalars;
   // the rest of S was zeroed at finalize and is never written
   {
@@ -353,16 +398,17 @@ int do_linearize(bslam_solver* s) {
     a.used = s->d_used.p;
     a.rhs = s->rhs(); a.n_rhs = s->n_pad + BSLAM_N_SCALARS;
     a.vg_tail = s->d_Vg.p + 9 * (size_t)s->n_regular; a.n_vg_tail = 9 * (s->n_lm - s->n_regular);
-    a.n_slot_entries = s->n_lmblocks > 0 ? s->n_slot_entries : 0;
+    a.n_slot_entries = nb > 0 ? s->n_slot_entries : 0;
     a.slot_pose = s->d_slot_pose.p; a.poses = s->d_se3.p; a.slot_poses = s->d_slot_poses.p;
     const int work = std::max(std::max(a.n_rhs, a.n_vg_tail), 12 * a.n_slot_entries);
     LAUNCH(s, bs::prepare_kernel, s->n_dirty_tiles + std::max(1, cdiv(work, 256)), 256, 0, a);   // one element per thread: all gathers in flight at once
   }
   record(s, 1);
-  if (s->n_lmblocks > 0) {
-    const int grid = std::min(s->n_lmblocks, 148 * bs::kReprojCtas);      // persistent CTAs, all resident
+  if (nb > 0) {
+    const int grid = std::min(nb, 148 * bs::kReprojCtas);      // persistent CTAs, all resident
     const size_t smem = 2 * (size_t)s->stage_len * sizeof(double);
-    const bs::ReprojArgs ra = reproj_args(s);
+    bs::ReprojArgs ra = reproj_args(s);
+    ra.blocks += b0; ra.n_blocks = nb;
     switch (s->loss_kind) {
       case 0: LAUNCH(s, bs::reproj_block_kernel<0>, grid, bs::kBlkObs, smem, ra); break;
       case 1: LAUNCH(s, bs::reproj_block_kernel<1>, grid, bs::kBlkObs, smem, ra); break;
@@ -376,34 +422,57 @@ int do_linearize(bslam_solver* s) {
   record(s, 2);
   if (s->n_obs > s->tail_begin)
     LAUNCH(s, bs::reproj_generic_kernel, cdiv(s->n_obs - s->tail_begin, 128), 128, 0, reproj_args(s));
-  for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
-  launch_photos<false>(s, BSLAM_S_COST_LIN);
-  if (s->dn_blocks > 0) {
-    bs::DenseArgs a;
-    a.n_blocks = s->dn_blocks;
-    a.row_ptr = s->d_dn_row_ptr.p; a.col_ptr = s->d_dn_col_ptr.p; a.j_ptr = s->d_dn_j_ptr.p;
-    a.col_index = s->d_dn_col_index.p; a.J = s->d_dn_J.p; a.e = s->d_dn_e.p;
-    a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
-    int max_rows = 1;
-    for (int r : s->dn_rows) max_rows = std::max(max_rows, r);
-    dim3 grid(s->dn_blocks, cdiv(max_rows, bs::kDenseRowChunk));
-    LAUNCH(s, bs::dense_blocks_kernel, grid, 256, 0, a);
-    // the host computed sum rho(r) of its own blocks
-    LAUNCH(s, bs::add_scalar_kernel, 1, 1, 0, s->scalars() + BSLAM_S_COST_LIN, s->dn_cost);
-    s->dn_uploaded = false;
+  // blocks that are not sharded over GPUs (pose priors, relative-pose factors, photometric and
+  // host-evaluated blocks) are assembled on shard 0 only: the all-reduce must count them once
+  if (s->shard_rank == 0) {
+    for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
+    launch_photos<false>(s, BSLAM_S_COST_LIN);
+    if (s->dn_blocks > 0) {
+      bs::DenseArgs a;
+      a.n_blocks = s->dn_blocks;
+      a.row_ptr = s->d_dn_row_ptr.p; a.col_ptr = s->d_dn_col_ptr.p; a.j_ptr = s->d_dn_j_ptr.p;
+      a.col_index = s->d_dn_col_index.p; a.J = s->d_dn_J.p; a.e = s->d_dn_e.p;
+      a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs();
+      int max_rows = 1;
+      for (int r : s->dn_rows) max_rows = std::max(max_rows, r);
+      dim3 grid(s->dn_blocks, cdiv(max_rows, bs::kDenseRowChunk));
+      LAUNCH(s, bs::dense_blocks_kernel, grid, 256, 0, a);
+      // the host computed sum rho(r) of its own blocks
+      LAUNCH(s, bs::add_scalar_kernel, 1, 1, 0, s->scalars() + BSLAM_S_COST_LIN, s->dn_cost);
+    }
   }
+  s->dn_uploaded = false;
   record(s, 3);
   CU(cudaGetLastError());
   return BSLAM_OK;
 }
 
-int do_reduce(bslam_solver* s, double lambda) {
+int do_reduce(bslam_solver* s, double lambda, bool panels) {
   if (lambda > 0.0 && s->n_red > 0)
     LAUNCH(s, bs::damp_diag_kernel, cdiv(s->n_red, 128), 128, 0, s->S(), s->n_pad, s->n_red, lambda);
-  if (s->n_lm > 0) {
+  record(s, 10);
+  if (panels && s->n_panels > 0) {
+    // after the damping of everything assembled so far: the kernel damps its own U_c diagonals
+    const bs::PanelArgs pa = panel_args(s, lambda);
+    const size_t smem = bs::panel_smem_bytes(s->panel_max_var);
+    const int grid = std::min(s->n_panels, s->panel_grid);
+    switch (s->loss_kind) {
+      case 0: LAUNCH(s, bs::fused_panel_kernel<0>, grid, bs::kPanelThreads, smem, pa); break;
+      case 1: LAUNCH(s, bs::fused_panel_kernel<1>, grid, bs::kPanelThreads, smem, pa); break;
+      case 2: LAUNCH(s, bs::fused_panel_kernel<2>, grid, bs::kPanelThreads, smem, pa); break;
+      case 3: LAUNCH(s, bs::fused_panel_kernel<3>, grid, bs::kPanelThreads, smem, pa); break;
+      case 4: LAUNCH(s, bs::fused_panel_kernel<4>, grid, bs::kPanelThreads, smem, pa); break;
+      case 5: LAUNCH(s, bs::fused_panel_kernel<5>, grid, bs::kPanelThreads, smem, pa); break;
+      default: LAUNCH(s, bs::fused_panel_kernel<-1>, grid, bs::kPanelThreads, smem, pa); break;
+    }
+  }
+  record(s, 11);
+  const int b0 = panels ? s->nb_fused : 0;
+  const int nb = s->n_lmblocks - b0;
+  if (s->n_lm > 0 && (nb > 0 || s->n_lm > s->n_regular)) {
     bs::SchurArgs a;
     a.n_obs = s->n_obs; a.n_lm = s->n_lm; a.obs_begin = s->tail_begin; a.lambda = lambda;
-    a.n_blocks = s->n_lmblocks; a.blocks = s->d_blocks.p; a.slot_pose = s->d_slot_pose.p; a.obs_code = s->d_obs_code.p;
+    a.n_blocks = nb; a.blocks = s->d_blocks.p + b0; a.slot_pose = s->d_slot_pose.p; a.obs_code = s->d_obs_code.p;
     a.Vinv_out = s->d_Vinv.p;
     a.obs_pose = s->d_opose.p; a.obs_pt = s->d_opt.p; a.lm_start = s->d_lm_start.p; a.lm_obs = s->d_lm_obs.p;
     a.pose_off = s->d_se3_off.p;
@@ -412,9 +481,9 @@ int do_reduce(bslam_solver* s, double lambda) {
     a.slot_off = s->d_slot_off.p;
     a.pairs = s->d_sch_pairs.p; a.combos = s->d_sch_combos.p;
     a.max_lms = s->schur_max_lms; a.max_pairs = s->schur_max_pairs; a.max_runs = s->schur_max_runs;
-    a.descs = s->d_sch_descs.p;
-    if (s->n_lmblocks > 0) {
-      LAUNCH(s, bs::schur_block_kernel, std::min(s->n_lmblocks, s->schur_grid), bs::kSchurThreads, s->schur_smem, a);
+    a.descs = s->d_sch_descs.p + b0;
+    if (nb > 0) {
+      LAUNCH(s, bs::schur_block_kernel, std::min(nb, s->schur_grid), bs::kSchurThreads, s->schur_smem, a);
     }
     if (s->n_lm > s->n_regular) {
       LAUNCH(s, bs::landmark_invert_kernel, cdiv(s->n_lm - s->n_regular, 256), 256, 0, s->n_regular, s->n_lm, s->d_Vg.p,
@@ -620,14 +689,18 @@ int do_solve_reduced(bslam_solver* s) {
   return BSLAM_OK;
 }
 
-int do_retract(bslam_solver* s, int eval_new_cost) {
+int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
   const double* dx = s->d_dx.p;
   // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
   const int n_red_here = s->shard_rank == 0 ? s->n_red : 0;
+  const int b0 = panels ? s->nb_fused : 0;
+  const int nb = s->n_lmblocks - b0;
+  const bool use_panels = panels && s->n_panels > 0;
   if (s->n_se3 > 0) {
-    const int n_slots = s->n_lmblocks > 0 ? s->n_slot_entries : 0;
+    const int n_slots = nb > 0 ? s->n_slot_entries : 0;
     LAUNCH(s, bs::retract_se3_slots_kernel, cdiv(s->n_se3 + n_slots, 128), 128, 0, s->n_se3, s->d_se3.p, s->d_se3_off.p, dx, n_slots,
-           s->d_slot_off.p, s->d_slot_poses.p, s->d_slot_dx.p, n_red_here, s->scalars() + BSLAM_S_DX_NORM2);
+           s->d_slot_off.p, s->d_slot_poses.p, s->d_slot_dx.p, n_red_here, s->scalars() + BSLAM_S_DX_NORM2,
+           use_panels ? s->d_se3_prev.p : nullptr);
   }
   if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
   if (s->n_vec_entries > 0)
@@ -639,12 +712,28 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
   if (s->n_se3 == 0 && n_red_here > 0)
     LAUNCH(s, bs::sumsq_kernel, std::min(cdiv(s->n_red, 256), 148), 256, 0, s->n_red, dx, s->scalars() + BSLAM_S_DX_NORM2);
   record(s, 8);
-  // landmark blocks: back-substitution + retraction + ||dx_p||^2 + cost at the new point, fused
-  if (s->n_lmblocks > 0) {
+  // panels: back-substitution (W^T dx_c recomputed) + retraction + ||dx_p||^2 + cost at the new point, fused
+  if (use_panels) {
+    bs::PanelArgs pa = panel_args(s, 0.0);
+    pa.poses = s->d_se3_prev.p; pa.poses_new = s->d_se3.p; pa.eval_cost = eval_new_cost;
+    const size_t smem = bs::panel_finish_smem_bytes();
+    const int grid = std::min(s->n_panels, s->finish_grid);
+    switch (s->loss_kind) {
+      case 0: LAUNCH(s, bs::panel_finish_kernel<0>, grid, bs::kPanelThreads, smem, pa); break;
+      case 1: LAUNCH(s, bs::panel_finish_kernel<1>, grid, bs::kPanelThreads, smem, pa); break;
+      case 2: LAUNCH(s, bs::panel_finish_kernel<2>, grid, bs::kPanelThreads, smem, pa); break;
+      case 3: LAUNCH(s, bs::panel_finish_kernel<3>, grid, bs::kPanelThreads, smem, pa); break;
+      case 4: LAUNCH(s, bs::panel_finish_kernel<4>, grid, bs::kPanelThreads, smem, pa); break;
+      case 5: LAUNCH(s, bs::panel_finish_kernel<5>, grid, bs::kPanelThreads, smem, pa); break;
+      default: LAUNCH(s, bs::panel_finish_kernel<-1>, grid, bs::kPanelThreads, smem, pa); break;
+    }
+  }
+  // landmark blocks: the same from the materialised W
+  if (nb > 0) {
     bs::FinishArgs a;
-    a.n_obs = s->n_obs; a.lm_off = s->n_pad; a.eval_cost = eval_new_cost; a.n_blocks = s->n_lmblocks;
+    a.n_obs = s->n_obs; a.lm_off = s->n_pad; a.eval_cost = eval_new_cost; a.n_blocks = nb;
     a.max_slots = s->max_slots;
-    a.blocks = s->d_blocks.p; a.obs_code = s->d_obs_code.p;
+    a.blocks = s->d_blocks.p + b0; a.obs_code = s->d_obs_code.p;
     a.slot_poses = s->d_slot_poses.p; a.slot_dx = s->d_slot_dx.p;
     a.lm_obs_local = s->d_lm_obs_local.p;
     a.obs_pose = s->d_opose.p; a.groups = s->d_groups.p;
@@ -653,7 +742,7 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
     a.obs_u = s->d_ou.p; a.obs_v = s->d_ov.p; a.obs_d = s->d_od.p;
     a.poses = s->d_se3.p; a.pts = s->d_pts.p; a.W = s->d_W.p; a.Vg = s->d_Vg.p; a.Vinv = s->d_Vinv.p;
     a.dx = s->d_dx.p; a.scalars = s->scalars();
-    const int fgrid = std::min(s->n_lmblocks, 148 * bs::kFinishCtas);      // persistent CTAs, all resident
+    const int fgrid = std::min(nb, 148 * bs::kFinishCtas);      // persistent CTAs, all resident
     const size_t fsmem = bs::finish_smem_bytes(s->max_slots);
     switch (s->loss_kind) {
       case 0: LAUNCH(s, bs::lm_finish_kernel<0>, fgrid, bs::kBlkObs, fsmem, a); break;
@@ -678,8 +767,10 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
       const int n = s->n_obs - s->tail_begin;
       LAUNCH(s, bs::reproj_cost_kernel, std::min(cdiv(n, 256), 148 * 8), 256, 0, reproj_args(s), BSLAM_S_COST_NEW, s->tail_begin);
     }
-    for (auto* b : s->edges) launch_edges<true>(s, b, BSLAM_S_COST_NEW);
-    launch_photos<true>(s, BSLAM_S_COST_NEW);
+    if (s->shard_rank == 0) {
+      for (auto* b : s->edges) launch_edges<true>(s, b, BSLAM_S_COST_NEW);
+      launch_photos<true>(s, BSLAM_S_COST_NEW);
+    }
   }
   record(s, 9);
   CU(cudaGetLastError());
@@ -687,6 +778,14 @@ int do_retract(bslam_solver* s, int eval_new_cost) {
 }
 
 int sync_and_timings(bslam_solver* s);
+
+// everything bslam_iterate* allocates lazily, before a graph capture starts
+int prepare_iterate(bslam_solver* s) {
+  int rc;
+  if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+  if (s->n_lmblocks > s->nb_fused || s->n_obs > s->tail_begin) return ensure_W(s);
+  return BSLAM_OK;
+}
 
 int fetch_scalars(bslam_solver* s) {
   CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -711,6 +810,7 @@ int sync_and_timings(bslam_solver* s) {
     s->timings[BSLAM_T_RETRACT] = el(7, 8);
     s->timings[BSLAM_T_COST] = el(8, 9);
     s->timings[BSLAM_T_TOTAL] = el(0, 9);
+    s->timings[BSLAM_T_FUSED] = el(10, 11);
   }
   return BSLAM_OK;
 }
@@ -773,6 +873,7 @@ int bslam_create(bslam_solver** out, int device) {
   }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
   { const char* e = getenv("BSLAM_NO_GRAPH"); if (e && atoi(e)) h->use_graph = false; }
+  { const char* e = getenv("BSLAM_FUSED"); if (e) h->fused_mode = std::max(0, std::min(2, atoi(e))); }
   cudaFuncSetAttribute(bs::chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::kCholSmem);
   *out = h;
   return BSLAM_OK;
@@ -1090,6 +1191,68 @@ int bslam_finalize(bslam_solver* s) {
     else big.push_back(p);
   }
   std::stable_sort(regular.begin(), regular.end(), [&](int a, int b) { return first_pose[a] < first_pose[b]; });
+
+  // ---- dense landmark panels (panel.cuh) ----------------------------------------------
+  // Greedy runs of consecutive regular landmarks: up to kPanelLm landmarks whose observing poses number
+  // at most kPanelRows.  A run becomes a panel when its (row, landmark) grid is well filled (mode 1) or
+  // always (mode 2); the landmarks of rejected runs keep the landmark-block kernels.  Panel landmarks
+  // come first in the internal order.
+  struct HostPanel { int first, n_lms; std::vector<int> poses; int n_var; };
+  std::vector<HostPanel> hpanels;
+  std::vector<int> obs_ptr(s->n_pt + 1, 0), obs_ids(N);
+  {
+    for (int i = 0; i < N; ++i) obs_ptr[s->ob_pt[i] + 1]++;
+    for (int p = 0; p < s->n_pt; ++p) obs_ptr[p + 1] += obs_ptr[p];
+    std::vector<int> cur(obs_ptr.begin(), obs_ptr.end() - 1);
+    for (int i = 0; i < N; ++i) obs_ids[cur[s->ob_pt[i]]++] = i;
+  }
+  if (s->fused_mode > 0 && s->groups.size() < 65536) {
+    std::vector<int> fused_lms, irregular, poses, trial;
+    size_t q = 0;
+    while (q < regular.size()) {
+      poses.clear();
+      size_t q1 = q;
+      long long n_cells = 0;
+      while (q1 < regular.size() && q1 - q < (size_t)bs::kPanelLm) {
+        trial = poses;
+        const int p = regular[q1];
+        for (int k = obs_ptr[p]; k < obs_ptr[p + 1]; ++k) {
+          const int pose = s->ob_pose[obs_ids[k]];
+          if (std::find(trial.begin(), trial.end(), pose) == trial.end()) trial.push_back(pose);
+        }
+        if ((int)trial.size() > bs::kPanelRows) break;
+        poses.swap(trial);
+        n_cells += obs_ptr[p + 1] - obs_ptr[p];
+        ++q1;
+      }
+      if (q1 == q) {                               // a single landmark seen by more poses than a panel holds
+        irregular.push_back(regular[q]);
+        ++q;
+        continue;
+      }
+      const int n_lms = (int)(q1 - q);
+      const bool dense = n_lms >= 16 && 2 * n_cells >= (long long)poses.size() * n_lms;
+      if (s->fused_mode >= 2 || dense) {
+        HostPanel hp;
+        hp.first = (int)fused_lms.size(); hp.n_lms = n_lms;
+        std::sort(poses.begin(), poses.end());
+        for (int pose : poses) if (!s->se3_const[pose]) hp.poses.push_back(pose);
+        hp.n_var = (int)hp.poses.size();
+        for (int pose : poses) if (s->se3_const[pose]) hp.poses.push_back(pose);
+        hpanels.push_back(std::move(hp));
+        fused_lms.insert(fused_lms.end(), regular.begin() + q, regular.begin() + q1);
+      } else {
+        irregular.insert(irregular.end(), regular.begin() + q, regular.begin() + q1);
+      }
+      q = q1;
+    }
+    s->n_fused = (int)fused_lms.size();
+    regular.swap(fused_lms);
+    regular.insert(regular.end(), irregular.begin(), irregular.end());
+  } else {
+    s->n_fused = 0;
+  }
+  s->n_panels = (int)hpanels.size();
   s->pt_iperm.clear();
   s->pt_iperm.insert(s->pt_iperm.end(), regular.begin(), regular.end());
   s->pt_iperm.insert(s->pt_iperm.end(), big.begin(), big.end());
@@ -1365,6 +1528,43 @@ int bslam_finalize(bslam_solver* s) {
   }
   for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
 
+  // ---- panel grids: cell (row, landmark) -> observation, padded to kPanelLm landmarks per row ----
+  std::vector<bs::Panel> panels;
+  std::vector<bs::PanelRow> prows;
+  std::vector<double> pu, pv, pd;
+  std::vector<unsigned short> pgrp;
+  s->panel_max_var = 1;
+  for (const HostPanel& hp : hpanels) {
+    bs::Panel pn{};
+    pn.lm_begin = hp.first; pn.n_lms = hp.n_lms;
+    pn.row_begin = (int)prows.size(); pn.n_rows = (int)hp.poses.size(); pn.n_var = hp.n_var;
+    s->panel_max_var = std::max(s->panel_max_var, hp.n_var);
+    const size_t base = prows.size() * bs::kPanelLm;
+    pu.resize(base + (size_t)pn.n_rows * bs::kPanelLm, 0.0);
+    pv.resize(pu.size(), 0.0); pd.resize(pu.size(), 0.0); pgrp.resize(pu.size(), 0);
+    for (int r = 0; r < pn.n_rows; ++r) {
+      bs::PanelRow row{};
+      row.pose = hp.poses[r];
+      row.off = s->se3_off[row.pose];
+      prows.push_back(row);
+    }
+    for (int j = 0; j < hp.n_lms; ++j) {
+      const int q = hp.first + j;
+      for (int k = lm_start[q]; k < lm_start[q + 1]; ++k) {
+        const int r = (int)(std::find(hp.poses.begin(), hp.poses.end(), opose[k]) - hp.poses.begin());
+        bs::PanelRow& row = prows[pn.row_begin + r];
+        if (j < 32) row.mask_lo |= 1u << j; else row.mask_hi |= 1u << (j - 32);
+        const size_t cell = base + (size_t)r * bs::kPanelLm + j;
+        pu[cell] = ou[k]; pv[cell] = ov[k]; pd[cell] = od[k]; pgrp[cell] = (unsigned short)ogrp[k];
+      }
+    }
+    panels.push_back(pn);
+  }
+  s->n_panel_rows = (int)prows.size();
+  if (panels.empty()) panels.push_back(bs::Panel{});
+  if (prows.empty()) prows.push_back(bs::PanelRow{});
+  if (pu.empty()) { pu.push_back(0.0); pv.push_back(0.0); pd.push_back(0.0); pgrp.push_back(0); }
+
   // ---- landmark blocks: whole landmarks, <= kBlkObs observations, bounded Schur operands ----
   // Inside a block the observations are re-ordered SLOT-MAJOR (grouped by pose, constant poses last):
   // a warp of the block kernels then reads one or two poses (shared-memory broadcasts) and the camera-side
@@ -1386,12 +1586,15 @@ int bslam_finalize(bslam_solver* s) {
     std::vector<int> slot_of, new_pos;
     std::vector<double> tu, tv, td;
     std::vector<int> tpose, tpt, tgrp;
+    s->nb_fused = 0;
     while (q < n_regular) {
+      if (q == s->n_fused) s->nb_fused = (int)blocks.size();
+      const int q_lim = q < s->n_fused ? s->n_fused : n_regular;     // no block straddles the panel boundary
       bs::LmBlock b{};
       b.obs_begin = lm_start[q]; b.lm_begin = q;
       cur.clear();
       int q1 = q;
-      while (q1 < n_regular && lm_start[q1 + 1] - b.obs_begin <= bs::kBlkObs) {
+      while (q1 < q_lim && lm_start[q1 + 1] - b.obs_begin <= bs::kBlkObs) {
         std::vector<int> trial = cur;
         for (int k = lm_start[q1]; k < lm_start[q1 + 1]; ++k)
           if (s->se3_off[opose[k]] >= 0 && std::find(trial.begin(), trial.end(), opose[k]) == trial.end())
@@ -1484,6 +1687,7 @@ int bslam_finalize(bslam_solver* s) {
       blocks.push_back(b);
       q = q1;
     }
+    if (s->n_fused >= n_regular) s->nb_fused = (int)blocks.size();
   }
   s->loss_kind = s->groups.size() == 1 ? s->groups[0].loss.kind : -1;
   NEED(s->groups.size() < 65536, "too many reprojection groups (%zu)", s->groups.size());
@@ -1599,7 +1803,34 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_dn_col_index, s->dn_col_index, st));
   CU(s->d_dn_J.alloc((size_t)s->dn_j_ptr.back()));
   CU(s->d_dn_e.alloc((size_t)s->dn_row_ptr.back()));
-  CU(s->d_W.alloc(bs::w_alloc_len(N)));
+  s->d_W.release();                             // allocated on first use (ensure_W)
+  CU(upload(s->d_panels, panels, st));
+  CU(upload(s->d_prows, prows, st));
+  CU(upload(s->d_pu, pu, st)); CU(upload(s->d_pv, pv, st)); CU(upload(s->d_pd, pd, st));
+  CU(upload(s->d_pgrp, pgrp, st));
+  CU(s->d_se3_prev.alloc(std::max<size_t>(1, s->d_se3.n)));
+  if (s->n_panels > 0) {
+    const size_t psm = bs::panel_smem_bytes(s->panel_max_var), fsm = bs::panel_finish_smem_bytes();
+    const void *fk = nullptr, *ff = nullptr;
+    switch (s->loss_kind) {
+      case 0: fk = (const void*)bs::fused_panel_kernel<0>; ff = (const void*)bs::panel_finish_kernel<0>; break;
+      case 1: fk = (const void*)bs::fused_panel_kernel<1>; ff = (const void*)bs::panel_finish_kernel<1>; break;
+      case 2: fk = (const void*)bs::fused_panel_kernel<2>; ff = (const void*)bs::panel_finish_kernel<2>; break;
+      case 3: fk = (const void*)bs::fused_panel_kernel<3>; ff = (const void*)bs::panel_finish_kernel<3>; break;
+      case 4: fk = (const void*)bs::fused_panel_kernel<4>; ff = (const void*)bs::panel_finish_kernel<4>; break;
+      case 5: fk = (const void*)bs::fused_panel_kernel<5>; ff = (const void*)bs::panel_finish_kernel<5>; break;
+      default: fk = (const void*)bs::fused_panel_kernel<-1>; ff = (const void*)bs::panel_finish_kernel<-1>; break;
+    }
+    CU(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    CU(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    int per_sm = 1, per_sm_f = 1, sms = 148;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, bs::kPanelThreads, psm));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, ff, bs::kPanelThreads, fsm));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    NEED(per_sm >= 1 && per_sm_f >= 1, "panel kernels do not fit on an SM (%zu bytes of shared memory)", psm);
+    s->panel_grid = per_sm * sms;               // persistent CTAs, all resident
+    s->finish_grid = per_sm_f * sms;
+  }
   CU(s->d_Vg.alloc(9 * (size_t)s->n_lm));
   CU(s->d_Vinv.alloc(6 * (size_t)s->n_lm));
   CU(s->d_red.alloc(s->red_len()));
@@ -1609,7 +1840,6 @@ int bslam_finalize(bslam_solver* s) {
   CU(s->b_pts.alloc(s->d_pts.n)); CU(s->b_vec.alloc(s->d_vec.n));
   CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), st));
   CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
-  if (N > 0) CU(cudaMemsetAsync(s->d_W.p, 0, s->d_W.n * sizeof(double), st));
   CU(cudaStreamSynchronize(st));
   build_tile_mask(s, opose_lm, lm_start);
   s->finalized = true;
@@ -1649,7 +1879,7 @@ int bslam_eval_cost(bslam_solver* s, double* cost) {
 int bslam_linearize(bslam_solver* s, double* cost_lin) {
   NEED(s, "NULL solver");
   CU(cudaSetDevice(s->device));
-  int rc = do_linearize(s);
+  int rc = do_linearize(s, false);
   if (rc) return rc;
   if (cost_lin) {
     CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -1663,7 +1893,7 @@ int bslam_reduce(bslam_solver* s, double lambda) {
   NEED(s && s->finalized, "bslam_reduce: solver not finalized");
   NEED(lambda >= 0.0, "bslam_reduce: lambda must be >= 0");
   CU(cudaSetDevice(s->device));
-  return do_reduce(s, lambda);
+  return do_reduce(s, lambda, false);
 }
 
 int bslam_solve_reduced(bslam_solver* s) {
@@ -1675,7 +1905,38 @@ int bslam_solve_reduced(bslam_solver* s) {
 int bslam_retract(bslam_solver* s, int eval_new_cost) {
   NEED(s && s->finalized, "bslam_retract: solver not finalized");
   CU(cudaSetDevice(s->device));
-  return do_retract(s, eval_new_cost);
+  return do_retract(s, eval_new_cost, false);
+}
+
+int bslam_linearize_reduce(bslam_solver* s, double lambda) {
+  NEED(s && s->finalized, "bslam_linearize_reduce: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_linearize_reduce: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  int rc;
+  if ((rc = prepare_iterate(s))) return rc;
+  if ((rc = do_linearize(s, true))) return rc;
+  return do_reduce(s, lambda, true);
+}
+
+int bslam_retract_iterate(bslam_solver* s, int eval_new_cost) {
+  NEED(s && s->finalized, "bslam_retract_iterate: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  return do_retract(s, eval_new_cost, true);
+}
+
+int bslam_set_fused(bslam_solver* s, int mode) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_set_fused after finalize; call bslam_clear_blocks first");
+  NEED(mode >= 0 && mode <= 2, "bslam_set_fused: mode must be 0, 1 or 2");
+  s->fused_mode = mode;
+  return BSLAM_OK;
+}
+
+int bslam_get_fused(bslam_solver* s, int32_t* n_panels, int32_t* n_landmarks) {
+  NEED(s && s->finalized, "bslam_get_fused: solver not finalized");
+  if (n_panels) *n_panels = s->n_panels;
+  if (n_landmarks) *n_landmarks = s->n_fused;
+  return BSLAM_OK;
 }
 
 int bslam_get_scalars(bslam_solver* s, double* out) {
@@ -1693,7 +1954,7 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
   const bool graphable = s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr;
   if (graphable) {
     // the whole iteration (6 kernels + the scalar read-back) is one graph launch
-    if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+    if ((rc = prepare_iterate(s))) return rc;
     if (s->graph_exec && (s->graph_lambda != lambda || s->graph_eval != eval_new_cost)) {
       cudaGraphExecDestroy(s->graph_exec);
       s->graph_exec = nullptr;
@@ -1701,20 +1962,20 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
     s->graph_lambda = lambda;
     s->graph_eval = eval_new_cost;
     return run_graphed(s, &s->graph_exec, &s->graph_launches, [&]() {
-      int r = do_linearize(s);
-      if (!r) r = do_reduce(s, lambda);
+      int r = do_linearize(s, true);
+      if (!r) r = do_reduce(s, lambda, true);
       if (!r) r = do_solve_reduced(s);
-      if (!r) r = do_retract(s, eval_new_cost);
+      if (!r) r = do_retract(s, eval_new_cost, true);
       if (!r && cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost,
                                 s->stream) != cudaSuccess)
         r = fail(s, BSLAM_E_CUDA, "scalar read-back could not be captured");
       return r;
     });
   }
-  if ((rc = do_linearize(s))) return rc;
-  if ((rc = do_reduce(s, lambda))) return rc;
+  if ((rc = do_linearize(s, true))) return rc;
+  if ((rc = do_reduce(s, lambda, true))) return rc;
   if ((rc = do_solve_reduced(s))) return rc;
-  if ((rc = do_retract(s, eval_new_cost))) return rc;
+  if ((rc = do_retract(s, eval_new_cost, true))) return rc;
   CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   return BSLAM_OK;
 }
@@ -1805,10 +2066,10 @@ int bslam_iterate_pre(bslam_solver* s, double lambda) {
   NEED(lambda >= 0.0, "bslam_iterate_pre: lambda must be >= 0");
   CU(cudaSetDevice(s->device));
   int rc;
-  if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+  if ((rc = prepare_iterate(s))) return rc;
   auto body = [&]() {
-    int r = do_linearize(s);
-    if (!r) r = do_reduce(s, lambda);
+    int r = do_linearize(s, true);
+    if (!r) r = do_reduce(s, lambda, true);
     if (!r) r = do_pack(s, 0);
     return r;
   };
@@ -1824,11 +2085,11 @@ int bslam_iterate_post(bslam_solver* s, int eval_new_cost) {
   NEED(s && s->finalized, "bslam_iterate_post: solver not finalized");
   CU(cudaSetDevice(s->device));
   int rc;
-  if (!s->plan_valid && (rc = build_chol_plan(s))) return rc;
+  if ((rc = prepare_iterate(s))) return rc;
   auto body = [&]() {
     int r = do_pack(s, 1);
     if (!r) r = do_solve_reduced(s);
-    if (!r) r = do_retract(s, eval_new_cost);
+    if (!r) r = do_retract(s, eval_new_cost, true);
     return r;
   };
   if (s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr) {
@@ -1909,6 +2170,7 @@ int bslam_get_reduced_system(bslam_solver* s, double* Sout, double* rhs) {
 int bslam_get_normal_equations(bslam_solver* s, double* H, double* b) {
   NEED(s && s->finalized && H && b, "bslam_get_normal_equations: bad arguments");
   NEED(s->dim <= 20000, "bslam_get_normal_equations: D = %d too large for a dense export", s->dim);
+  NEED(s->n_obs == 0 || s->d_W.p, "bslam_get_normal_equations: call bslam_linearize first");
   CU(cudaSetDevice(s->device));
   const int D = s->dim, n = s->n_red, ld = s->n_pad, N = s->n_obs;
   std::vector<double> Sd((size_t)ld * ld), W(bs::w_alloc_len(N)), Vg(9 * (size_t)s->n_lm);
@@ -1951,8 +2213,8 @@ int bslam_covariance(bslam_solver* s, double* cov) {
   NEED(s->dim <= 8192, "bslam_covariance: D = %d too large for a dense covariance (limit 8192)", s->dim);
   CU(cudaSetDevice(s->device));
   int rc;
-  if ((rc = do_linearize(s))) return rc;
-  if ((rc = do_reduce(s, 0.0))) return rc;
+  if ((rc = do_linearize(s, false))) return rc;
+  if ((rc = do_reduce(s, 0.0, false))) return rc;
   if ((rc = do_solve_reduced(s))) return rc;          // factor L (in S), diagonal inverses (Linv)
   const size_t D = (size_t)s->dim;
   const int nt = s->nblk, ld = s->n_pad;

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('BSLAM_LIB') or os.path.join(_HERE, 'libbslam.so')
 N_SCALARS = 16
 N_TIMINGS = 16
 S_COST_LIN, S_COST_NEW, S_DX_NORM2, S_CHOL_FAIL, S_COST_EVAL = 0, 1, 2, 3, 4
-TIMING_NAMES = ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total')
+TIMING_NAMES = ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total', 'fused')
 SE2, SE3 = 2, 3
 KIND_SE3, KIND_SE2, KIND_POINT, KIND_VEC = 0, 1, 2, 3
 
@@ -63,6 +63,10 @@ SIGNATURES = {
     'bslam_solve_reduced': (C.c_int, [_h]),
     'bslam_retract': (C.c_int, [_h, C.c_int]),
     'bslam_get_scalars': (C.c_int, [_h, _dp]),
+    'bslam_linearize_reduce': (C.c_int, [_h, C.c_double]),
+    'bslam_retract_iterate': (C.c_int, [_h, C.c_int]),
+    'bslam_set_fused': (C.c_int, [_h, C.c_int]),
+    'bslam_get_fused': (C.c_int, [_h, _ip, _ip]),
     'bslam_reduced_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), _ip]),
     'bslam_packed_buffer': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     'bslam_iterate_pre': (C.c_int, [_h, C.c_double]),
@@ -314,6 +318,23 @@ class Engine:
 
     def solve_reduced(self):
         self._ck(self._lib.bslam_solve_reduced(self._h))
+
+    def linearize_reduce(self, lam=0.):
+        """What `iterate` runs before the reduced solve (fused panels included)."""
+        self._ck(self._lib.bslam_linearize_reduce(self._h, float(lam)))
+
+    def retract_iterate(self, eval_new_cost=True):
+        self._ck(self._lib.bslam_retract_iterate(self._h, int(bool(eval_new_cost))))
+
+    def set_fused(self, mode):
+        """0: landmark-block kernels (W materialised); 1: dense panels fused (default); 2: fuse whatever fits."""
+        self._ck(self._lib.bslam_set_fused(self._h, int(mode)))
+
+    def fused_info(self):
+        """(number of panels, number of landmarks inside panels) after finalize."""
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self._lib.bslam_get_fused(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def retract(self, eval_new_cost=True):
         self._ck(self._lib.bslam_retract(self._h, int(bool(eval_new_cost))))

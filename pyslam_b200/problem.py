@@ -32,8 +32,32 @@ import numpy as np
 from . import engine as _engine
 from .lie import group_of
 from .losses import L2Loss, loss_descriptor
-from .residuals.blocks import BLOCK_POSE, BLOCK_POSE_TO_POSE, BLOCK_REPROJECTION
-from .residuals.photometric import BLOCK_PHOTOMETRIC
+from .residuals.blocks import (BLOCK_POSE, BLOCK_POSE_TO_POSE, BLOCK_REPROJECTION, PoseResidual, PoseToPoseResidual,
+                               ReprojectionResidual)
+from .residuals.photometric import BLOCK_PHOTOMETRIC, PhotometricResidualSE3
+from .sensors.stereo_camera import StereoCamera
+
+_BUILTIN_BLOCKS = {BLOCK_REPROJECTION: ReprojectionResidual, BLOCK_POSE: PoseResidual,
+                   BLOCK_POSE_TO_POSE: PoseToPoseResidual, BLOCK_PHOTOMETRIC: PhotometricResidualSE3}
+
+
+def _builtin_kind(block):
+    """BLOCK_KIND of a residual whose arithmetic IS the built-in class's: the class itself, or a subclass
+    that does not override `evaluate`.  A subclass with its own `evaluate` is a user plug-in: the reference
+    always calls the object's method (pyslam/problem.py:349), so it must not be lowered to a CUDA kernel."""
+    kind = getattr(type(block), 'BLOCK_KIND', None)
+    cls = _BUILTIN_BLOCKS.get(kind)
+    if cls is None or getattr(type(block), 'evaluate', None) is not cls.evaluate:
+        return None
+    return kind
+
+
+def _builtin_camera(camera):
+    """A StereoCamera whose projection is the built-in one (a subclass that overrides `project`, e.g. to add
+    distortion, keeps the Python plug-in path)."""
+    t = type(camera)
+    return (isinstance(camera, StereoCamera) and t.project is StereoCamera.project
+            and getattr(t, 'intrinsics', None) is StereoCamera.intrinsics)
 
 
 class Options:
@@ -58,6 +82,7 @@ class Options:
         # --- extensions ---
         self.device = 0               # CUDA device ordinal
         self.lm_lambda = 0.           # lambda * diag(H) damping; 0 = the reference's Gauss-Newton
+        self.fused_mode = None        # None: library default; 0/1/2 see bslam_set_fused (include/bslam.h)
 
 
 class _ReprojectionBatch:
@@ -176,15 +201,15 @@ class Problem:
 
         # which 3-vectors act as landmarks of built-in reprojection blocks
         def fusable_reproj(block, keys, loss):
-            if getattr(type(block), 'BLOCK_KIND', None) != BLOCK_REPROJECTION or len(keys) != 2:
+            if _builtin_kind(block) != BLOCK_REPROJECTION or len(keys) != 2:
                 return False
-            if loss_descriptor(loss) is None or not hasattr(block.camera, 'intrinsics'):
+            if loss_descriptor(loss) is None or not _builtin_camera(block.camera):
                 return False
             T, p = pd.get(keys[0]), pd.get(keys[1])
             return group_of(T) == 'se3' and group_of(p) is None and np.size(p) == 3 and not np.isscalar(p)
 
         def fusable_pose(block, keys, loss, kind, nkeys):
-            if getattr(type(block), 'BLOCK_KIND', None) != kind or len(keys) != nkeys:
+            if _builtin_kind(block) != kind or len(keys) != nkeys:
                 return None
             if loss_descriptor(loss) is None:
                 return None
@@ -195,8 +220,8 @@ class Problem:
             return g
 
         def fusable_photo(block, keys, loss):
-            return (getattr(type(block), 'BLOCK_KIND', None) == BLOCK_PHOTOMETRIC and len(keys) == 1
-                    and loss_descriptor(loss) is not None and hasattr(block.camera, 'intrinsics')
+            return (_builtin_kind(block) == BLOCK_PHOTOMETRIC and len(keys) == 1
+                    and loss_descriptor(loss) is not None and _builtin_camera(block.camera)
                     and group_of(pd.get(keys[0])) == 'se3')
 
         kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('photo',) | ('dense',)
@@ -222,7 +247,7 @@ class Problem:
                 continue
             kinds.append(('dense',))
         for bt in self._batches:
-            if loss_descriptor(bt.loss) is None or not hasattr(bt.camera, 'intrinsics'):
+            if loss_descriptor(bt.loss) is None or not _builtin_camera(bt.camera):
                 raise ValueError('add_reprojection_batch needs a built-in camera and loss')
             for k in set(bt.pose_keys) | set(bt.point_keys):
                 if k not in pd:
@@ -252,6 +277,8 @@ class Problem:
 
         eng = self._engine
         eng.clear_blocks()
+        if getattr(self.options, 'fused_mode', None) is not None:
+            eng.set_fused(self.options.fused_mode)
         self._upload_params(pd, structure=True)
 
         # --- built-in blocks -> batches grouped by (kind, loss, camera) ---
@@ -302,9 +329,12 @@ class Problem:
             ld = loss_descriptor(bt.loss)
             pose_idx = np.fromiter((low.table[k][1] for k in bt.pose_keys), np.int32, len(bt.pose_keys))
             pt_idx = np.fromiter((low.table[k][1] for k in bt.point_keys), np.int32, len(bt.point_keys))
-            for k in bt.pose_keys[:1]:
+            for k in set(bt.pose_keys):
                 if low.table[k][0] != 'se3':
-                    raise ValueError('reprojection batch pose keys must be SE3 parameters')
+                    raise ValueError('reprojection batch pose key {} is not an SE3 parameter'.format(k))
+            for k in set(bt.point_keys):
+                if low.table[k][0] != 'pt':
+                    raise ValueError('reprojection batch point key {} is not a 3-vector parameter'.format(k))
             eng.add_reprojection_blocks(pose_idx, pt_idx, bt.obs, bt.stiffness, bt.camera.intrinsics(), ld[0], ld[1])
 
         # --- host-evaluated blocks: structure ---
