@@ -18,7 +18,7 @@
 //
 //   P1  warp = row, lane = two landmarks: structured linearisation (reproj_blocks), cost;
 //       camera values U_c, b_c (27) summed over the row by a register butterfly (no shared memory)
-//       -> one fp64 atomic per value; landmark values V_p, b_p (9) -> shared partials;
+//       -> one fp64 atomic per value; landmark values V_p, b_p (9) -> shared partials (one slot per row);
 //       W (6x3) -> shared memory, already in the operand layout of P4.
 //   P2  thread = landmark: V_p = sum of partials, (V_p + lambda diag)^-1 -> HBM (back-substitution),
 //       Cholesky V = L L^T, c = L^-1 b_p.
@@ -87,7 +87,7 @@ struct PanelArgs {
 };
 
 BS_HD size_t panel_smem_bytes(int max_var) {
-  return sizeof(double) * ((size_t)max_var * kZRow + (kPanelLm / 4) * kCGroup + 4 * 9 * kPanelLm + 6 * kPanelLm + 3 * kPanelLm) +
+  return sizeof(double) * ((size_t)max_var * kZRow + (kPanelLm / 4) * kCGroup + kPanelRows * 9 * kPanelLm + 6 * kPanelLm + 3 * kPanelLm) +
          sizeof(int) * 64 + sizeof(PanelRow) * kPanelRows;
 }
 
@@ -114,19 +114,25 @@ BS_D void tile_ij(int t, int& I, int& J) {
   J = t - i * (i + 1) / 2;
 }
 
+constexpr int kMaxTiles = 28;       // lower-triangular 8x8 tiles of a (6 * 8 + 1)-row operand
+constexpr int kTilesPerWarp = 4;    // ceil(28 / 8)
+
 template <int kLoss>
 __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const PanelArgs a) {
   extern __shared__ __align__(16) double psm[];
   __shared__ double sred[kPanelThreads / 32];
+  __shared__ unsigned char sTileI[kMaxTiles], sTileJ[kMaxTiles];
+  __shared__ int sZoff[64];                                   // operand row -> offset of its first element in psm
   double* sZ = psm;                                           // [max_var][16 groups][76]
   double* sC = sZ + (size_t)a.max_var * kZRow;                // [16 groups][12]
-  double* sVp = sC + (kPanelLm / 4) * kCGroup;                // [4][9][64]
-  double* sL = sVp + 4 * 9 * kPanelLm;                        // [6][64]: 1/l00, l10, 1/l11, l20, l21, 1/l22
+  double* sVp = sC + (kPanelLm / 4) * kCGroup;                // [8 rows][9][64]
+  double* sL = sVp + kPanelRows * 9 * kPanelLm;               // [6][64]: 1/l00, l10, 1/l11, l20, l21, 1/l22
   double* sPts = sL + 6 * kPanelLm;                           // [64][3]
   int* sIdx = reinterpret_cast<int*>(sPts + 3 * kPanelLm);    // operand row -> index in S / rhs
   PanelRow* sRows = reinterpret_cast<PanelRow*>(sIdx + 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  const int c_off = a.max_var * kZRow;                        // offset of sC
   double cost = 0.0;
   // lane -> position of its camera value inside the pose's diagonal block of S (lower triangle, row-major)
   int tri_off;
@@ -135,20 +141,45 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
     while ((r + 1) * (r + 2) / 2 <= lane) ++r;
     tri_off = lane < 21 ? r * a.ldS + (lane - r * (r + 1) / 2) : 0;
   }
+  if (tid < kMaxTiles) {
+    int I, J;
+    tile_ij(tid, I, J);
+    sTileI[tid] = (unsigned char)I; sTileJ[tid] = (unsigned char)J;
+  }
   const double damp = 1.0 + a.lambda;
 
-  for (int pn = blockIdx.x; pn < a.n_panels; pn += gridDim.x) {
-    const Panel pan = a.panels[pn];
+  // header (rows, points) and observations of a panel: requested one panel ahead
+  struct Obs { double u[2], v[2], d[2]; };
+  auto load_header = [&](const Panel& pan) {
     if (tid < pan.n_rows) sRows[tid] = a.rows[pan.row_begin + tid];
     if (tid < 3 * kPanelLm) sPts[tid] = tid < 3 * pan.n_lms ? a.pts_in[3 * (size_t)pan.lm_begin + tid] : 0.0;
+  };
+  auto load_obs = [&](const Panel& pan, Obs& ob) {
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) ob.u[sub] = ob.v[sub] = ob.d[sub] = 0.0;
+    if (warp < pan.n_rows) {
+      const PanelRow row = a.rows[pan.row_begin + warp];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        if (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) {
+          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + lane + 32 * sub;
+          ob.u[sub] = ld_stream(a.pu + cell); ob.v[sub] = ld_stream(a.pv + cell); ob.d[sub] = ld_stream(a.pd + cell);
+        }
+      }
+    }
+  };
+
+  int pn = blockIdx.x;
+  if (pn >= a.n_panels) return;
+  Panel pan = a.panels[pn];
+  Obs ob;
+  load_header(pan);
+  load_obs(pan, ob);
+
+  for (;;) {
     __syncthreads();        // header visible; the tile phase of the previous panel is over
 
     // ---------------------------------------------------------------- P1: one row per warp
-    double vp[2][9];
-#pragma unroll
-    for (int s_ = 0; s_ < 2; ++s_)
-#pragma unroll
-      for (int k = 0; k < 9; ++k) vp[s_][k] = 0.0;
     if (warp < pan.n_rows) {
       const PanelRow row = sRows[warp];
       const bool isvar = warp < pan.n_var;
@@ -156,7 +187,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
       {
         const double* Pg = a.poses + 12 * (size_t)row.pose;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+        for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
       }
       double U[32];
 #pragma unroll
@@ -166,26 +197,26 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
         const int j = lane + 32 * sub;
         const bool present = (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) != 0;
         double* zc = sZ + warp * kZRow + (j >> 2) * kZGroup + 3 * (j & 3);
+        double* vq = sVp + warp * 9 * kPanelLm + j;            // landmark partials of this row: [9][64]
         if (present) {
           const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + j;
-          const double u = ld_stream(a.pu + cell), v = ld_stream(a.pv + cell), d = ld_stream(a.pd + cell);
           const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[cell]];
           double X[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) X[k] = sPts[3 * j + k];
           ReprojBlocks o;
-          reproj_blocks<kLoss>(grp, P, X, u, v, d, o);
+          reproj_blocks<kLoss>(grp, P, X, ob.u[sub], ob.v[sub], ob.d[sub], o);
           cost += o.cost;
           // V_p = R^T (M R) (xx xy xz yy yz zz), b_p = -R^T t
-          vp[sub][0] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
-          vp[sub][1] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
-          vp[sub][2] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
-          vp[sub][3] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
-          vp[sub][4] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
-          vp[sub][5] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
-          vp[sub][6] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
-          vp[sub][7] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
-          vp[sub][8] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
+          vq[0] = P[0] * o.MR[0] + P[3] * o.MR[3] + P[6] * o.MR[6];
+          vq[kPanelLm] = P[0] * o.MR[1] + P[3] * o.MR[4] + P[6] * o.MR[7];
+          vq[2 * kPanelLm] = P[0] * o.MR[2] + P[3] * o.MR[5] + P[6] * o.MR[8];
+          vq[3 * kPanelLm] = P[1] * o.MR[1] + P[4] * o.MR[4] + P[7] * o.MR[7];
+          vq[4 * kPanelLm] = P[1] * o.MR[2] + P[4] * o.MR[5] + P[7] * o.MR[8];
+          vq[5 * kPanelLm] = P[2] * o.MR[2] + P[5] * o.MR[5] + P[8] * o.MR[8];
+          vq[6 * kPanelLm] = -(P[0] * o.t[0] + P[3] * o.t[1] + P[6] * o.t[2]);
+          vq[7 * kPanelLm] = -(P[1] * o.t[0] + P[4] * o.t[1] + P[7] * o.t[2]);
+          vq[8 * kPanelLm] = -(P[2] * o.t[0] + P[5] * o.t[1] + P[8] * o.t[2]);
           if (isvar) {
             // U_c lower triangle (row-major): rows 0-2 M; rows 3-5 [(M B)^T | B^T M B]; then b_c = -[t; B^T t]
             U[0] += o.M[0]; U[1] += o.M[1]; U[2] += o.M[3]; U[3] += o.M[2]; U[4] += o.M[4]; U[5] += o.M[5];
@@ -207,11 +238,15 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
               zc[60 + c] = o.x * o.MR[3 + c] - o.y * o.MR[c];
             }
           }
-        } else if (isvar) {
+        } else {
 #pragma unroll
-          for (int r = 0; r < 6; ++r)
+          for (int k = 0; k < 9; ++k) vq[k * kPanelLm] = 0.0;
+          if (isvar) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) zc[12 * r + c] = 0.0;
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) zc[12 * r + c] = 0.0;
+          }
         }
       }
       if (isvar) {
@@ -221,20 +256,6 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
         else if (lane < 27) red_add(a.rhs + row.off + (lane - 21), U[0]);
       }
     }
-    // landmark partials: rows 0-3 store, rows 4-7 add after the barrier
-    if (warp < 4) {
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) sVp[(warp * 9 + k) * kPanelLm + lane + 32 * sub] = vp[sub][k];
-    }
-    __syncthreads();
-    if (warp >= 4 && warp < pan.n_rows) {
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) sVp[((warp - 4) * 9 + k) * kPanelLm + lane + 32 * sub] += vp[sub][k];
-    }
     __syncthreads();
 
     // ---------------------------------------------------------------- P2: one landmark per thread
@@ -242,8 +263,11 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
       const int j = tid;
       double V[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k)
-        V[k] = (sVp[k * kPanelLm + j] + sVp[(9 + k) * kPanelLm + j]) + (sVp[(18 + k) * kPanelLm + j] + sVp[(27 + k) * kPanelLm + j]);
+      for (int k = 0; k < 9; ++k) V[k] = 0.0;
+      for (int rr = 0; rr < pan.n_rows; ++rr) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) V[k] += sVp[(rr * 9 + k) * kPanelLm + j];
+      }
       double i00 = 1.0, l10 = 0.0, i11 = 1.0, l20 = 0.0, l21 = 0.0, i22 = 1.0, c0 = 0.0, c1 = 0.0, c2 = 0.0;
       if (j < pan.n_lms) {
         const size_t q = (size_t)pan.lm_begin + j;
@@ -270,10 +294,16 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
       cc[0] = c0; cc[1] = c1; cc[2] = c2;
     } else if (tid < kPanelLm + 64) {
       const int zr = tid - kPanelLm;
-      int idx = -1;
-      if (zr < 6 * pan.n_var) idx = sRows[zr / 6].off + zr % 6;
-      else if (zr == 6 * pan.n_var) idx = -2;         // the row of c: its products go to the right-hand side
+      int idx = -1, zo = c_off;
+      if (zr < 6 * pan.n_var) {
+        const int rr = zr / 6, ri = zr - 6 * rr;
+        idx = sRows[rr].off + ri;
+        zo = rr * kZRow + ri * 12;
+      } else if (zr == 6 * pan.n_var) {
+        idx = -2;                                   // the row of c: its products go to the right-hand side
+      }
       sIdx[zr] = idx;
+      sZoff[zr] = zo;
     }
     __syncthreads();
 
@@ -299,70 +329,79 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
     }
     __syncthreads();
 
+    // ---- everything the NEXT panel needs goes in flight now (sRows / sPts are not read by the tile phase)
+    const int pn_next = pn + gridDim.x;
+    const bool has_next = pn_next < a.n_panels;
+    Panel npan = pan;
+    if (has_next) {
+      npan = a.panels[pn_next];
+      load_header(npan);
+      load_obs(npan, ob);
+    }
+
     // ---------------------------------------------------------------- P4: S -= Zbig Zbig^T on DMMA tiles
     {
       const int n_zr = 6 * pan.n_var + 1;
       const int T = (n_zr + 7) >> 3;
       const int ntiles = T * (T + 1) / 2;
       const int ng = (pan.n_lms + 3) >> 2;
-      auto zptr = [&](int x, const double*& p, int& stride) {
-        if (x < 6 * pan.n_var) { p = sZ + (x / 6) * kZRow + (x % 6) * 12 + t; stride = kZGroup; }
-        else { p = sC + t; stride = kCGroup; }
-      };
-      auto emit = [&](int I, int J, double c0, double c1) {
-        const int x = 8 * I + g;
+      // consecutive tiles per warp (they mostly share their row operand)
+      const int base = ntiles / kPanelRows, rem = ntiles % kPanelRows;
+      const int t_first = warp * base + min(warp, rem);
+      const int nt_w = base + (warp < rem ? 1 : 0);
+      int tI[kTilesPerWarp], tJ[kTilesPerWarp];
+      const double* pa[kTilesPerWarp];
+      const double* pb[kTilesPerWarp];
+      int sa[kTilesPerWarp], sb[kTilesPerWarp];
+      double acc[kTilesPerWarp][2];
+#pragma unroll
+      for (int k = 0; k < kTilesPerWarp; ++k) {
+        const int ti = min(t_first + k, ntiles - 1);
+        tI[k] = sTileI[ti]; tJ[k] = sTileJ[ti];
+        const int xa = 8 * tI[k] + g, xb = 8 * tJ[k] + g;
+        const int oa = sZoff[xa], ob_ = sZoff[xb];
+        pa[k] = psm + oa + t; sa[k] = oa >= c_off ? kCGroup : kZGroup;
+        pb[k] = psm + ob_ + t; sb[k] = ob_ >= c_off ? kCGroup : kZGroup;
+        acc[k][0] = acc[k][1] = 0.0;
+      }
+      for (int G = 0; G < ng; ++G) {
+#pragma unroll
+        for (int s_ = 0; s_ < 3; ++s_) {
+          double av[kTilesPerWarp];
+#pragma unroll
+          for (int k = 0; k < kTilesPerWarp; ++k) {
+            if (k < nt_w) {
+              av[k] = (k > 0 && tI[k] == tI[k - 1]) ? av[k - 1] : pa[k][G * sa[k] + 4 * s_];
+              const double bv = pb[k][G * sb[k] + 4 * s_];
+              dmma_8x8x4(acc[k][0], acc[k][1], av[k], bv);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kTilesPerWarp; ++k) {
+        if (k >= nt_w) continue;
+        const int x = 8 * tI[k] + g;
         const int ix = sIdx[x];
-        if (ix == -1) return;
+        if (ix == -1) continue;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int y = 8 * J + 2 * t + h;
+          const int y = 8 * tJ[k] + 2 * t + h;
           if (y > x) continue;
           const int iy = sIdx[y];
           if (iy < 0) continue;
-          const double c = h ? c1 : c0;
+          const double c = acc[k][h];
           if (ix == -2) red_add(a.rhs + iy, -c);
           else {
             const int hi = max(ix, iy), lo = min(ix, iy);
             red_add(a.S + (size_t)hi * a.ldS + lo, -c);
           }
         }
-      };
-      for (int p2 = 2 * warp; p2 < ntiles; p2 += 2 * kPanelRows) {
-        int I0, J0, I1, J1;
-        tile_ij(p2, I0, J0);
-        const bool two = p2 + 1 < ntiles;
-        if (two) tile_ij(p2 + 1, I1, J1);
-        else { I1 = I0; J1 = J0; }
-        const double *pa0, *pb0, *pa1, *pb1;
-        int sa0, sb0, sa1, sb1;
-        zptr(8 * I0 + g, pa0, sa0); zptr(8 * J0 + g, pb0, sb0);
-        zptr(8 * I1 + g, pa1, sa1); zptr(8 * J1 + g, pb1, sb1);
-        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-        if (I0 == I1) {          // the two tiles share their row operand
-          for (int G = 0; G < ng; ++G) {
-#pragma unroll
-            for (int s_ = 0; s_ < 3; ++s_) {
-              const double av = pa0[G * sa0 + 4 * s_];
-              const double b0 = pb0[G * sb0 + 4 * s_], b1 = pb1[G * sb1 + 4 * s_];
-              dmma_8x8x4(c00, c01, av, b0);
-              dmma_8x8x4(c10, c11, av, b1);
-            }
-          }
-        } else {
-          for (int G = 0; G < ng; ++G) {
-#pragma unroll
-            for (int s_ = 0; s_ < 3; ++s_) {
-              const double a0 = pa0[G * sa0 + 4 * s_], b0 = pb0[G * sb0 + 4 * s_];
-              const double a1 = pa1[G * sa1 + 4 * s_], b1 = pb1[G * sb1 + 4 * s_];
-              dmma_8x8x4(c00, c01, a0, b0);
-              dmma_8x8x4(c10, c11, a1, b1);
-            }
-          }
-        }
-        emit(I0, J0, c00, c01);
-        if (two) emit(I1, J1, c10, c11);
       }
     }
+    if (!has_next) break;
+    pn = pn_next;
+    pan = npan;
   }
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
 }
@@ -372,131 +411,124 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
 // observation, the pose and the point at the linearisation point (poses = table before retraction,
 // pts = not yet updated) -- ~250 flop per observation instead of a 144-byte read of W; then
 // p <- p + dx_p, ||dx_p||^2, and the cost at the new point with the retracted poses.
-BS_HD size_t panel_finish_smem_bytes() {
-  return sizeof(double) * (kPanelRows * 3 * kPanelLm + 3 * kPanelLm + 3 * kPanelLm) + sizeof(PanelRow) * kPanelRows;
-}
+//
+// Warp-autonomous: the unit of work is a CHUNK of 4 landmarks of a panel, lane = (row = lane / 4,
+// landmark = lane % 4).  The sum over the poses of a landmark is three xor-shuffles; there is no shared
+// memory and no block barrier, chunks are dealt round-robin to all resident warps, and the inputs of a
+// warp's next chunk are requested before the current one is computed.
+constexpr int kFinishThreads = 128;
+constexpr int kChunkLm = 4;
+constexpr int kChunksPerPanel = kPanelLm / kChunkLm;
 
 template <int kLoss>
-__global__ void __launch_bounds__(kPanelThreads, 2) panel_finish_kernel(const PanelArgs a) {
-  extern __shared__ __align__(16) double psm[];
-  __shared__ double sred[2 * (kPanelThreads / 32)];
-  double* sAcc = psm;                                  // [8 rows][3][64]
-  double* sPts = sAcc + kPanelRows * 3 * kPanelLm;     // [64][3] old
-  double* sNew = sPts + 3 * kPanelLm;                  // [64][3] new
-  PanelRow* sRows = reinterpret_cast<PanelRow*>(sNew + 3 * kPanelLm);
+__global__ void __launch_bounds__(kFinishThreads, 4) panel_finish_kernel(const PanelArgs a) {
+  __shared__ double sred[2 * (kFinishThreads / 32)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, m = lane & 3;
+  const int n_warps = gridDim.x * (kFinishThreads / 32);
+  const int n_units = a.n_panels * kChunksPerPanel;
   double cost = 0.0, dx2 = 0.0;
 
-  for (int pn = blockIdx.x; pn < a.n_panels; pn += gridDim.x) {
-    const Panel pan = a.panels[pn];
-    if (tid < pan.n_rows) sRows[tid] = a.rows[pan.row_begin + tid];
-    if (tid < 3 * kPanelLm) sPts[tid] = tid < 3 * pan.n_lms ? a.pts_in[3 * (size_t)pan.lm_begin + tid] : 0.0;
-    // landmark data of thread j, requested early
-    double bp[3] = {0, 0, 0}, vi[6] = {0, 0, 0, 0, 0, 0};
-    if (tid < pan.n_lms) {
-      const size_t q = (size_t)pan.lm_begin + tid;
+  struct In {            // everything a chunk reads from HBM, as loaded
+    double u, v, d, X[3];
+    int pose, off, present, valid, grp;
+  };
+  auto fetch = [&](int unit, In& in) {
+    in.u = in.v = in.d = 0.0; in.X[0] = in.X[1] = in.X[2] = 0.0;
+    in.pose = 0; in.off = -1; in.present = 0; in.valid = 0; in.grp = 0;
+    if (unit >= n_units) return;
+    const Panel pan = a.panels[unit / kChunksPerPanel];
+    const int j = (unit % kChunksPerPanel) * kChunkLm + m;
+    if (j >= pan.n_lms) return;
+    in.valid = 1;
+    const double* Xg = a.pts_in + 3 * (size_t)(pan.lm_begin + j);
+    in.X[0] = Xg[0]; in.X[1] = Xg[1]; in.X[2] = Xg[2];
+    if (r >= pan.n_rows) return;
+    const PanelRow row = a.rows[pan.row_begin + r];
+    in.pose = row.pose; in.off = row.off;
+    in.present = (((j < 32 ? row.mask_lo : row.mask_hi) >> (j & 31)) & 1u);
+    if (in.present) {
+      const size_t cell = (size_t)(pan.row_begin + r) * kPanelLm + j;
+      in.u = ld_stream(a.pu + cell); in.v = ld_stream(a.pv + cell); in.d = ld_stream(a.pd + cell);
+      if (kLoss < 0) in.grp = a.pgrp[cell];
+    }
+  };
+
+  int unit = blockIdx.x * (kFinishThreads / 32) + warp;
+  In cur, nxt;
+  fetch(unit, cur);
+  for (; unit < n_units; unit += n_warps) {
+    fetch(unit + n_warps, nxt);
+    const Panel pan = a.panels[unit / kChunksPerPanel];
+    const int j = (unit % kChunksPerPanel) * kChunkLm + m;
+    const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[cur.grp];
+    // ---- W^T dx_c of this cell
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    if (cur.present && cur.off >= 0) {
+      double P[12], dxa[6];
+      const double* Pg = a.poses + 12 * (size_t)cur.pose;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) bp[k] = ld_stream(a.Vg + 9 * q + 6 + k);
+      for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) dxa[k] = __ldg(a.dx_red + cur.off + k);
+      ReprojBlocks o;
+      reproj_blocks<kLoss>(grp, P, cur.X, cur.u, cur.v, cur.d, o);
+      // e = d rho + B d phi,  B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
+      const double e0 = dxa[0] + o.z * dxa[4] - o.y * dxa[5];
+      const double e1 = dxa[1] - o.z * dxa[3] + o.x * dxa[5];
+      const double e2 = dxa[2] + o.y * dxa[3] - o.x * dxa[4];
+      c0 = o.MR[0] * e0 + o.MR[3] * e1 + o.MR[6] * e2;
+      c1 = o.MR[1] * e0 + o.MR[4] * e1 + o.MR[7] * e2;
+      c2 = o.MR[2] * e0 + o.MR[5] * e1 + o.MR[8] * e2;
+    }
+    // ---- sum over the rows (lane bits 2..4), every lane gets the total
+#pragma unroll
+    for (int h = 4; h < 32; h <<= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, h);
+      c1 += __shfl_xor_sync(0xffffffffu, c1, h);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, h);
+    }
+    // ---- back-substitution and retraction (row 0 of every landmark), new point to all rows
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+    if (r == 0 && cur.valid) {
+      const size_t q = (size_t)pan.lm_begin + j;
+      const double s0 = ld_stream(a.Vg + 9 * q + 6) - c0, s1 = ld_stream(a.Vg + 9 * q + 7) - c1, s2 = ld_stream(a.Vg + 9 * q + 8) - c2;
+      double vi[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * q + k);
-    }
-    __syncthreads();
-
-    // ---- F1: W^T dx_c per cell
-    PanelRow row{0, -1, 0u, 0u};
-    double ou[2] = {0, 0}, ov[2] = {0, 0}, od[2] = {0, 0};
-    int grp_id[2] = {0, 0};
-    if (warp < pan.n_rows) {
-      row = sRows[warp];
-      const bool isvar = row.off >= 0;
-      double P[12], dxa[6];
-      if (isvar) {
-        const double* Pg = a.poses + 12 * (size_t)row.pose;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = Pg[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) dxa[k] = a.dx_red[row.off + k];
-      }
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int j = lane + 32 * sub;
-        const bool present = (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) != 0;
-        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-        if (present) {
-          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + j;
-          ou[sub] = ld_stream(a.pu + cell); ov[sub] = ld_stream(a.pv + cell); od[sub] = ld_stream(a.pd + cell);
-          if (kLoss < 0) grp_id[sub] = a.pgrp[cell];
-          if (isvar) {
-            const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[grp_id[sub]];
-            double X[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) X[k] = sPts[3 * j + k];
-            ReprojBlocks o;
-            reproj_blocks<kLoss>(grp, P, X, ou[sub], ov[sub], od[sub], o);
-            // e = d rho + B d phi,  B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
-            const double e0 = dxa[0] + o.z * dxa[4] - o.y * dxa[5];
-            const double e1 = dxa[1] - o.z * dxa[3] + o.x * dxa[5];
-            const double e2 = dxa[2] + o.y * dxa[3] - o.x * dxa[4];
-            c0 = o.MR[0] * e0 + o.MR[3] * e1 + o.MR[6] * e2;
-            c1 = o.MR[1] * e0 + o.MR[4] * e1 + o.MR[7] * e2;
-            c2 = o.MR[2] * e0 + o.MR[5] * e1 + o.MR[8] * e2;
-          }
-        }
-        sAcc[(warp * 3 + 0) * kPanelLm + j] = c0;
-        sAcc[(warp * 3 + 1) * kPanelLm + j] = c1;
-        sAcc[(warp * 3 + 2) * kPanelLm + j] = c2;
-      }
-    }
-    __syncthreads();
-
-    // ---- F2: back-substitution and retraction, one landmark per thread
-    if (tid < pan.n_lms) {
-      const int j = tid;
-      double s0 = bp[0], s1 = bp[1], s2 = bp[2];
-      for (int r = 0; r < pan.n_rows; ++r) {
-        s0 -= sAcc[(r * 3 + 0) * kPanelLm + j];
-        s1 -= sAcc[(r * 3 + 1) * kPanelLm + j];
-        s2 -= sAcc[(r * 3 + 2) * kPanelLm + j];
-      }
       const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
       const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
       const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
-      const size_t q = (size_t)pan.lm_begin + j;
       a.dx_lm[3 * q] = d0; a.dx_lm[3 * q + 1] = d1; a.dx_lm[3 * q + 2] = d2;
       dx2 += d0 * d0 + d1 * d1 + d2 * d2;
-      const double n0 = sPts[3 * j] + d0, n1 = sPts[3 * j + 1] + d1, n2 = sPts[3 * j + 2] + d2;
-      sNew[3 * j] = n0; sNew[3 * j + 1] = n1; sNew[3 * j + 2] = n2;
+      n0 = cur.X[0] + d0; n1 = cur.X[1] + d1; n2 = cur.X[2] + d2;
       a.pts[3 * q] = n0; a.pts[3 * q + 1] = n1; a.pts[3 * q + 2] = n2;
     }
-    __syncthreads();
-
-    // ---- F3: cost at the new point
-    if (a.eval_cost && warp < pan.n_rows) {
+    n0 = __shfl_sync(0xffffffffu, n0, m);
+    n1 = __shfl_sync(0xffffffffu, n1, m);
+    n2 = __shfl_sync(0xffffffffu, n2, m);
+    // ---- cost at the new point
+    if (a.eval_cost && cur.present) {
       double P[12];
-      const double* Pg = a.poses_new + 12 * (size_t)row.pose;
+      const double* Pg = a.poses_new + 12 * (size_t)cur.pose;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = Pg[k];
+      for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
+      const double Xn[3] = {n0, n1, n2};
+      double rr[3];
+      reproj_residual_only(grp, P, Xn, cur.u, cur.v, cur.d, rr);
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int j = lane + 32 * sub;
-        if (!((((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u))) continue;
-        const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[grp_id[sub]];
-        double r[3];
-        reproj_residual_only(grp, P, sNew + 3 * j, ou[sub], ov[sub], od[sub], r);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, r[k]);
-      }
+      for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, rr[k]);
     }
-    // the next panel's header writes sPts / sRows: every read of them above precedes the last barrier
+    cur = nxt;
   }
   cost = warp_sum(cost);
   dx2 = warp_sum(dx2);
-  if (lane == 0) { sred[warp] = cost; sred[kPanelThreads / 32 + warp] = dx2; }
+  if (lane == 0) { sred[warp] = cost; sred[kFinishThreads / 32 + warp] = dx2; }
   __syncthreads();
   if (tid == 0) {
     double c = 0.0, d = 0.0;
 #pragma unroll
-    for (int w = 0; w < kPanelThreads / 32; ++w) { c += sred[w]; d += sred[kPanelThreads / 32 + w]; }
+    for (int w = 0; w < kFinishThreads / 32; ++w) { c += sred[w]; d += sred[kFinishThreads / 32 + w]; }
     if (a.eval_cost) red_add(a.scalars + 1 /*COST_NEW*/, c);
     red_add(a.scalars + 2 /*DX_NORM2*/, d);
   }

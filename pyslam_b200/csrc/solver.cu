@@ -716,16 +716,16 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
   if (use_panels) {
     bs::PanelArgs pa = panel_args(s, 0.0);
     pa.poses = s->d_se3_prev.p; pa.poses_new = s->d_se3.p; pa.eval_cost = eval_new_cost;
-    const size_t smem = bs::panel_finish_smem_bytes();
-    const int grid = std::min(s->n_panels, s->finish_grid);
+    const size_t smem = 0;
+    const int grid = std::min(cdiv((long long)s->n_panels * bs::kChunksPerPanel, bs::kFinishThreads / 32), s->finish_grid);
     switch (s->loss_kind) {
-      case 0: LAUNCH(s, bs::panel_finish_kernel<0>, grid, bs::kPanelThreads, smem, pa); break;
-      case 1: LAUNCH(s, bs::panel_finish_kernel<1>, grid, bs::kPanelThreads, smem, pa); break;
-      case 2: LAUNCH(s, bs::panel_finish_kernel<2>, grid, bs::kPanelThreads, smem, pa); break;
-      case 3: LAUNCH(s, bs::panel_finish_kernel<3>, grid, bs::kPanelThreads, smem, pa); break;
-      case 4: LAUNCH(s, bs::panel_finish_kernel<4>, grid, bs::kPanelThreads, smem, pa); break;
-      case 5: LAUNCH(s, bs::panel_finish_kernel<5>, grid, bs::kPanelThreads, smem, pa); break;
-      default: LAUNCH(s, bs::panel_finish_kernel<-1>, grid, bs::kPanelThreads, smem, pa); break;
+      case 0: LAUNCH(s, bs::panel_finish_kernel<0>, grid, bs::kFinishThreads, smem, pa); break;
+      case 1: LAUNCH(s, bs::panel_finish_kernel<1>, grid, bs::kFinishThreads, smem, pa); break;
+      case 2: LAUNCH(s, bs::panel_finish_kernel<2>, grid, bs::kFinishThreads, smem, pa); break;
+      case 3: LAUNCH(s, bs::panel_finish_kernel<3>, grid, bs::kFinishThreads, smem, pa); break;
+      case 4: LAUNCH(s, bs::panel_finish_kernel<4>, grid, bs::kFinishThreads, smem, pa); break;
+      case 5: LAUNCH(s, bs::panel_finish_kernel<5>, grid, bs::kFinishThreads, smem, pa); break;
+      default: LAUNCH(s, bs::panel_finish_kernel<-1>, grid, bs::kFinishThreads, smem, pa); break;
     }
   }
   // landmark blocks: the same from the materialised W
@@ -1810,7 +1810,7 @@ int bslam_finalize(bslam_solver* s) {
   CU(upload(s->d_pgrp, pgrp, st));
   CU(s->d_se3_prev.alloc(std::max<size_t>(1, s->d_se3.n)));
   if (s->n_panels > 0) {
-    const size_t psm = bs::panel_smem_bytes(s->panel_max_var), fsm = bs::panel_finish_smem_bytes();
+    const size_t psm = bs::panel_smem_bytes(s->panel_max_var), fsm = 0;
     const void *fk = nullptr, *ff = nullptr;
     switch (s->loss_kind) {
       case 0: fk = (const void*)bs::fused_panel_kernel<0>; ff = (const void*)bs::panel_finish_kernel<0>; break;
@@ -1822,10 +1822,9 @@ int bslam_finalize(bslam_solver* s) {
       default: fk = (const void*)bs::fused_panel_kernel<-1>; ff = (const void*)bs::panel_finish_kernel<-1>; break;
     }
     CU(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    CU(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     int per_sm = 1, per_sm_f = 1, sms = 148;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, bs::kPanelThreads, psm));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, ff, bs::kPanelThreads, fsm));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, ff, bs::kFinishThreads, fsm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     NEED(per_sm >= 1 && per_sm_f >= 1, "panel kernels do not fit on an SM (%zu bytes of shared memory)", psm);
     s->panel_grid = per_sm * sms;               // persistent CTAs, all resident
