@@ -67,6 +67,7 @@ typedef struct bslam_solver bslam_solver;
 #define BSLAM_S_DX_NORM2   2   /* ||dx||^2 over the whole update vector                                   */
 #define BSLAM_S_CHOL_FAIL  3   /* >0 if a non-positive pivot was met                                       */
 #define BSLAM_S_COST_EVAL  4   /* result of bslam_eval_cost                                                */
+#define BSLAM_S_PEER_TIMEOUT 5 /* >0 if a rendezvous of the sharded iteration timed out (bslam_peer_connect) */
 #define BSLAM_N_SCALARS   16
 
 /* ---- timing slots (milliseconds, CUDA events on the handle's stream) ------ */
@@ -264,6 +265,31 @@ BSLAM_API int bslam_tile_structure(bslam_solver* s, uint8_t* mask, size_t n, int
 /* Shard rank of this handle when landmarks are partitioned over several GPUs
  * (rank 0 alone counts the replicated reduced part in ||dx||^2). */
 BSLAM_API int bslam_set_shard(bslam_solver* s, int rank);
+/* ---- sharded iteration over NVLink peer memory (pyslam_b200/csrc/peer.cuh; the reference has no distributed
+ * path, SURVEY 2.2 -- this is the B200-native replacement for the single-process spsolve on the full system) ----
+ *
+ * bslam_add_coupling: declare (before bslam_finalize) that poses idx1[k] and idx2[k] of `group` are coupled in the
+ * reduced system WITHOUT adding a residual.  A rank that holds only a shard of the landmarks declares the
+ * co-visibility pairs of ALL shards, so that every rank derives the same ordering, offsets and tile structure
+ * (bslam_layout_hash must then agree across ranks).
+ * bslam_peer_region: device address, size and CUDA-IPC handle (64 bytes, may be NULL) of this handle's exchange
+ * region [packed non-zero tiles | rhs | scalars | mailbox | flags].
+ * bslam_peer_connect: map the regions of all `world` ranks -- from their IPC handles (world x 64 bytes, other
+ * processes) or from plain device pointers (dev_ptrs[r] != NULL: handles of the same process) -- and switch
+ * bslam_iterate / bslam_iterate_async / bslam_iterate_host to the sharded schedule: linearise + eliminate the
+ * local landmarks, publish the partial reduced system, rendezvous, factorise sum_r S_r read tile by tile from
+ * the peers' regions (the all-reduce is fused into the Cholesky kernel's operand loads), back-substitute the
+ * local landmarks, exchange the partial scalars -- ONE CUDA graph, no host code or library collective inside.
+ * The returned scalars are the sums over all ranks; every rank must call iterate the same number of times. */
+BSLAM_API int bslam_add_coupling(bslam_solver* s, int group, int n, const int32_t* idx1, const int32_t* idx2);
+BSLAM_API int bslam_layout_hash(bslam_solver* s, uint64_t* hash);
+BSLAM_API int bslam_peer_region(bslam_solver* s, void** dev_ptr, size_t* n_bytes, uint8_t* ipc_handle /* 64 bytes */);
+BSLAM_API int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_handles, void* const* dev_ptrs);
+/* bslam_iterate split in two: enqueue the iteration (no synchronisation) / wait for it and read the scalars.
+ * Several handles of one process (e.g. the shards of a sharded iteration on different streams) are enqueued
+ * first and waited for afterwards. */
+BSLAM_API int bslam_iterate_async(bslam_solver* s, double lambda, int eval_new_cost);
+BSLAM_API int bslam_iterate_wait(bslam_solver* s, double* cost_lin, double* cost_new, double* dx_norm);
 /* The handle's cudaStream_t, so the host can order collectives and record
  * events on it. */
 BSLAM_API void* bslam_stream(bslam_solver* s);

@@ -54,10 +54,12 @@ struct CholTask {
   int early;       // off-diagonal (i, j): e + 1 = also publish C_ij = S_ij - sum L_ik L_jk^T (before the triangular
                    //                    solve) into early slot e of row i
                    // diagonal (i, i): take the LAST `early` (0..kEarly) producer columns of klist through early C tiles
-  int pad;
+  int slot;       // multi-GPU: index of the tile in the packed exchange payload (structurally non-zero tiles of S
+                   // before fill-in); -1: fill-in only (no initial data); -2: right-hand-side row
 };
 
-constexpr int kEarly = 2;   // early C tiles per diagonal task (a separator has two children in the nested-dissection tree)
+constexpr int kEarly = 2;
+constexpr int kCholMaxPeers = 8;   // early C tiles per diagonal task (a separator has two children in the nested-dissection tree)
 
 struct CholPlan {
   int nt;
@@ -77,6 +79,12 @@ struct CholPlan {
   int* ticket;           // [0] ticket counter, [1] epoch of the last completed launch, [2] CTAs finished
                          // (the last CTA to finish resets [0], [2] and advances [1]: no memsets between launches)
   long long* trace;      // optional [n_tasks][4]: start, dependencies satisfied, end (globaltimer ns), SM id
+  // Landmark-sharded iteration (peer.cuh): S = sum over the ranks of their partial Schur complements.  The sum is
+  // never formed in memory: a tile task reads its own tile as  sum_r peer_pack[r][slot]  straight from the ranks'
+  // exchange regions (mapped peer memory over NVLink), in rank order, and writes L into the private S.
+  int world;             // 1: single GPU, the own tile comes from S
+  int rhs_off;           // offset of the right-hand side inside a packed payload (= n_nz_tiles * kNB * kNB)
+  const double* peer_pack[kCholMaxPeers];
 };
 
 BS_D void dmma_8x8x4(double& d0, double& d1, double a, double b) {
@@ -389,11 +397,29 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       // the task's own tile of S is final before the kernel starts: fetch it now, off the dependency chain
       double* Cij = S + (size_t)ti * kNB * ld + (size_t)tj * kNB;
       TileAcc own;
-      acc_foreach([&](int i, int j, int r, int c) {
-        double2 v = make_double2(0.0, 0.0);
-        if (r < rows_i) v = __ldcg(reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c));
-        own.c[i][j][0] = v.x; own.c[i][j][1] = v.y;
-      });
+      if (p.world <= 1) {
+        acc_foreach([&](int i, int j, int r, int c) {
+          double2 v = make_double2(0.0, 0.0);
+          if (r < rows_i) v = __ldcg(reinterpret_cast<const double2*>(Cij + (size_t)r * ld + c));
+          own.c[i][j][0] = v.x; own.c[i][j][1] = v.y;
+        });
+      } else {
+        // fused all-reduce: the tile of the summed matrix, read from every rank's partial sum over NVLink
+        const size_t off0 = task.slot == -2 ? (size_t)p.rhs_off + (size_t)tj * kNB : (size_t)task.slot * kNB * kNB;
+        acc_foreach([&](int i, int j, int r, int c) {
+          double2 part[kCholMaxPeers];
+          const bool live = r < rows_i && task.slot != -1;
+#pragma unroll
+          for (int q = 0; q < kCholMaxPeers; ++q) {
+            part[q] = make_double2(0.0, 0.0);
+            if (live && q < p.world) part[q] = __ldcg(reinterpret_cast<const double2*>(p.peer_pack[q] + off0 + (size_t)r * kNB + c));
+          }
+          double2 v = part[0];
+#pragma unroll
+          for (int q = 1; q < kCholMaxPeers; ++q) { v.x += part[q].x; v.y += part[q].y; }
+          own.c[i][j][0] = v.x; own.c[i][j][1] = v.y;
+        });
+      }
       const int n_early = (ti == tj) ? task.early : 0;
       const int kend_l = task.kend - n_early;
       for (int kk = task.kbeg; kk < kend_l; ++kk) {

@@ -23,6 +23,7 @@
 #include "retract.cuh"
 #include "schur.cuh"
 #include "panel.cuh"
+#include "peer.cuh"
 
 namespace {
 
@@ -174,7 +175,16 @@ struct bslam_solver {
   int n_dirty_tiles = 0;
   DevBuf<int> d_nz_tiles;                          // structurally non-zero tiles BEFORE fill-in (what assembly/Schur write)
   int n_nz_tiles = 0;
-  DevBuf<double> d_pack;                           // [n_nz_tiles * 4096 | rhs n_pad | scalars]: the multi-GPU all-reduce payload
+  DevBuf<double> d_pack;                           // exchange region: [n_nz_tiles * kNB^2 | rhs n_pad | scalars] = the multi-GPU
+                                                   // payload, then the mailbox and flags of peer.cuh (kXchgTail doubles)
+  size_t pack_len = 0;                             // doubles before the mailbox
+  // declared couplings without residuals (bslam_add_coupling): rank-independent ordering of sharded problems
+  std::vector<int> cp_group, cp_i1, cp_i2;
+  // peer exchange (peer.cuh): world > 1 after bslam_peer_connect
+  int world = 1;
+  double* peer_region[bs::kMaxPeers] = {};
+  bool peer_opened[bs::kMaxPeers] = {};
+  DevBuf<long long> d_peer_ctl;
 
   double* S() { return d_red.p; }
   double* rhs() { return d_red.p + (size_t)n_pad * n_pad; }
@@ -190,6 +200,8 @@ struct bslam_solver {
     if (graph_pre) cudaGraphExecDestroy(graph_pre);
     if (graph_post) cudaGraphExecDestroy(graph_post);
     if (h_scalars) cudaFreeHost(h_scalars);
+    for (int r = 0; r < bs::kMaxPeers; ++r)
+      if (peer_opened[r]) cudaIpcCloseMemHandle(peer_region[r]);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -540,6 +552,14 @@ void build_tile_mask(bslam_solver* s, const std::vector<int>& opose, const std::
     for (int c = s->dn_col_ptr[b]; c < s->dn_col_ptr[b + 1]; ++c) tiles_of(s->dn_col_index[c], 1, tiles);
     mark_tiles(s, tiles);
   }
+  for (size_t e = 0; e < s->cp_i1.size(); ++e) {                             // declared couplings (bslam_add_coupling)
+    const std::vector<int>& off = s->cp_group[e] == 3 ? s->se3_off : s->se2_off;
+    const int dof = s->cp_group[e] == 3 ? 6 : 3;
+    tiles.clear();
+    tiles_of(off[s->cp_i1[e]], dof, tiles);
+    tiles_of(off[s->cp_i2[e]], dof, tiles);
+    mark_tiles(s, tiles);
+  }
   s->plan_valid = false;
 }
 
@@ -559,10 +579,16 @@ int build_chol_plan(bslam_solver* s) {
   }
   std::vector<bs::CholTask> tasks;
   std::vector<int> klist, bwd_ptr(nt + 1, 0), bwd_rows;
+  // position of every structurally non-zero tile (before fill-in) in the packed multi-GPU payload
+  std::vector<int> nz, nz_slot((size_t)nt * nt, -1);
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j)
+      if (s->tile_mask[(size_t)i * nt + j]) { nz_slot[(size_t)i * nt + j] = (int)nz.size(); nz.push_back(i * nt + j); }
   for (int j = 0; j < nt; ++j)
     for (int i = j; i <= nt; ++i) {
       if (!at(i, j)) continue;
       bs::CholTask t{};
+      t.slot = i == nt ? -2 : nz_slot[(size_t)i * nt + j];
       t.i = i; t.j = j; t.kbeg = (int)klist.size();
       for (int k = 0; k < j; ++k)
         if (at(i, k) && at(j, k)) klist.push_back(k);
@@ -627,14 +653,13 @@ int build_chol_plan(bslam_solver* s) {
     s->n_dirty_tiles = (int)dirty.size();
     if (dirty.empty()) dirty.push_back(0);
     CU(upload(s->d_dirty_tiles, dirty, st));
-    std::vector<int> nz;
-    for (int i = 0; i < nt; ++i)
-      for (int j = 0; j <= i; ++j)
-        if (s->tile_mask[(size_t)i * nt + j]) nz.push_back(i * nt + j);
     s->n_nz_tiles = (int)nz.size();
     if (nz.empty()) nz.push_back(0);
     CU(upload(s->d_nz_tiles, nz, st));
-    CU(s->d_pack.alloc((size_t)s->n_nz_tiles * bs::kNB * bs::kNB + s->n_pad + BSLAM_N_SCALARS));
+    if (s->world > 1) return fail(s, BSLAM_E_INVALID, "the tile structure changed after bslam_peer_connect");
+    s->pack_len = (size_t)s->n_nz_tiles * bs::kNB * bs::kNB + s->n_pad + BSLAM_N_SCALARS;
+    CU(s->d_pack.alloc(s->pack_len + bs::kXchgTail));
+    CU(cudaMemsetAsync(s->d_pack.p, 0, s->d_pack.n * sizeof(double), st));
   }
   CU(upload(s->d_fill_mask, m, st));
   CU(upload(s->d_tasks, tasks, st));
@@ -672,6 +697,9 @@ int do_solve_reduced(bslam_solver* s) {
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
   p.cready = s->d_cready.p; p.cscr = s->d_cscr.p;
   p.trace = s->d_trace.p;
+  p.world = s->world;
+  p.rhs_off = s->n_nz_tiles * bs::kNB * bs::kNB;
+  for (int r = 0; r < bs::kCholMaxPeers; ++r) p.peer_pack[r] = r < s->world ? s->peer_region[r] : nullptr;
   // no per-launch memsets: the flags carry the launch epoch, which the kernel advances itself
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
          s->d_dx.p, s->scalars(), p);
@@ -773,6 +801,30 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
     }
   }
   record(s, 9);
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+bs::PeerCtx peer_ctx(bslam_solver* s) {
+  bs::PeerCtx pc{};
+  pc.world = s->world; pc.rank = s->shard_rank;
+  for (int r = 0; r < bs::kMaxPeers; ++r) pc.region[r] = s->peer_region[r];
+  pc.pack_len = s->pack_len;
+  pc.ctl = s->d_peer_ctl.p;
+  return pc;
+}
+
+// sharded iteration, after the rank's linearise + eliminate kernels: publish the partial reduced system to the peers
+int do_peer_publish(bslam_solver* s) {
+  LAUNCH(s, bs::peer_pack_signal_kernel, s->n_nz_tiles + 1, 256, 0, s->S(), s->n_pad, s->nblk, s->d_nz_tiles.p, s->n_nz_tiles,
+         s->rhs(), s->n_pad + BSLAM_N_SCALARS, s->scalars(), peer_ctx(s));
+  CU(cudaGetLastError());
+  return BSLAM_OK;
+}
+
+// sharded iteration, end: sum the partial scalars over the ranks (and order the next iteration after the peers' reads)
+int do_peer_scalars(bslam_solver* s) {
+  LAUNCH(s, bs::peer_scalar_exchange_kernel, 1, 32, 0, s->scalars(), peer_ctx(s));
   CU(cudaGetLastError());
   return BSLAM_OK;
 }
@@ -1012,7 +1064,7 @@ int bslam_add_reprojection_blocks(bslam_solver* s, int n, const int32_t* pose_id
          pt_idx[i], s->n_pt);
   }
   auto make_group = [&](const double* S9) {
-    bs::ReprojGroup g;
+    bs::ReprojGroup g{};
     g.cu = intr[0]; g.cv = intr[1]; g.fu = intr[2]; g.fv = intr[3]; g.b = intr[4];
     for (int k = 0; k < 9; ++k) g.S[k] = S9[k];
     g.loss.kind = loss_kind;
@@ -1021,8 +1073,14 @@ int bslam_add_reprojection_blocks(bslam_solver* s, int n, const int32_t* pose_id
   };
   auto find_group = [&](const bs::ReprojGroup& g) {
     // newest groups first: consecutive blocks nearly always share their constants
-    for (int k = (int)s->groups.size() - 1; k >= 0 && k >= (int)s->groups.size() - 8; --k)
-      if (std::memcmp(&s->groups[k], &g, sizeof g) == 0) return k;
+    auto same = [](const bs::ReprojGroup& a, const bs::ReprojGroup& b) {
+      if (a.cu != b.cu || a.cv != b.cv || a.fu != b.fu || a.fv != b.fv || a.b != b.b) return false;
+      if (a.loss.kind != b.loss.kind || a.loss.k != b.loss.k) return false;
+      for (int k = 0; k < 9; ++k) if (a.S[k] != b.S[k]) return false;
+      return true;
+    };
+    for (int k = (int)s->groups.size() - 1; k >= 0 && k >= (int)s->groups.size() - 64; --k)
+      if (same(s->groups[k], g)) return k;
     s->groups.push_back(g);
     return (int)s->groups.size() - 1;
   };
@@ -1138,6 +1196,13 @@ int bslam_clear_blocks(bslam_solver* s) {
   s->photos.clear();
   s->dn_blocks = 0;
   s->dn_rows.clear(); s->dn_pptr.clear(); s->dn_pkind.clear(); s->dn_pindex.clear();
+  s->cp_group.clear(); s->cp_i1.clear(); s->cp_i2.clear();
+  for (int r = 0; r < bs::kMaxPeers; ++r) {
+    if (s->peer_opened[r]) cudaIpcCloseMemHandle(s->peer_region[r]);
+    s->peer_opened[r] = false;
+    s->peer_region[r] = nullptr;
+  }
+  s->world = 1;
   drop_graph(s);
   s->finalized = false;
   return BSLAM_OK;
@@ -1336,6 +1401,13 @@ int bslam_finalize(bslam_solver* s) {
         if (m[b->i2[e]] >= 0) g.push_back(m[b->i2[e]]);
         couple(g);
       }
+    }
+    for (size_t e = 0; e < s->cp_i1.size(); ++e) {
+      const std::vector<int>& m = s->cp_group[e] == 3 ? se3_sn : se2_sn;
+      g.clear();
+      if (m[s->cp_i1[e]] >= 0) g.push_back(m[s->cp_i1[e]]);
+      if (m[s->cp_i2[e]] >= 0) g.push_back(m[s->cp_i2[e]]);
+      couple(g);
     }
     for (int b = 0; b < s->dn_blocks; ++b) {
       g.clear();
@@ -1963,8 +2035,10 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
     return run_graphed(s, &s->graph_exec, &s->graph_launches, [&]() {
       int r = do_linearize(s, true);
       if (!r) r = do_reduce(s, lambda, true);
+      if (!r && s->world > 1) r = do_peer_publish(s);
       if (!r) r = do_solve_reduced(s);
       if (!r) r = do_retract(s, eval_new_cost, true);
+      if (!r && s->world > 1) r = do_peer_scalars(s);
       if (!r && cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost,
                                 s->stream) != cudaSuccess)
         r = fail(s, BSLAM_E_CUDA, "scalar read-back could not be captured");
@@ -1973,8 +2047,10 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
   }
   if ((rc = do_linearize(s, true))) return rc;
   if ((rc = do_reduce(s, lambda, true))) return rc;
+  if (s->world > 1 && (rc = do_peer_publish(s))) return rc;
   if ((rc = do_solve_reduced(s))) return rc;
   if ((rc = do_retract(s, eval_new_cost, true))) return rc;
+  if (s->world > 1 && (rc = do_peer_scalars(s))) return rc;
   CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   return BSLAM_OK;
 }
@@ -1982,6 +2058,8 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
 static int iterate_finish(bslam_solver* s, double* cost_lin, double* cost_new, double* dx_norm) {
   int rc;
   if ((rc = sync_and_timings(s))) return rc;       // one synchronisation (the scalar read-back is already enqueued)
+  if (s->h_scalars[BSLAM_S_PEER_TIMEOUT] != 0.0)
+    return fail(s, BSLAM_E_CUDA, "peer exchange timed out: a rank of the sharded iteration did not arrive");
   if (cost_lin) *cost_lin = s->h_scalars[BSLAM_S_COST_LIN];
   if (cost_new) *cost_new = s->h_scalars[BSLAM_S_COST_NEW];
   if (dx_norm) *dx_norm = std::sqrt(s->h_scalars[BSLAM_S_DX_NORM2]);
@@ -1995,6 +2073,91 @@ int bslam_iterate(bslam_solver* s, double lambda, int eval_new_cost, double* cos
   int rc;
   if ((rc = iterate_enqueue(s, lambda, eval_new_cost))) return rc;
   return iterate_finish(s, cost_lin, cost_new, dx_norm);
+}
+
+int bslam_iterate_async(bslam_solver* s, double lambda, int eval_new_cost) {
+  NEED(s && s->finalized, "bslam_iterate_async: solver not finalized");
+  NEED(lambda >= 0.0, "bslam_iterate_async: lambda must be >= 0");
+  CU(cudaSetDevice(s->device));
+  return iterate_enqueue(s, lambda, eval_new_cost);
+}
+
+int bslam_iterate_wait(bslam_solver* s, double* cost_lin, double* cost_new, double* dx_norm) {
+  NEED(s && s->finalized, "bslam_iterate_wait: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  return iterate_finish(s, cost_lin, cost_new, dx_norm);
+}
+
+int bslam_add_coupling(bslam_solver* s, int group, int n, const int32_t* idx1, const int32_t* idx2) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_add_coupling after finalize; call bslam_clear_blocks first");
+  NEED(group == BSLAM_SE2 || group == BSLAM_SE3, "bslam_add_coupling: group must be BSLAM_SE2 or BSLAM_SE3");
+  NEED(n >= 0 && (n == 0 || (idx1 && idx2)), "bslam_add_coupling: bad arguments");
+  const int table = group == 3 ? s->n_se3 : s->n_se2;
+  for (int i = 0; i < n; ++i)
+    NEED(idx1[i] >= 0 && idx1[i] < table && idx2[i] >= 0 && idx2[i] < table, "bslam_add_coupling %d: pose index outside the table (%d)", i, table);
+  for (int i = 0; i < n; ++i) { s->cp_group.push_back(group); s->cp_i1.push_back(idx1[i]); s->cp_i2.push_back(idx2[i]); }
+  return BSLAM_OK;
+}
+
+int bslam_layout_hash(bslam_solver* s, uint64_t* hash) {
+  NEED(s && s->finalized && hash, "bslam_layout_hash: bad arguments");
+  uint64_t h = 1469598103934665603ULL;                       // FNV-1a over the reduced offsets and the tile structure
+  auto mix = [&](const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+  };
+  mix(s->se3_off.data(), s->se3_off.size() * sizeof(int));
+  mix(s->se2_off.data(), s->se2_off.size() * sizeof(int));
+  mix(s->vec_off.data(), s->vec_off.size() * sizeof(int));
+  mix(s->tile_mask.data(), s->tile_mask.size());
+  mix(&s->n_pad, sizeof(int));
+  *hash = h;
+  return BSLAM_OK;
+}
+
+int bslam_peer_region(bslam_solver* s, void** dev_ptr, size_t* n_bytes, uint8_t* ipc_handle) {
+  NEED(s && s->finalized, "bslam_peer_region: solver not finalized");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  CU(cudaStreamSynchronize(s->stream));                      // the region is zeroed before anybody can map it
+  if (dev_ptr) *dev_ptr = s->d_pack.p;
+  if (n_bytes) *n_bytes = s->d_pack.n * sizeof(double);
+  if (ipc_handle) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->d_pack.p));
+    std::memcpy(ipc_handle, &h, sizeof h);
+  }
+  return BSLAM_OK;
+}
+
+int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_handles, void* const* dev_ptrs) {
+  NEED(s && s->finalized, "bslam_peer_connect: solver not finalized");
+  NEED(world >= 1 && world <= bs::kMaxPeers && rank >= 0 && rank < world, "bslam_peer_connect: world %d / rank %d invalid (max %d ranks)",
+       world, rank, bs::kMaxPeers);
+  NEED(world == 1 || ipc_handles || dev_ptrs, "bslam_peer_connect: neither IPC handles nor device pointers given");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  CU(cudaStreamSynchronize(s->stream));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { s->peer_region[r] = s->d_pack.p; continue; }
+    if (dev_ptrs && dev_ptrs[r]) { s->peer_region[r] = static_cast<double*>(dev_ptrs[r]); continue; }
+    NEED(ipc_handles, "bslam_peer_connect: no handle for rank %d", r);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handles + 64 * (size_t)r, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_region[r] = static_cast<double*>(p);
+    s->peer_opened[r] = true;
+  }
+  CU(s->d_peer_ctl.alloc(4));
+  CU(cudaMemsetAsync(s->d_peer_ctl.p, 0, 4 * sizeof(long long), s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->world = world;
+  s->shard_rank = rank;
+  drop_graph(s);
+  return BSLAM_OK;
 }
 
 int bslam_iterate_host(bslam_solver* s, double lambda, int eval_new_cost, const double* Rt_in, const double* xyz_in,
@@ -2109,6 +2272,7 @@ int bslam_tile_structure(bslam_solver* s, uint8_t* mask, size_t n, int set) {
   NEED(s && s->finalized && mask, "bslam_tile_structure: bad arguments");
   NEED(n == s->tile_mask.size(), "bslam_tile_structure: expected %zu bytes, got %zu", s->tile_mask.size(), n);
   if (set) {
+    NEED(s->world == 1, "bslam_tile_structure: the structure is frozen after bslam_peer_connect");
     for (size_t i = 0; i < n; ++i) s->tile_mask[i] = s->tile_mask[i] || mask[i];
     s->plan_valid = false;
     drop_graph(s);

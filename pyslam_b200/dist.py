@@ -1,20 +1,31 @@
 """Landmark-sharded bundle adjustment over several GPUs.
 
-One process per GPU (torch.distributed, NCCL over NVLink).  Landmarks -- and
-the observations that reference them -- are partitioned contiguously over the
-ranks; the poses and the reduced camera system are replicated.  Per iteration:
+One process per GPU; `torch.distributed` (NCCL or gloo) is the set-up plumbing only.  Landmarks -- and the
+observations that reference them -- are partitioned contiguously over the ranks; the poses and the reduced
+camera system are replicated.
 
-    every rank : linearise its observations, eliminate its landmarks
-                 -> partial [S | rhs | cost]     (bslam_iterate_pre: one CUDA graph)
-    all ranks  : ONE all-reduce (sum, fp64) of that buffer, packed to its
-                 structurally non-zero 32x32 tiles                 (NCCL)
-    every rank : factorise S, solve dx_c (redundantly, bit-identical inputs),
-                 back-substitute and retract its own landmarks, cost at the
-                 new point                      (bslam_iterate_post: one CUDA graph)
-    all ranks  : all-reduce of two scalars (new cost, ||dx_p||^2)
+Default schedule (`mode='peer'`, pyslam_b200/csrc/peer.cuh): ONE CUDA graph per rank and iteration, no host code
+and no library collective inside it:
 
-The reference has no distributed path at all; this is the
-B200-native replacement for the single-process `spsolve` on the full system.
+    every rank : linearise its observations, eliminate its landmarks  -> partial [S | rhs]
+                 gather the structurally non-zero tiles into the rank's exchange region; rendezvous (flags
+                 written into the peers' regions over NVLink)
+    every rank : tile Cholesky of  sum_r S_r : each tile task reads its operand from ALL ranks' regions
+                 (mapped peer memory, fixed rank order => bit-identical on every rank) -- the all-reduce is
+                 fused into the factorisation kernel's loads; solve dx_c, back-substitute and retract the
+                 rank's own landmarks, cost at the new point
+    every rank : partial scalars (cost, new cost, ||dx_p||^2) to every peer's mailbox, rendezvous, sum
+
+Set-up (once): the ranks exchange their pose co-visibility pairs so that every rank derives the SAME reduced
+ordering / tile structure from the full coupling graph (`bslam_add_coupling`; checked with `bslam_layout_hash`),
+then their CUDA-IPC handles of the exchange regions (`bslam_peer_region` / `bslam_peer_connect`).
+
+Fallback schedule (`mode='nccl'`): two graph replays around a `torch.distributed` all-reduce of the packed
+tiles (`bslam_iterate_pre` / `bslam_iterate_post`), used when peer mapping is unavailable and by the CPU test
+double of tests/test_dist_gloo.py.
+
+The reference has no distributed path at all; this is the B200-native replacement for the
+single-process `spsolve` on the full system.
 """
 import numpy as np
 
@@ -37,14 +48,125 @@ def shard_stereo_ba(d, rank, world):
     return out
 
 
+def covisibility_pairs(pose_idx, pt_idx):
+    """Unique unordered pairs (a < b) of poses that observe a common landmark: the couplings the Schur complement
+    of these observations creates in the reduced camera system.  [n_pairs, 2] int32."""
+    pose_idx, pt_idx = np.asarray(pose_idx, np.int64), np.asarray(pt_idx, np.int64)
+    if len(pose_idx) == 0:
+        return np.zeros((0, 2), np.int32)
+    order = np.argsort(pt_idx, kind='stable')
+    p, q = pose_idx[order], pt_idx[order]
+    n_pose = int(p.max()) + 1
+    longest = int(np.bincount(q - q.min()).max())
+    codes = []
+    for dlt in range(1, longest):
+        same = q[dlt:] == q[:-dlt]
+        a, b = p[:-dlt][same], p[dlt:][same]
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        codes.append(np.unique(lo[lo != hi] * n_pose + hi[lo != hi]))
+    if not codes:
+        return np.zeros((0, 2), np.int32)
+    code = np.unique(np.concatenate(codes))
+    return np.stack([code // n_pose, code % n_pose], axis=1).astype(np.int32)
+
+
+def _all_gather_object(obj, group=None):
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def build_sharded_ba(full, rank=0, world=1, device=0, group=None, mode='auto'):
+    """Shard a stereo-BA problem (dict of `pyslam_b200.synthetic.stereo_ba` form) over `world` ranks and lower
+    this rank's part: (ShardedSolver, this rank's sub-problem, initial pose table)."""
+    from . import configs
+    d = shard_stereo_ba(full, rank, world) if world > 1 else full
+    eng, Rt0 = configs.ba_engine(d, device)
+    if world > 1:
+        # every rank orders the reduced system from the couplings of ALL shards
+        pairs = np.unique(np.concatenate(_all_gather_object(covisibility_pairs(d['pose_idx'], d['pt_idx']), group)), axis=0)
+        eng.add_coupling(3, pairs[:, 0], pairs[:, 1])
+    eng.finalize()
+    return ShardedSolver(eng, rank, world, group, mode), d, Rt0
+
+
+def connect_local(engines):
+    """Shards held by several handles of ONE process (tests, single-GPU studies): map the exchange regions by
+    plain device pointers.  Returns the ShardedSolvers; drive them with `iterate_local`."""
+    world = len(engines)
+    hashes = {e.layout_hash() for e in engines}
+    if len(hashes) != 1:
+        raise RuntimeError('the shards derived different reduced layouts: declare the couplings of all shards '
+                           '(add_coupling) before finalize')
+    ptrs = [e.peer_region()[0] for e in engines]
+    solvers = []
+    for r, e in enumerate(engines):
+        e.peer_connect(world, r, dev_ptrs=ptrs)
+        solvers.append(ShardedSolver(e, r, world, mode='connected'))
+    return solvers
+
+
+def iterate_local(solvers, lam=0., eval_new_cost=True):
+    """One sharded iteration of handles that live in this process: enqueue all, then wait for all."""
+    for s in solvers:
+        s.engine.iterate_async(lam, eval_new_cost)
+    return [s.engine.iterate_wait() for s in solvers]
+
+
 class ShardedSolver:
     """Drives one engine per rank through the sharded iteration."""
 
-    def __init__(self, engine, rank=0, world=1, group=None):
+    def __init__(self, engine, rank=0, world=1, group=None, mode='auto'):
         self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        self.mode = 'single' if world == 1 else mode
+        if world == 1:
+            engine.set_shard(0)
+            return
+        if mode == 'connected':          # connect_local did the mapping
+            self.mode = 'peer'
+            return
+        import torch.distributed as dist
+        if mode == 'auto':
+            mode = 'peer' if (dist.get_backend(group) == 'nccl' and hasattr(engine, 'peer_region')) else 'nccl'
         engine.set_shard(rank)
-        if world > 1:
-            self._merge_structure()
+        if hasattr(engine, 'layout_hash'):
+            hashes = _all_gather_object(engine.layout_hash(), group)
+            if len(set(hashes)) != 1:
+                raise RuntimeError('ranks derived different reduced-system layouts (%s): every rank must declare the pose '
+                                   'couplings of all shards before finalize (build_sharded_ba does)' % hashes)
+        if mode == 'peer':
+            # every collective below is entered by every rank whatever failed locally: the ranks fall back together
+            ok, err, handle = 1, '', b''
+            try:
+                handle = engine.peer_region()[2].tobytes()
+            except Exception as e:
+                ok, err = 0, repr(e)
+            got = _all_gather_object((ok, err, handle), group)
+            if all(g[0] for g in got):
+                try:
+                    engine.peer_connect(world, rank, ipc_handles=np.frombuffer(b''.join(g[2] for g in got), np.uint8))
+                except Exception as e:      # e.g. no peer access between the devices
+                    ok, err = 0, repr(e)
+                got = _all_gather_object((ok, err, b''), group)
+            if all(g[0] for g in got):
+                self.mode = 'peer'
+                return
+            engine.peer_connect(1, 0)
+            engine.set_shard(rank)
+            self.fallback_reason = [g[1] for g in got if not g[0]][0]
+        self.mode = 'nccl'
+        self._merge_structure()
+
+    def describe(self):
+        if self.world == 1:
+            return 'single GPU'
+        if self.mode == 'peer':
+            return ('landmarks sharded over %d GPUs; per iteration ONE CUDA graph per rank: partial reduced systems published '
+                    'to peer-mapped exchange regions (CUDA IPC over NVLink), all-reduce fused into the tile loads of the '
+                    'Cholesky kernel, scalar exchange through peer mailboxes; no NCCL call inside the iteration' % self.world)
+        return ('landmarks sharded over %d GPUs, two CUDA graphs around one torch.distributed all-reduce of the packed '
+                'reduced system per iteration (fallback: %s)' % (self.world, getattr(self, 'fallback_reason', 'requested')))
 
     def _merge_structure(self):
         """The summed reduced matrix has the UNION of the ranks' tile structures."""
@@ -58,23 +180,24 @@ class ShardedSolver:
         self.engine.merge_tile_structure(t.cpu().numpy().astype(np.uint8))
 
     def eval_cost(self):
-        import torch
-        import torch.distributed as dist
         c = self.engine.eval_cost()
         if self.world == 1:
             return c
-        t = torch.tensor([c], dtype=torch.float64, device=self.engine.scalars_tensor().device)
+        import torch
+        import torch.distributed as dist
+        dev = 'cuda:%d' % self.engine.device if dist.get_backend(self.group) == 'nccl' else 'cpu'
+        t = torch.tensor([c], dtype=torch.float64, device=dev)
         dist.all_reduce(t, group=self.group)
         return float(t.item())
 
     def iterate(self, lam=0., eval_new_cost=True):
         """(cost at the linearisation point, cost at x [+] dx, ||dx||), identical on every rank."""
         eng = self.engine
-        if self.world == 1:
+        if self.mode in ('single', 'peer'):
             return eng.iterate(lam, eval_new_cost)
         import torch.distributed as dist
         stream = eng.torch_stream()
-        # two graph replays around the NCCL all-reduce of the packed non-zero tiles of S (+ rhs + scalars)
+        # two graph replays around the all-reduce of the packed non-zero tiles of S (+ rhs + scalars)
         eng.iterate_pre(lam)
         with _on_stream(stream):
             dist.all_reduce(eng.packed_tensor(), group=self.group)
@@ -83,6 +206,18 @@ class ShardedSolver:
             dist.all_reduce(eng.scalars_tensor()[1:3], group=self.group)      # COST_NEW, DX_NORM2
         s = eng.scalars()
         return float(s[0]), float(s[1]), float(np.sqrt(s[2]))
+
+    def iterate_host(self, Rt, xyz, lam=0., eval_new_cost=True):
+        """One iteration on HOST (pinned) parameter tables of this rank: upload, iterate, download in place."""
+        eng = self.engine
+        if self.mode in ('single', 'peer'):
+            return eng.iterate_host(Rt, xyz, lam, eval_new_cost)      # one C-ABI call, one synchronisation
+        eng.set_poses_se3(Rt)
+        eng.set_points(xyz)
+        r = self.iterate(lam, eval_new_cost)
+        eng.get_poses_se3(Rt)
+        eng.get_points(xyz)
+        return r
 
 
 class _on_stream:

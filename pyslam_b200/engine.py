@@ -74,6 +74,12 @@ SIGNATURES = {
     'bslam_pack_reduced': (C.c_int, [_h, C.c_int]),
     'bslam_tile_structure': (C.c_int, [_h, _bp, C.c_size_t, C.c_int]),
     'bslam_set_shard': (C.c_int, [_h, C.c_int]),
+    'bslam_add_coupling': (C.c_int, [_h, C.c_int, C.c_int, _ip, _ip]),
+    'bslam_layout_hash': (C.c_int, [_h, C.POINTER(C.c_uint64)]),
+    'bslam_peer_region': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _bp]),
+    'bslam_peer_connect': (C.c_int, [_h, C.c_int, C.c_int, _bp, C.POINTER(C.c_void_p)]),
+    'bslam_iterate_async': (C.c_int, [_h, C.c_double, C.c_int]),
+    'bslam_iterate_wait': (C.c_int, [_h, _dp, _dp, _dp]),
     'bslam_stream': (C.c_void_p, [_h]),
     'bslam_snapshot': (C.c_int, [_h]),
     'bslam_restore': (C.c_int, [_h]),
@@ -382,6 +388,41 @@ class Engine:
             self._pcache = torch.as_tensor(_DevArray(p.value, n.value), device='cuda:%d' % self.device)
             self._pcache_key = key
         return self._pcache
+
+    # ---- sharded iteration over peer memory (csrc/peer.cuh) ----------------------
+    def add_coupling(self, group, idx1, idx2):
+        """Declare reduced-system couplings (pose pairs) without residuals: rank-independent ordering."""
+        i1, i2 = _i32(idx1), _i32(idx2)
+        self._ck(self._lib.bslam_add_coupling(self._h, int(group), len(i1), _i(i1), _i(i2)))
+
+    def layout_hash(self):
+        h = C.c_uint64()
+        self._ck(self._lib.bslam_layout_hash(self._h, C.byref(h)))
+        return int(h.value)
+
+    def peer_region(self):
+        """(device pointer, bytes, 64-byte CUDA-IPC handle as uint8 array) of this handle's exchange region."""
+        p, n = C.c_void_p(), C.c_size_t()
+        handle = np.zeros(64, np.uint8)
+        self._ck(self._lib.bslam_peer_region(self._h, C.byref(p), C.byref(n), _b(handle)))
+        return p.value, n.value, handle
+
+    def peer_connect(self, world, rank, ipc_handles=None, dev_ptrs=None):
+        """Map the exchange regions of all ranks (IPC handles [world, 64] uint8, or device pointers of handles
+        of this process) and switch `iterate` to the sharded schedule."""
+        hb = None if ipc_handles is None else np.ascontiguousarray(ipc_handles, dtype=np.uint8).reshape(world, 64)
+        pa = None
+        if dev_ptrs is not None:
+            pa = (C.c_void_p * world)(*[C.c_void_p(int(x) if x else 0) for x in dev_ptrs])
+        self._ck(self._lib.bslam_peer_connect(self._h, int(world), int(rank), _b(hb), pa))
+
+    def iterate_async(self, lam=0., eval_new_cost=True):
+        self._ck(self._lib.bslam_iterate_async(self._h, float(lam), int(bool(eval_new_cost))))
+
+    def iterate_wait(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.bslam_iterate_wait(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def set_shard(self, rank):
         self._ck(self._lib.bslam_set_shard(self._h, int(rank)))

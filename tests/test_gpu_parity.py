@@ -233,6 +233,29 @@ def test_config3_against_oracle():
         assert abs(cost_new - ref['cost_new']) < 1e-6 * ref['cost_new']
 
 
+def test_config4_against_full_size_golden(golden):
+    """BASELINE config 4 -- the configuration every bench number is quoted on: 500 keyframes x 100 000 landmarks x
+    600 000 reprojections, Huber(1.5) -- against tests/golden/c4_summary.npz, which oracle/make_c4_golden.py
+    produced with the CPU oracle on the FULL 302 994-dimensional system (3 iterations, ~100 s each).  Through
+    Problem -> ctypes -> C ABI, the default (fused panel) lowering.  Tolerance 1e-6 relative (north_star)."""
+    from pyslam_b200 import synthetic
+    g = golden('c4_summary')
+    d = synthetic.stereo_ba(int(g['n_kf']), int(g['n_lm']), track=int(g['track']), seed=int(g['seed']))
+    pr = B.product_ba_problem(d, bulk=True)
+    low = pr._ensure_lowered()
+    eng = pr._engine
+    assert eng.fused_info()[0] > 0            # the product path of this shape is the fused panel path
+    n_pose = g['dx_pose'].shape[1]
+    for it in range(int(g['n_iter'])):
+        cost_lin, cost_new, dx_norm = eng.iterate(0., True)
+        dx = eng.get_update(low.dim)[low.ref_from_internal]
+        assert abs(cost_lin - g['cost_lin'][it]) < 1e-9 * g['cost_lin'][it], 'iteration %d' % it
+        assert rel_err(dx[:n_pose], g['dx_pose'][it]) < 1e-6, 'iteration %d' % it
+        assert rel_err(dx[g['sample_idx']], g['dx_sample'][it]) < 1e-6, 'iteration %d' % it
+        assert abs(dx_norm - g['dx_norm'][it]) < 1e-6 * dx_norm
+        assert abs(cost_new - g['cost_new'][it]) < 1e-6 * g['cost_new'][it]
+
+
 def test_long_tracks_use_the_tail_path():
     """Landmarks with more than 128 observations (beyond one landmark block) are
     linearised by the generic atomic kernel; mixed here with regular landmarks."""
