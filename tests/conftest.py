@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# several solver handles (one CUDA stream each) of one process rendezvous on the device in tests/test_gpu_multi.py:
+# more hardware queues than the default 8, so that two streams never share one (read at CUDA context creation)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -37,7 +37,9 @@ def _single(full, n_iter):
     eng, _ = configs.ba_engine(full, 0)
     eng.finalize()
     ref = [eng.eval_cost()] + [eng.iterate(0., True) for _ in range(n_iter)]
-    return ref, eng.get_poses_se3(), eng.get_points()
+    out = ref, eng.get_poses_se3(), eng.get_points()
+    eng.close()
+    return out
 
 
 def _local_shards(full, world, couple=True):
@@ -78,6 +80,8 @@ def test_local_shards_match_single_gpu(world, sort_ids):
         assert np.array_equal(eng.get_poses_se3(), poses0)       # replicated solve: bit-identical poses
         np.testing.assert_allclose(eng.get_poses_se3(), poses_ref, rtol=1e-9, atol=1e-11)
         np.testing.assert_allclose(eng.get_points(), pts_ref[lo:hi], rtol=1e-9, atol=1e-11)
+    for eng in engines:
+        eng.close()
 
 
 def test_shards_without_declared_couplings_are_rejected():
@@ -91,6 +95,8 @@ def test_shards_without_declared_couplings_are_rejected():
         pytest.skip('the two shards happened to derive the same layout')
     with pytest.raises(RuntimeError):
         connect_local(engines)
+    for eng in engines:
+        eng.close()
 
 
 def test_local_shards_with_unsharded_blocks_and_lm():
@@ -129,6 +135,8 @@ def test_local_shards_with_unsharded_blocks_and_lm():
         for r in iterate_local(solvers, 1e-3, True):
             np.testing.assert_allclose(r, ref[it], rtol=1e-8)
     np.testing.assert_allclose(engines[1].get_poses_se3(), eng1.get_poses_se3(), rtol=1e-9, atol=1e-11)
+    for eng in engines + [eng1]:
+        eng.close()
 
 
 # ---------------------------------------------------------------- one process per rank
