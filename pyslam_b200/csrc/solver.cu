@@ -805,6 +805,45 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
   return BSLAM_OK;
 }
 
+// CUDA loads kernels lazily, and a first-use load may synchronise the context.  Handles of ONE process that
+// rendezvous on the device (one spinning while another is still enqueueing) must therefore have every kernel of the
+// iteration resident before the first sharded iteration (CUDA programming guide, "lazy loading", concurrent execution).
+template <int kLoss>
+void preload_loss_kernels() {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, (const void*)bs::reproj_block_kernel<kLoss>);
+  cudaFuncGetAttributes(&fa, (const void*)bs::fused_panel_kernel<kLoss>);
+  cudaFuncGetAttributes(&fa, (const void*)bs::panel_finish_kernel<kLoss>);
+  cudaFuncGetAttributes(&fa, (const void*)bs::lm_finish_kernel<kLoss>);
+}
+void preload_iteration_kernels(bslam_solver* s) {
+  cudaFuncAttributes fa;
+  const void* fns[] = {
+      (const void*)bs::prepare_kernel, (const void*)bs::reproj_generic_kernel, (const void*)bs::reproj_cost_kernel,
+      (const void*)bs::edge_kernel<3, true, false>, (const void*)bs::edge_kernel<3, false, false>,
+      (const void*)bs::edge_kernel<2, true, false>, (const void*)bs::edge_kernel<2, false, false>,
+      (const void*)bs::edge_kernel<3, true, true>, (const void*)bs::edge_kernel<3, false, true>,
+      (const void*)bs::edge_kernel<2, true, true>, (const void*)bs::edge_kernel<2, false, true>,
+      (const void*)bs::photometric_kernel<false>, (const void*)bs::photometric_kernel<true>,
+      (const void*)bs::dense_blocks_kernel, (const void*)bs::add_scalar_kernel, (const void*)bs::damp_diag_kernel,
+      (const void*)bs::schur_block_kernel, (const void*)bs::landmark_invert_kernel, (const void*)bs::schur_generic_kernel,
+      (const void*)bs::chol_solve_kernel, (const void*)bs::backsub_kernel, (const void*)bs::retract_se3_slots_kernel,
+      (const void*)bs::retract_poses_kernel<2>, (const void*)bs::retract_flat_kernel, (const void*)bs::sumsq_kernel,
+      (const void*)bs::retract_landmarks_kernel, (const void*)bs::pack_tiles_kernel,
+      (const void*)bs::peer_pack_signal_kernel, (const void*)bs::peer_scalar_exchange_kernel, (const void*)permute_rows_kernel};
+  for (const void* f : fns) cudaFuncGetAttributes(&fa, f);
+  switch (s->loss_kind) {
+    case 0: preload_loss_kernels<0>(); break;
+    case 1: preload_loss_kernels<1>(); break;
+    case 2: preload_loss_kernels<2>(); break;
+    case 3: preload_loss_kernels<3>(); break;
+    case 4: preload_loss_kernels<4>(); break;
+    case 5: preload_loss_kernels<5>(); break;
+    default: preload_loss_kernels<-1>(); break;
+  }
+  cudaGetLastError();
+}
+
 bs::PeerCtx peer_ctx(bslam_solver* s) {
   bs::PeerCtx pc{};
   pc.world = s->world; pc.rank = s->shard_rank;
@@ -2151,6 +2190,7 @@ int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_
     s->peer_region[r] = static_cast<double*>(p);
     s->peer_opened[r] = true;
   }
+  if (world > 1) preload_iteration_kernels(s);
   CU(s->d_peer_ctl.alloc(4));
   CU(cudaMemsetAsync(s->d_peer_ctl.p, 0, 4 * sizeof(long long), s->stream));
   CU(cudaStreamSynchronize(s->stream));
