@@ -114,6 +114,11 @@ BSLAM_API int bslam_set_points(bslam_solver* s, int n, const double* xyz /* n x 
  * n vectors, dims[i] entries each, values concatenated. */
 BSLAM_API int bslam_set_vectors(bslam_solver* s, int n, const int32_t* dims, const double* values, const uint8_t* is_const);
 
+/* SO(3) parameters (9 doubles, row-major; liegroups SO3: dof 3, perturb R <- exp(phi) R): the rotation half of the
+ * (SO3, t) parameter form of the photometric residual (photometric_residual.py:83-84, pipelines/dense.py:185-190). */
+BSLAM_API int bslam_set_rotations_so3(bslam_solver* s, int n, const double* R /* n x 9 */, const uint8_t* is_const);
+BSLAM_API int bslam_get_rotations_so3(bslam_solver* s, double* R /* n x 9 */);
+
 BSLAM_API int bslam_get_poses_se3(bslam_solver* s, double* Rt /* n x 12 */);
 BSLAM_API int bslam_get_poses_se2(bslam_solver* s, double* Rt /* n x 6  */);
 BSLAM_API int bslam_get_points(bslam_solver* s, double* xyz /* n x 3 */);
@@ -126,7 +131,8 @@ BSLAM_API int bslam_get_vectors(bslam_solver* s, double* values);
 /* ReprojectionResidual + StereoCamera.project (pyslam/residuals/
  * reprojection_residual.py:13-37, pyslam/sensors/stereo_camera.py:100-134).
  * pose_idx -> SE3 table, pt_idx -> point table, obs = (u,v,d),
- * stiffness 3x3, intr = (cu,cv,fu,fv,b). */
+ * stiffness 3x3, intr = (cu,cv,fu,fv,b).  b > 0: StereoCamera (d = disparity); b <= 0 selects the RGB-D pinhole
+ * model RGBDCamera (pyslam/sensors/rgbd_camera.py:7-168: third measurement = depth z) in every kernel that takes intr. */
 BSLAM_API int bslam_add_reprojection_blocks(bslam_solver* s, int n,
                                   const int32_t* pose_idx, const int32_t* pt_idx,
                                   const double* obs /* n x 3 */,
@@ -157,6 +163,14 @@ BSLAM_API int bslam_add_photometric_block(bslam_solver* s, int pose_idx, int n_p
                                           int width, int height, const double intr[5],
                                           double intensity_stiffness, double depth_stiffness,
                                           int loss_kind, double loss_k);
+/* The same block on the two-parameter form ['R_1_0', 't_1_0_1'] (photometric_residual.py:83-84,147-157: T = SE3(R, t),
+ * Jacobians J[:, 3:6] for the rotation and J[:, 0:3] for the translation; either may be constant, e.g. the
+ * translation on the coarse pyramid levels, pipelines/dense.py:188-189).  rot_idx -> SO3 table, vec_idx -> a
+ * 3-vector of the generic vector table. */
+BSLAM_API int bslam_add_photometric_block_split(bslam_solver* s, int rot_idx, int vec_idx, int n_px, const double* uvd_ref,
+                                      const double* im_ref, const double* im_jac, const double* im_track, int width,
+                                      int height, const double intr[5], double intensity_stiffness, double depth_stiffness,
+                                      int loss_kind, double loss_k);
 
 /* Host-evaluated blocks (user-defined Python residuals, the plug-in surface of
  * pyslam/problem.py:338-360).  Declares the STRUCTURE once: n_blocks blocks,
@@ -201,6 +215,7 @@ BSLAM_API int bslam_finalize(bslam_solver* s);
  * the reduced (camera) system. */
 BSLAM_API int bslam_get_layout(bslam_solver* s, int32_t* se3_off, int32_t* se2_off, int32_t* pt_off,
                      int32_t* vec_off, int32_t* dim, int32_t* n_reduced);
+BSLAM_API int bslam_get_layout_so3(bslam_solver* s, int32_t* so3_off);   /* offsets of the SO3 table entries (-1: constant) */
 
 /* ---- the hot path -------------------------------------------------------------- */
 
@@ -293,6 +308,35 @@ BSLAM_API int bslam_iterate_wait(bslam_solver* s, double* cost_lin, double* cost
 /* The handle's cudaStream_t, so the host can order collectives and record
  * events on it. */
 BSLAM_API void* bslam_stream(bslam_solver* s);
+
+/* ---- frame-to-frame motion -------------------------------------------------------------------------
+ * ReprojectionMotionOnlyBatchResidual / ReprojectionMotionOnlyResidual (pyslam/residuals/
+ * reprojection_motion_only_residual.py:36-113): n points triangulated in frame 1 (pts_1, n x 3) observed in frame 2
+ * (obs_2, n x 3), one SE3 parameter T_2_1 = pose_idx; stiffness 3x3 shared; intr as above. */
+BSLAM_API int bslam_add_motion_only_blocks(bslam_solver* s, int pose_idx, int n, const double* pts_1, const double* obs_2,
+                                 const double* stiffness, const double intr[5], int loss_kind, double loss_k);
+/* PoseToPoseOrientationResidual (pyslam/residuals/pose_to_pose_orientation_residual.py:4-38): binary factor on two SE3
+ * poses from a relative rotation measurement C_2_1_obs (n x 9, row-major), stiffness 3x3. */
+BSLAM_API int bslam_add_orientation_blocks(bslam_solver* s, int n, const int32_t* idx1, const int32_t* idx2, const double* C21_obs,
+                                 const double* stiffness, int per_block, int loss_kind, double loss_k);
+/* FrameToFrameRANSAC.perform_ransac on the device (pyslam/pipelines/ransac.py:12-56,107-165), no solver handle:
+ * n_hyp hypotheses.  idx != NULL: minimal sets idx[n_hyp][n_min] (rows of pts_1 / pts_2, n_pts x 3 each) -> rigid
+ * transforms by the SVD method (compute_transform_fast), returned in T_21_out (n_hyp x 16, 4x4 row-major);
+ * idx == NULL: the hypotheses are given in T_21_in.  Then compute_ransac_cost: inlier counts
+ * |project(T_21 pts_1) - obs_2|^2 < thresh per hypothesis (counts, n_hyp), the first arg-max and its count
+ * (best[0], best[1]) and the winner's inlier mask (best_mask, n_pts bytes).  Outputs may be NULL. */
+BSLAM_API int bslam_ransac(int device, int n_hyp, int n_min, const int32_t* idx, const double* T_21_in, int n_pts,
+                 const double* pts_1, const double* pts_2, const double* obs_2, const double intr[5], double thresh,
+                 double* T_21_out, int32_t* counts, int32_t* best, uint8_t* best_mask);
+/* ---- pyramids of the dense pipeline (pyslam/pipelines/keyframes.py:30-46,59-72,92-114), no handle ----
+ * bslam_image_pyramid: 8-bit image -> `levels` levels (cv2.pyrDown chain on the 8-bit data), each as float / 255
+ * (im_out) with 0.5 * Sobel gradients (gx_out, gy_out; may both be NULL); levels concatenated, level l has
+ * ceil(w / 2^l) x ceil(h / 2^l) pixels.  bslam_subsample_pyramid: disparity / depth maps: level l = map[::2^l, ::2^l]
+ * * scale_per_level^l (0.5 for disparities in pixels, 1 for depths). */
+BSLAM_API int bslam_image_pyramid(int device, const uint8_t* image, int width, int height, int levels, double* im_out,
+                        double* gx_out, double* gy_out);
+BSLAM_API int bslam_subsample_pyramid(int device, const double* map, int width, int height, int levels,
+                            double scale_per_level, double* out);
 
 /* Best-parameter snapshot used by `allow_nondecreasing_steps` (problem.py:163-175). */
 BSLAM_API int bslam_snapshot(bslam_solver* s);

@@ -27,8 +27,11 @@ struct PhotoArgs {
   double cu, cv, fu, fv, b;
   double intensity_covar, depth_covar;
   Loss loss;
-  const double* __restrict__ pose;    // 12 doubles [R|t] of T_track_ref
-  int pose_off;                        // reduced offset or -1
+  const double* __restrict__ R;       // rotation (9, row-major) and translation (3) of T_track_ref: the two halves of an
+  const double* __restrict__ t;       // SE3 table entry, or an SO3 parameter + a 3-vector parameter ((SO3, t) form,
+                                      // photometric_residual.py:83-84)
+  int off_trans, off_rot;             // reduced offsets of the rho columns (J[:, 0:3]) and the phi columns (J[:, 3:6]),
+                                      // -1: that parameter is constant (its columns are dropped, problem.py:343-356)
   double* __restrict__ S;
   int ldS;
   double* __restrict__ rhs;
@@ -55,8 +58,11 @@ __global__ void __launch_bounds__(kPhotoThreads) photometric_kernel(const PhotoA
   __shared__ double sred[28][kPhotoThreads / 32];
   double P[12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) P[k] = a.pose[k];
+  for (int k = 0; k < 9; ++k) P[k] = a.R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) P[9 + k] = a.t[k];
   const double fu_over_fv = a.fu / a.fv;
+  const bool stereo = a.b > 0.0;       // b <= 0: RGB-D pinhole model
   double acc[28];            // 21 lower-triangle entries of J^T w J, 6 of -J^T w r, cost
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
@@ -64,18 +70,24 @@ __global__ void __launch_bounds__(kPhotoThreads) photometric_kernel(const PhotoA
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_px; i += gridDim.x * blockDim.x) {
     const double u = ld_stream(a.uvd + 3 * (size_t)i), v = ld_stream(a.uvd + 3 * (size_t)i + 1),
                  d = ld_stream(a.uvd + 3 * (size_t)i + 2);
-    // triangulate (stereo_camera.py:137-174)
-    const double b_over_d = a.b / d;
-    const double b_over_d2 = b_over_d / d;
-    const double X = (u - a.cu) * b_over_d, Y = (v - a.cv) * b_over_d * fu_over_fv, Z = a.fu * b_over_d;
-    const double tj0 = (a.cu - u) * b_over_d2, tj1 = (a.cv - v) * b_over_d2 * fu_over_fv, tj2 = -a.fu * b_over_d2;
+    double X, Y, Z, tj0, tj1, tj2;       // point and the third column of the triangulation Jacobian
+    if (stereo) {                        // stereo_camera.py:137-174
+      const double b_over_d = a.b / d;
+      const double b_over_d2 = b_over_d / d;
+      X = (u - a.cu) * b_over_d; Y = (v - a.cv) * b_over_d * fu_over_fv; Z = a.fu * b_over_d;
+      tj0 = (a.cu - u) * b_over_d2; tj1 = (a.cv - v) * b_over_d2 * fu_over_fv; tj2 = -a.fu * b_over_d2;
+    } else {                             // rgbd_camera.py:149-180: d is the depth
+      tj0 = (u - a.cu) / a.fu; tj1 = (v - a.cv) / a.fv; tj2 = 1.0;
+      X = tj0 * d; Y = tj1 * d; Z = d;
+    }
     // transform + project
     const double x = P[0] * X + P[1] * Y + P[2] * Z + P[9];
     const double y = P[3] * X + P[4] * Y + P[5] * Z + P[10];
     const double z = P[6] * X + P[7] * Y + P[8] * Z + P[11];
     const double iz = 1.0 / z, iz2 = iz * iz;
-    const double ut = a.fu * x * iz + a.cu, vt = a.fv * y * iz + a.cv, dt = a.fu * a.b * iz;
-    const bool valid = (dt > 0.0) && (dt < a.w) && (vt > 0.0) && (vt < a.h) && (ut > 0.0) && (ut < a.w);
+    const double ut = a.fu * x * iz + a.cu, vt = a.fv * y * iz + a.cv, dt = stereo ? a.fu * a.b * iz : z;
+    // stereo_camera.py:90-97 (disparity compared with the image width); rgbd_camera.py:103-110 (depth > 0)
+    const bool valid = (dt > 0.0) && (!stereo || dt < a.w) && (vt > 0.0) && (vt < a.h) && (ut > 0.0) && (ut < a.w);
     if (!valid) continue;
     const double r0 = bilinear(a.im_track, a.w, a.h, ut, vt) - ld_stream(a.im_ref + i);
     // image gradient (1x2) times the first two rows of the projection Jacobian -> 1x3
@@ -123,14 +135,19 @@ __global__ void __launch_bounds__(kPhotoThreads) photometric_kernel(const PhotoA
 #pragma unroll
     for (int w8 = 0; w8 < kPhotoThreads / 32; ++w8) v += sred[k][w8];
     if (k == 27) { if (v != 0.0) red_add(a.scalars + slot, v); return; }
-    if (a.pose_off < 0 || v == 0.0) return;
+    if (v == 0.0) return;
+    // tangent index 0..5 = [rho; phi] -> position in the reduced system
+    auto pos = [&](int q) { return q < 3 ? (a.off_trans < 0 ? -1 : a.off_trans + q) : (a.off_rot < 0 ? -1 : a.off_rot + q - 3); };
     if (k < 21) {
       // k -> (row, col) of the lower triangle, row-major
       int rr = 0, base = 0;
       while (base + rr + 1 <= k) { base += rr + 1; ++rr; }
-      red_add(a.S + (size_t)(a.pose_off + rr) * a.ldS + a.pose_off + (k - base), v);
+      const int gr = pos(rr), gc = pos(k - base);
+      if (gr < 0 || gc < 0) return;
+      red_add(a.S + (size_t)max(gr, gc) * a.ldS + min(gr, gc), v);
     } else {
-      red_add(a.rhs + a.pose_off + (k - 21), v);
+      const int g = pos(k - 21);
+      if (g >= 0) red_add(a.rhs + g, v);
     }
   }
 }

@@ -148,4 +148,68 @@ __global__ void __launch_bounds__(128) edge_kernel(const EdgeArgs a, int cost_sl
   block_sum_to(cost, a.scalars + cost_slot, sred);
 }
 
+// PoseToPoseOrientationResidual.evaluate (pyslam/residuals/pose_to_pose_orientation_residual.py:12-38): binary factor on two
+// SE(3) poses from a relative ROTATION measurement C_2_1_obs (SO3):
+//     r = S log_SO3( rot(T2 T1^-1) C_obs^-1 ),   J1 = -S [0 | rot(T2 T1^-1)],   J2 = S [0 | I]        (3 x 6 each)
+// Tobs holds the 9 entries of C_obs per factor; stiffness 3x3.
+template <bool kCostOnly>
+__global__ void __launch_bounds__(128) orientation_edge_kernel(const EdgeArgs a, int cost_slot) {
+  __shared__ double sred[4];
+  double cost = 0.0;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.n) {
+    const int p1 = a.i1[e], p2 = a.i2[e];
+    const int o1 = a.pose_off[p1], o2 = a.pose_off[p2];
+    if (kCostOnly || o1 >= 0 || o2 >= 0) {
+      const double* R1 = a.poses + 12 * (size_t)p1;
+      const double* R2 = a.poses + 12 * (size_t)p2;
+      const double* Co = a.Tobs + 9 * (size_t)e;
+      double C21[9];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C21[3 * i + j] = R2[3 * i] * R1[3 * j] + R2[3 * i + 1] * R1[3 * j + 1] + R2[3 * i + 2] * R1[3 * j + 2];
+      SE3 E;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) E.R[3 * i + j] = C21[3 * i] * Co[3 * j] + C21[3 * i + 1] * Co[3 * j + 1] + C21[3 * i + 2] * Co[3 * j + 2];
+      E.t[0] = E.t[1] = E.t[2] = 0.0;
+      double xi[6], r[3], w[3], wr[3];
+      se3_log(E, xi);                           // zero translation: xi[3..5] = SO3.log(E.R)
+      const double* Sm = a.stiff + (a.stiff_per_block ? (size_t)9 * e : 0);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        r[i] = Sm[3 * i] * xi[3] + Sm[3 * i + 1] * xi[4] + Sm[3 * i + 2] * xi[5];
+        cost += loss_rho(a.loss, r[i]);
+      }
+      if (!kCostOnly) {
+        double J1[9], J2[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          w[i] = loss_weight(a.loss, r[i]);
+          wr[i] = w[i] * r[i];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            J2[3 * i + j] = Sm[3 * i + j];
+            J1[3 * i + j] = -(Sm[3 * i] * C21[j] + Sm[3 * i + 1] * C21[3 + j] + Sm[3 * i + 2] * C21[6 + j]);
+          }
+        }
+        auto rhs3 = [&](int o, const double* J) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) red_add(a.rhs + o + 3 + c, -(J[c] * wr[0] + J[3 + c] * wr[1] + J[6 + c] * wr[2]));
+        };
+        if (o1 >= 0) { add_block<3>(a.S, a.ldS, o1 + 3, o1 + 3, J1, J1, w, true); rhs3(o1, J1); }
+        if (o2 >= 0) { add_block<3>(a.S, a.ldS, o2 + 3, o2 + 3, J2, J2, w, true); rhs3(o2, J2); }
+        if (o1 >= 0 && o2 >= 0) {
+          if (o2 > o1) add_block<3>(a.S, a.ldS, o2 + 3, o1 + 3, J2, J1, w, false);
+          else if (o1 > o2) add_block<3>(a.S, a.ldS, o1 + 3, o2 + 3, J1, J2, w, false);
+          else { add_block<3>(a.S, a.ldS, o1 + 3, o1 + 3, J2, J1, w, true); add_block<3>(a.S, a.ldS, o1 + 3, o1 + 3, J1, J2, w, true); }
+        }
+      }
+    }
+  }
+  block_sum_to(cost, a.scalars + cost_slot, sred);
+}
+
 }  // namespace bs

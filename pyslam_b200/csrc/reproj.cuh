@@ -39,7 +39,7 @@
 namespace bs {
 
 struct ReprojGroup {     // constants shared by a batch of blocks
-  double cu, cv, fu, fv, b;
+  double cu, cv, fu, fv, b;   // b > 0: stereo camera (third measurement = disparity fu b / z); b <= 0: RGB-D camera (= depth z)
   double S[9];           // stiffness, row-major
   Loss loss;
 };
@@ -108,7 +108,7 @@ BS_D void reproj_residual_only(const ReprojGroup& g, const double* __restrict__ 
   const double iz = fast_rcp(z);
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
-  const double e2 = g.fu * g.b * iz - d;
+  const double e2 = (g.b > 0.0 ? g.fu * g.b * iz : z) - d;       // b <= 0: RGB-D pinhole model, third measurement = depth
 #pragma unroll
   for (int i = 0; i < 3; ++i) r[i] = g.S[3 * i] * e0 + g.S[3 * i + 1] * e1 + g.S[3 * i + 2] * e2;
 }
@@ -122,10 +122,11 @@ BS_D void reproj_linearize_one(const ReprojGroup& g, const double* __restrict__ 
   const double iz2 = iz * iz;
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
-  const double e2 = g.fu * g.b * iz - d;
-  // camera Jacobian non-zeros (stereo_camera.py:112-134)
+  const bool stereo = g.b > 0.0;
+  const double e2 = (stereo ? g.fu * g.b * iz : z) - d;
+  // camera Jacobian non-zeros (stereo_camera.py:112-134; rgbd_camera.py:127-146: last row [0 0 1])
   const double j00 = g.fu * iz, j11 = g.fv * iz;
-  const double j02 = -g.fu * x * iz2, j12 = -g.fv * y * iz2, j22 = -g.fu * g.b * iz2;
+  const double j02 = -g.fu * x * iz2, j12 = -g.fv * y * iz2, j22 = stereo ? -g.fu * g.b * iz2 : 1.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const double s0 = g.S[3 * i], s1 = g.S[3 * i + 1], s2 = g.S[3 * i + 2];
@@ -175,7 +176,8 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
   const double iz2 = iz * iz;
   const double e0 = g.fu * x * iz + g.cu - u;
   const double e1 = g.fv * y * iz + g.cv - v;
-  const double e2 = g.fu * g.b * iz - d;
+  const bool stereo = g.b > 0.0;                                  // b <= 0: RGB-D pinhole model (rgbd_camera.py:113-146)
+  const double e2 = (stereo ? g.fu * g.b * iz : z) - d;
   // residual, weights, cost;  Q = S^T diag(w) S
   double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0;
   double cost = 0.0;
@@ -195,7 +197,7 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
   const double qe2 = q02 * e0 + q12 * e1 + q22 * e2;
   // camera Jacobian non-zeros (stereo_camera.py:112-134): [[a,0,c0],[0,b,c1],[0,0,c2]]
   const double a = g.fu * iz, b = g.fv * iz;
-  const double c0 = -g.fu * x * iz2, c1 = -g.fv * y * iz2, c2 = -g.fu * g.b * iz2;
+  const double c0 = -g.fu * x * iz2, c1 = -g.fv * y * iz2, c2 = stereo ? -g.fu * g.b * iz2 : 1.0;
   // QJ = Q Jc (only the entries M needs), M = Jc^T QJ
   const double k02 = c0 * q00 + c1 * q01 + c2 * q02;
   const double k12 = c0 * q01 + c1 * q11 + c2 * q12;

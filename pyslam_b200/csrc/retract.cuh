@@ -24,6 +24,24 @@ __global__ void __launch_bounds__(128) retract_poses_kernel(int n, double* __res
   Gr::store(p, Gr::mul(Gr::exp(xi), Gr::load(p)));
 }
 
+// SO(3) parameters (9 doubles, row-major): R <- exp(phi) R  (liegroups SO3.perturb)
+__global__ void __launch_bounds__(128) retract_so3_kernel(int n, double* __restrict__ rots, const int* __restrict__ off,
+                                                          const double* __restrict__ dx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = off[i];
+  if (o < 0) return;
+  const double xi[6] = {0.0, 0.0, 0.0, dx[o], dx[o + 1], dx[o + 2]};
+  SE3 A{};
+  double* p = rots + 9 * (size_t)i;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) A.R[k] = p[k];
+  A.t[0] = A.t[1] = A.t[2] = 0.0;
+  const SE3 B = se3_mul(se3_exp(xi), A);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[k] = B.R[k];
+}
+
 // SE3 poses of a bundle-adjustment problem, one launch: threads [0, n) retract the pose table; threads
 // [n, n + n_slot_entries) retract the per-slot copies the landmark-block kernels read (slot_poses holds the
 // poses gathered at linearisation time, so the copies never read the table while it is being rewritten) and

@@ -24,6 +24,9 @@
 #include "schur.cuh"
 #include "panel.cuh"
 #include "peer.cuh"
+#include "motion_only.cuh"
+#include "ransac.cuh"
+#include "image.cuh"
 
 namespace {
 
@@ -52,6 +55,7 @@ struct DevBuf {
 struct EdgeBatch {
   int group = 3;
   bool binary = false;
+  bool orient = false;     // PoseToPoseOrientationResidual: Tobs holds 9 doubles (C_2_1_obs) per factor, stiffness 3x3
   int n = 0;
   int per_block = 0;
   bs::Loss loss{0, 0.0};
@@ -61,8 +65,16 @@ struct EdgeBatch {
   DevBuf<double> d_Tobs, d_stiff;
 };
 
+struct MotionBlock {       // ReprojectionMotionOnly(Batch)Residual: one pose, n fixed points
+  int pose_idx = 0, n = 0;
+  bs::ReprojGroup g{};
+  std::vector<double> pts1, obs2;
+  DevBuf<double> d_pts1, d_obs2;
+};
+
 struct PhotoBlock {
   int pose_idx = 0, n_px = 0, w = 0, h = 0;
+  int rot_idx = -1, vec_idx = -1;       // (SO3, t) parameter form: indices into the SO3 and vector tables (pose_idx unused)
   double intr[5] = {}, intensity_covar = 0, depth_covar = 0;
   bs::Loss loss{0, 0.0};
   std::vector<double> uvd, im_ref, im_jac, im_track;
@@ -83,8 +95,12 @@ struct bslam_solver {
   int shard_rank = 0;
 
   // ---- parameter tables (user order) ----
-  int n_se3 = 0, n_se2 = 0, n_pt = 0, n_vec = 0, n_vec_entries = 0;
-  std::vector<uint8_t> se3_const, se2_const, pt_const, vec_const;
+  int n_se3 = 0, n_se2 = 0, n_pt = 0, n_vec = 0, n_vec_entries = 0, n_so3 = 0;
+  std::vector<uint8_t> se3_const, se2_const, pt_const, vec_const, so3_const;
+  std::vector<double> h_so3;
+  std::vector<int> so3_off;
+  DevBuf<double> d_so3, b_so3;
+  DevBuf<int> d_so3_off;
   std::vector<int> vec_dims, vec_start;
   std::vector<double> h_se3, h_se2, h_pts, h_vec;   // staging until finalize
 
@@ -94,6 +110,7 @@ struct bslam_solver {
   std::vector<bs::ReprojGroup> groups;
   std::vector<EdgeBatch*> edges;
   std::vector<PhotoBlock*> photos;
+  std::vector<MotionBlock*> motions;
   // dense (host-evaluated) blocks
   int dn_blocks = 0;
   std::vector<int> dn_rows, dn_pptr, dn_pkind, dn_pindex;
@@ -194,6 +211,7 @@ struct bslam_solver {
   ~bslam_solver() {
     for (auto* e : edges) delete e;
     for (auto* e : photos) delete e;
+    for (auto* e : motions) delete e;
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -321,6 +339,10 @@ void launch_edges(bslam_solver* s, EdgeBatch* b, int slot) {
   if (b->n == 0) return;
   const bs::EdgeArgs a = edge_args(s, b);
   const int grid = cdiv(b->n, 128);
+  if (b->orient) {
+    LAUNCH(s, (bs::orientation_edge_kernel<kCostOnly>), grid, 128, 0, a, slot);
+    return;
+  }
   if (b->group == 3) {
     if (b->binary) LAUNCH(s, (bs::edge_kernel<3, true, kCostOnly>), grid, 128, 0, a, slot);
     else LAUNCH(s, (bs::edge_kernel<3, false, kCostOnly>), grid, 128, 0, a, slot);
@@ -338,8 +360,17 @@ bs::PhotoArgs photo_args(bslam_solver* s, PhotoBlock* b) {
   a.cu = b->intr[0]; a.cv = b->intr[1]; a.fu = b->intr[2]; a.fv = b->intr[3]; a.b = b->intr[4];
   a.intensity_covar = b->intensity_covar; a.depth_covar = b->depth_covar;
   a.loss = b->loss;
-  a.pose = s->d_se3.p + 12 * (size_t)b->pose_idx;
-  a.pose_off = s->se3_off[b->pose_idx];
+  if (b->rot_idx >= 0) {          // (SO3, t) form: photometric_residual.py:83-84,147-157
+    a.R = s->d_so3.p + 9 * (size_t)b->rot_idx;
+    a.t = s->d_vec.p + s->vec_start[b->vec_idx];
+    a.off_rot = s->so3_off[b->rot_idx];
+    a.off_trans = s->vec_off[b->vec_idx];
+  } else {
+    a.R = s->d_se3.p + 12 * (size_t)b->pose_idx;
+    a.t = a.R + 9;
+    a.off_trans = s->se3_off[b->pose_idx];
+    a.off_rot = a.off_trans < 0 ? -1 : a.off_trans + 3;
+  }
   a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
   return a;
 }
@@ -348,9 +379,27 @@ template <bool kCostOnly>
 void launch_photos(bslam_solver* s, int slot) {
   for (auto* b : s->photos) {
     if (b->n_px == 0) continue;
-    if (!kCostOnly && s->se3_off[b->pose_idx] < 0) continue;    // all parameters constant: dropped (problem.py:343-348)
+    if (!kCostOnly) {                                            // all parameters constant: dropped (problem.py:343-348)
+      const bool all_const = b->rot_idx >= 0 ? (s->so3_off[b->rot_idx] < 0 && s->vec_off[b->vec_idx] < 0) : s->se3_off[b->pose_idx] < 0;
+      if (all_const) continue;
+    }
     const int grid = std::min(cdiv(b->n_px, bs::kPhotoThreads), 148 * 2);
     LAUNCH(s, bs::photometric_kernel<kCostOnly>, grid, bs::kPhotoThreads, 0, photo_args(s, b), slot);
+  }
+}
+
+template <bool kCostOnly>
+void launch_motions(bslam_solver* s, int slot) {
+  for (auto* b : s->motions) {
+    if (b->n == 0) continue;
+    if (!kCostOnly && s->se3_off[b->pose_idx] < 0) continue;    // the only parameter is constant: dropped (problem.py:343-348)
+    bs::MotionArgs a;
+    a.n = b->n; a.pts1 = b->d_pts1.p; a.obs2 = b->d_obs2.p; a.g = b->g;
+    a.pose = s->d_se3.p + 12 * (size_t)b->pose_idx;
+    a.pose_off = s->se3_off[b->pose_idx];
+    a.S = s->S(); a.ldS = s->n_pad; a.rhs = s->rhs(); a.scalars = s->scalars();
+    const int grid = std::max(1, std::min(cdiv(b->n, bs::kMotionThreads), 148));
+    LAUNCH(s, bs::motion_only_kernel<kCostOnly>, grid, bs::kMotionThreads, 0, a, slot);
   }
 }
 
@@ -363,6 +412,7 @@ void launch_cost(bslam_solver* s, int slot) {
   if (s->shard_rank == 0) {      // not sharded: counted once across GPUs
     for (auto* b : s->edges) launch_edges<true>(s, b, slot);
     launch_photos<true>(s, slot);
+    launch_motions<true>(s, slot);
   }
 }
 
@@ -439,6 +489,7 @@ int do_linearize(bslam_solver* s, bool panels) {
   if (s->shard_rank == 0) {
     for (auto* b : s->edges) launch_edges<false>(s, b, BSLAM_S_COST_LIN);
     launch_photos<false>(s, BSLAM_S_COST_LIN);
+    launch_motions<false>(s, BSLAM_S_COST_LIN);
     if (s->dn_blocks > 0) {
       bs::DenseArgs a;
       a.n_blocks = s->dn_blocks;
@@ -550,6 +601,13 @@ void build_tile_mask(bslam_solver* s, const std::vector<int>& opose, const std::
   for (int b = 0; b < s->dn_blocks; ++b) {
     tiles.clear();
     for (int c = s->dn_col_ptr[b]; c < s->dn_col_ptr[b + 1]; ++c) tiles_of(s->dn_col_index[c], 1, tiles);
+    mark_tiles(s, tiles);
+  }
+  for (auto* b : s->photos) {                                                // (SO3, t) photometric blocks couple their two parameters
+    if (b->rot_idx < 0) continue;
+    tiles.clear();
+    tiles_of(s->so3_off[b->rot_idx], 3, tiles);
+    tiles_of(s->vec_off[b->vec_idx], 3, tiles);
     mark_tiles(s, tiles);
   }
   for (size_t e = 0; e < s->cp_i1.size(); ++e) {                             // declared couplings (bslam_add_coupling)
@@ -731,6 +789,7 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
            use_panels ? s->d_se3_prev.p : nullptr);
   }
   if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
+  if (s->n_so3 > 0) LAUNCH(s, bs::retract_so3_kernel, cdiv(s->n_so3, 128), 128, 0, s->n_so3, s->d_so3.p, s->d_so3_off.p, dx);
   if (s->n_vec_entries > 0)
     LAUNCH(s, bs::retract_flat_kernel, cdiv(s->n_vec_entries, 256), 256, 0, s->n_vec_entries, s->d_vec.p, s->d_vec_entry_off.p, dx);
   if (s->n_pt > s->n_lm) {
@@ -798,6 +857,7 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
     if (s->shard_rank == 0) {
       for (auto* b : s->edges) launch_edges<true>(s, b, BSLAM_S_COST_NEW);
       launch_photos<true>(s, BSLAM_S_COST_NEW);
+      launch_motions<true>(s, BSLAM_S_COST_NEW);
     }
   }
   record(s, 9);
@@ -1010,6 +1070,11 @@ int bslam_set_poses_se2(bslam_solver* s, int n, const double* Rt, const uint8_t*
   return set_table(s, "bslam_set_poses_se2", n, 6, Rt, is_const, s->n_se2, s->se2_const, s->h_se2, s->d_se2);
 }
 
+int bslam_set_rotations_so3(bslam_solver* s, int n, const double* R, const uint8_t* is_const) {
+  NEED(s, "NULL solver");
+  return set_table(s, "bslam_set_rotations_so3", n, 9, R, is_const, s->n_so3, s->so3_const, s->h_so3, s->d_so3);
+}
+
 int bslam_set_points(bslam_solver* s, int n, const double* xyz, const uint8_t* is_const) {
   NEED(s, "NULL solver");
   if (!s->finalized) return set_table(s, "bslam_set_points", n, 3, xyz, is_const, s->n_pt, s->pt_const, s->h_pts, s->d_pts);
@@ -1070,6 +1135,10 @@ int bslam_get_poses_se3(bslam_solver* s, double* Rt) {
 int bslam_get_poses_se2(bslam_solver* s, double* Rt) {
   NEED(s, "NULL solver");
   return get_table(s, "bslam_get_poses_se2", s->n_se2, 6, Rt, s->d_se2);
+}
+int bslam_get_rotations_so3(bslam_solver* s, double* R) {
+  NEED(s, "NULL solver");
+  return get_table(s, "bslam_get_rotations_so3", s->n_so3, 9, R, s->d_so3);
 }
 int bslam_get_points(bslam_solver* s, double* xyz) {
   NEED(s && s->finalized, "bslam_get_points: solver not finalized");
@@ -1190,6 +1259,64 @@ int bslam_add_photometric_block(bslam_solver* s, int pose_idx, int n_px, const d
   return BSLAM_OK;
 }
 
+int bslam_add_motion_only_blocks(bslam_solver* s, int pose_idx, int n, const double* pts_1, const double* obs_2,
+                                 const double* stiffness, const double intr[5], int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_add_motion_only_blocks after finalize; call bslam_clear_blocks first");
+  NEED(n >= 0 && stiffness && intr && (n == 0 || (pts_1 && obs_2)), "bslam_add_motion_only_blocks: bad arguments");
+  NEED(pose_idx >= 0 && pose_idx < s->n_se3, "motion-only block: pose index %d outside the SE3 table (%d)", pose_idx, s->n_se3);
+  NEED(valid_loss(loss_kind, loss_k), "bslam_add_motion_only_blocks: invalid loss (kind %d, k %g)", loss_kind, loss_k);
+  MotionBlock* b = new MotionBlock();
+  b->pose_idx = pose_idx; b->n = n;
+  b->g.cu = intr[0]; b->g.cv = intr[1]; b->g.fu = intr[2]; b->g.fv = intr[3]; b->g.b = intr[4];
+  for (int k = 0; k < 9; ++k) b->g.S[k] = stiffness[k];
+  b->g.loss.kind = loss_kind; b->g.loss.k = loss_k;
+  b->pts1.assign(pts_1, pts_1 + 3 * (size_t)n);
+  b->obs2.assign(obs_2, obs_2 + 3 * (size_t)n);
+  s->motions.push_back(b);
+  return BSLAM_OK;
+}
+
+int bslam_add_orientation_blocks(bslam_solver* s, int n, const int32_t* idx1, const int32_t* idx2, const double* C21_obs,
+                                 const double* stiffness, int per_block, int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(!s->finalized, "bslam_add_orientation_blocks after finalize; call bslam_clear_blocks first");
+  NEED(n >= 0 && (n == 0 || (idx1 && idx2 && C21_obs && stiffness)), "bslam_add_orientation_blocks: bad arguments");
+  NEED(valid_loss(loss_kind, loss_k), "bslam_add_orientation_blocks: invalid loss (kind %d, k %g)", loss_kind, loss_k);
+  if (n == 0) return BSLAM_OK;
+  for (int i = 0; i < n; ++i)
+    NEED(idx1[i] >= 0 && idx1[i] < s->n_se3 && idx2[i] >= 0 && idx2[i] < s->n_se3, "orientation block %d: pose index outside the SE3 table (%d)", i,
+         s->n_se3);
+  EdgeBatch* b = new EdgeBatch();
+  b->group = 3; b->binary = true; b->orient = true; b->n = n; b->per_block = per_block ? 1 : 0;
+  b->loss.kind = loss_kind; b->loss.k = loss_k;
+  b->i1.assign(idx1, idx1 + n);
+  b->i2.assign(idx2, idx2 + n);
+  b->Tobs.assign(C21_obs, C21_obs + 9 * (size_t)n);
+  b->stiff.assign(stiffness, stiffness + (size_t)(per_block ? n : 1) * 9);
+  s->edges.push_back(b);
+  return BSLAM_OK;
+}
+
+int bslam_add_photometric_block_split(bslam_solver* s, int rot_idx, int vec_idx, int n_px, const double* uvd_ref, const double* im_ref,
+                                      const double* im_jac, const double* im_track, int width, int height, const double intr[5],
+                                      double intensity_stiffness, double depth_stiffness, int loss_kind, double loss_k) {
+  NEED(s, "NULL solver");
+  NEED(rot_idx >= 0 && rot_idx < s->n_so3, "photometric block: rotation index %d outside the SO3 table (%d)", rot_idx, s->n_so3);
+  NEED(vec_idx >= 0 && vec_idx < s->n_vec && s->vec_dims[vec_idx] == 3, "photometric block: translation %d is not a 3-vector of the vector table",
+       vec_idx);
+  // same validation and storage as the SE3 form; the pose index is replaced by the (SO3, t) pair
+  const int n_se3 = s->n_se3;
+  s->n_se3 = std::max(1, n_se3);
+  const int rc = bslam_add_photometric_block(s, 0, n_px, uvd_ref, im_ref, im_jac, im_track, width, height, intr, intensity_stiffness,
+                                             depth_stiffness, loss_kind, loss_k);
+  s->n_se3 = n_se3;
+  if (rc) return rc;
+  s->photos.back()->rot_idx = rot_idx;
+  s->photos.back()->vec_idx = vec_idx;
+  return BSLAM_OK;
+}
+
 int bslam_set_dense_blocks(bslam_solver* s, int n_blocks, const int32_t* rows, const int32_t* param_ptr,
                            const int32_t* param_kind, const int32_t* param_index) {
   NEED(s, "NULL solver");
@@ -1233,6 +1360,8 @@ int bslam_clear_blocks(bslam_solver* s) {
   s->edges.clear();
   for (auto* e : s->photos) delete e;
   s->photos.clear();
+  for (auto* e : s->motions) delete e;
+  s->motions.clear();
   s->dn_blocks = 0;
   s->dn_rows.clear(); s->dn_pptr.clear(); s->dn_pkind.clear(); s->dn_pindex.clear();
   s->cp_group.clear(); s->cp_i1.clear(); s->cp_i2.clear();
@@ -1378,6 +1507,7 @@ int bslam_finalize(bslam_solver* s) {
   std::vector<Item> items;
   for (int i = 0; i < s->n_se3; ++i) if (!s->se3_const[i]) items.push_back({0, i, 6});
   for (int i = 0; i < s->n_se2; ++i) if (!s->se2_const[i]) items.push_back({1, i, 3});
+  for (int i = 0; i < s->n_so3; ++i) if (!s->so3_const[i]) items.push_back({4, i, 3});
   for (int i = 0; i < s->n_vec; ++i) if (!s->vec_const[i] && s->vec_dims[i] > 0) items.push_back({3, i, s->vec_dims[i]});
   for (int q = s->n_lm; q < s->n_pt; ++q) if (!s->pt_const[s->pt_iperm[q]]) items.push_back({2, s->pt_iperm[q], 3});
   std::vector<int> sn_first, sn_tiles;          // supernode -> first item, number of tiles
@@ -1395,9 +1525,9 @@ int bslam_finalize(bslam_solver* s) {
     }
   }
   const int n_sn = (int)sn_first.size();
-  std::vector<int> se3_sn(s->n_se3, -1), se2_sn(s->n_se2, -1), vec_sn(s->n_vec, -1), pt_sn(s->n_pt, -1);
+  std::vector<int> se3_sn(s->n_se3, -1), se2_sn(s->n_se2, -1), vec_sn(s->n_vec, -1), pt_sn(s->n_pt, -1), so3_sn(s->n_so3, -1);
   for (size_t k = 0; k < items.size(); ++k) {
-    std::vector<int>& m = items[k].kind == 0 ? se3_sn : items[k].kind == 1 ? se2_sn : items[k].kind == 3 ? vec_sn : pt_sn;
+    std::vector<int>& m = items[k].kind == 0 ? se3_sn : items[k].kind == 1 ? se2_sn : items[k].kind == 3 ? vec_sn : items[k].kind == 4 ? so3_sn : pt_sn;
     m[items[k].idx] = item_sn[k];
   }
   // coupling graph of the supernodes
@@ -1440,6 +1570,13 @@ int bslam_finalize(bslam_solver* s) {
         if (m[b->i2[e]] >= 0) g.push_back(m[b->i2[e]]);
         couple(g);
       }
+    }
+    for (auto* b : s->photos) {
+      if (b->rot_idx < 0) continue;
+      g.clear();
+      if (so3_sn[b->rot_idx] >= 0) g.push_back(so3_sn[b->rot_idx]);
+      if (vec_sn[b->vec_idx] >= 0) g.push_back(vec_sn[b->vec_idx]);
+      couple(g);
     }
     for (size_t e = 0; e < s->cp_i1.size(); ++e) {
       const std::vector<int>& m = s->cp_group[e] == 3 ? se3_sn : se2_sn;
@@ -1586,6 +1723,7 @@ int bslam_finalize(bslam_solver* s) {
   s->se3_off.assign(s->n_se3, -1);
   s->se2_off.assign(s->n_se2, -1);
   s->vec_off.assign(s->n_vec, -1);
+  s->so3_off.assign(s->n_so3, -1);
   s->vec_entry_off.assign(s->n_vec_entries, -1);
   s->pt_off_user.assign(s->n_pt, -1);
   s->pt_red_entry_off.assign(3 * (size_t)(s->n_pt - s->n_lm), -1);
@@ -1598,6 +1736,7 @@ int bslam_finalize(bslam_solver* s) {
       const Item& it = items[k];
       if (it.kind == 0) s->se3_off[it.idx] = off;
       else if (it.kind == 1) s->se2_off[it.idx] = off;
+      else if (it.kind == 4) s->so3_off[it.idx] = off;
       else if (it.kind == 3) {
         s->vec_off[it.idx] = off;
         for (int c = 0; c < it.dof; ++c) s->vec_entry_off[s->vec_start[it.idx] + c] = off + c;
@@ -1616,7 +1755,7 @@ int bslam_finalize(bslam_solver* s) {
   auto mark_used = [&](int off, int dof) { for (int c = 0; c < dof; ++c) used[off + c] = 1; };
   for (const Item& it : items) {
     const int off = it.kind == 0 ? s->se3_off[it.idx] : it.kind == 1 ? s->se2_off[it.idx] : it.kind == 3 ? s->vec_off[it.idx]
-                                                                                                            : s->pt_off_user[it.idx];
+                  : it.kind == 4 ? s->so3_off[it.idx] : s->pt_off_user[it.idx];
     mark_used(off, it.dof);
   }
   for (int q = 0; q < s->n_lm; ++q) s->pt_off_user[s->pt_iperm[q]] = s->n_red + 3 * q;
@@ -1849,6 +1988,9 @@ int bslam_finalize(bslam_solver* s) {
     for (int k = 0; k < 3; ++k) pts_int[3 * (size_t)q + k] = s->h_pts[3 * (size_t)s->pt_iperm[q] + k];
   CU(upload(s->d_se3, s->h_se3, st));
   CU(upload(s->d_se2, s->h_se2, st));
+  CU(upload(s->d_so3, s->h_so3, st));
+  CU(upload(s->d_so3_off, s->so3_off, st));
+  CU(s->b_so3.alloc(s->d_so3.n));
   CU(upload(s->d_pts, pts_int, st));
   CU(upload(s->d_vec, s->h_vec, st));
   CU(s->d_stage.alloc(3 * (size_t)s->n_pt));
@@ -1901,6 +2043,10 @@ int bslam_finalize(bslam_solver* s) {
     CU(upload(b->d_i2, b->i2, st));
     CU(upload(b->d_Tobs, b->Tobs, st));
     CU(upload(b->d_stiff, b->stiff, st));
+  }
+  for (auto* b : s->motions) {
+    CU(upload(b->d_pts1, b->pts1, st));
+    CU(upload(b->d_obs2, b->obs2, st));
   }
   for (auto* b : s->photos) {
     CU(upload(b->d_uvd, b->uvd, st));
@@ -1966,6 +2112,12 @@ int bslam_get_layout(bslam_solver* s, int32_t* se3_off, int32_t* se2_off, int32_
   if (vec_off) std::copy(s->vec_off.begin(), s->vec_off.end(), vec_off);
   if (dim) *dim = s->dim;
   if (n_reduced) *n_reduced = s->n_red;
+  return BSLAM_OK;
+}
+
+int bslam_get_layout_so3(bslam_solver* s, int32_t* so3_off) {
+  NEED(s && s->finalized, "bslam_get_layout_so3: solver not finalized");
+  if (so3_off) std::copy(s->so3_off.begin(), s->so3_off.end(), so3_off);
   return BSLAM_OK;
 }
 
@@ -2149,6 +2301,7 @@ int bslam_layout_hash(bslam_solver* s, uint64_t* hash) {
   mix(s->se3_off.data(), s->se3_off.size() * sizeof(int));
   mix(s->se2_off.data(), s->se2_off.size() * sizeof(int));
   mix(s->vec_off.data(), s->vec_off.size() * sizeof(int));
+  mix(s->so3_off.data(), s->so3_off.size() * sizeof(int));
   mix(s->tile_mask.data(), s->tile_mask.size());
   mix(&s->n_pad, sizeof(int));
   *hash = h;
@@ -2331,6 +2484,7 @@ int bslam_snapshot(bslam_solver* s) {
     return src.n ? cudaMemcpyAsync(dst.p, src.p, src.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) : cudaSuccess;
   };
   CU(cp(s->b_se3, s->d_se3)); CU(cp(s->b_se2, s->d_se2)); CU(cp(s->b_pts, s->d_pts)); CU(cp(s->b_vec, s->d_vec));
+  CU(cp(s->b_so3, s->d_so3));
   return BSLAM_OK;
 }
 
@@ -2341,6 +2495,7 @@ int bslam_restore(bslam_solver* s) {
     return src.n ? cudaMemcpyAsync(dst.p, src.p, src.n * sizeof(double), cudaMemcpyDeviceToDevice, s->stream) : cudaSuccess;
   };
   CU(cp(s->d_se3, s->b_se3)); CU(cp(s->d_se2, s->b_se2)); CU(cp(s->d_pts, s->b_pts)); CU(cp(s->d_vec, s->b_vec));
+  CU(cp(s->d_so3, s->b_so3));
   return BSLAM_OK;
 }
 
@@ -2480,5 +2635,118 @@ int bslam_get_timings(bslam_solver* s, double* ms) {
 }
 
 int64_t bslam_launch_count(const bslam_solver* s) { return s ? s->launches : 0; }
+
+// ---------------------------------------------------------------- stand-alone device routines (no solver handle)
+
+#define CUG(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) return fail(nullptr, BSLAM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+int bslam_ransac(int device, int n_hyp, int n_min, const int32_t* idx, const double* T_21_in, int n_pts, const double* pts_1,
+                 const double* pts_2, const double* obs_2, const double intr[5], double thresh, double* T_21_out,
+                 int32_t* counts, int32_t* best, uint8_t* best_mask) {
+  bslam_solver* s = nullptr;
+  if (n_hyp <= 0 || n_pts <= 0 || !pts_1 || !obs_2 || !intr || (!idx && !T_21_in) || (idx && (!pts_2 || n_min < 3)))
+    return fail(s, BSLAM_E_INVALID, "bslam_ransac: bad arguments");
+  if (idx)
+    for (size_t k = 0; k < (size_t)n_hyp * n_min; ++k)
+      if (idx[k] < 0 || idx[k] >= n_pts) return fail(s, BSLAM_E_INVALID, "bslam_ransac: sample index %d outside [0,%d)", idx[k], n_pts);
+  CUG(cudaSetDevice(device));
+  DevBuf<double> d_p1, d_p2, d_o2, d_T;
+  DevBuf<int> d_idx, d_cnt, d_best;
+  DevBuf<unsigned char> d_mask;
+  CUG(d_p1.alloc(3 * (size_t)n_pts)); CUG(d_o2.alloc(3 * (size_t)n_pts)); CUG(d_T.alloc(16 * (size_t)n_hyp));
+  CUG(d_cnt.alloc(n_hyp)); CUG(d_best.alloc(2)); CUG(d_mask.alloc(n_pts));
+  CUG(cudaMemcpy(d_p1.p, pts_1, 3 * (size_t)n_pts * sizeof(double), cudaMemcpyHostToDevice));
+  CUG(cudaMemcpy(d_o2.p, obs_2, 3 * (size_t)n_pts * sizeof(double), cudaMemcpyHostToDevice));
+  if (idx) {
+    CUG(d_p2.alloc(3 * (size_t)n_pts)); CUG(d_idx.alloc((size_t)n_hyp * n_min));
+    CUG(cudaMemcpy(d_p2.p, pts_2, 3 * (size_t)n_pts * sizeof(double), cudaMemcpyHostToDevice));
+    CUG(cudaMemcpy(d_idx.p, idx, (size_t)n_hyp * n_min * sizeof(int), cudaMemcpyHostToDevice));
+    bs::ransac_transform_kernel<<<cdiv(n_hyp, 128), 128>>>(n_hyp, n_min, d_idx.p, d_p1.p, d_p2.p, d_T.p);
+  } else {
+    CUG(cudaMemcpy(d_T.p, T_21_in, 16 * (size_t)n_hyp * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  bs::ransac_count_kernel<<<n_hyp, 256>>>(n_pts, d_T.p, d_p1.p, d_o2.p, intr[0], intr[1], intr[2], intr[3], intr[4], thresh, d_cnt.p);
+  bs::ransac_best_kernel<<<1, 256>>>(n_hyp, n_pts, d_cnt.p, d_T.p, d_p1.p, d_o2.p, intr[0], intr[1], intr[2], intr[3], intr[4], thresh,
+                                     d_best.p, d_mask.p);
+  CUG(cudaGetLastError());
+  if (T_21_out) CUG(cudaMemcpy(T_21_out, d_T.p, 16 * (size_t)n_hyp * sizeof(double), cudaMemcpyDeviceToHost));
+  if (counts) CUG(cudaMemcpy(counts, d_cnt.p, n_hyp * sizeof(int), cudaMemcpyDeviceToHost));
+  if (best) CUG(cudaMemcpy(best, d_best.p, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (best_mask) CUG(cudaMemcpy(best_mask, d_mask.p, n_pts, cudaMemcpyDeviceToHost));
+  CUG(cudaDeviceSynchronize());
+  return BSLAM_OK;
+}
+
+int bslam_image_pyramid(int device, const uint8_t* image, int width, int height, int levels, double* im_out, double* gx_out,
+                        double* gy_out) {
+  bslam_solver* s = nullptr;
+  if (!image || width <= 0 || height <= 0 || levels <= 0 || !im_out) return fail(s, BSLAM_E_INVALID, "bslam_image_pyramid: bad arguments");
+  CUG(cudaSetDevice(device));
+  size_t total = 0;
+  { int w = width, h = height; for (int l = 0; l < levels; ++l) { total += (size_t)w * h; w = (w + 1) / 2; h = (h + 1) / 2; } }
+  DevBuf<unsigned char> d_a, d_b;
+  DevBuf<double> d_im, d_gx, d_gy;
+  CUG(d_a.alloc((size_t)width * height)); CUG(d_b.alloc((size_t)width * height));
+  CUG(d_im.alloc(total)); CUG(d_gx.alloc(total)); CUG(d_gy.alloc(total));
+  CUG(cudaMemcpy(d_a.p, image, (size_t)width * height, cudaMemcpyHostToDevice));
+  unsigned char *cur = d_a.p, *nxt = d_b.p;
+  size_t off = 0;
+  int w = width, h = height;
+  for (int l = 0; l < levels; ++l) {
+    const size_t n = (size_t)w * h;
+    bs::u8_to_unit_kernel<<<cdiv((long long)n, 256), 256>>>(cur, n, d_im.p + off);
+    if (gx_out && gy_out)
+      bs::sobel_half_kernel<<<dim3(cdiv(w, 16), cdiv(h, 16)), 256>>>(d_im.p + off, w, h, d_gx.p + off, d_gy.p + off);
+    off += n;
+    if (l + 1 < levels) {
+      const int wo = (w + 1) / 2, ho = (h + 1) / 2;
+      bs::pyr_down_u8_kernel<<<dim3(cdiv(wo, 16), cdiv(ho, 16)), 256>>>(cur, w, h, nxt, wo, ho);
+      std::swap(cur, nxt);
+      w = wo; h = ho;
+    }
+  }
+  CUG(cudaGetLastError());
+  CUG(cudaMemcpy(im_out, d_im.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gx_out && gy_out) {
+    CUG(cudaMemcpy(gx_out, d_gx.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+    CUG(cudaMemcpy(gy_out, d_gy.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  CUG(cudaDeviceSynchronize());
+  return BSLAM_OK;
+}
+
+int bslam_subsample_pyramid(int device, const double* map, int width, int height, int levels, double scale_per_level, double* out) {
+  bslam_solver* s = nullptr;
+  if (!map || width <= 0 || height <= 0 || levels <= 0 || !out) return fail(s, BSLAM_E_INVALID, "bslam_subsample_pyramid: bad arguments");
+  CUG(cudaSetDevice(device));
+  size_t total = 0;
+  { int w = width, h = height; for (int l = 0; l < levels; ++l) { total += (size_t)w * h; w = (w + 1) / 2; h = (h + 1) / 2; } }
+  // keyframes.py:100-112: the UNSCALED map is sub-sampled level after level ([0::2, 0::2]); level l is stored times scale^l
+  DevBuf<double> d_raw, d_out;
+  CUG(d_raw.alloc(total)); CUG(d_out.alloc(total));
+  CUG(cudaMemcpy(d_raw.p, map, (size_t)width * height * sizeof(double), cudaMemcpyHostToDevice));
+  CUG(cudaMemcpy(d_out.p, d_raw.p, (size_t)width * height * sizeof(double), cudaMemcpyDeviceToDevice));
+  size_t off = 0;
+  int w = width, h = height;
+  double scale = 1.0;
+  for (int l = 1; l < levels; ++l) {
+    const int wo = (w + 1) / 2, ho = (h + 1) / 2;
+    const size_t n = (size_t)w * h;
+    scale *= scale_per_level;
+    const dim3 grid(cdiv(wo, 16), cdiv(ho, 16));
+    bs::subsample2_kernel<<<grid, 256>>>(d_raw.p + off, w, h, d_raw.p + off + n, wo, ho, 1.0);
+    bs::subsample2_kernel<<<grid, 256>>>(d_raw.p + off, w, h, d_out.p + off + n, wo, ho, scale);
+    off += n;
+    w = wo; h = ho;
+  }
+  CUG(cudaGetLastError());
+  CUG(cudaMemcpy(out, d_out.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+  CUG(cudaDeviceSynchronize());
+  return BSLAM_OK;
+}
 
 }  // extern "C"

@@ -41,6 +41,11 @@ SIGNATURES = {
     'bslam_set_poses_se2': (C.c_int, [_h, C.c_int, _dp, _bp]),
     'bslam_set_points': (C.c_int, [_h, C.c_int, _dp, _bp]),
     'bslam_set_vectors': (C.c_int, [_h, C.c_int, _ip, _dp, _bp]),
+    'bslam_set_rotations_so3': (C.c_int, [_h, C.c_int, _dp, _bp]),
+    'bslam_get_rotations_so3': (C.c_int, [_h, _dp]),
+    'bslam_get_layout_so3': (C.c_int, [_h, _ip]),
+    'bslam_add_photometric_block_split': (C.c_int, [_h, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp,
+                                                    C.c_double, C.c_double, C.c_int, C.c_double]),
     'bslam_get_poses_se3': (C.c_int, [_h, _dp]),
     'bslam_get_poses_se2': (C.c_int, [_h, _dp]),
     'bslam_get_points': (C.c_int, [_h, _dp]),
@@ -50,6 +55,11 @@ SIGNATURES = {
     'bslam_add_pose_to_pose_blocks': (C.c_int, [_h, C.c_int, C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
     'bslam_add_photometric_block': (C.c_int, [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_double,
                                               C.c_double, C.c_int, C.c_double]),
+    'bslam_add_motion_only_blocks': (C.c_int, [_h, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_double]),
+    'bslam_add_orientation_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    'bslam_ransac': (C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_double, _dp, _ip, _ip, _bp]),
+    'bslam_image_pyramid': (C.c_int, [C.c_int, _bp, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
+    'bslam_subsample_pyramid': (C.c_int, [C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp]),
     'bslam_set_dense_blocks': (C.c_int, [_h, C.c_int, _ip, _ip, _ip, _ip]),
     'bslam_upload_dense_values': (C.c_int, [_h, _dp, C.c_size_t, _dp, C.c_size_t, C.c_double]),
     'bslam_clear_blocks': (C.c_int, [_h]),
@@ -164,7 +174,7 @@ class Engine:
             self._h = None
             raise EngineError('bslam_create failed ({}): {}'.format(rc, (msg or b'').decode()))
         self.device = int(device)
-        self.n = dict(se3=0, se2=0, pt=0, vec=0, vec_entries=0)
+        self.n = dict(se3=0, se2=0, pt=0, vec=0, vec_entries=0, so3=0)
         self._scal = np.zeros(N_SCALARS)
 
     def close(self):
@@ -188,6 +198,16 @@ class Engine:
         Rt = _f64(Rt, (-1, 6))
         self.n['se2'] = len(Rt)
         self._ck(self._lib.bslam_set_poses_se2(self._h, len(Rt), _d(Rt), _b(_flags(is_const, len(Rt)))))
+
+    def set_rotations_so3(self, R, is_const=None):
+        R = _f64(R, (-1, 9))
+        self.n['so3'] = len(R)
+        self._ck(self._lib.bslam_set_rotations_so3(self._h, len(R), _d(R), _b(_flags(is_const, len(R)))))
+
+    def get_rotations_so3(self):
+        out = np.empty((self.n['so3'], 9))
+        self._ck(self._lib.bslam_get_rotations_so3(self._h, _d(out)))
+        return out
 
     def set_points(self, xyz, is_const=None):
         xyz = _f64(xyz, (-1, 3))
@@ -265,6 +285,32 @@ class Engine:
             self._h, int(pose_idx), len(uvd_ref), _d(uvd_ref), _d(im_ref), _d(im_jac), _d(im_track), im_track.shape[1],
             im_track.shape[0], _d(intr), float(intensity_stiffness), float(depth_stiffness), int(loss_kind), float(loss_k)))
 
+    def add_photometric_block_split(self, rot_idx, vec_idx, uvd_ref, im_ref, im_jac, im_track, intr, intensity_stiffness,
+                                    depth_stiffness, loss_kind=0, loss_k=0.):
+        """The (SO3, t) parameter form: rot_idx -> SO3 table, vec_idx -> a 3-vector of the vector table."""
+        uvd_ref, im_ref, im_jac = _f64(uvd_ref, (-1, 3)), _f64(im_ref).ravel(), _f64(im_jac, (-1, 2))
+        im_track, intr = _f64(im_track), _f64(intr, (5,))
+        assert im_track.ndim == 2 and len(im_ref) == len(uvd_ref) == len(im_jac)
+        self._ck(self._lib.bslam_add_photometric_block_split(
+            self._h, int(rot_idx), int(vec_idx), len(uvd_ref), _d(uvd_ref), _d(im_ref), _d(im_jac), _d(im_track),
+            im_track.shape[1], im_track.shape[0], _d(intr), float(intensity_stiffness), float(depth_stiffness),
+            int(loss_kind), float(loss_k)))
+
+    def add_motion_only_blocks(self, pose_idx, pts_1, obs_2, stiffness, intr, loss_kind=0, loss_k=0.):
+        """ReprojectionMotionOnly(Batch)Residual: n fixed points seen from pose `pose_idx` (T_2_1)."""
+        pts_1, obs_2 = _f64(pts_1, (-1, 3)), _f64(obs_2, (-1, 3))
+        S, intr = _f64(stiffness, (3, 3)), _f64(intr, (5,))
+        assert len(pts_1) == len(obs_2)
+        self._ck(self._lib.bslam_add_motion_only_blocks(self._h, int(pose_idx), len(pts_1), _d(pts_1), _d(obs_2), _d(S), _d(intr),
+                                                        int(loss_kind), float(loss_k)))
+
+    def add_orientation_blocks(self, idx1, idx2, C21_obs, stiffness, loss_kind=0, loss_k=0.):
+        """PoseToPoseOrientationResidual: relative rotation measurements (n x 9) between SE3 poses."""
+        i1, i2 = _i32(idx1), _i32(idx2)
+        C = _f64(C21_obs, (-1, 9))
+        S, per = self._stiff(stiffness, len(i1), 3)
+        self._ck(self._lib.bslam_add_orientation_blocks(self._h, len(i1), _i(i1), _i(i2), _d(C), _d(S), per, int(loss_kind), float(loss_k)))
+
     def set_dense_blocks(self, rows, param_ptr, param_kind, param_index):
         rows, param_ptr = _i32(rows), _i32(param_ptr)
         param_kind, param_index = _i32(param_kind), _i32(param_index)
@@ -288,6 +334,8 @@ class Engine:
         self._ck(self._lib.bslam_get_layout(self._h, _i(o['se3']), _i(o['se2']), _i(o['pt']), _i(o['vec']),
                                             C.byref(dim), C.byref(nred)))
         o['dim'], o['n_reduced'] = dim.value, nred.value
+        o['so3'] = np.empty(self.n['so3'], np.int32)
+        self._ck(self._lib.bslam_get_layout_so3(self._h, _i(o['so3'])))
         return o
 
     # ---- hot path -----------------------------------------------------------
@@ -511,3 +559,75 @@ def _engine_torch_stream(self):
 Engine.reduced_tensor = _engine_reduced_tensor
 Engine.scalars_tensor = _engine_scalars_tensor
 Engine.torch_stream = _engine_torch_stream
+
+
+# ---- stand-alone device routines (no solver handle) ---------------------------------------------
+def _ck_global(lib, rc):
+    if rc != 0:
+        raise EngineError('libbslam error {}: {}'.format(rc, (lib.bslam_last_error(None) or b'').decode()))
+
+
+def ransac(pts_1, obs_2, intr, thresh, sample_idx=None, pts_2=None, T_21=None, device=0):
+    """FrameToFrameRANSAC on the device (csrc/ransac.cuh).  Either `sample_idx` [n_hyp, n_min] + `pts_2` (the
+    hypotheses are computed from the minimal sets) or `T_21` [n_hyp, 4, 4].  Returns (T_21 [n_hyp,4,4],
+    inlier counts [n_hyp], index of the first best hypothesis, its inlier mask [n_pts] bool)."""
+    lib = load_library()
+    pts_1, obs_2 = _f64(pts_1, (-1, 3)), _f64(obs_2, (-1, 3))
+    n_pts = len(pts_1)
+    if sample_idx is not None:
+        idx = _i32(sample_idx)
+        n_hyp, n_min = idx.shape
+        p2, Tin = _f64(pts_2, (-1, 3)), None
+    else:
+        Tin = _f64(T_21, (-1, 16))
+        n_hyp, n_min, idx, p2 = len(Tin), 0, None, None
+    T_out = np.empty((n_hyp, 16))
+    counts, best, mask = np.zeros(n_hyp, np.int32), np.zeros(2, np.int32), np.zeros(n_pts, np.uint8)
+    intr = _f64(intr, (5,))
+    _ck_global(lib, lib.bslam_ransac(int(device), n_hyp, n_min, _i(idx), _d(Tin), n_pts, _d(pts_1), _d(p2), _d(obs_2), _d(intr),
+                                     float(thresh), _d(T_out), _i(counts), _i(best), _b(mask)))
+    return T_out.reshape(n_hyp, 4, 4), counts, int(best[0]), mask.astype(bool)
+
+
+def _level_shapes(w, h, levels):
+    out = []
+    for _ in range(levels):
+        out.append((h, w))
+        w, h = (w + 1) // 2, (h + 1) // 2
+    return out
+
+
+def image_pyramid(image_u8, levels, gradients=True, device=0):
+    """cv2.pyrDown chain of an 8-bit image as float / 255 per level, with 0.5 * Sobel gradients per level
+    (csrc/image.cuh).  Returns (list of images, list of [gradx, grady] arrays or None)."""
+    lib = load_library()
+    im = np.ascontiguousarray(image_u8, dtype=np.uint8)
+    h, w = im.shape
+    shapes = _level_shapes(w, h, levels)
+    total = sum(a * b for a, b in shapes)
+    out = np.empty(total)
+    gx, gy = (np.empty(total), np.empty(total)) if gradients else (None, None)
+    _ck_global(lib, lib.bslam_image_pyramid(int(device), _b(im.ravel()), w, h, int(levels), _d(out), _d(gx), _d(gy)))
+    ims, jac, off = [], [], 0
+    for hh, ww in shapes:
+        n = hh * ww
+        ims.append(out[off:off + n].reshape(hh, ww).copy())
+        if gradients:
+            jac.append(np.array([gx[off:off + n].reshape(hh, ww), gy[off:off + n].reshape(hh, ww)]))
+        off += n
+    return ims, (jac if gradients else None)
+
+
+def subsample_pyramid(depth_map, levels, scale_per_level=1., device=0):
+    """Level l = map[::2^l, ::2^l] * scale_per_level^l (disparity: 0.5; depth: 1)."""
+    lib = load_library()
+    m = np.ascontiguousarray(depth_map, dtype=np.float64)
+    h, w = m.shape
+    shapes = _level_shapes(w, h, levels)
+    out = np.empty(sum(a * b for a, b in shapes))
+    _ck_global(lib, lib.bslam_subsample_pyramid(int(device), _d(m.ravel()), w, h, int(levels), float(scale_per_level), _d(out)))
+    res, off = [], 0
+    for hh, ww in shapes:
+        res.append(out[off:off + hh * ww].reshape(hh, ww).copy())
+        off += hh * ww
+    return res

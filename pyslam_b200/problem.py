@@ -34,11 +34,18 @@ from .lie import group_of
 from .losses import L2Loss, loss_descriptor
 from .residuals.blocks import (BLOCK_POSE, BLOCK_POSE_TO_POSE, BLOCK_REPROJECTION, PoseResidual, PoseToPoseResidual,
                                ReprojectionResidual)
+from .residuals.motion_only import (BLOCK_MOTION_ONLY, BLOCK_MOTION_ONLY_BATCH, BLOCK_ORIENTATION,
+                                    PoseToPoseOrientationResidual, ReprojectionMotionOnlyBatchResidual,
+                                    ReprojectionMotionOnlyResidual)
 from .residuals.photometric import BLOCK_PHOTOMETRIC, PhotometricResidualSE3
+from .sensors.rgbd_camera import RGBDCamera
 from .sensors.stereo_camera import StereoCamera
 
 _BUILTIN_BLOCKS = {BLOCK_REPROJECTION: ReprojectionResidual, BLOCK_POSE: PoseResidual,
-                   BLOCK_POSE_TO_POSE: PoseToPoseResidual, BLOCK_PHOTOMETRIC: PhotometricResidualSE3}
+                   BLOCK_POSE_TO_POSE: PoseToPoseResidual, BLOCK_PHOTOMETRIC: PhotometricResidualSE3,
+                   BLOCK_MOTION_ONLY: ReprojectionMotionOnlyResidual,
+                   BLOCK_MOTION_ONLY_BATCH: ReprojectionMotionOnlyBatchResidual,
+                   BLOCK_ORIENTATION: PoseToPoseOrientationResidual}
 
 
 def _builtin_kind(block):
@@ -56,8 +63,11 @@ def _builtin_camera(camera):
     """A StereoCamera whose projection is the built-in one (a subclass that overrides `project`, e.g. to add
     distortion, keeps the Python plug-in path)."""
     t = type(camera)
-    return (isinstance(camera, StereoCamera) and t.project is StereoCamera.project
-            and getattr(t, 'intrinsics', None) is StereoCamera.intrinsics)
+    for base in (StereoCamera, RGBDCamera):
+        if (isinstance(camera, base) and t.project is base.project and t.triangulate is base.triangulate
+                and getattr(t, 'intrinsics', None) is base.intrinsics):
+            return True
+    return False
 
 
 class Options:
@@ -119,7 +129,10 @@ class _Lowered:
 class Problem:
     """Builds and solves a non-linear least-squares problem (pyslam/problem.py:40)."""
 
-    def __init__(self, options=None):
+    def __init__(self, options=None, engine=None):
+        """`engine` (extension): an existing `pyslam_b200.engine.Engine` handle to lower this problem onto, so that a
+        caller that solves many small problems in a row (the dense pipeline's pyramid loop) creates the device
+        context, stream and buffers once."""
         self.options = options if options is not None else Options()
         self.param_dict = dict()
         self.residual_blocks = []
@@ -130,7 +143,7 @@ class Problem:
         self._covariance_matrix = None
         self._cost_history = []
         self._batches = []
-        self._engine = None
+        self._engine = engine
         self._low = None
         self.last_timings = None
         self._timing = False
@@ -220,11 +233,31 @@ class Problem:
             return g
 
         def fusable_photo(block, keys, loss):
-            return (_builtin_kind(block) == BLOCK_PHOTOMETRIC and len(keys) == 1
-                    and loss_descriptor(loss) is not None and _builtin_camera(block.camera)
-                    and group_of(pd.get(keys[0])) == 'se3')
+            """'se3': single SE3 parameter; 'split': the (SO3, t) form of pipelines/dense.py:185-190; else None."""
+            if (_builtin_kind(block) != BLOCK_PHOTOMETRIC or loss_descriptor(loss) is None
+                    or not _builtin_camera(block.camera)):
+                return None
+            if len(keys) == 1 and group_of(pd.get(keys[0])) == 'se3':
+                return 'se3'
+            if (len(keys) == 2 and keys[0] != keys[1] and group_of(pd.get(keys[0])) == 'so3'
+                    and hasattr(self._engine, 'add_photometric_block_split')):
+                t = pd.get(keys[1])
+                if group_of(t) is None and isinstance(t, np.ndarray) and t.size == 3:
+                    return 'split'
+            return None
 
-        kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('photo',) | ('dense',)
+        def fusable_motion(block, keys, loss):
+            return (_builtin_kind(block) in (BLOCK_MOTION_ONLY, BLOCK_MOTION_ONLY_BATCH) and len(keys) == 1
+                    and hasattr(self._engine, 'add_motion_only_blocks') and loss_descriptor(loss) is not None
+                    and _builtin_camera(block.camera) and group_of(pd.get(keys[0])) == 'se3'
+                    and np.shape(block.stiffness) == (3, 3))
+
+        def fusable_orientation(block, keys, loss):
+            return (_builtin_kind(block) == BLOCK_ORIENTATION and len(keys) == 2
+                    and hasattr(self._engine, 'add_orientation_blocks') and loss_descriptor(loss) is not None
+                    and group_of(block.C_2_1_obs) == 'so3' and all(group_of(pd.get(k)) == 'se3' for k in keys))
+
+        kinds = []      # per block: ('reproj',) | ('pose', g) | ('p2p', g) | ('photo', 'se3' | 'split') | ('dense',)
         point_keys = set()
         for block, keys, loss in zip(self.residual_blocks, self.block_param_keys, self.block_loss_functions):
             for k in keys:
@@ -234,8 +267,15 @@ class Problem:
                 kinds.append(('reproj',))
                 point_keys.add(keys[1])
                 continue
-            if fusable_photo(block, keys, loss):
-                kinds.append(('photo',))
+            ph = fusable_photo(block, keys, loss)
+            if ph:
+                kinds.append(('photo', ph))
+                continue
+            if fusable_motion(block, keys, loss):
+                kinds.append(('motion',))
+                continue
+            if fusable_orientation(block, keys, loss):
+                kinds.append(('orient',))
                 continue
             g = fusable_pose(block, keys, loss, BLOCK_POSE, 1)
             if g:
@@ -254,14 +294,27 @@ class Problem:
                     raise KeyError('Parameter {} has not been initialized'.format(k))
             point_keys.update(bt.point_keys)
 
+        # SO3 parameters live in the library's SO3 table when only fused (SO3, t) photometric blocks use them as
+        # their rotation; any other use keeps the host-side (opaque manifold) path for the key AND its blocks
+        rot_keys = {keys[0] for k, keys in zip(kinds, self.block_param_keys) if k == ('photo', 'split')}
+        for k, keys in zip(kinds, self.block_param_keys):
+            if k != ('photo', 'split'):
+                rot_keys.difference_update(keys)
+        for i, (k, keys) in enumerate(zip(kinds, self.block_param_keys)):
+            if k == ('photo', 'split') and (keys[0] not in rot_keys or keys[1] in point_keys):
+                kinds[i] = ('dense',)
+                rot_keys.discard(keys[0])
+
         # parameter tables, each in param_dict insertion order
         low.table = {}                      # key -> (kind id, index)
-        low.keys = {'se3': [], 'se2': [], 'pt': [], 'vec': []}
+        low.keys = {'se3': [], 'se2': [], 'pt': [], 'vec': [], 'so3': []}
         low.opaque = set()
         for key, p in pd.items():
             g = group_of(p)
             if g in ('se3', 'se2'):
                 name = g
+            elif g == 'so3' and key in rot_keys:
+                name = 'so3'
             elif g is None and key in point_keys:
                 name = 'pt'
             else:
@@ -291,16 +344,41 @@ class Problem:
                 continue
             ld = loss_descriptor(loss)
             if k[0] == 'photo':
-                eng.add_photometric_block(low.table[keys[0]][1], block.uvd_ref, block.im_ref, block.im_jac, block.im_track,
-                                          block.camera.intrinsics(), block.intensity_stiffness, block.depth_stiffness,
-                                          ld[0], ld[1])
+                args = (block.uvd_ref, block.im_ref, block.im_jac, block.im_track, block.camera.intrinsics(),
+                        block.intensity_stiffness, block.depth_stiffness, ld[0], ld[1])
+                if k[1] == 'split':
+                    eng.add_photometric_block_split(low.table[keys[0]][1], low.table[keys[1]][1], *args)
+                else:
+                    eng.add_photometric_block(low.table[keys[0]][1], *args)
                 continue
-            if k[0] == 'reproj':
+            if k[0] == 'motion':
+                # blocks on the same pose with the same camera / stiffness / loss are concatenated into one batch
+                gk = ('motion', ld, tuple(block.camera.intrinsics()), keys[0],
+                      tuple(np.asarray(block.stiffness, dtype=float).ravel()))
+            elif k[0] == 'orient':
+                gk = ('orient', ld)
+            elif k[0] == 'reproj':
                 gk = ('reproj', ld, tuple(block.camera.intrinsics()))
             else:
                 gk = (k[0], k[1], ld)
             groups.setdefault(gk, []).append(i)
         for gk, ids in groups.items():
+            if gk[0] == 'motion':
+                blocks = [self.residual_blocks[i] for i in ids]
+                pts = np.vstack([np.atleast_2d(b.pts_1 if hasattr(b, 'pts_1') else b.pt_1) for b in blocks])
+                obs = np.vstack([np.atleast_2d(np.asarray(b.obs_2, dtype=float)) for b in blocks])
+                eng.add_motion_only_blocks(low.table[gk[3]][1], pts, obs, np.array(gk[4]).reshape(3, 3), gk[2],
+                                           gk[1][0], gk[1][1])
+                continue
+            if gk[0] == 'orient':
+                i1 = [low.table[self.block_param_keys[i][0]][1] for i in ids]
+                i2 = [low.table[self.block_param_keys[i][1]][1] for i in ids]
+                C = np.array([np.asarray(self.residual_blocks[i].C_2_1_obs.mat, dtype=float).ravel() for i in ids])
+                S = np.array([np.asarray(self.residual_blocks[i].stiffness, dtype=float).reshape(3, 3) for i in ids])
+                if np.all(S == S[0]):
+                    S = S[0]
+                eng.add_orientation_blocks(i1, i2, C, S, gk[1][0], gk[1][1])
+                continue
             if gk[0] == 'reproj':
                 pose_idx = [low.table[self.block_param_keys[i][0]][1] for i in ids]
                 pt_idx = [low.table[self.block_param_keys[i][1]][1] for i in ids]
@@ -389,6 +467,9 @@ class Problem:
             eng.set_poses_se3(np.array([_pose_row(pd[k], 3) for k in ks['se3']]).reshape(-1, 12), flags(ks['se3']))
         if ks['se2'] or structure:
             eng.set_poses_se2(np.array([_pose_row(pd[k], 2) for k in ks['se2']]).reshape(-1, 6), flags(ks['se2']))
+        if ks['so3'] or (structure and hasattr(eng, 'set_rotations_so3')):
+            eng.set_rotations_so3(np.array([np.asarray(pd[k].mat, dtype=float).ravel() for k in ks['so3']]).reshape(-1, 9),
+                                  flags(ks['so3']))
         if ks['pt'] or structure:
             eng.set_points(np.array([np.asarray(pd[k], dtype=float).reshape(3) for k in ks['pt']]).reshape(-1, 3),
                            flags(ks['pt']))
@@ -414,6 +495,10 @@ class Problem:
                 if k not in const:
                     pd[k].rot.mat = row[:4].reshape(2, 2).copy()
                     pd[k].trans = row[4:].copy()
+        if ks['so3']:
+            for k, row in zip(ks['so3'], eng.get_rotations_so3()):
+                if k not in const:
+                    pd[k].mat = row.reshape(3, 3).copy()
         if ks['pt']:
             for k, row in zip(ks['pt'], eng.get_points()):
                 if k not in const:

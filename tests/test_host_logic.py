@@ -231,12 +231,12 @@ def test_photometric_lowering_and_dense_options():
     g = load_golden('photometric')
     pr, _ = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
     pr.solve()
-    assert pr._low.kinds == [('photo',)] and pr._engine.photo_b
+    assert pr._low.kinds == [('photo', 'se3')] and pr._engine.photo_b
     assert len(pr._cost_history) - 1 == int(g['n_iters'])
     np.testing.assert_allclose(pr._cost_history, g['cost_history'], rtol=1e-7)
     assert pr._cost_history[0] == pr._cost_history[1]
     assert rel_err(B.rows_of([pr.param_dict['T_1_0']])[0], g['T_final']) < 1e-7
-    # the (SO3, t) two-parameter form is not a GPU batch: it must fall back to the plug-in path
+    # the (SO3, t) two-parameter form on an engine without bslam_add_photometric_block_split (this test double): plug-in path
     from pyslam_b200.lie import SE3
     pr2, res = B.product_photometric_problem(g, min_grad=float(g['min_grad']))
     pr2.residual_blocks, pr2.block_param_keys, pr2.block_loss_functions = [], [], []
