@@ -32,6 +32,7 @@
 // fp64 factorisation can use on sm_100a.
 #pragma once
 #include "common.cuh"
+#include "lie.cuh"
 
 namespace bs {
 
@@ -82,6 +83,14 @@ struct CholPlan {
   // Landmark-sharded iteration (peer.cuh): S = sum over the ranks of their partial Schur complements.  The sum is
   // never formed in memory: a tile task reads its own tile as  sum_r peer_pack[r][slot]  straight from the ranks'
   // exchange regions (mapped peer memory over NVLink), in rank order, and writes L into the private S.
+  // Fused retraction (iteration path of pure panel problems): the backward task of tile k applies T <- exp(xi) T to the SE3
+  // poses whose tangent block lies in tile k as soon as x_k is known, and adds ||x_k||^2 to scalars[DX_NORM2]; the
+  // separate retraction kernel and its launch disappear from the iteration.  rt_poses == nullptr: off.
+  double* rt_poses;            // [K][12] SE3 table
+  const int* rt_pose_off;      // [K] reduced offsets
+  const int* rt_tile_ptr;      // [nt + 1] CSR: poses per tile
+  const int* rt_tile_pose;
+  int rt_norm;                 // add ||x||^2 (the replicated reduced part is counted on shard 0 only)
   int world;             // 1: single GPU, the own tile comes from S
   int rhs_off;           // offset of the right-hand side inside a packed payload (= n_nz_tiles * kNB * kNB)
   const double* peer_pack[kCholMaxPeers];
@@ -545,8 +554,26 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
 #pragma unroll
         for (int q = 0; q < kG; ++q) sum += sred[q * kNB + c];
         x[(size_t)k * kNB + c] = sum;
+        scol[c] = sum;
       }
       post_flag(p.xready + k, epoch);
+      if (p.rt_poses) {                      // off the dependency chain: the flag is already posted
+        const int q0 = p.rt_tile_ptr[k], np = p.rt_tile_ptr[k + 1] - q0;
+        if (tid < np) {
+          const int pi = p.rt_tile_pose[q0 + tid];
+          const int o = p.rt_pose_off[pi] - k * kNB;
+          double xi[6];
+#pragma unroll
+          for (int e = 0; e < 6; ++e) xi[e] = scol[o + e];
+          double* P = p.rt_poses + 12 * (size_t)pi;
+          se3_store(P, se3_mul(se3_exp(xi), se3_load(P)));
+        }
+        if (p.rt_norm && tid >= 32 && tid < 64) {
+          const double v = scol[tid - 32];
+          const double ss = warp_sum(v * v);
+          if (tid == 32 && ss != 0.0) red_add(scalars + 2 /*DX_NORM2*/, ss);
+        }
+      }
     }
     if (p.trace && tid == 0) {
       unsigned smid;
@@ -584,6 +611,7 @@ struct PrepareArgs {
   const int* slot_pose;
   const double* poses;
   double* slot_poses;
+  double* poses_prev; int n_prev;   // copy of the SE3 table at the linearisation point (panel_finish_kernel re-linearises there)
 };
 __global__ void __launch_bounds__(256) prepare_kernel(const PrepareArgs a) {
   if ((int)blockIdx.x < a.n_tiles) {
@@ -603,6 +631,7 @@ __global__ void __launch_bounds__(256) prepare_kernel(const PrepareArgs a) {
   for (int e = t0; e < a.n_rhs; e += stride) a.rhs[e] = 0.0;
   for (int e = t0; e < a.n_vg_tail; e += stride) a.vg_tail[e] = 0.0;
   for (int e = t0; e < 12 * a.n_slot_entries; e += stride) a.slot_poses[e] = a.poses[12 * (size_t)a.slot_pose[e / 12] + e % 12];
+  for (int e = t0; e < a.n_prev; e += stride) a.poses_prev[e] = a.poses[e];
 }
 
 // gather (unpack == 0) / scatter (unpack != 0) the listed tiles between S and a contiguous buffer

@@ -146,7 +146,7 @@ struct bslam_solver {
   int max_slots = 1;
   int n_slot_entries = 0, stage_len = 0;
   DevBuf<bs::LmBlock> d_blocks;
-  DevBuf<int> d_slot_pose;
+  DevBuf<int> d_slot_pose, d_tile_pose_ptr, d_tile_pose;     // tile of the reduced system -> SE3 poses inside it (fused retraction)
   DevBuf<unsigned char> d_lm_obs_local, d_seg_start;
   DevBuf<bs::ReprojGroup> d_groups;
   DevBuf<double> d_W, d_Vg, d_Vinv, d_red, d_dx, d_Linv;
@@ -462,7 +462,8 @@ int do_linearize(bslam_solver* s, bool panels) {
     a.vg_tail = s->d_Vg.p + 9 * (size_t)s->n_regular; a.n_vg_tail = 9 * (s->n_lm - s->n_regular);
     a.n_slot_entries = nb > 0 ? s->n_slot_entries : 0;
     a.slot_pose = s->d_slot_pose.p; a.poses = s->d_se3.p; a.slot_poses = s->d_slot_poses.p;
-    const int work = std::max(std::max(a.n_rhs, a.n_vg_tail), 12 * a.n_slot_entries);
+    a.poses_prev = s->d_se3_prev.p; a.n_prev = panels && s->n_panels > 0 ? 12 * s->n_se3 : 0;
+    const int work = std::max(std::max(std::max(a.n_rhs, a.n_vg_tail), 12 * a.n_slot_entries), a.n_prev);
     LAUNCH(s, bs::prepare_kernel, s->n_dirty_tiles + std::max(1, cdiv(work, 256)), 256, 0, a);   // one element per thread: all gathers in flight at once
   }
   record(s, 1);
@@ -743,7 +744,12 @@ int build_chol_plan(bslam_solver* s) {
   return BSLAM_OK;
 }
 
-int do_solve_reduced(bslam_solver* s) {
+// iteration path of pure panel problems: the Cholesky kernel's backward tasks retract the SE3 poses themselves
+bool fuse_retract(bslam_solver* s, bool panels) {
+  return panels && s->n_panels > 0 && s->n_lmblocks == s->nb_fused && s->n_se3 > 0 && s->d_trace.p == nullptr;
+}
+
+int do_solve_reduced(bslam_solver* s, bool retract_poses = false) {
   if (!s->plan_valid) {
     int rc = build_chol_plan(s);
     if (rc) return rc;
@@ -755,6 +761,9 @@ int do_solve_reduced(bslam_solver* s) {
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
   p.cready = s->d_cready.p; p.cscr = s->d_cscr.p;
   p.trace = s->d_trace.p;
+  p.rt_poses = retract_poses ? s->d_se3.p : nullptr;
+  p.rt_pose_off = s->d_se3_off.p; p.rt_tile_ptr = s->d_tile_pose_ptr.p; p.rt_tile_pose = s->d_tile_pose.p;
+  p.rt_norm = s->shard_rank == 0 ? 1 : 0;
   p.world = s->world;
   p.rhs_off = s->n_nz_tiles * bs::kNB * bs::kNB;
   for (int r = 0; r < bs::kCholMaxPeers; ++r) p.peer_pack[r] = r < s->world ? s->peer_region[r] : nullptr;
@@ -775,18 +784,18 @@ int do_solve_reduced(bslam_solver* s) {
   return BSLAM_OK;
 }
 
-int do_retract(bslam_solver* s, int eval_new_cost, bool panels) {
+// poses_done: the SE3 table was already retracted (and ||dx_c||^2 accumulated) by the Cholesky kernel (fuse_retract)
+int do_retract(bslam_solver* s, int eval_new_cost, bool panels, bool poses_done = false) {
   const double* dx = s->d_dx.p;
   // ||dx||^2: the reduced part is replicated across shards, count it on shard 0 only
   const int n_red_here = s->shard_rank == 0 ? s->n_red : 0;
   const int b0 = panels ? s->nb_fused : 0;
   const int nb = s->n_lmblocks - b0;
   const bool use_panels = panels && s->n_panels > 0;
-  if (s->n_se3 > 0) {
+  if (s->n_se3 > 0 && !poses_done) {
     const int n_slots = nb > 0 ? s->n_slot_entries : 0;
     LAUNCH(s, bs::retract_se3_slots_kernel, cdiv(s->n_se3 + n_slots, 128), 128, 0, s->n_se3, s->d_se3.p, s->d_se3_off.p, dx, n_slots,
-           s->d_slot_off.p, s->d_slot_poses.p, s->d_slot_dx.p, n_red_here, s->scalars() + BSLAM_S_DX_NORM2,
-           use_panels ? s->d_se3_prev.p : nullptr);
+           s->d_slot_off.p, s->d_slot_poses.p, s->d_slot_dx.p, n_red_here, s->scalars() + BSLAM_S_DX_NORM2, nullptr);
   }
   if (s->n_se2 > 0) LAUNCH(s, bs::retract_poses_kernel<2>, cdiv(s->n_se2, 128), 128, 0, s->n_se2, s->d_se2.p, s->d_se2_off.p, dx);
   if (s->n_so3 > 0) LAUNCH(s, bs::retract_so3_kernel, cdiv(s->n_so3, 128), 128, 0, s->n_so3, s->d_so3.p, s->d_so3_off.p, dx);
@@ -1761,6 +1770,17 @@ int bslam_finalize(bslam_solver* s) {
   for (int q = 0; q < s->n_lm; ++q) s->pt_off_user[s->pt_iperm[q]] = s->n_red + 3 * q;
   s->dim = s->n_red + 3 * s->n_lm;
 
+  {   // tile of the reduced system -> SE3 poses whose tangent block starts inside it (a block never straddles tiles)
+    std::vector<int> ptr(s->nblk + 1, 0), idx;
+    for (int i = 0; i < s->n_se3; ++i) if (s->se3_off[i] >= 0) ptr[s->se3_off[i] / bs::kNB + 1]++;
+    for (int t = 0; t < s->nblk; ++t) ptr[t + 1] += ptr[t];
+    idx.assign(std::max(1, ptr[s->nblk]), 0);
+    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+    for (int i = 0; i < s->n_se3; ++i) if (s->se3_off[i] >= 0) idx[cur[s->se3_off[i] / bs::kNB]++] = i;
+    CU(upload(s->d_tile_pose_ptr, ptr, s->stream));
+    CU(upload(s->d_tile_pose, idx, s->stream));
+  }
+
   // ---- observations sorted by internal point index (stable) ----
   std::vector<int> order(N);
   std::iota(order.begin(), order.end(), 0);
@@ -2227,8 +2247,8 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
       int r = do_linearize(s, true);
       if (!r) r = do_reduce(s, lambda, true);
       if (!r && s->world > 1) r = do_peer_publish(s);
-      if (!r) r = do_solve_reduced(s);
-      if (!r) r = do_retract(s, eval_new_cost, true);
+      if (!r) r = do_solve_reduced(s, fuse_retract(s, true));
+      if (!r) r = do_retract(s, eval_new_cost, true, fuse_retract(s, true));
       if (!r && s->world > 1) r = do_peer_scalars(s);
       if (!r && cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost,
                                 s->stream) != cudaSuccess)
@@ -2239,8 +2259,8 @@ static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
   if ((rc = do_linearize(s, true))) return rc;
   if ((rc = do_reduce(s, lambda, true))) return rc;
   if (s->world > 1 && (rc = do_peer_publish(s))) return rc;
-  if ((rc = do_solve_reduced(s))) return rc;
-  if ((rc = do_retract(s, eval_new_cost, true))) return rc;
+  if ((rc = do_solve_reduced(s, fuse_retract(s, true)))) return rc;
+  if ((rc = do_retract(s, eval_new_cost, true, fuse_retract(s, true)))) return rc;
   if (s->world > 1 && (rc = do_peer_scalars(s))) return rc;
   CU(cudaMemcpyAsync(s->h_scalars, s->scalars(), BSLAM_N_SCALARS * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   return BSLAM_OK;
@@ -2443,8 +2463,8 @@ int bslam_iterate_post(bslam_solver* s, int eval_new_cost) {
   if ((rc = prepare_iterate(s))) return rc;
   auto body = [&]() {
     int r = do_pack(s, 1);
-    if (!r) r = do_solve_reduced(s);
-    if (!r) r = do_retract(s, eval_new_cost, true);
+    if (!r) r = do_solve_reduced(s, fuse_retract(s, true));
+    if (!r) r = do_retract(s, eval_new_cost, true, fuse_retract(s, true));
     return r;
   };
   if (s->use_graph && !s->timing && s->dn_blocks == 0 && s->d_trace.p == nullptr) {
