@@ -407,119 +407,112 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
 }
 
 // ---- the tail of the iteration for panels -------------------------------------------------------
-// dx_p = V^-1 (b_p - sum_a W_a^T dx_a) with W_a^T dx_a = (M R)^T (d rho + B d phi) RECOMPUTED from the
-// observation, the pose and the point at the linearisation point (poses = table before retraction,
-// pts = not yet updated) -- ~250 flop per observation instead of a 144-byte read of W; then
-// p <- p + dx_p, ||dx_p||^2, and the cost at the new point with the retracted poses.
+// dx_p = V^-1 (b_p - sum_a W_a^T dx_a) with W_a^T dx_a = R^T (M e), e = d rho + B d phi RECOMPUTED from the
+// observation, the pose and the point at the linearisation point (poses_prev = table before retraction, pts = not
+// yet updated) -- ~150 flop per observation instead of a 144-byte read of W; then p <- p + dx_p, ||dx_p||^2, and the
+// cost at the new point with the retracted poses.
 //
-// Warp-autonomous: the unit of work is a CHUNK of 4 landmarks of a panel, lane = (row = lane / 4,
-// landmark = lane % 4).  The sum over the poses of a landmark is three xor-shuffles; there is no shared
-// memory and no block barrier, chunks are dealt round-robin to all resident warps, and the inputs of a
-// warp's next chunk are requested before the current one is computed.
+// Warp-autonomous, no shared memory, no barrier, no shuffle: the unit of work is HALF a panel, lane = landmark,
+// and the lane walks the panel's rows (poses) itself -- the observations of a row are one coalesced 256-byte read
+// per array, the pose and its update are warp-uniform (L1 broadcasts), the sum over the poses of a landmark stays in
+// registers.  All observations of a unit are requested before the first is used; units are dealt round-robin to the
+// resident warps.
 constexpr int kFinishThreads = 128;
-constexpr int kChunkLm = 4;
-constexpr int kChunksPerPanel = kPanelLm / kChunkLm;
+constexpr int kUnitsPerPanel = kPanelLm / 32;
 
 template <int kLoss>
-__global__ void __launch_bounds__(kFinishThreads, 4) panel_finish_kernel(const PanelArgs a) {
+__global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const PanelArgs a) {
   __shared__ double sred[2 * (kFinishThreads / 32)];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = lane >> 2, m = lane & 3;
   const int n_warps = gridDim.x * (kFinishThreads / 32);
-  const int n_units = a.n_panels * kChunksPerPanel;
+  const int n_units = a.n_panels * kUnitsPerPanel;
   double cost = 0.0, dx2 = 0.0;
 
-  struct In {            // everything a chunk reads from HBM, as loaded
-    double u, v, d, X[3];
-    int pose, off, present, valid, grp;
-  };
-  auto fetch = [&](int unit, In& in) {
-    in.u = in.v = in.d = 0.0; in.X[0] = in.X[1] = in.X[2] = 0.0;
-    in.pose = 0; in.off = -1; in.present = 0; in.valid = 0; in.grp = 0;
-    if (unit >= n_units) return;
-    const Panel pan = a.panels[unit / kChunksPerPanel];
-    const int j = (unit % kChunksPerPanel) * kChunkLm + m;
-    if (j >= pan.n_lms) return;
-    in.valid = 1;
-    const double* Xg = a.pts_in + 3 * (size_t)(pan.lm_begin + j);
-    in.X[0] = Xg[0]; in.X[1] = Xg[1]; in.X[2] = Xg[2];
-    if (r >= pan.n_rows) return;
-    const PanelRow row = a.rows[pan.row_begin + r];
-    in.pose = row.pose; in.off = row.off;
-    in.present = (((j < 32 ? row.mask_lo : row.mask_hi) >> (j & 31)) & 1u);
-    if (in.present) {
-      const size_t cell = (size_t)(pan.row_begin + r) * kPanelLm + j;
-      in.u = ld_stream(a.pu + cell); in.v = ld_stream(a.pv + cell); in.d = ld_stream(a.pd + cell);
-      if (kLoss < 0) in.grp = a.pgrp[cell];
+  for (int unit = blockIdx.x * (kFinishThreads / 32) + warp; unit < n_units; unit += n_warps) {
+    const Panel pan = a.panels[unit / kUnitsPerPanel];
+    const int half = unit % kUnitsPerPanel;
+    const int j = 32 * half + lane;
+    if (32 * half >= pan.n_lms) continue;                  // warp-uniform
+    const bool valid = j < pan.n_lms;
+    const size_t q = (size_t)pan.lm_begin + (valid ? j : 0);
+    // everything the unit reads from HBM, requested up front
+    double ou[kPanelRows], ov[kPanelRows], od[kPanelRows];
+    unsigned present = 0;
+#pragma unroll
+    for (int r = 0; r < kPanelRows; ++r) {
+      ou[r] = ov[r] = od[r] = 0.0;
+      if (r < pan.n_rows) {
+        const PanelRow row = a.rows[pan.row_begin + r];
+        const unsigned m = half ? row.mask_hi : row.mask_lo;
+        if (valid && ((m >> lane) & 1u)) {
+          const size_t cell = (size_t)(pan.row_begin + r) * kPanelLm + j;
+          ou[r] = ld_stream(a.pu + cell); ov[r] = ld_stream(a.pv + cell); od[r] = ld_stream(a.pd + cell);
+          present |= 1u << r;
+        }
+      }
     }
-  };
-
-  int unit = blockIdx.x * (kFinishThreads / 32) + warp;
-  In cur, nxt;
-  fetch(unit, cur);
-  for (; unit < n_units; unit += n_warps) {
-    fetch(unit + n_warps, nxt);
-    const Panel pan = a.panels[unit / kChunksPerPanel];
-    const int j = (unit % kChunksPerPanel) * kChunkLm + m;
-    const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[cur.grp];
-    // ---- W^T dx_c of this cell
+    double X[3] = {0.0, 0.0, 0.0}, bp[3] = {0.0, 0.0, 0.0}, vi[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { X[k] = a.pts_in[3 * q + k]; bp[k] = ld_stream(a.Vg + 9 * q + 6 + k); }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * q + k);
+    }
+    // ---- sum over the rows of W^T dx_c
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-    if (cur.present && cur.off >= 0) {
-      double P[12], dxa[6];
-      const double* Pg = a.poses + 12 * (size_t)cur.pose;
+#pragma unroll
+    for (int r = 0; r < kPanelRows; ++r) {
+      if (r >= pan.n_var) break;                           // constant poses carry no update (rows: variable poses first)
+      const PanelRow row = a.rows[pan.row_begin + r];      // warp-uniform
+      if (!((present >> r) & 1u)) continue;
+      const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[(size_t)(pan.row_begin + r) * kPanelLm + j]];
+      double P[12], dxa[6], M[6], x, y, z;
+      const double* Pg = a.poses + 12 * (size_t)row.pose;
 #pragma unroll
       for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dxa[k] = __ldg(a.dx_red + cur.off + k);
-      ReprojBlocks o;
-      reproj_blocks<kLoss>(grp, P, cur.X, cur.u, cur.v, cur.d, o);
+      for (int k = 0; k < 6; ++k) dxa[k] = __ldg(a.dx_red + row.off + k);
+      reproj_M<kLoss>(grp, P, X, ou[r], ov[r], od[r], M, x, y, z);
       // e = d rho + B d phi,  B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
-      const double e0 = dxa[0] + o.z * dxa[4] - o.y * dxa[5];
-      const double e1 = dxa[1] - o.z * dxa[3] + o.x * dxa[5];
-      const double e2 = dxa[2] + o.y * dxa[3] - o.x * dxa[4];
-      c0 = o.MR[0] * e0 + o.MR[3] * e1 + o.MR[6] * e2;
-      c1 = o.MR[1] * e0 + o.MR[4] * e1 + o.MR[7] * e2;
-      c2 = o.MR[2] * e0 + o.MR[5] * e1 + o.MR[8] * e2;
+      const double e0 = dxa[0] + z * dxa[4] - y * dxa[5];
+      const double e1 = dxa[1] - z * dxa[3] + x * dxa[5];
+      const double e2 = dxa[2] + y * dxa[3] - x * dxa[4];
+      const double f0 = M[0] * e0 + M[1] * e1 + M[2] * e2;
+      const double f1 = M[1] * e0 + M[3] * e1 + M[4] * e2;
+      const double f2 = M[2] * e0 + M[4] * e1 + M[5] * e2;
+      c0 += P[0] * f0 + P[3] * f1 + P[6] * f2;
+      c1 += P[1] * f0 + P[4] * f1 + P[7] * f2;
+      c2 += P[2] * f0 + P[5] * f1 + P[8] * f2;
     }
-    // ---- sum over the rows (lane bits 2..4), every lane gets the total
-#pragma unroll
-    for (int h = 4; h < 32; h <<= 1) {
-      c0 += __shfl_xor_sync(0xffffffffu, c0, h);
-      c1 += __shfl_xor_sync(0xffffffffu, c1, h);
-      c2 += __shfl_xor_sync(0xffffffffu, c2, h);
-    }
-    // ---- back-substitution and retraction (row 0 of every landmark), new point to all rows
-    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-    if (r == 0 && cur.valid) {
-      const size_t q = (size_t)pan.lm_begin + j;
-      const double s0 = ld_stream(a.Vg + 9 * q + 6) - c0, s1 = ld_stream(a.Vg + 9 * q + 7) - c1, s2 = ld_stream(a.Vg + 9 * q + 8) - c2;
-      double vi[6];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * q + k);
+    // ---- back-substitution and retraction
+    double Xn[3] = {0.0, 0.0, 0.0};
+    if (valid) {
+      const double s0 = bp[0] - c0, s1 = bp[1] - c1, s2 = bp[2] - c2;
       const double d0 = vi[0] * s0 + vi[1] * s1 + vi[2] * s2;
       const double d1 = vi[1] * s0 + vi[3] * s1 + vi[4] * s2;
       const double d2 = vi[2] * s0 + vi[4] * s1 + vi[5] * s2;
       a.dx_lm[3 * q] = d0; a.dx_lm[3 * q + 1] = d1; a.dx_lm[3 * q + 2] = d2;
       dx2 += d0 * d0 + d1 * d1 + d2 * d2;
-      n0 = cur.X[0] + d0; n1 = cur.X[1] + d1; n2 = cur.X[2] + d2;
-      a.pts[3 * q] = n0; a.pts[3 * q + 1] = n1; a.pts[3 * q + 2] = n2;
+      Xn[0] = X[0] + d0; Xn[1] = X[1] + d1; Xn[2] = X[2] + d2;
+      a.pts[3 * q] = Xn[0]; a.pts[3 * q + 1] = Xn[1]; a.pts[3 * q + 2] = Xn[2];
     }
-    n0 = __shfl_sync(0xffffffffu, n0, m);
-    n1 = __shfl_sync(0xffffffffu, n1, m);
-    n2 = __shfl_sync(0xffffffffu, n2, m);
-    // ---- cost at the new point
-    if (a.eval_cost && cur.present) {
-      double P[12];
-      const double* Pg = a.poses_new + 12 * (size_t)cur.pose;
+    // ---- cost at the new point (all rows, constant poses included)
+    if (a.eval_cost) {
 #pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
-      const double Xn[3] = {n0, n1, n2};
-      double rr[3];
-      reproj_residual_only(grp, P, Xn, cur.u, cur.v, cur.d, rr);
+      for (int r = 0; r < kPanelRows; ++r) {
+        if (r >= pan.n_rows) break;
+        if (!((present >> r) & 1u)) continue;
+        const PanelRow row = a.rows[pan.row_begin + r];
+        const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[(size_t)(pan.row_begin + r) * kPanelLm + j]];
+        double P[12], rr[3];
+        const double* Pg = a.poses_new + 12 * (size_t)row.pose;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, rr[k]);
+        for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
+        reproj_residual_only(grp, P, Xn, ou[r], ov[r], od[r], rr);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, rr[k]);
+      }
     }
-    cur = nxt;
   }
   cost = warp_sum(cost);
   dx2 = warp_sum(dx2);

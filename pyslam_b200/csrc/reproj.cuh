@@ -230,6 +230,41 @@ BS_D void reproj_blocks(const ReprojGroup& g, const double* __restrict__ P, cons
       o.MR[3 * i + j] = Mr[3 * i] * P[j] + Mr[3 * i + 1] * P[3 + j] + Mr[3 * i + 2] * P[6 + j];
 }
 
+// Only what the back-substitution needs of an observation: M = Jc^T Q Jc (xx xy xz yy yz zz) and p_c, so that
+//   W^T dx_c = (M R)^T (d rho + B d phi) = R^T (M e),  e = d rho + B d phi
+// costs one 3x3 symmetric product instead of forming M R.  Same arithmetic for M as reproj_blocks.
+template <int kLoss>
+BS_D void reproj_M(const ReprojGroup& g, const double* __restrict__ P, const double* __restrict__ X, double u, double v, double d,
+                   double* __restrict__ M, double& x, double& y, double& z) {
+  x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9];
+  y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10];
+  z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
+  const double iz = fast_rcp(z);
+  const double iz2 = iz * iz;
+  const bool stereo = g.b > 0.0;
+  const double e0 = g.fu * x * iz + g.cu - u;
+  const double e1 = g.fv * y * iz + g.cv - v;
+  const double e2 = (stereo ? g.fu * g.b * iz : z) - d;
+  double q00 = 0, q01 = 0, q02 = 0, q11 = 0, q12 = 0, q22 = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double s0 = g.S[3 * k], s1 = g.S[3 * k + 1], s2 = g.S[3 * k + 2];
+    const double r = s0 * e0 + s1 * e1 + s2 * e2;
+    const double w = loss_weight_t<kLoss>(g.loss, r);
+    const double ws0 = w * s0, ws1 = w * s1, ws2 = w * s2;
+    q00 = fma(ws0, s0, q00); q01 = fma(ws0, s1, q01); q02 = fma(ws0, s2, q02);
+    q11 = fma(ws1, s1, q11); q12 = fma(ws1, s2, q12); q22 = fma(ws2, s2, q22);
+  }
+  const double a = g.fu * iz, b = g.fv * iz;
+  const double c0 = -g.fu * x * iz2, c1 = -g.fv * y * iz2, c2 = stereo ? -g.fu * g.b * iz2 : 1.0;
+  const double k02 = c0 * q00 + c1 * q01 + c2 * q02;
+  const double k12 = c0 * q01 + c1 * q11 + c2 * q12;
+  const double k22 = c0 * q02 + c1 * q12 + c2 * q22;
+  M[0] = a * a * q00; M[1] = a * b * q01; M[2] = a * k02;
+  M[3] = b * b * q11; M[4] = b * k12;
+  M[5] = c0 * k02 + c1 * k12 + c2 * k22;
+}
+
 // ---- cp.async helpers (LDGSTS): global -> shared without staging registers -------------------
 BS_D void cp_async8(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -813,7 +813,7 @@ int do_retract(bslam_solver* s, int eval_new_cost, bool panels, bool poses_done 
     bs::PanelArgs pa = panel_args(s, 0.0);
     pa.poses = s->d_se3_prev.p; pa.poses_new = s->d_se3.p; pa.eval_cost = eval_new_cost;
     const size_t smem = 0;
-    const int grid = std::min(cdiv((long long)s->n_panels * bs::kChunksPerPanel, bs::kFinishThreads / 32), s->finish_grid);
+    const int grid = std::min(cdiv((long long)s->n_panels * bs::kUnitsPerPanel, bs::kFinishThreads / 32), s->finish_grid);
     switch (s->loss_kind) {
       case 0: LAUNCH(s, bs::panel_finish_kernel<0>, grid, bs::kFinishThreads, smem, pa); break;
       case 1: LAUNCH(s, bs::panel_finish_kernel<1>, grid, bs::kFinishThreads, smem, pa); break;
