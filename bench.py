@@ -201,12 +201,16 @@ class Timer:
             dist.barrier()
             self.torch.cuda.synchronize()
 
-    def device_ms(self, step, steps):
-        """Sum of the per-step device times (CUDA events on the library's stream)."""
+    def device_ms(self, step, steps, align=None):
+        """Sum of the per-step device times (CUDA events on the library's stream).  `align`: enqueues a device-side
+        rendezvous of the ranks (bslam_peer_barrier) right before the first event, so that every rank starts the
+        step together -- each rank's flush / host synchronisation ends at a slightly different time."""
         ev = [(self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         self.barrier()
         for e0, e1 in ev:
             self.flush()
+            if align is not None:
+                align()
             e0.record(self.stream)
             step()
             e1.record(self.stream)
@@ -306,6 +310,7 @@ def run_ours(args):
         eng.set_points(d['pts0'])
 
     step = lambda: solver.iterate(0., True)
+    align = eng.peer_barrier if solver.mode == 'peer' else None      # ranks start every timed step together
 
     # ---- device-resident: K iterations of Gauss-Newton from the initial guess, `rounds` times ----
     for _ in range(max(3, args.warmup)):
@@ -319,7 +324,7 @@ def run_ours(args):
         reset()
         l0 = eng.launch_count()
         costs = []
-        rounds_ms.append(tm.device_ms(lambda: costs.append(step()), args.steps))
+        rounds_ms.append(tm.device_ms(lambda: costs.append(step()), args.steps, align))
         launches = eng.launch_count() - l0
     ms = float(np.median(rounds_ms))
     ms_per_step = ms / args.steps
@@ -373,7 +378,7 @@ def run_ours(args):
             s30.iterate(0., True)
         e30.set_poses_se3(Rt30); e30.set_points(d30['pts0'])
         tm30 = Timer(torch, e30.torch_stream(), world)
-        ms30 = tm30.device_ms(lambda: s30.iterate(0., True), 20) / 20
+        ms30 = tm30.device_ms(lambda: s30.iterate(0., True), 20, e30.peer_barrier if s30.mode == 'peer' else None) / 20
         series['C4 track 30 (500 kf x 100000 lm x 3000000 obs), %d GPU(s)' % world] = {
             'iterations_per_s': round(1e3 / ms30, 1), 'us_per_iteration': round(1e3 * ms30, 1), 'steps': 20,
             'fused_panels': int(e30.fused_info()[0])}
@@ -415,7 +420,8 @@ def run_ours(args):
                                 '(observations 19 MB, points/V/V^-1 14 MB, reduced tiles 4 MB, updates) would fit the 126 MB L2'
                                 % (FLUSH_BYTES >> 20),
                    'timing': 'per-step CUDA events on the library stream, summed over the K steps, max over ranks; '
-                             'median of %d rounds' % args.rounds,
+                             'median of %d rounds' % args.rounds + ('; N > 1: a device-side rendezvous of the ranks '
+                             '(bslam_peer_barrier) is enqueued before the first event of every step' if align else ''),
                    'reduced_system_dim': 6 * (N_KF - 1), 'fused_panels': int(n_pan), 'fused_landmarks': int(n_fused)},
         'rounds_ms_per_step': [r / args.steps for r in rounds_ms],
         'clocks': clocks,

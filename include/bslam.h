@@ -300,6 +300,17 @@ BSLAM_API int bslam_add_coupling(bslam_solver* s, int group, int n, const int32_
 BSLAM_API int bslam_layout_hash(bslam_solver* s, uint64_t* hash);
 BSLAM_API int bslam_peer_region(bslam_solver* s, void** dev_ptr, size_t* n_bytes, uint8_t* ipc_handle /* 64 bytes */);
 BSLAM_API int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_handles, void* const* dev_ptrs);
+/* The same with caller-provided SYMMETRIC memory (one allocation of >= bslam_peer_region's size per rank, zero-filled,
+ * e.g. torch.distributed._symmetric_memory): region_ptrs[r] = rank r's allocation as mapped in this process (the own
+ * one included -- the handle publishes its partial system there), multicast_ptr = the NVLS multicast mapping of all of
+ * them or NULL.  With a multicast mapping the Cholesky kernel reads every element of sum_r S_r with ONE
+ * multimem.ld_reduce (reduced inside the NVSwitch) instead of one load per rank. */
+BSLAM_API int bslam_peer_connect_symmetric(bslam_solver* s, int world, int rank, void* const* region_ptrs, void* multicast_ptr,
+                                 size_t n_bytes);
+/* Device-side rendezvous of all connected ranks, enqueued on the handle's stream (no host synchronisation): the
+ * kernels enqueued after it start on every rank within a few microseconds of each other (bench.py aligns the ranks
+ * with it before each timed step).  No-op for a single rank. */
+BSLAM_API int bslam_peer_barrier(bslam_solver* s);
 /* bslam_iterate split in two: enqueue the iteration (no synchronisation) / wait for it and read the scalars.
  * Several handles of one process (e.g. the shards of a sharded iteration on different streams) are enqueued
  * first and waited for afterwards. */

@@ -94,7 +94,16 @@ struct CholPlan {
   int world;             // 1: single GPU, the own tile comes from S
   int rhs_off;           // offset of the right-hand side inside a packed payload (= n_nz_tiles * kNB * kNB)
   const double* peer_pack[kCholMaxPeers];
+  const double* mc_pack; // NVLS multicast address of the ranks' exchange regions (symmetric memory), or nullptr: one
+                         // multimem.ld_reduce per element returns the sum over all ranks, reduced inside the NVSwitch
 };
+
+// sum over all ranks of the double at the multicast address (LDGMC.E.ADD.F64: the reduction happens in the switch)
+BS_D double multimem_sum(const double* mc) {
+  double v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc) : "memory");
+  return v;
+}
 
 BS_D void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -415,6 +424,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       } else {
         // fused all-reduce: the tile of the summed matrix, read from every rank's partial sum over NVLink
         const size_t off0 = task.slot == -2 ? (size_t)p.rhs_off + (size_t)tj * kNB : (size_t)task.slot * kNB * kNB;
+        if (p.mc_pack) {
+          acc_foreach([&](int i, int j, int r, int c) {
+            const bool live = r < rows_i && task.slot != -1;
+            const double* src = p.mc_pack + off0 + (size_t)r * kNB + c;
+            own.c[i][j][0] = live ? multimem_sum(src) : 0.0;
+            own.c[i][j][1] = live ? multimem_sum(src + 1) : 0.0;
+          });
+        } else
         acc_foreach([&](int i, int j, int r, int c) {
           double2 part[kCholMaxPeers];
           const bool live = r < rows_i && task.slot != -1;

@@ -101,15 +101,17 @@ __global__ void __launch_bounds__(256) peer_pack_signal_kernel(const double* __r
   if (r < pc.world && !peer_wait(peer_flags(pc.region[pc.rank], pc.pack_len) + r, s_epoch)) scalars[5 /*PEER_TIMEOUT*/] = 1.0;
 }
 
-// one warp
-__global__ void __launch_bounds__(32) peer_scalar_exchange_kernel(double* __restrict__ scalars, const PeerCtx pc) {
+// one warp; with_data == 0: rendezvous only (bslam_peer_barrier)
+__global__ void __launch_bounds__(32) peer_scalar_exchange_kernel(double* __restrict__ scalars, const PeerCtx pc, int with_data) {
   const int r = threadIdx.x;
   long long e = 0;
   if (r == 0) e = ++pc.ctl[1];
   e = __shfl_sync(0xffffffffu, e, 0);
   if (r < pc.world) {
-    double* mb = pc.region[r] + pc.pack_len + kXchgMailbox * pc.rank;
-    mb[0] = scalars[0]; mb[1] = scalars[1]; mb[2] = scalars[2];
+    if (with_data) {
+      double* mb = pc.region[r] + pc.pack_len + kXchgMailbox * pc.rank;
+      mb[0] = scalars[0]; mb[1] = scalars[1]; mb[2] = scalars[2];
+    }
     __threadfence_system();
     st_release_sys(peer_flags(pc.region[r], pc.pack_len) + kMaxPeers + pc.rank, e);
   }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(32) peer_scalar_exchange_kernel(double* __rest
   if (r < pc.world) ok = peer_wait(peer_flags(pc.region[pc.rank], pc.pack_len) + kMaxPeers + r, e);
   if (!ok) scalars[5 /*PEER_TIMEOUT*/] = 1.0;
   __syncwarp();
-  if (r < 3) {                 // lane r sums scalar r over the ranks, in rank order (identical on every rank)
+  if (with_data && r < 3) {    // lane r sums scalar r over the ranks, in rank order (identical on every rank)
     const double* mb = pc.region[pc.rank] + pc.pack_len + r;
     double s = 0.0;
     for (int q = 0; q < pc.world; ++q) s += __ldcg(mb + kXchgMailbox * q);

@@ -201,6 +201,7 @@ struct bslam_solver {
   int world = 1;
   double* peer_region[bs::kMaxPeers] = {};
   bool peer_opened[bs::kMaxPeers] = {};
+  double* mc_region = nullptr;                     // NVLS multicast mapping of the regions (bslam_peer_connect_symmetric)
   DevBuf<long long> d_peer_ctl;
 
   double* S() { return d_red.p; }
@@ -767,6 +768,7 @@ int do_solve_reduced(bslam_solver* s, bool retract_poses = false) {
   p.world = s->world;
   p.rhs_off = s->n_nz_tiles * bs::kNB * bs::kNB;
   for (int r = 0; r < bs::kCholMaxPeers; ++r) p.peer_pack[r] = r < s->world ? s->peer_region[r] : nullptr;
+  p.mc_pack = s->world > 1 ? s->mc_region : nullptr;
   // no per-launch memsets: the flags carry the launch epoch, which the kernel advances itself
   LAUNCH(s, bs::chol_solve_kernel, s->chol_grid, bs::kCholThreads, bs::kCholSmem, s->S(), s->n_pad, s->d_Linv.p,
          s->d_dx.p, s->scalars(), p);
@@ -932,7 +934,7 @@ int do_peer_publish(bslam_solver* s) {
 
 // sharded iteration, end: sum the partial scalars over the ranks (and order the next iteration after the peers' reads)
 int do_peer_scalars(bslam_solver* s) {
-  LAUNCH(s, bs::peer_scalar_exchange_kernel, 1, 32, 0, s->scalars(), peer_ctx(s));
+  LAUNCH(s, bs::peer_scalar_exchange_kernel, 1, 32, 0, s->scalars(), peer_ctx(s), 1);
   CU(cudaGetLastError());
   return BSLAM_OK;
 }
@@ -1379,6 +1381,7 @@ int bslam_clear_blocks(bslam_solver* s) {
     s->peer_opened[r] = false;
     s->peer_region[r] = nullptr;
   }
+  s->mc_region = nullptr;
   s->world = 1;
   drop_graph(s);
   s->finalized = false;
@@ -1449,13 +1452,22 @@ int bslam_finalize(bslam_solver* s) {
     for (int i = 0; i < N; ++i) obs_ids[cur[s->ob_pt[i]]++] = i;
   }
   if (s->fused_mode > 0 && s->groups.size() < 65536) {
+    // Panel capacity: 64 landmarks, or 32 when that many panels would not fill the GPU twice over (a landmark shard of
+    // a multi-GPU problem): a panel is one CTA's unit of work and its latency, not its throughput, bounds a small grid.
+    // Two passes: panels only where the grid is well filled; if only a few landmarks are left over, they are packed
+    // into (sparser / shorter) panels as well, so that the iteration does not pay the whole landmark-block path
+    // (three more kernels and a separate retraction) for a handful of landmarks.
+    const size_t cap = regular.size() / bs::kPanelLm < 4 * 296 ? 32 : (size_t)bs::kPanelLm;
     std::vector<int> fused_lms, irregular, poses, trial;
+    for (int pass = 0; pass < 2; ++pass) {
+    const bool accept_all = s->fused_mode >= 2 || pass == 1;
+    fused_lms.clear(); irregular.clear(); hpanels.clear();
     size_t q = 0;
     while (q < regular.size()) {
       poses.clear();
       size_t q1 = q;
       long long n_cells = 0;
-      while (q1 < regular.size() && q1 - q < (size_t)bs::kPanelLm) {
+      while (q1 < regular.size() && q1 - q < cap) {
         trial = poses;
         const int p = regular[q1];
         for (int k = obs_ptr[p]; k < obs_ptr[p + 1]; ++k) {
@@ -1474,7 +1486,7 @@ int bslam_finalize(bslam_solver* s) {
       }
       const int n_lms = (int)(q1 - q);
       const bool dense = n_lms >= 16 && 2 * n_cells >= (long long)poses.size() * n_lms;
-      if (s->fused_mode >= 2 || dense) {
+      if (accept_all || dense) {
         HostPanel hp;
         hp.first = (int)fused_lms.size(); hp.n_lms = n_lms;
         std::sort(poses.begin(), poses.end());
@@ -1487,6 +1499,9 @@ int bslam_finalize(bslam_solver* s) {
         irregular.insert(irregular.end(), regular.begin() + q, regular.begin() + q1);
       }
       q = q1;
+    }
+    // second pass only when the first left a small remainder (<= 10 % of the landmarks) outside the panels
+    if (accept_all || irregular.empty() || 10 * irregular.size() > regular.size()) break;
     }
     s->n_fused = (int)fused_lms.size();
     regular.swap(fused_lms);
@@ -2353,6 +2368,7 @@ int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_
   if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
   CU(cudaStreamSynchronize(s->stream));
   for (int r = 0; r < world; ++r) {
+    s->mc_region = nullptr;
     if (r == rank) { s->peer_region[r] = s->d_pack.p; continue; }
     if (dev_ptrs && dev_ptrs[r]) { s->peer_region[r] = static_cast<double*>(dev_ptrs[r]); continue; }
     NEED(ipc_handles, "bslam_peer_connect: no handle for rank %d", r);
@@ -2370,6 +2386,37 @@ int bslam_peer_connect(bslam_solver* s, int world, int rank, const uint8_t* ipc_
   s->world = world;
   s->shard_rank = rank;
   drop_graph(s);
+  return BSLAM_OK;
+}
+
+int bslam_peer_connect_symmetric(bslam_solver* s, int world, int rank, void* const* region_ptrs, void* multicast_ptr, size_t n_bytes) {
+  NEED(s && s->finalized, "bslam_peer_connect_symmetric: solver not finalized");
+  NEED(world >= 2 && world <= bs::kMaxPeers && rank >= 0 && rank < world && region_ptrs, "bslam_peer_connect_symmetric: bad arguments");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  NEED(n_bytes >= s->d_pack.n * sizeof(double), "bslam_peer_connect_symmetric: regions of %zu bytes, need %zu", n_bytes,
+       s->d_pack.n * sizeof(double));
+  for (int r = 0; r < world; ++r) {
+    NEED(region_ptrs[r], "bslam_peer_connect_symmetric: no region for rank %d", r);
+    s->peer_region[r] = static_cast<double*>(region_ptrs[r]);       // the own region too: the caller's symmetric allocation
+  }
+  s->mc_region = static_cast<double*>(multicast_ptr);
+  preload_iteration_kernels(s);
+  CU(s->d_peer_ctl.alloc(4));
+  CU(cudaMemsetAsync(s->d_peer_ctl.p, 0, 4 * sizeof(long long), s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->world = world;
+  s->shard_rank = rank;
+  drop_graph(s);
+  return BSLAM_OK;
+}
+
+int bslam_peer_barrier(bslam_solver* s) {
+  NEED(s && s->finalized, "bslam_peer_barrier: solver not finalized");
+  if (s->world <= 1) return BSLAM_OK;
+  CU(cudaSetDevice(s->device));
+  LAUNCH(s, bs::peer_scalar_exchange_kernel, 1, 32, 0, s->scalars(), peer_ctx(s), 0);
+  CU(cudaGetLastError());
   return BSLAM_OK;
 }
 

@@ -27,6 +27,8 @@ double of tests/test_dist_gloo.py.
 The reference has no distributed path at all; this is the B200-native replacement for the
 single-process `spsolve` on the full system.
 """
+import os
+
 import numpy as np
 
 
@@ -136,6 +138,11 @@ class ShardedSolver:
                 raise RuntimeError('ranks derived different reduced-system layouts (%s): every rank must declare the pose '
                                    'couplings of all shards before finalize (build_sharded_ba does)' % hashes)
         if mode == 'peer':
+            # 1) symmetric memory with an NVLS multicast mapping (in-switch reduction), when the box offers it
+            if os.environ.get('BSLAM_NVLS', '1') != '0' and dist.get_backend(group) == 'nccl' and self._connect_symmetric(group):
+                self.mode = 'peer'
+                return
+            # 2) CUDA-IPC mappings of cudaMalloc regions
             # every collective below is entered by every rank whatever failed locally: the ranks fall back together
             ok, err, handle = 1, '', b''
             try:
@@ -158,13 +165,46 @@ class ShardedSolver:
         self.mode = 'nccl'
         self._merge_structure()
 
+    def _connect_symmetric(self, group):
+        """Exchange regions in torch symmetric memory; True when every rank got a multicast mapping and connected."""
+        import torch
+        import torch.distributed as dist
+        eng = self.engine
+        ok, err = 1, ''
+        try:
+            import torch.distributed._symmetric_memory as symm
+            _, n_bytes, _ = eng.peer_region()
+            t = symm.empty(n_bytes // 8, dtype=torch.float64, device='cuda:%d' % eng.device)
+            t.zero_()
+            torch.cuda.synchronize()
+            hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0)
+            if mc == 0:
+                raise RuntimeError('no multicast mapping')
+            hdl.barrier()
+            eng.peer_connect_symmetric(self.world, self.rank, [int(p) for p in hdl.buffer_ptrs], mc, n_bytes)
+            self._symm = (t, hdl)            # keep the allocation alive
+        except Exception as e:
+            ok, err = 0, repr(e)
+        got = _all_gather_object((ok, err), group)
+        if all(g[0] for g in got):
+            self.transport = 'symmetric memory + NVLS multicast (multimem.ld_reduce)'
+            return True
+        if ok:                               # somebody else failed: back to a single-rank handle before the IPC attempt
+            eng.peer_connect(1, 0)
+            eng.set_shard(self.rank)
+            self._symm = None
+        self.nvls_reason = [g[1] for g in got if not g[0]][0]
+        return False
+
     def describe(self):
         if self.world == 1:
             return 'single GPU'
         if self.mode == 'peer':
             return ('landmarks sharded over %d GPUs; per iteration ONE CUDA graph per rank: partial reduced systems published '
-                    'to peer-mapped exchange regions (CUDA IPC over NVLink), all-reduce fused into the tile loads of the '
-                    'Cholesky kernel, scalar exchange through peer mailboxes; no NCCL call inside the iteration' % self.world)
+                    'to peer-mapped exchange regions (%s), all-reduce fused into the tile loads of the Cholesky kernel, '
+                    'scalar exchange through peer mailboxes; no NCCL call inside the iteration'
+                    % (self.world, getattr(self, 'transport', 'CUDA IPC over NVLink, one load per rank')))
         return ('landmarks sharded over %d GPUs, two CUDA graphs around one torch.distributed all-reduce of the packed '
                 'reduced system per iteration (fallback: %s)' % (self.world, getattr(self, 'fallback_reason', 'requested')))
 

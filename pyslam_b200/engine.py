@@ -88,6 +88,8 @@ SIGNATURES = {
     'bslam_layout_hash': (C.c_int, [_h, C.POINTER(C.c_uint64)]),
     'bslam_peer_region': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _bp]),
     'bslam_peer_connect': (C.c_int, [_h, C.c_int, C.c_int, _bp, C.POINTER(C.c_void_p)]),
+    'bslam_peer_barrier': (C.c_int, [_h]),
+    'bslam_peer_connect_symmetric': (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]),
     'bslam_iterate_async': (C.c_int, [_h, C.c_double, C.c_int]),
     'bslam_iterate_wait': (C.c_int, [_h, _dp, _dp, _dp]),
     'bslam_stream': (C.c_void_p, [_h]),
@@ -463,6 +465,16 @@ class Engine:
         if dev_ptrs is not None:
             pa = (C.c_void_p * world)(*[C.c_void_p(int(x) if x else 0) for x in dev_ptrs])
         self._ck(self._lib.bslam_peer_connect(self._h, int(world), int(rank), _b(hb), pa))
+
+    def peer_connect_symmetric(self, world, rank, region_ptrs, multicast_ptr, n_bytes):
+        """Exchange regions in caller-provided symmetric memory (+ optional NVLS multicast mapping)."""
+        pa = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in region_ptrs])
+        self._ck(self._lib.bslam_peer_connect_symmetric(self._h, int(world), int(rank), pa, C.c_void_p(int(multicast_ptr) or None),
+                                                        int(n_bytes)))
+
+    def peer_barrier(self):
+        """Enqueue a device-side rendezvous of all connected ranks on the handle's stream."""
+        self._ck(self._lib.bslam_peer_barrier(self._h))
 
     def iterate_async(self, lam=0., eval_new_cost=True):
         self._ck(self._lib.bslam_iterate_async(self._h, float(lam), int(bool(eval_new_cost))))

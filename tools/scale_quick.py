@@ -21,12 +21,21 @@ for _ in range(5):
     solver.iterate(0., True)
 eng.set_poses_se3(Rt0); eng.set_points(d['pts0'])
 K = 50
-ms = tm.device_ms(lambda: solver.iterate(0., True), K) / K
+align = eng.peer_barrier if solver.mode == 'peer' else None
+ms = tm.device_ms(lambda: solver.iterate(0., True), K, align) / K
+ms_unaligned = tm.device_ms(lambda: solver.iterate(0., True), K) / K
+eng.enable_timing(True)
+acc = {}
+for _ in range(10):
+    solver.iterate(0., True)
+    for k, v in eng.timings().items():
+        acc[k] = acc.get(k, 0.) + v / 10
+eng.enable_timing(False)
 par = None
 if track == 6:
     par = bench.c4_parity(solver, eng, d, rank, world, lambda: (eng.set_poses_se3(Rt0), eng.set_points(d['pts0'])))
 if rank == 0:
     print(json.dumps({'n_gpus': world, 'track': track, 'iterations_per_s': round(1e3 / ms, 1), 'us_per_iteration': round(1e3 * ms, 1),
-                      'mode': solver.mode, 'parity_dx': None if par is None else par['dx_rel_err']}))
+                      'mode': solver.mode, 'transport': getattr(solver, 'transport', None), 'nvls_reason': getattr(solver, 'nvls_reason', None), 'panels': eng.fused_info(), 'us_unaligned': round(1e3 * ms_unaligned, 1), 'phases_us': {k: round(1e3 * v, 1) for k, v in acc.items() if v > 0}, 'parity_dx': None if par is None else par['dx_rel_err']}))
 if world > 1:
     dist.destroy_process_group()
