@@ -81,6 +81,8 @@ typedef struct bslam_solver bslam_solver;
 #define BSLAM_T_COST       7   /* cost at the new point                             */
 #define BSLAM_T_TOTAL      8
 #define BSLAM_T_FUSED      9   /* fused_panel_kernel alone (linearise + eliminate the panels) */
+#define BSLAM_T_PEER_PUBLISH 10 /* sharded iteration: pack + rendezvous of the partial reduced systems  */
+#define BSLAM_T_PEER_SCALARS 11 /* sharded iteration: scalar exchange + rendezvous at the end            */
 #define BSLAM_N_TIMINGS   16
 
 /* ---- life cycle ------------------------------------------------------------ */

@@ -42,6 +42,7 @@ namespace bs {
 
 constexpr int kPanelLm = 64;        // landmarks per panel (two per lane)
 constexpr int kPanelRows = 8;       // poses per panel = warps per CTA
+constexpr int kPanelMaxVar = 7;     // variable poses per panel (unless a single landmark needs 8): two CTAs of 110 KB per SM
 constexpr int kPanelThreads = 32 * kPanelRows;
 constexpr int kZGroup = 76;         // doubles per group of 4 landmarks of one row: 6 x 12 + 4 (bank shift)
 constexpr int kZRow = (kPanelLm / 4) * kZGroup;

@@ -6,7 +6,7 @@
 // Every rank owns an EXCHANGE REGION (one cudaMalloc, mapped into the peers through CUDA IPC, or plain
 // device pointers when the ranks are handles of one process):
 //     [ pack: structurally non-zero tiles of the rank's partial S | rhs | scalars ]   (bslam_packed_buffer)
-//     [ mailbox: kMaxPeers x 4 doubles, slot r written by rank r ]
+//     [ mailbox: kMaxPeers x 4 records (value, epoch), slot r written by rank r ]
 //     [ flags: 2 x kMaxPeers 64-bit epochs, slot r written by rank r ]
 //
 //   peer_pack_signal_kernel   after the rank's linearise + Schur kernels: gather the non-zero tiles into
@@ -23,7 +23,7 @@
 //                             rendezvous also orders the next iteration's overwrite of a rank's pack
 //                             after every peer's reads of it.
 //
-// Every wait is bounded (kPeerTimeoutNs): a missing peer raises BSLAM_S_PEER_TIMEOUT instead of hanging the GPU.
+// Every wait is bounded (kPeerSpinLimit): a missing peer raises BSLAM_S_PEER_TIMEOUT instead of hanging the GPU.
 #pragma once
 #include "cholesky.cuh"
 #include "common.cuh"
@@ -31,9 +31,9 @@
 namespace bs {
 
 constexpr int kMaxPeers = 8;
-constexpr int kXchgMailbox = 4;                                          // doubles per mailbox slot
+constexpr int kXchgMailbox = 8;                                          // doubles per mailbox slot: 4 records (value, epoch)
 constexpr int kXchgTail = kMaxPeers * kXchgMailbox + 2 * kMaxPeers;      // doubles after the pack
-constexpr long long kPeerTimeoutNs = 4000000000LL;
+constexpr long long kPeerSpinLimit = 40000000LL;                         // polls before a rendezvous is declared dead (~4 s)
 
 struct PeerCtx {
   int world, rank;
@@ -42,24 +42,38 @@ struct PeerCtx {
   long long* ctl;               // local: [0] epoch of the pre rendezvous, [1] of the end rendezvous, [2] CTAs done
 };
 
+// The rendezvous avoid every fence they can: a system-scope fence waits for all outstanding writes of the SM, and an
+// acquire load is a load plus such a fence -- measured, a fence-per-poll rendezvous costs ~15 us, the protocol below ~3.
+//   flags     : relaxed (volatile) system-scope stores / loads; ONE fence.sys before the flag of the bulk payload
+//   mailbox   : NCCL-LL style records -- value and epoch travel in ONE 16-byte store, so no fence orders them
 BS_D long long* peer_flags(double* region, size_t pack_len) {
   return reinterpret_cast<long long*>(region + pack_len + kMaxPeers * kXchgMailbox);
 }
-BS_D void st_release_sys(long long* p, long long v) {
-  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+BS_D void st_flag(long long* p, long long v) {
+  asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-BS_D long long ld_acquire_sys(const long long* p) {
+BS_D long long ld_flag(const long long* p) {
   long long v;
-  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 // wait until *flag >= epoch; false on timeout
 BS_D bool peer_wait(const long long* flag, long long epoch) {
-  const long long t0 = gtime();
-  while (ld_acquire_sys(flag) < epoch) {
-    __nanosleep(64);
-    if (gtime() - t0 > kPeerTimeoutNs) return false;
+  for (long long spin = 0; ld_flag(flag) < epoch; ++spin)
+    if (spin > kPeerSpinLimit) return false;
+  return true;
+}
+BS_D void st_record(double* p, double value, long long epoch) {       // 16-byte aligned
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(value)), "l"(epoch) : "memory");
+}
+BS_D bool ld_record(const double* p, long long epoch, double& value) {
+  long long v, e;
+  for (long long spin = 0;; ++spin) {
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(p) : "memory");
+    if (e >= epoch) break;
+    if (spin > kPeerSpinLimit) return false;
   }
+  value = __longlong_as_double(v);
   return true;
 }
 
@@ -81,7 +95,7 @@ __global__ void __launch_bounds__(256) peer_pack_signal_kernel(const double* __r
     double* P = pack + (size_t)n_tiles * kNB * kNB;
     for (int e = threadIdx.x; e < n_tail; e += 256) P[e] = tail_src[e];
   }
-  __threadfence_system();
+  __threadfence();                      // the CTA's tile is in L2 (the point of coherence the peers read through)
   __syncthreads();
   __shared__ int s_last;
   __shared__ long long s_epoch;
@@ -91,39 +105,37 @@ __global__ void __launch_bounds__(256) peer_pack_signal_kernel(const double* __r
     if (s_last) {
       pc.ctl[2] = 0;
       s_epoch = ++pc.ctl[0];
+      __threadfence_system();           // once: everything every CTA published is visible system-wide before the flags
     }
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
   const int r = threadIdx.x;
-  if (r < pc.world) st_release_sys(peer_flags(pc.region[r], pc.pack_len) + pc.rank, s_epoch);
+  if (r < pc.world) st_flag(peer_flags(pc.region[r], pc.pack_len) + pc.rank, s_epoch);
   if (r < pc.world && !peer_wait(peer_flags(pc.region[pc.rank], pc.pack_len) + r, s_epoch)) scalars[5 /*PEER_TIMEOUT*/] = 1.0;
 }
 
-// one warp; with_data == 0: rendezvous only (bslam_peer_barrier)
+// one warp; with_data == 0: rendezvous only (bslam_peer_barrier).  Lane = (peer r = lane / 4, record k = lane % 4):
+// records 0..2 carry the partial scalars, record 3 is the bare rendezvous.
 __global__ void __launch_bounds__(32) peer_scalar_exchange_kernel(double* __restrict__ scalars, const PeerCtx pc, int with_data) {
-  const int r = threadIdx.x;
+  const int lane = threadIdx.x, r = lane >> 2, k = lane & 3;
   long long e = 0;
-  if (r == 0) e = ++pc.ctl[1];
+  if (lane == 0) e = ++pc.ctl[1];
   e = __shfl_sync(0xffffffffu, e, 0);
-  if (r < pc.world) {
-    if (with_data) {
-      double* mb = pc.region[r] + pc.pack_len + kXchgMailbox * pc.rank;
-      mb[0] = scalars[0]; mb[1] = scalars[1]; mb[2] = scalars[2];
-    }
-    __threadfence_system();
-    st_release_sys(peer_flags(pc.region[r], pc.pack_len) + kMaxPeers + pc.rank, e);
-  }
+  const bool mine = r < pc.world && (with_data ? k < 3 : k == 3);
+  if (mine) st_record(pc.region[r] + pc.pack_len + kXchgMailbox * pc.rank + 2 * k, with_data ? scalars[k] : 0.0, e);
+  double v = 0.0;
   bool ok = true;
-  if (r < pc.world) ok = peer_wait(peer_flags(pc.region[pc.rank], pc.pack_len) + kMaxPeers + r, e);
+  if (mine) ok = ld_record(pc.region[pc.rank] + pc.pack_len + kXchgMailbox * r + 2 * k, e, v);
   if (!ok) scalars[5 /*PEER_TIMEOUT*/] = 1.0;
-  __syncwarp();
-  if (with_data && r < 3) {    // lane r sums scalar r over the ranks, in rank order (identical on every rank)
-    const double* mb = pc.region[pc.rank] + pc.pack_len + r;
+  if (with_data) {             // sum scalar k over the ranks in rank order (identical on every rank)
     double s = 0.0;
-    for (int q = 0; q < pc.world; ++q) s += __ldcg(mb + kXchgMailbox * q);
-    scalars[r] = s;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+      const double t = __shfl_sync(0xffffffffu, v, 4 * q + k);
+      if (q < pc.world) s += t;
+    }
+    if (lane < 3) scalars[lane] = s;
   }
 }
 

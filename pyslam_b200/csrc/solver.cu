@@ -928,6 +928,7 @@ bs::PeerCtx peer_ctx(bslam_solver* s) {
 int do_peer_publish(bslam_solver* s) {
   LAUNCH(s, bs::peer_pack_signal_kernel, s->n_nz_tiles + 1, 256, 0, s->S(), s->n_pad, s->nblk, s->d_nz_tiles.p, s->n_nz_tiles,
          s->rhs(), s->n_pad + BSLAM_N_SCALARS, s->scalars(), peer_ctx(s));
+  record(s, 12);
   CU(cudaGetLastError());
   return BSLAM_OK;
 }
@@ -935,6 +936,7 @@ int do_peer_publish(bslam_solver* s) {
 // sharded iteration, end: sum the partial scalars over the ranks (and order the next iteration after the peers' reads)
 int do_peer_scalars(bslam_solver* s) {
   LAUNCH(s, bs::peer_scalar_exchange_kernel, 1, 32, 0, s->scalars(), peer_ctx(s), 1);
+  record(s, 13);
   CU(cudaGetLastError());
   return BSLAM_OK;
 }
@@ -973,6 +975,11 @@ int sync_and_timings(bslam_solver* s) {
     s->timings[BSLAM_T_COST] = el(8, 9);
     s->timings[BSLAM_T_TOTAL] = el(0, 9);
     s->timings[BSLAM_T_FUSED] = el(10, 11);
+    if (s->world > 1) {          // sharded iteration: publish + rendezvous, and the scalar exchange, on their own
+      s->timings[BSLAM_T_PEER_PUBLISH] = el(4, 12);
+      s->timings[BSLAM_T_CHOLESKY] = el(12, 5);
+      s->timings[BSLAM_T_PEER_SCALARS] = el(9, 13);
+    }
   }
   return BSLAM_OK;
 }
@@ -1452,12 +1459,13 @@ int bslam_finalize(bslam_solver* s) {
     for (int i = 0; i < N; ++i) obs_ids[cur[s->ob_pt[i]]++] = i;
   }
   if (s->fused_mode > 0 && s->groups.size() < 65536) {
-    // Panel capacity: 64 landmarks, or 32 when that many panels would not fill the GPU twice over (a landmark shard of
-    // a multi-GPU problem): a panel is one CTA's unit of work and its latency, not its throughput, bounds a small grid.
+    // Panels of at most kPanelLm = 64 landmarks.  (32-landmark panels were measured for small landmark shards --
+    // tools/panel_cap_study.py, BSLAM_PANEL_CAP -- and never won once every panel keeps two CTAs per SM resident.)
     // Two passes: panels only where the grid is well filled; if only a few landmarks are left over, they are packed
     // into (sparser / shorter) panels as well, so that the iteration does not pay the whole landmark-block path
     // (three more kernels and a separate retraction) for a handful of landmarks.
-    const size_t cap = regular.size() / bs::kPanelLm < 4 * 296 ? 32 : (size_t)bs::kPanelLm;
+    size_t cap = (size_t)bs::kPanelLm;
+    { const char* e = getenv("BSLAM_PANEL_CAP"); if (e && (atoi(e) == 32 || atoi(e) == 64)) cap = (size_t)atoi(e); }   // study knob
     std::vector<int> fused_lms, irregular, poses, trial;
     for (int pass = 0; pass < 2; ++pass) {
     const bool accept_all = s->fused_mode >= 2 || pass == 1;
@@ -1475,6 +1483,9 @@ int bslam_finalize(bslam_solver* s) {
           if (std::find(trial.begin(), trial.end(), pose) == trial.end()) trial.push_back(pose);
         }
         if ((int)trial.size() > bs::kPanelRows) break;
+        // at most kPanelMaxVar VARIABLE rows: the kernel's shared memory grows with them, and the 8th row would cost the
+        // second resident CTA per SM (half the throughput of the whole grid for a few wider panels)
+        if (!poses.empty() && std::count_if(trial.begin(), trial.end(), [&](int q2) { return !s->se3_const[q2]; }) > bs::kPanelMaxVar) break;
         poses.swap(trial);
         n_cells += obs_ptr[p + 1] - obs_ptr[p];
         ++q1;

@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get('BSLAM_LIB') or os.path.join(_HERE, 'libbslam.so')
 N_SCALARS = 16
 N_TIMINGS = 16
 S_COST_LIN, S_COST_NEW, S_DX_NORM2, S_CHOL_FAIL, S_COST_EVAL = 0, 1, 2, 3, 4
-TIMING_NAMES = ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total', 'fused')
+TIMING_NAMES = ('linearize', 'reproj', 'schur', 'cholesky', 'trsv', 'backsub', 'retract', 'cost', 'total', 'fused', 'peer_publish',
+                'peer_scalars')
 SE2, SE3 = 2, 3
 KIND_SE3, KIND_SE2, KIND_POINT, KIND_VEC = 0, 1, 2, 3
 
