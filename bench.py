@@ -405,6 +405,33 @@ def run_ours(args):
         except Exception as ex:
             series['C2/C3/C5'] = {'error': repr(ex)[:300]}
 
+    # ---- the drop-in API end to end: Problem.solve() on the same problem (host lowering + iterations + download) ----
+    api = None
+    if world == 1:
+        try:
+            t0 = time.perf_counter()
+            pr = configs.ba_problem(full)
+            t_build = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            pr._ensure_lowered()
+            torch.cuda.synchronize()
+            t_lower = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            pr.solve()
+            t_solve = time.perf_counter() - t0
+            n_it = len(pr._cost_history) - 1
+            api = {'iterations': n_it, 'final_cost': float(pr._cost_history[-1]),
+                   'register_blocks_s': t_build, 'lower_s': t_lower, 'solve_s': t_solve,
+                   'iterations_per_s_solve_only': n_it / t_solve,
+                   'iterations_per_s_with_lowering': n_it / (t_lower + t_solve),
+                   'what': 'pyslam_b200.Problem with 500 SE3 + 100 000 point parameters (string keys) and one '
+                           'add_reprojection_batch of 600 000 blocks; lower_s = key -> table lowering + bslam_finalize (ordering, '
+                           'panels, uploads), once per problem; solve_s = Problem.solve(): eval_cost + iterations with the '
+                           'reference termination logic + download into the parameter objects'}
+            del pr
+        except Exception as ex:
+            api = {'error': repr(ex)[:300]}
+
     pk, pk_src = peaks()
     n_pan, n_fused = eng.fused_info()
     out = {
@@ -430,6 +457,7 @@ def run_ours(args):
                 'api': 'bslam_iterate_host (C ABI): pinned host pose/point tables up, one iteration, updated tables down; '
                        'host wall clock per step, same flush protocol'},
         'gpu_launches': int(launches),
+        'e2e_problem_solve': api,
         'parity': parity,
         'final_cost': costs[-1][1], 'first_cost': costs[0][0],
         'series': series,

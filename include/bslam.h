@@ -248,6 +248,8 @@ BSLAM_API int bslam_reduce(bslam_solver* s, double lambda);                /* da
 BSLAM_API int bslam_solve_reduced(bslam_solver* s);                        /* Cholesky + substitution + landmark back-substitution */
 BSLAM_API int bslam_retract(bslam_solver* s, int eval_new_cost);           /* x <- x [+] dx (+ cost) */
 BSLAM_API int bslam_get_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS */);   /* syncs */
+/* The scalars as the last bslam_iterate* / bslam_get_scalars call read them back (host mirror: no device work, no sync). */
+BSLAM_API int bslam_last_scalars(bslam_solver* s, double* out /* BSLAM_N_SCALARS */);
 /* Exactly what bslam_iterate runs before the reduced solve (fused panels included): linearise + damping +
  * landmark elimination.  bslam_get_reduced_system then returns the Schur complement the iteration
  * factorises; bslam_solve_reduced and bslam_retract_iterate complete the iteration. */

@@ -2256,6 +2256,12 @@ int bslam_get_scalars(bslam_solver* s, double* out) {
   return BSLAM_OK;
 }
 
+int bslam_last_scalars(bslam_solver* s, double* out) {
+  NEED(s && s->finalized && out, "bslam_last_scalars: bad arguments");
+  std::memcpy(out, s->h_scalars, BSLAM_N_SCALARS * sizeof(double));     // pinned mirror filled by the last iterate / get_scalars
+  return BSLAM_OK;
+}
+
 // One full iteration enqueued on the handle's stream, scalars copied to the pinned host mirror, NO synchronisation.
 static int iterate_enqueue(bslam_solver* s, double lambda, int eval_new_cost) {
   int rc;

@@ -74,6 +74,7 @@ SIGNATURES = {
     'bslam_solve_reduced': (C.c_int, [_h]),
     'bslam_retract': (C.c_int, [_h, C.c_int]),
     'bslam_get_scalars': (C.c_int, [_h, _dp]),
+    'bslam_last_scalars': (C.c_int, [_h, _dp]),
     'bslam_linearize_reduce': (C.c_int, [_h, C.c_double]),
     'bslam_retract_iterate': (C.c_int, [_h, C.c_int]),
     'bslam_set_fused': (C.c_int, [_h, C.c_int]),
@@ -398,6 +399,11 @@ class Engine:
 
     def scalars(self):
         self._ck(self._lib.bslam_get_scalars(self._h, _d(self._scal)))
+        return self._scal.copy()
+
+    def last_scalars(self):
+        """Scalars as read back by the last iterate (no device work, no synchronisation)."""
+        self._ck(self._lib.bslam_last_scalars(self._h, _d(self._scal)))
         return self._scal.copy()
 
     def reduced_buffer(self):

@@ -105,6 +105,15 @@ class _ReprojectionBatch:
         self.stiffness, self.loss = np.asarray(stiffness, dtype=float), loss
         if not (len(self.pose_keys) == len(self.point_keys) == len(self.obs)):
             raise ValueError('pose_keys, point_keys and obs must have the same length')
+        # keys factorised once (first-seen order): the lowering then touches each distinct key once, not each block
+        self.pose_uniq, self.pose_inv = self._factorise(self.pose_keys)
+        self.point_uniq, self.point_inv = self._factorise(self.point_keys)
+
+    @staticmethod
+    def _factorise(keys):
+        uniq = {}
+        inv = np.fromiter((uniq.setdefault(k, len(uniq)) for k in keys), np.int32, len(keys))
+        return list(uniq), inv
 
 
 def _param_dof(p):
@@ -289,10 +298,10 @@ class Problem:
         for bt in self._batches:
             if loss_descriptor(bt.loss) is None or not _builtin_camera(bt.camera):
                 raise ValueError('add_reprojection_batch needs a built-in camera and loss')
-            for k in set(bt.pose_keys) | set(bt.point_keys):
+            for k in bt.pose_uniq + bt.point_uniq:
                 if k not in pd:
                     raise KeyError('Parameter {} has not been initialized'.format(k))
-            point_keys.update(bt.point_keys)
+            point_keys.update(bt.point_uniq)
 
         # SO3 parameters live in the library's SO3 table when only fused (SO3, t) photometric blocks use them as
         # their rotation; any other use keeps the host-side (opaque manifold) path for the key AND its blocks
@@ -405,14 +414,14 @@ class Problem:
                     eng.add_pose_to_pose_blocks(grp, i1, i2, Tobs, S, gk[2][0], gk[2][1])
         for bt in self._batches:
             ld = loss_descriptor(bt.loss)
-            pose_idx = np.fromiter((low.table[k][1] for k in bt.pose_keys), np.int32, len(bt.pose_keys))
-            pt_idx = np.fromiter((low.table[k][1] for k in bt.point_keys), np.int32, len(bt.point_keys))
-            for k in set(bt.pose_keys):
+            for k in bt.pose_uniq:
                 if low.table[k][0] != 'se3':
                     raise ValueError('reprojection batch pose key {} is not an SE3 parameter'.format(k))
-            for k in set(bt.point_keys):
+            for k in bt.point_uniq:
                 if low.table[k][0] != 'pt':
                     raise ValueError('reprojection batch point key {} is not a 3-vector parameter'.format(k))
+            pose_idx = np.fromiter((low.table[k][1] for k in bt.pose_uniq), np.int32, len(bt.pose_uniq))[bt.pose_inv]
+            pt_idx = np.fromiter((low.table[k][1] for k in bt.point_uniq), np.int32, len(bt.point_uniq))[bt.point_inv]
             eng.add_reprojection_blocks(pose_idx, pt_idx, bt.obs, bt.stiffness, bt.camera.intrinsics(), ld[0], ld[1])
 
         # --- host-evaluated blocks: structure ---
@@ -471,8 +480,11 @@ class Problem:
             eng.set_rotations_so3(np.array([np.asarray(pd[k].mat, dtype=float).ravel() for k in ks['so3']]).reshape(-1, 9),
                                   flags(ks['so3']))
         if ks['pt'] or structure:
-            eng.set_points(np.array([np.asarray(pd[k], dtype=float).reshape(3) for k in ks['pt']]).reshape(-1, 3),
-                           flags(ks['pt']))
+            try:        # one conversion when every point already is a float 3-vector (the common case)
+                xyz = np.array([pd[k] for k in ks['pt']], dtype=float).reshape(len(ks['pt']), 3)
+            except ValueError:
+                xyz = np.array([np.asarray(pd[k], dtype=float).reshape(3) for k in ks['pt']]).reshape(-1, 3)
+            eng.set_points(xyz, flags(ks['pt']))
         if ks['vec'] or structure:
             vals = [self._vec_values(k, pd[k]) for k in ks['vec']]
             dims = [v.size for v in vals]
@@ -502,7 +514,11 @@ class Problem:
         if ks['pt']:
             for k, row in zip(ks['pt'], eng.get_points()):
                 if k not in const:
-                    self._assign_vector(k, row)
+                    p = pd[k]
+                    if type(p) is np.ndarray and p.shape == (3,) and p.dtype == np.float64:
+                        p[:] = row                     # in place, as the reference's `+=` (problem.py:405-409)
+                    else:
+                        self._assign_vector(k, row)
         if ks['vec']:
             vals, pos = eng.get_vectors(), 0
             for k in ks['vec']:
@@ -607,7 +623,8 @@ class Problem:
             self._download_params(dx_ref)
             if linesearch:
                 cost_new += self._dense_cost(low.dense_ids, self.param_dict)
-        if eng.scalars()[_engine.S_CHOL_FAIL] > 0:
+        last = eng.last_scalars() if hasattr(eng, 'last_scalars') else eng.scalars()    # mirror of the iterate's read-back
+        if last[_engine.S_CHOL_FAIL] > 0:
             warnings.warn('reduced normal matrix is not positive definite; the update is unreliable')
         if linesearch:
             cost = cost_new if np.isfinite(cost_new) else np.inf     # problem.py:362-398 net effect
