@@ -413,21 +413,24 @@ def run_ours(args):
             pr = configs.ba_problem(full)
             t_build = time.perf_counter() - t0
             t0 = time.perf_counter()
-            pr._ensure_lowered()
+            pr.solve()                                   # fresh problem: lowering happens inside
+            torch.cuda.synchronize()
+            t_total = time.perf_counter() - t0
+            pr2 = configs.ba_problem(full)
+            t0 = time.perf_counter()
+            pr2._ensure_lowered()                        # the lowering on its own, second instance
             torch.cuda.synchronize()
             t_lower = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            pr.solve()
-            t_solve = time.perf_counter() - t0
+            del pr2
             n_it = len(pr._cost_history) - 1
             api = {'iterations': n_it, 'final_cost': float(pr._cost_history[-1]),
-                   'register_blocks_s': t_build, 'lower_s': t_lower, 'solve_s': t_solve,
-                   'iterations_per_s_solve_only': n_it / t_solve,
-                   'iterations_per_s_with_lowering': n_it / (t_lower + t_solve),
+                   'register_blocks_s': t_build, 'solve_s_total': t_total, 'lower_s': t_lower,
+                   'iterations_per_s_total': n_it / t_total,
+                   'iterations_per_s_after_lowering': n_it / max(t_total - t_lower, 1e-9),
                    'what': 'pyslam_b200.Problem with 500 SE3 + 100 000 point parameters (string keys) and one '
                            'add_reprojection_batch of 600 000 blocks; lower_s = key -> table lowering + bslam_finalize (ordering, '
-                           'panels, uploads), once per problem; solve_s = Problem.solve(): eval_cost + iterations with the '
-                           'reference termination logic + download into the parameter objects'}
+                           'panels, uploads), once per problem; solve_s_total = Problem.solve() on the fresh problem: lowering + eval_cost + '
+                           'iterations with the reference termination logic + download into the 100 500 parameter objects'}
             del pr
         except Exception as ex:
             api = {'error': repr(ex)[:300]}
@@ -571,7 +574,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gn_oracle as O
-    budget_s = float(os.environ.get('BSLAM_REF_BUDGET_S', '330'))
+    budget_s = float(os.environ.get('BSLAM_REF_BUDGET_S', '170'))
     t_build = time.perf_counter()
     ba = oracle_problem(N_KF, N_LM)
     t_build = time.perf_counter() - t_build

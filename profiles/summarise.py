@@ -28,12 +28,16 @@ def full(rep, out, title):
             'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
             'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
             'smsp__inst_executed.sum', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+            'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+            'l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed',
+            'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+            'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__cycles_active.avg',
             'sm__inst_executed_pipe_tensor.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
             'launch__occupancy_limit_shared_mem', 'launch__grid_size', 'launch__block_size']
     stalls = [h for h in hdr if h.startswith('smsp__pcsamp_warps_issue_stalled_') and not h.endswith('_not_issued')]
     traffic = {}
     with open(out, 'w') as f:
-        f.write('# %s\n\n`ncu --set full --clock-control none --import-source on` (one launch per kernel, warm)\n\n' % title)
+        f.write('# %s\n\n`ncu --set full --clock-control none --import-source on` (one launch per kernel, warm; the default of ncu, `--cache-control all`: caches are flushed before every replay pass, so dram__bytes are cold-cache figures)\n\n' % title)
         for r in rows[2:]:
             name = r[idx['Kernel Name']].split('(')[0].replace('void ', '')
             f.write('## %s\n\n| metric | value |\n|---|---|\n' % name)
