@@ -55,19 +55,27 @@ struct PanelRow {
 };
 struct Panel {
   int lm_begin, n_lms;      // landmarks [lm_begin, lm_begin + n_lms)
-  int row_begin, n_rows;    // rows [row_begin, row_begin + n_rows): the variable poses first
+  int n_rows;               // rows of the panel: the variable poses first
   int n_var;                // number of variable rows
-  int pad0, pad1, pad2;
+  int pad0, pad1, pad2, pad3;
 };
+// Everything a CTA needs to know about a panel, 160 contiguous bytes at a FIXED stride: fetched with one bulk copy
+// (cp.async.bulk + mbarrier), and nothing else that is prefetched depends on its contents:
+//   observations   pobs[panel][u|v|d][8 rows][64]   fixed stride (zeros where a pose does not see a landmark)
+//   points         pts + 3 * lm_begin               (lm_begin / n_lms requested one panel earlier)
+//   poses          poses + 12 * rows[warp].pose     (pose index requested one panel earlier)
+struct PanelDesc {
+  Panel hdr;
+  PanelRow rows[kPanelRows];
+};
+static_assert(sizeof(PanelDesc) == 160, "PanelDesc is one 160-byte bulk copy");
+constexpr int kPanelObs = 3 * kPanelRows * kPanelLm;      // doubles of observations per panel
 
 struct PanelArgs {
   int n_panels;
-  const Panel* __restrict__ panels;
-  const PanelRow* __restrict__ rows;
-  const double* __restrict__ pu;            // [n_rows_total][64] observations of the cells (0 where absent)
-  const double* __restrict__ pv;
-  const double* __restrict__ pd;
-  const unsigned short* __restrict__ pgrp;  // group per cell (kLoss < 0 only)
+  const PanelDesc* __restrict__ descs;      // [n_panels]
+  const double* __restrict__ pobs;          // [n_panels][3][8][64] observations of the cells (0 where absent)
+  const unsigned short* __restrict__ pgrp;  // [n_panels][8][64] group per cell (kLoss < 0 only)
   const ReprojGroup* __restrict__ groups;
   ReprojGroup g0;
   const double* __restrict__ poses;         // [K][12] at the linearisation point
@@ -88,8 +96,9 @@ struct PanelArgs {
 };
 
 BS_HD size_t panel_smem_bytes(int max_var) {
-  return sizeof(double) * ((size_t)max_var * kZRow + (kPanelLm / 4) * kCGroup + kPanelRows * 9 * kPanelLm + 6 * kPanelLm + 3 * kPanelLm) +
-         sizeof(int) * 64 + sizeof(PanelRow) * kPanelRows;
+  return sizeof(double) * ((size_t)max_var * kZRow + (kPanelLm / 4) * kCGroup + kPanelRows * 9 * kPanelLm + 6 * kPanelLm + 3 * kPanelLm + 2 +
+                           12 * kPanelRows) +
+         sizeof(int) * 64 + sizeof(PanelDesc);
 }
 
 // Sum over the 32 lanes of 32 values per lane; on return v[0] of lane L holds the total of value L.
@@ -118,19 +127,54 @@ BS_D void tile_ij(int t, int& I, int& J) {
 constexpr int kMaxTiles = 28;       // lower-triangular 8x8 tiles of a (6 * 8 + 1)-row operand
 constexpr int kTilesPerWarp = 4;    // ceil(28 / 8)
 
+// ---- TMA bulk copies (cp.async.bulk, UBLKCP in SASS) completing on an mbarrier (SYNCS): the panel descriptor and the
+// panel's points are staged global -> shared by the copy engine, one elected thread issues them, nobody blocks on them
+// until the next panel starts.
+BS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+BS_D void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+BS_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+BS_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+BS_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// The point run of a panel starts at byte 24 * lm_begin: 16-byte aligned for even lm_begin, else the copy starts one
+// double earlier (and the staged points are read at an offset of one double).
+BS_HD unsigned panel_pts_bytes(int lm_begin, int n_lms) { return (unsigned)((24 * n_lms + 8 * (lm_begin & 1) + 15) & ~15); }
+
 template <int kLoss>
 __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const PanelArgs a) {
   extern __shared__ __align__(16) double psm[];
   __shared__ double sred[kPanelThreads / 32];
   __shared__ unsigned char sTileI[kMaxTiles], sTileJ[kMaxTiles];
   __shared__ int sZoff[64];                                   // operand row -> offset of its first element in psm
+  __shared__ __align__(8) unsigned long long s_mbar;          // completion of the staged descriptor + points
   double* sZ = psm;                                           // [max_var][16 groups][76]
   double* sC = sZ + (size_t)a.max_var * kZRow;                // [16 groups][12]
   double* sVp = sC + (kPanelLm / 4) * kCGroup;                // [8 rows][9][64]
   double* sL = sVp + kPanelRows * 9 * kPanelLm;               // [6][64]: 1/l00, l10, 1/l11, l20, l21, 1/l22
-  double* sPts = sL + 6 * kPanelLm;                           // [64][3]
-  int* sIdx = reinterpret_cast<int*>(sPts + 3 * kPanelLm);    // operand row -> index in S / rhs
-  PanelRow* sRows = reinterpret_cast<PanelRow*>(sIdx + 64);
+  double* sPtsBase = sL + 6 * kPanelLm;                       // [64][3] + 2 (bulk copy, 16-byte aligned)
+  double* sPose = sPtsBase + 3 * kPanelLm + 2;                // [8 rows][12]  (bulk copies, one per warp)
+  int* sIdx = reinterpret_cast<int*>(sPose + 12 * kPanelRows);   // operand row -> index in S / rhs
+  PanelDesc* sDesc = reinterpret_cast<PanelDesc*>(sIdx + 64); // header + rows of the current panel (bulk copy)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int c_off = a.max_var * kZRow;                        // offset of sC
@@ -149,47 +193,70 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
   }
   const double damp = 1.0 + a.lambda;
 
-  // header (rows, points) and observations of a panel: requested one panel ahead
-  struct Obs { double u[2], v[2], d[2]; };
-  auto load_header = [&](const Panel& pan) {
-    if (tid < pan.n_rows) sRows[tid] = a.rows[pan.row_begin + tid];
-    if (tid < 3 * kPanelLm) sPts[tid] = tid < 3 * pan.n_lms ? a.pts_in[3 * (size_t)pan.lm_begin + tid] : 0.0;
-  };
-  auto load_obs = [&](const Panel& pan, Obs& ob) {
-#pragma unroll
-    for (int sub = 0; sub < 2; ++sub) ob.u[sub] = ob.v[sub] = ob.d[sub] = 0.0;
-    if (warp < pan.n_rows) {
-      const PanelRow row = a.rows[pan.row_begin + warp];
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        if (((sub ? row.mask_hi : row.mask_lo) >> lane) & 1u) {
-          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + lane + 32 * sub;
-          ob.u[sub] = ld_stream(a.pu + cell); ob.v[sub] = ld_stream(a.pv + cell); ob.d[sub] = ld_stream(a.pd + cell);
-        }
-      }
-    }
-  };
-
   int pn = blockIdx.x;
   if (pn >= a.n_panels) return;
-  Panel pan = a.panels[pn];
+  if (tid == 0) mbar_init(&s_mbar, 1 + kPanelRows);   // thread 0 (descriptor + points) and lane 0 of every warp (its pose)
+  __syncthreads();
+
+  // What is prefetched for a panel, and from where:
+  //   descriptor + points  -> shared memory, bulk copies issued by thread 0 (lm_begin / n_lms come from `hdr`, which
+  //                           was requested with a plain load a whole panel earlier)
+  //   observations         -> registers, fixed-stride addresses (no dependency on anything loaded)
+  //   pose of the row      -> shared memory, one 96-byte bulk copy per warp, index requested a whole panel earlier
+  struct Obs { double u[2], v[2], d[2]; };
+  auto stage = [&](int panel, int lm_begin, int n_lms, int pose) {
+    if (lane == 0) {
+      mbar_expect_tx(&s_mbar, 96u);
+      bulk_g2s(sPose + 12 * warp, a.poses + 12 * (size_t)pose, 96u, &s_mbar);
+    }
+    if (tid == 0) {
+      Panel hdr; hdr.lm_begin = lm_begin; hdr.n_lms = n_lms;
+      const unsigned nb = panel_pts_bytes(hdr.lm_begin, hdr.n_lms);
+      mbar_expect_tx(&s_mbar, (unsigned)sizeof(PanelDesc) + nb);
+      bulk_g2s(sDesc, a.descs + panel, (unsigned)sizeof(PanelDesc), &s_mbar);
+      bulk_g2s(sPtsBase, a.pts_in + 3 * (size_t)hdr.lm_begin - (hdr.lm_begin & 1), nb, &s_mbar);
+    }
+  };
+  auto load_obs = [&](int panel, Obs& ob) {
+    const double* base = a.pobs + (size_t)panel * kPanelObs + warp * kPanelLm + lane;
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      ob.u[sub] = ld_stream(base + 32 * sub);
+      ob.v[sub] = ld_stream(base + kPanelRows * kPanelLm + 32 * sub);
+      ob.d[sub] = ld_stream(base + 2 * kPanelRows * kPanelLm + 32 * sub);
+    }
+  };
   Obs ob;
-  load_header(pan);
-  load_obs(pan, ob);
+  {   // first panel of the CTA: nothing was requested ahead
+    const Panel hdr = a.descs[pn].hdr;
+    stage(pn, hdr.lm_begin, hdr.n_lms, a.descs[pn].rows[warp].pose);
+    load_obs(pn, ob);
+  }
+  unsigned parity = 0;
 
   for (;;) {
-    __syncthreads();        // header visible; the tile phase of the previous panel is over
+    // scalars of the NEXT panel: requested now, first used after P3 (never waited for)
+    const int pn_next = pn + gridDim.x;
+    const bool has_next = pn_next < a.n_panels;
+    int n_lm_begin = 0, n_n_lms = 0, npose = 0;
+    if (has_next) {
+      n_lm_begin = a.descs[pn_next].hdr.lm_begin;
+      n_n_lms = a.descs[pn_next].hdr.n_lms;
+      npose = a.descs[pn_next].rows[warp].pose;
+    }
+    __syncthreads();                 // the tile phase of the previous panel is over
+    mbar_wait(&s_mbar, parity);      // descriptor + points of this panel have landed
+    parity ^= 1u;
+    const Panel pan = sDesc->hdr;
+    const double* sPts = sPtsBase + (pan.lm_begin & 1);
 
     // ---------------------------------------------------------------- P1: one row per warp
     if (warp < pan.n_rows) {
-      const PanelRow row = sRows[warp];
+      const PanelRow row = sDesc->rows[warp];
       const bool isvar = warp < pan.n_var;
       double P[12];
-      {
-        const double* Pg = a.poses + 12 * (size_t)row.pose;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
-      }
+      for (int k = 0; k < 12; ++k) P[k] = sPose[12 * warp + k];
       double U[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) U[k] = 0.0;
@@ -200,7 +267,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
         double* zc = sZ + warp * kZRow + (j >> 2) * kZGroup + 3 * (j & 3);
         double* vq = sVp + warp * 9 * kPanelLm + j;            // landmark partials of this row: [9][64]
         if (present) {
-          const size_t cell = (size_t)(pan.row_begin + warp) * kPanelLm + j;
+          const size_t cell = ((size_t)pn * kPanelRows + warp) * kPanelLm + j;
           const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[cell]];
           double X[3];
 #pragma unroll
@@ -298,7 +365,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
       int idx = -1, zo = c_off;
       if (zr < 6 * pan.n_var) {
         const int rr = zr / 6, ri = zr - 6 * rr;
-        idx = sRows[rr].off + ri;
+        idx = sDesc->rows[rr].off + ri;
         zo = rr * kZRow + ri * 12;
       } else if (zr == 6 * pan.n_var) {
         idx = -2;                                   // the row of c: its products go to the right-hand side
@@ -310,7 +377,7 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
 
     // ---------------------------------------------------------------- P3: Z = W L^-T in place
     if (warp < pan.n_var) {
-      const PanelRow row = sRows[warp];
+      const PanelRow row = sDesc->rows[warp];
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         const int j = lane + 32 * sub;
@@ -330,14 +397,11 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
     }
     __syncthreads();
 
-    // ---- everything the NEXT panel needs goes in flight now (sRows / sPts are not read by the tile phase)
-    const int pn_next = pn + gridDim.x;
-    const bool has_next = pn_next < a.n_panels;
-    Panel npan = pan;
+    // ---- everything the NEXT panel needs goes in flight now: sDesc / sPts are not read by the tile phase, the
+    //      addresses come from values requested at the top of this panel
     if (has_next) {
-      npan = a.panels[pn_next];
-      load_header(npan);
-      load_obs(npan, ob);
+      stage(pn_next, n_lm_begin, n_n_lms, npose);
+      load_obs(pn_next, ob);
     }
 
     // ---------------------------------------------------------------- P4: S -= Zbig Zbig^T on DMMA tiles
@@ -402,7 +466,6 @@ __global__ void __launch_bounds__(kPanelThreads, 2) fused_panel_kernel(const Pan
     }
     if (!has_next) break;
     pn = pn_next;
-    pan = npan;
   }
   block_sum_to(cost, a.scalars + 0 /*COST_LIN*/, sred);
 }
@@ -430,7 +493,9 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
   double cost = 0.0, dx2 = 0.0;
 
   for (int unit = blockIdx.x * (kFinishThreads / 32) + warp; unit < n_units; unit += n_warps) {
-    const Panel pan = a.panels[unit / kUnitsPerPanel];
+    const int pn = unit / kUnitsPerPanel;
+    const PanelDesc* dsc = a.descs + pn;
+    const Panel pan = dsc->hdr;
     const int half = unit % kUnitsPerPanel;
     const int j = 32 * half + lane;
     if (32 * half >= pan.n_lms) continue;                  // warp-uniform
@@ -443,11 +508,11 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
     for (int r = 0; r < kPanelRows; ++r) {
       ou[r] = ov[r] = od[r] = 0.0;
       if (r < pan.n_rows) {
-        const PanelRow row = a.rows[pan.row_begin + r];
+        const PanelRow row = dsc->rows[r];
         const unsigned m = half ? row.mask_hi : row.mask_lo;
         if (valid && ((m >> lane) & 1u)) {
-          const size_t cell = (size_t)(pan.row_begin + r) * kPanelLm + j;
-          ou[r] = ld_stream(a.pu + cell); ov[r] = ld_stream(a.pv + cell); od[r] = ld_stream(a.pd + cell);
+          const double* cellp = a.pobs + (size_t)pn * kPanelObs + r * kPanelLm + j;
+          ou[r] = ld_stream(cellp); ov[r] = ld_stream(cellp + kPanelRows * kPanelLm); od[r] = ld_stream(cellp + 2 * kPanelRows * kPanelLm);
           present |= 1u << r;
         }
       }
@@ -464,9 +529,9 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
 #pragma unroll
     for (int r = 0; r < kPanelRows; ++r) {
       if (r >= pan.n_var) break;                           // constant poses carry no update (rows: variable poses first)
-      const PanelRow row = a.rows[pan.row_begin + r];      // warp-uniform
+      const PanelRow row = dsc->rows[r];                   // warp-uniform
       if (!((present >> r) & 1u)) continue;
-      const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[(size_t)(pan.row_begin + r) * kPanelLm + j]];
+      const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[((size_t)pn * kPanelRows + r) * kPanelLm + j]];
       double P[12], dxa[6], M[6], x, y, z;
       const double* Pg = a.poses + 12 * (size_t)row.pose;
 #pragma unroll
@@ -503,8 +568,8 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
       for (int r = 0; r < kPanelRows; ++r) {
         if (r >= pan.n_rows) break;
         if (!((present >> r) & 1u)) continue;
-        const PanelRow row = a.rows[pan.row_begin + r];
-        const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[(size_t)(pan.row_begin + r) * kPanelLm + j]];
+        const PanelRow row = dsc->rows[r];
+        const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[((size_t)pn * kPanelRows + r) * kPanelLm + j]];
         double P[12], rr[3];
         const double* Pg = a.poses_new + 12 * (size_t)row.pose;
 #pragma unroll

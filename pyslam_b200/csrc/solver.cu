@@ -156,10 +156,8 @@ struct bslam_solver {
   // which keeps the materialised-W kernels.  bslam_iterate uses the panels and blocks [nb_fused, n_lmblocks).
   int fused_mode = 1;                                // 0: off, 1: well-filled panels only, 2: every panel that fits
   int n_panels = 0, n_fused = 0, nb_fused = 0, panel_max_var = 1, panel_grid = 1, finish_grid = 1;
-  int n_panel_rows = 0;
-  DevBuf<bs::Panel> d_panels;
-  DevBuf<bs::PanelRow> d_prows;
-  DevBuf<double> d_pu, d_pv, d_pd, d_se3_prev;
+  DevBuf<bs::PanelDesc> d_pdescs;
+  DevBuf<double> d_pobs, d_se3_prev;
   DevBuf<unsigned short> d_pgrp;
   DevBuf<int> d_dn_row_ptr, d_dn_col_ptr, d_dn_col_index;
   DevBuf<long long> d_dn_j_ptr;
@@ -429,8 +427,7 @@ int ensure_W(bslam_solver* s) {
 bs::PanelArgs panel_args(bslam_solver* s, double lambda) {
   bs::PanelArgs a{};
   a.n_panels = s->n_panels;
-  a.panels = s->d_panels.p; a.rows = s->d_prows.p;
-  a.pu = s->d_pu.p; a.pv = s->d_pv.p; a.pd = s->d_pd.p; a.pgrp = s->d_pgrp.p;
+  a.descs = s->d_pdescs.p; a.pobs = s->d_pobs.p; a.pgrp = s->d_pgrp.p;
   a.groups = s->d_groups.p;
   if (!s->groups.empty()) a.g0 = s->groups[0];
   a.poses = s->d_se3.p; a.poses_new = s->d_se3.p; a.pts_in = s->d_pts.p; a.pts = s->d_pts.p;
@@ -1825,41 +1822,41 @@ int bslam_finalize(bslam_solver* s) {
   for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
 
   // ---- panel grids: cell (row, landmark) -> observation, padded to kPanelLm landmarks per row ----
-  std::vector<bs::Panel> panels;
-  std::vector<bs::PanelRow> prows;
-  std::vector<double> pu, pv, pd;
+  std::vector<bs::PanelDesc> pdescs;
+  std::vector<double> pobs;
   std::vector<unsigned short> pgrp;
   s->panel_max_var = 1;
-  for (const HostPanel& hp : hpanels) {
-    bs::Panel pn{};
-    pn.lm_begin = hp.first; pn.n_lms = hp.n_lms;
-    pn.row_begin = (int)prows.size(); pn.n_rows = (int)hp.poses.size(); pn.n_var = hp.n_var;
+  pdescs.reserve(hpanels.size());
+  pobs.assign(std::max<size_t>(1, hpanels.size()) * bs::kPanelObs, 0.0);
+  pgrp.assign(std::max<size_t>(1, hpanels.size()) * bs::kPanelRows * bs::kPanelLm, 0);
+  for (size_t ip = 0; ip < hpanels.size(); ++ip) {
+    const HostPanel& hp = hpanels[ip];
+    bs::PanelDesc pd{};
+    pd.hdr.lm_begin = hp.first; pd.hdr.n_lms = hp.n_lms;
+    pd.hdr.n_rows = (int)hp.poses.size(); pd.hdr.n_var = hp.n_var;
     s->panel_max_var = std::max(s->panel_max_var, hp.n_var);
-    const size_t base = prows.size() * bs::kPanelLm;
-    pu.resize(base + (size_t)pn.n_rows * bs::kPanelLm, 0.0);
-    pv.resize(pu.size(), 0.0); pd.resize(pu.size(), 0.0); pgrp.resize(pu.size(), 0);
-    for (int r = 0; r < pn.n_rows; ++r) {
-      bs::PanelRow row{};
-      row.pose = hp.poses[r];
-      row.off = s->se3_off[row.pose];
-      prows.push_back(row);
+    for (int r = 0; r < bs::kPanelRows; ++r) { pd.rows[r].pose = 0; pd.rows[r].off = -1; }
+    for (int r = 0; r < pd.hdr.n_rows; ++r) {
+      pd.rows[r].pose = hp.poses[r];
+      pd.rows[r].off = s->se3_off[hp.poses[r]];
     }
+    double* ob = pobs.data() + ip * bs::kPanelObs;
     for (int j = 0; j < hp.n_lms; ++j) {
       const int q = hp.first + j;
       for (int k = lm_start[q]; k < lm_start[q + 1]; ++k) {
         const int r = (int)(std::find(hp.poses.begin(), hp.poses.end(), opose[k]) - hp.poses.begin());
-        bs::PanelRow& row = prows[pn.row_begin + r];
+        bs::PanelRow& row = pd.rows[r];
         if (j < 32) row.mask_lo |= 1u << j; else row.mask_hi |= 1u << (j - 32);
-        const size_t cell = base + (size_t)r * bs::kPanelLm + j;
-        pu[cell] = ou[k]; pv[cell] = ov[k]; pd[cell] = od[k]; pgrp[cell] = (unsigned short)ogrp[k];
+        const size_t cell = (size_t)r * bs::kPanelLm + j;
+        ob[cell] = ou[k];
+        ob[bs::kPanelRows * bs::kPanelLm + cell] = ov[k];
+        ob[2 * bs::kPanelRows * bs::kPanelLm + cell] = od[k];
+        pgrp[(ip * bs::kPanelRows + r) * bs::kPanelLm + j] = (unsigned short)ogrp[k];
       }
     }
-    panels.push_back(pn);
+    pdescs.push_back(pd);
   }
-  s->n_panel_rows = (int)prows.size();
-  if (panels.empty()) panels.push_back(bs::Panel{});
-  if (prows.empty()) prows.push_back(bs::PanelRow{});
-  if (pu.empty()) { pu.push_back(0.0); pv.push_back(0.0); pd.push_back(0.0); pgrp.push_back(0); }
+  if (pdescs.empty()) pdescs.push_back(bs::PanelDesc{});
 
   // ---- landmark blocks: whole landmarks, <= kBlkObs observations, bounded Schur operands ----
   // Inside a block the observations are re-ordered SLOT-MAJOR (grouped by pose, constant poses last):
@@ -2029,7 +2026,7 @@ int bslam_finalize(bslam_solver* s) {
 
   // ---- device memory ----
   cudaStream_t st = s->stream;
-  std::vector<double> pts_int(3 * (size_t)s->n_pt);
+  std::vector<double> pts_int(3 * (size_t)s->n_pt + 2, 0.0);    // + 2: a panel's point run is copied in 16-byte units
   for (int q = 0; q < s->n_pt; ++q)
     for (int k = 0; k < 3; ++k) pts_int[3 * (size_t)q + k] = s->h_pts[3 * (size_t)s->pt_iperm[q] + k];
   CU(upload(s->d_se3, s->h_se3, st));
@@ -2107,9 +2104,8 @@ int bslam_finalize(bslam_solver* s) {
   CU(s->d_dn_J.alloc((size_t)s->dn_j_ptr.back()));
   CU(s->d_dn_e.alloc((size_t)s->dn_row_ptr.back()));
   s->d_W.release();                             // allocated on first use (ensure_W)
-  CU(upload(s->d_panels, panels, st));
-  CU(upload(s->d_prows, prows, st));
-  CU(upload(s->d_pu, pu, st)); CU(upload(s->d_pv, pv, st)); CU(upload(s->d_pd, pd, st));
+  CU(upload(s->d_pdescs, pdescs, st));
+  CU(upload(s->d_pobs, pobs, st));
   CU(upload(s->d_pgrp, pgrp, st));
   CU(s->d_se3_prev.alloc(std::max<size_t>(1, s->d_se3.n)));
   if (s->n_panels > 0) {
