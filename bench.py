@@ -239,10 +239,12 @@ def c4_parity(solver, eng, d, rank, world, reset):
     # reference order: the variable poses in table order (6 each), then the points (3 each)
     var = np.flatnonzero(~np.asarray(d['pose_const']))
     pose_src = (lay['se3'][var][:, None] + np.arange(6)[None, :]).ravel()
-    lo, hi = d.get('lm_range', (0, len(d['pts0'])))
     s_idx = g['sample_idx'] - n_pose                    # entries of the landmark part, global numbering
-    mine = (s_idx >= 3 * lo) & (s_idx < 3 * hi)
-    lm_src = lay['pt'][(s_idx[mine] // 3) - lo] + s_idx[mine] % 3
+    n_glob = int(g['n_lm'])
+    local_of = np.full(n_glob, -1, np.int64)            # global landmark -> this rank's local landmark
+    local_of[np.asarray(d.get('lm_ids', np.arange(n_glob)))] = np.arange(len(d['pts0']))
+    mine = local_of[s_idx // 3] >= 0
+    lm_src = lay['pt'][local_of[s_idx[mine] // 3]] + s_idx[mine] % 3
     reset()
     worst_dx, worst_cost = 0., 0.
     n_it = int(g['n_iter'])

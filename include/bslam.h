@@ -311,6 +311,13 @@ BSLAM_API int bslam_peer_connect(bslam_solver* s, int world, int rank, const uin
  * multimem.ld_reduce (reduced inside the NVSwitch) instead of one load per rank. */
 BSLAM_API int bslam_peer_connect_symmetric(bslam_solver* s, int world, int rank, void* const* region_ptrs, void* multicast_ptr,
                                  size_t n_bytes);
+/* Which ranks contribute to which tile.  bslam_peer_local_slots: flags[k] != 0 when THIS handle's residual blocks can
+ * write slot k of the packed payload (n = number of packed tiles, bslam_packed_buffer's tile count); the ranks exchange
+ * the flags once and call bslam_peer_set_contributors with masks[k] = OR over ranks r of (flags_r[k] != 0) << r.  The
+ * Cholesky kernel then reads a tile only from the ranks that can have written it: with time-contiguous landmark shards
+ * the NVLink traffic of the fused all-reduce drops from (world - 1) x payload to ~1 x payload per rank.  Optional. */
+BSLAM_API int bslam_peer_local_slots(bslam_solver* s, uint8_t* flags, size_t n);
+BSLAM_API int bslam_peer_set_contributors(bslam_solver* s, const uint8_t* masks, size_t n);
 /* Device-side rendezvous of all connected ranks, enqueued on the handle's stream (no host synchronisation): the
  * kernels enqueued after it start on every rank within a few microseconds of each other (bench.py aligns the ranks
  * with it before each timed step).  No-op for a single rank. */

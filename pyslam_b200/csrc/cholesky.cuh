@@ -57,6 +57,8 @@ struct CholTask {
                    // diagonal (i, i): take the LAST `early` (0..kEarly) producer columns of klist through early C tiles
   int slot;       // multi-GPU: index of the tile in the packed exchange payload (structurally non-zero tiles of S
                    // before fill-in); -1: fill-in only (no initial data); -2: right-hand-side row
+  int ranks;       // multi-GPU: bit r set = rank r's landmark shard can contribute to this tile; the other ranks' copies are
+                   // structurally zero and are not read (time-contiguous shards touch ~1/N of the tiles each)
 };
 
 constexpr int kEarly = 2;
@@ -438,7 +440,8 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
 #pragma unroll
           for (int q = 0; q < kCholMaxPeers; ++q) {
             part[q] = make_double2(0.0, 0.0);
-            if (live && q < p.world) part[q] = __ldcg(reinterpret_cast<const double2*>(p.peer_pack[q] + off0 + (size_t)r * kNB + c));
+            if (live && q < p.world && ((task.ranks >> q) & 1))
+              part[q] = __ldcg(reinterpret_cast<const double2*>(p.peer_pack[q] + off0 + (size_t)r * kNB + c));
           }
           double2 v = part[0];
 #pragma unroll

@@ -186,6 +186,7 @@ struct bslam_solver {
   DevBuf<unsigned char> d_fill_mask;               // tile mask after symbolic fill-in
   DevBuf<long long> d_trace;                       // debug: per-task timestamps (bslam_debug_chol_trace)
   std::vector<bs::CholTask> h_tasks;
+  std::vector<int> h_opose_lm, h_lm_start;         // observations in landmark order (host copy): local tile contributions of a shard
   DevBuf<int> d_dirty_tiles;                       // tiles (i*nt+j) that carry data: zeroed before every linearisation
   int n_dirty_tiles = 0;
   DevBuf<int> d_nz_tiles;                          // structurally non-zero tiles BEFORE fill-in (what assembly/Schur write)
@@ -646,6 +647,7 @@ int build_chol_plan(bslam_solver* s) {
       if (!at(i, j)) continue;
       bs::CholTask t{};
       t.slot = i == nt ? -2 : nz_slot[(size_t)i * nt + j];
+      t.ranks = 0xff;
       t.i = i; t.j = j; t.kbeg = (int)klist.size();
       for (int k = 0; k < j; ++k)
         if (at(i, k) && at(j, k)) klist.push_back(k);
@@ -2140,6 +2142,8 @@ int bslam_finalize(bslam_solver* s) {
   CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
   CU(cudaStreamSynchronize(st));
   build_tile_mask(s, opose_lm, lm_start);
+  s->h_opose_lm = opose_lm;
+  s->h_lm_start = lm_start;
   s->finalized = true;
   s->dn_uploaded = false;
   return BSLAM_OK;
@@ -2424,6 +2428,84 @@ int bslam_peer_connect_symmetric(bslam_solver* s, int world, int rank, void* con
   return BSLAM_OK;
 }
 
+// Tiles (slots of the packed payload) THIS handle's residual blocks can write: its landmarks' co-visibility tiles, and on
+// shard 0 the blocks that are not sharded.  The ranks exchange these once; bslam_peer_set_contributors then tells the
+// Cholesky kernel which ranks to read for every tile.
+int bslam_peer_local_slots(bslam_solver* s, uint8_t* flags, size_t n) {
+  NEED(s && s->finalized && flags, "bslam_peer_local_slots: bad arguments");
+  CU(cudaSetDevice(s->device));
+  if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
+  NEED(n == (size_t)s->n_nz_tiles, "bslam_peer_local_slots: expected %d slots, got %zu", s->n_nz_tiles, n);
+  const int nt = s->nblk;
+  std::vector<uint8_t> local((size_t)nt * nt, 0);
+  std::vector<int> tiles;
+  auto mark = [&]() {
+    for (int a2 : tiles)
+      for (int b2 : tiles)
+        if (a2 >= b2) local[(size_t)a2 * nt + b2] = 1;
+  };
+  for (int q = 0; q < s->n_lm; ++q) {
+    tiles.clear();
+    for (int k = s->h_lm_start[q]; k < s->h_lm_start[q + 1]; ++k) tiles_of(s->se3_off[s->h_opose_lm[k]], 6, tiles);
+    mark();
+  }
+  if (s->shard_rank == 0) {
+    for (int t = 0; t < nt; ++t) local[(size_t)t * nt + t] = 1;        // priors, photometric / motion-only blocks: diagonal tiles
+    for (auto* b : s->edges) {
+      if (!b->binary) continue;
+      const std::vector<int>& off = b->group == 3 ? s->se3_off : s->se2_off;
+      const int dof = b->group == 3 ? 6 : 3;
+      for (int e = 0; e < b->n; ++e) {
+        tiles.clear();
+        tiles_of(off[b->i1[e]], dof, tiles);
+        tiles_of(off[b->i2[e]], dof, tiles);
+        mark();
+      }
+    }
+    for (auto* b : s->photos) {
+      if (b->rot_idx < 0) continue;
+      tiles.clear();
+      tiles_of(s->so3_off[b->rot_idx], 3, tiles);
+      tiles_of(s->vec_off[b->vec_idx], 3, tiles);
+      mark();
+    }
+    for (int b = 0; b < s->dn_blocks; ++b) {
+      tiles.clear();
+      for (int c = s->dn_col_ptr[b]; c < s->dn_col_ptr[b + 1]; ++c) tiles_of(s->dn_col_index[c], 1, tiles);
+      mark();
+    }
+  }
+  int slot = 0;
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j)
+      if (s->tile_mask[(size_t)i * nt + j]) flags[slot++] = local[(size_t)i * nt + j];
+  return BSLAM_OK;
+}
+
+int bslam_peer_set_contributors(bslam_solver* s, const uint8_t* masks, size_t n) {
+  NEED(s && s->finalized && masks, "bslam_peer_set_contributors: bad arguments");
+  NEED(s->plan_valid && n == (size_t)s->n_nz_tiles, "bslam_peer_set_contributors: expected %d slots, got %zu", s->n_nz_tiles, n);
+  CU(cudaSetDevice(s->device));
+  const int nt = s->nblk;
+  std::vector<int> diag_slot(nt, -1);
+  {
+    int slot = 0;
+    for (int i = 0; i < nt; ++i)
+      for (int j = 0; j <= i; ++j)
+        if (s->tile_mask[(size_t)i * nt + j]) { if (i == j) diag_slot[i] = slot; ++slot; }
+  }
+  for (bs::CholTask& t : s->h_tasks) {
+    if (t.slot >= 0) t.ranks = masks[t.slot];
+    else if (t.slot == -2) t.ranks = diag_slot[t.j] >= 0 ? masks[diag_slot[t.j]] : 0xff;     // rhs of the poses of tile column j
+    else t.ranks = 0;
+  }
+  CU(cudaStreamSynchronize(s->stream));
+  CU(upload(s->d_tasks, s->h_tasks, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  drop_graph(s);
+  return BSLAM_OK;
+}
+
 int bslam_peer_barrier(bslam_solver* s) {
   NEED(s && s->finalized, "bslam_peer_barrier: solver not finalized");
   if (s->world <= 1) return BSLAM_OK;
@@ -2472,7 +2554,7 @@ int bslam_packed_buffer(bslam_solver* s, void** dev_ptr, size_t* n_doubles) {
   CU(cudaSetDevice(s->device));
   if (!s->plan_valid) { int rc = build_chol_plan(s); if (rc) return rc; }
   if (dev_ptr) *dev_ptr = s->d_pack.p;
-  if (n_doubles) *n_doubles = s->d_pack.n;
+  if (n_doubles) *n_doubles = s->pack_len;        // the payload [tiles | rhs | scalars]; the exchange tail behind it is private
   return BSLAM_OK;
 }
 

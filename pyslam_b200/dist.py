@@ -39,14 +39,30 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_stereo_ba(d, rank, world):
-    """Sub-problem of rank `rank`: all poses, landmarks [lo, hi) and their
-    observations (point indices renumbered from 0)."""
-    lo, hi = shard_range(len(d['pts0']), rank, world)
-    keep = (d['pt_idx'] >= lo) & (d['pt_idx'] < hi)
+def shard_stereo_ba(d, rank, world, by_time=False):
+    """Sub-problem of rank `rank`: all poses, its share of the landmarks and their observations (point indices
+    renumbered from 0).  `lm_ids` = the global landmark index of every local landmark.
+
+    by_time=False: landmarks [lo, hi) by index.  by_time=True: the landmarks are first ordered by the first keyframe
+    that observes them and THEN cut into contiguous ranges: every rank's landmarks then couple ~1/world of the
+    trajectory, so its partial reduced system touches ~1/world of the tiles and the fused all-reduce reads a tile only
+    from the one or two ranks that can have written it (bslam_peer_set_contributors)."""
+    n = len(d['pts0'])
+    lo, hi = shard_range(n, rank, world)
+    if by_time:
+        first = np.full(n, np.iinfo(np.int64).max)
+        np.minimum.at(first, d['pt_idx'], d['pose_idx'].astype(np.int64))
+        order = np.argsort(first, kind='stable')
+    else:
+        order = np.arange(n)
+    lm_ids = order[lo:hi]
+    local_of = np.full(n, -1, np.int64)
+    local_of[lm_ids] = np.arange(hi - lo)
+    keep = local_of[d['pt_idx']] >= 0
     out = dict(d)
-    out.update(pts0=d['pts0'][lo:hi], pts_true=d['pts_true'][lo:hi], pose_idx=d['pose_idx'][keep],
-               pt_idx=(d['pt_idx'][keep] - lo).astype(np.int32), obs=d['obs'][keep], n_lm=hi - lo, lm_range=(lo, hi))
+    out.update(pts0=d['pts0'][lm_ids], pts_true=d['pts_true'][lm_ids], pose_idx=d['pose_idx'][keep],
+               pt_idx=local_of[d['pt_idx'][keep]].astype(np.int32), obs=d['obs'][keep], n_lm=hi - lo, lm_range=(lo, hi),
+               lm_ids=lm_ids)
     return out
 
 
@@ -83,7 +99,7 @@ def build_sharded_ba(full, rank=0, world=1, device=0, group=None, mode='auto'):
     """Shard a stereo-BA problem (dict of `pyslam_b200.synthetic.stereo_ba` form) over `world` ranks and lower
     this rank's part: (ShardedSolver, this rank's sub-problem, initial pose table)."""
     from . import configs
-    d = shard_stereo_ba(full, rank, world) if world > 1 else full
+    d = shard_stereo_ba(full, rank, world, by_time=True) if world > 1 else full
     eng, Rt0 = configs.ba_engine(d, device)
     if world > 1:
         # every rank orders the reduced system from the couplings of ALL shards
@@ -91,6 +107,16 @@ def build_sharded_ba(full, rank=0, world=1, device=0, group=None, mode='auto'):
         eng.add_coupling(3, pairs[:, 0], pairs[:, 1])
     eng.finalize()
     return ShardedSolver(eng, rank, world, group, mode), d, Rt0
+
+
+def _set_contributors(engines_or_engine, all_flags):
+    """masks[k] = OR_r (flags_r[k] != 0) << r, handed to every engine."""
+    masks = np.zeros(len(all_flags[0]), np.uint8)
+    for r, f in enumerate(all_flags):
+        masks |= (np.asarray(f, np.uint8) != 0).astype(np.uint8) << r
+    for e in (engines_or_engine if isinstance(engines_or_engine, (list, tuple)) else [engines_or_engine]):
+        e.peer_set_contributors(masks)
+    return masks
 
 
 def connect_local(engines):
@@ -106,6 +132,7 @@ def connect_local(engines):
     for r, e in enumerate(engines):
         e.peer_connect(world, r, dev_ptrs=ptrs)
         solvers.append(ShardedSolver(e, r, world, mode='connected'))
+    _set_contributors(engines, [e.peer_local_slots() for e in engines])
     return solvers
 
 
@@ -139,8 +166,11 @@ class ShardedSolver:
                                    'couplings of all shards before finalize (build_sharded_ba does)' % hashes)
         if mode == 'peer':
             # 1) symmetric memory with an NVLS multicast mapping (in-switch reduction), when the box offers it
-            if os.environ.get('BSLAM_NVLS', '1') != '0' and dist.get_backend(group) == 'nccl' and self._connect_symmetric(group):
+            # (opt-in: measured on 2, 4 and 8 B200s the per-element 8-byte multimem loads are slower than 16-byte loads from
+            #  the contributing ranks)
+            if os.environ.get('BSLAM_NVLS', '0') == '1' and dist.get_backend(group) == 'nccl' and self._connect_symmetric(group):
                 self.mode = 'peer'
+                self._exchange_contributors(group)
                 return
             # 2) CUDA-IPC mappings of cudaMalloc regions
             # every collective below is entered by every rank whatever failed locally: the ranks fall back together
@@ -158,12 +188,19 @@ class ShardedSolver:
                 got = _all_gather_object((ok, err, b''), group)
             if all(g[0] for g in got):
                 self.mode = 'peer'
+                self._exchange_contributors(group)
                 return
             engine.peer_connect(1, 0)
             engine.set_shard(rank)
             self.fallback_reason = [g[1] for g in got if not g[0]][0]
         self.mode = 'nccl'
         self._merge_structure()
+
+    def _exchange_contributors(self, group):
+        """Every rank learns which ranks can write which tile of the reduced system (read only those)."""
+        flags = _all_gather_object(self.engine.peer_local_slots().tobytes(), group)
+        masks = _set_contributors(self.engine, [np.frombuffer(f, np.uint8) for f in flags])
+        self.tiles_per_rank = [int(((masks >> r) & 1).sum()) for r in range(self.world)]
 
     def _connect_symmetric(self, group):
         """Exchange regions in torch symmetric memory; True when every rank got a multicast mapping and connected."""

@@ -91,6 +91,8 @@ SIGNATURES = {
     'bslam_peer_region': (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), _bp]),
     'bslam_peer_connect': (C.c_int, [_h, C.c_int, C.c_int, _bp, C.POINTER(C.c_void_p)]),
     'bslam_peer_barrier': (C.c_int, [_h]),
+    'bslam_peer_local_slots': (C.c_int, [_h, _bp, C.c_size_t]),
+    'bslam_peer_set_contributors': (C.c_int, [_h, _bp, C.c_size_t]),
     'bslam_peer_connect_symmetric': (C.c_int, [_h, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t]),
     'bslam_iterate_async': (C.c_int, [_h, C.c_double, C.c_int]),
     'bslam_iterate_wait': (C.c_int, [_h, _dp, _dp, _dp]),
@@ -478,6 +480,22 @@ class Engine:
         pa = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in region_ptrs])
         self._ck(self._lib.bslam_peer_connect_symmetric(self._h, int(world), int(rank), pa, C.c_void_p(int(multicast_ptr) or None),
                                                         int(n_bytes)))
+
+    def n_packed_tiles(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self._lib.bslam_packed_buffer(self._h, C.byref(p), C.byref(n)))
+        _, _, _, npad = self.reduced_buffer()
+        return (n.value - npad - N_SCALARS) // (self._lib.bslam_tile_edge() ** 2)
+
+    def peer_local_slots(self):
+        """uint8 flags per packed tile: this handle's blocks can write it."""
+        f = np.zeros(self.n_packed_tiles(), np.uint8)
+        self._ck(self._lib.bslam_peer_local_slots(self._h, _b(f), f.size))
+        return f
+
+    def peer_set_contributors(self, masks):
+        m = np.ascontiguousarray(masks, dtype=np.uint8)
+        self._ck(self._lib.bslam_peer_set_contributors(self._h, _b(m), m.size))
 
     def peer_barrier(self):
         """Enqueue a device-side rendezvous of all connected ranks on the handle's stream."""

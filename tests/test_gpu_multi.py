@@ -160,7 +160,7 @@ def _worker(rank, world, port, out, backend, same_device, mode):
     res = [solver.eval_cost()]
     for _ in range(3):
         res.append(solver.iterate(0., True))
-    out[rank] = (res, eng.get_poses_se3(), eng.get_points(), solver.mode)
+    out[rank] = (res, eng.get_poses_se3(), eng.get_points(), solver.mode, np.asarray(d['lm_ids']), getattr(solver, 'tiles_per_rank', None))
     torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
@@ -175,15 +175,16 @@ def _run_processes(world, backend, same_device, mode):
     full = time_sorted(synthetic.stereo_ba(40, 3000, track=6, seed=2))
     ref, poses_ref, pts_ref = _single(full, 3)
     for rank in range(world):
-        res, poses, pts, used = out[rank]
+        res, poses, pts, used, lm_ids, tiles_per_rank = out[rank]
         if mode != 'auto':
             assert used == mode
-        lo, hi = shard_range(3000, rank, world)
+        if used == 'peer':      # time-contiguous shards: no rank contributes to every tile of the reduced system
+            assert tiles_per_rank is not None and min(tiles_per_rank) < max(tiles_per_rank) + 1 and len(tiles_per_rank) == world
         assert abs(res[0] - ref[0]) < 1e-12 * ref[0]
         for a, b in zip(res[1:], ref[1:]):
             np.testing.assert_allclose(a, b, rtol=1e-8)
         np.testing.assert_allclose(poses, poses_ref, rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(pts, pts_ref[lo:hi], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(pts, pts_ref[lm_ids], rtol=1e-9, atol=1e-11)
     return out
 
 
