@@ -83,3 +83,33 @@ def test_shard_ranges_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_time_contiguous_shards_and_covisibility_pairs():
+    """shard_stereo_ba(by_time=True) partitions the landmarks in first-keyframe order (every landmark exactly once, local
+    indices consistent with lm_ids); covisibility_pairs = the pose pairs that share a landmark."""
+    from pyslam_b200 import synthetic
+    from pyslam_b200.dist import covisibility_pairs, shard_stereo_ba
+    full = synthetic.stereo_ba(30, 400, track=4, seed=3)
+    world, seen = 3, []
+    first = np.full(400, 1 << 30)
+    np.minimum.at(first, full['pt_idx'], full['pose_idx'])
+    prev_max = -1
+    for r in range(world):
+        d = shard_stereo_ba(full, r, world, by_time=True)
+        seen.append(d['lm_ids'])
+        assert np.array_equal(d['pts0'], full['pts0'][d['lm_ids']])
+        # the observations of the shard are exactly those of its landmarks, renumbered
+        keep = np.isin(full['pt_idx'], d['lm_ids'])
+        assert np.array_equal(d['lm_ids'][d['pt_idx']], full['pt_idx'][keep])
+        assert np.array_equal(d['pose_idx'], full['pose_idx'][keep])
+        # time-contiguous: no landmark of this shard starts before one of the previous shard
+        assert first[d['lm_ids']].min() >= prev_max
+        prev_max = first[d['lm_ids']].max()
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(400))
+    pairs = covisibility_pairs(full['pose_idx'], full['pt_idx'])
+    ref = set()
+    for q in range(400):
+        ps = sorted(set(full['pose_idx'][full['pt_idx'] == q]))
+        ref.update((a, b) for i, a in enumerate(ps) for b in ps[i + 1:])
+    assert set(map(tuple, pairs.tolist())) == ref

@@ -368,25 +368,36 @@ def test_short_tracks_many_landmarks_per_block():
 
 def test_iterate_host_equals_separate_calls():
     """bslam_iterate_host (upload + iterate + download, one synchronisation) against set / iterate / get on a
-    second handle.  The two handles sum their fp64 atomics in different orders, so the trajectories agree to
-    rounding amplified by the solve, not bit for bit."""
+    second handle.  The two handles sum their fp64 atomics in different orders (~1e-16 relative per sum), and
+    nothing else differs: ONE iteration agrees to 1e-10 whatever the loss; over several Gauss-Newton iterations the
+    rounding is amplified by the solves (conditioning of the reduced system), so later iterations are compared at 1e-6,
+    and the first iteration is also repeated on the SAME handle to show the run-to-run spread is of that size."""
     from pyslam_b200 import synthetic
-    d = synthetic.stereo_ba(12, 300, track=5, seed=21)
-    pr1 = B.product_ba_problem(d, bulk=True); pr1._ensure_lowered()
-    pr2 = B.product_ba_problem(d, bulk=True); pr2._ensure_lowered()
-    e1, e2 = pr1._engine, pr2._engine
-    Rt = np.ascontiguousarray(np.concatenate([d['R0'].reshape(-1, 9), d['t0']], axis=1))
-    pts = np.ascontiguousarray(d['pts0'], dtype=np.float64)
-    Rt2, pts2 = Rt.copy(), pts.copy()
-    for it in range(3):
-        e1.set_poses_se3(Rt); e1.set_points(pts)
-        r1 = e1.iterate(0., True)
-        e1.get_poses_se3(Rt); e1.get_points(pts)
-        r2 = e2.iterate_host(Rt2, pts2, 0., True)
-        np.testing.assert_allclose(r2, r1, rtol=1e-6)
-        np.testing.assert_allclose(Rt2, Rt, rtol=0, atol=1e-6)
-        np.testing.assert_allclose(pts2, pts, rtol=0, atol=1e-6)
-    assert r1[1] < r1[0]
+    for loss in (('l2', 0.), ('huber', 1.5)):
+        d = synthetic.stereo_ba(12, 300, track=5, seed=21)
+        d['loss'] = loss
+        pr1 = B.product_ba_problem(d, bulk=True); pr1._ensure_lowered()
+        pr2 = B.product_ba_problem(d, bulk=True); pr2._ensure_lowered()
+        e1, e2 = pr1._engine, pr2._engine
+        Rt0 = np.ascontiguousarray(np.concatenate([d['R0'].reshape(-1, 9), d['t0']], axis=1))
+        pts0 = np.ascontiguousarray(d['pts0'], dtype=np.float64)
+        Rt, pts, Rt2, pts2 = Rt0.copy(), pts0.copy(), Rt0.copy(), pts0.copy()
+        for it in range(3):
+            e1.set_poses_se3(Rt); e1.set_points(pts)
+            r1 = e1.iterate(0., True)
+            e1.get_poses_se3(Rt); e1.get_points(pts)
+            r2 = e2.iterate_host(Rt2, pts2, 0., True)
+            tol = 1e-10 if it == 0 else 1e-6
+            np.testing.assert_allclose(r2, r1, rtol=tol)
+            np.testing.assert_allclose(Rt2, Rt, rtol=0, atol=tol)
+            np.testing.assert_allclose(pts2, pts, rtol=0, atol=tol * 10)
+        assert r1[1] < r1[0]
+        # run-to-run spread of ONE handle on identical inputs (atomics order only)
+        e1.set_poses_se3(Rt0); e1.set_points(pts0)
+        a = e1.iterate(0., True)
+        e1.set_poses_se3(Rt0); e1.set_points(pts0)
+        b = e1.iterate(0., True)
+        np.testing.assert_allclose(a, b, rtol=1e-10)
 
 
 def test_mixed_groups_losses_and_stiffness():
