@@ -428,11 +428,11 @@ def run_ours(args):
             api = {'iterations': n_it, 'final_cost': float(pr._cost_history[-1]),
                    'register_blocks_s': t_build, 'solve_s_total': t_total, 'lower_s': t_lower,
                    'iterations_per_s_total': n_it / t_total,
-                   'iterations_per_s_after_lowering': n_it / max(t_total - t_lower, 1e-9),
                    'what': 'pyslam_b200.Problem with 500 SE3 + 100 000 point parameters (string keys) and one '
                            'add_reprojection_batch of 600 000 blocks; lower_s = key -> table lowering + bslam_finalize (ordering, '
-                           'panels, uploads), once per problem; solve_s_total = Problem.solve() on the fresh problem: lowering + eval_cost + '
-                           'iterations with the reference termination logic + download into the 100 500 parameter objects'}
+                           'panels, uploads), once per problem, measured on a second instance; solve_s_total = Problem.solve() on the fresh '
+                           'problem: that lowering + eval_cost + iterations with the reference termination logic + download into the '
+                           '100 500 parameter objects -- the drop-in API is bound by the per-key Python lowering, not by the iterations'}
             del pr
         except Exception as ex:
             api = {'error': repr(ex)[:300]}
