@@ -32,5 +32,5 @@ for w in want:
                 f.write('\n')
                 for op, n in h.most_common(60):
                     f.write('%-40s %6d\n' % (op, n))
-            print(name, tot, {k2: fam[k2] for k2 in ('DMMA', 'DFMA', 'LDGSTS', 'RED', 'ATOMG', 'LDGMC', 'SHFL', 'LDS', 'STS', 'BAR', 'MUFU', 'UTMALDG') if fam[k2]})
+            print(name, tot, {k2: fam[k2] for k2 in ('DMMA', 'DFMA', 'LDGSTS', 'RED', 'ATOMG', 'LDGMC', 'SHFL', 'LDS', 'STS', 'BAR', 'MUFU', 'UBLKCP', 'SYNCS', 'UTMALDG') if fam[k2]})
             break
