@@ -4,7 +4,7 @@
 
 Same loader and shims as oracle/make_golden.py, plus an empty `viso2` stub module (pyslam/pipelines/__init__.py
 imports every sub-module, and sparse.py imports the un-installable viso2; nothing of it is called).  Writes
-tests/golden/{motion_ransac,orientation,rgbd_camera,dense_pipeline,metrics}.npz: inputs + the reference's outputs.
+tests/golden/{motion_ransac,orientation,rgbd_camera,dense_pipeline,dense_rgbd_pipeline,metrics}.npz: inputs + the reference's outputs.
 """
 import os
 import sys
@@ -244,7 +244,44 @@ def dense_pipeline():
     print('dense_pipeline: %d level solves, final pose' % len(histories), out['T_final'][9:], 'split history', out['split_history'][:4])
 
 
+def dense_rgbd_pipeline():
+    """The reference's DenseRGBDPipeline on two synthetic RGB-D frames (depth maps, RGBDCamera, depth pyramid)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(4)
+    w, h = 160, 120
+    big = ndimage.gaussian_filter(rng.random((h + 16, w + 64)), 2.0)
+    big = (255 * (big - big.min()) / (big.max() - big.min())).astype(np.uint8)
+    im0 = np.ascontiguousarray(big[8:8 + h, 32:32 + w])
+    im1 = np.ascontiguousarray(big[8:8 + h, 33:33 + w])
+    depth0 = 4.0 + 0.5 * ndimage.gaussian_filter(rng.random((h, w)), 4.0)
+    depth1 = depth0.copy()
+    cam = RGBDCamera(w / 2., h / 2., 200., 200., w, h)
+    pipe = ref_pipe.DenseRGBDPipeline(cam)
+    histories = []
+    orig_solve = Problem.solve
+
+    def recording_solve(self):
+        res = orig_solve(self)
+        histories.append(np.array(self._cost_history))
+        return res
+    Problem.solve = recording_solve
+    try:
+        pipe.track(im0, depth0)
+        pipe.track(im1, depth1)
+    finally:
+        Problem.solve = orig_solve
+    kf = pipe.keyframes[0]
+    out = {'im0': im0, 'im1': im1, 'depth0': depth0, 'depth1': depth1, 'camera': np.array([w / 2., h / 2., 200., 200., w, h]),
+           'levels': pipe.pyrlevels, 'T_final': row(pipe.T_c_w[-1]), 'n_solves': len(histories)}
+    for l in range(pipe.pyrlevels):
+        out['depth_%d' % l] = kf.depth[l]
+    for k, hst in enumerate(histories):
+        out['history_%d' % k] = hst
+    np.savez_compressed(os.path.join(OUT, 'dense_rgbd_pipeline.npz'), **out)
+    print('dense_rgbd_pipeline: %d level solves, final pose' % len(histories), out['T_final'][9:], [len(x) for x in histories])
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['motion_ransac', 'orientation', 'rgbd_camera', 'metrics', 'dense_pipeline']
+    which = sys.argv[1:] or ['motion_ransac', 'orientation', 'rgbd_camera', 'metrics', 'dense_pipeline', 'dense_rgbd_pipeline']
     for name in which:
         globals()[name]()

@@ -235,3 +235,24 @@ def test_dense_stereo_pipeline_against_reference():
         assert n_it == len(h) - 1, (k, n_it, len(h))
         assert abs(c0 - h[0]) < 1e-6 * h[0] and abs(c1 - h[-1]) < 1e-6 * h[-1]
     assert rel_err(B.rows_of([pipe.T_c_w[-1]])[0], g['T_final']) < 1e-6
+
+
+def test_dense_rgbd_pipeline_against_reference():
+    """DenseRGBDPipeline.track twice (RGBDCamera, depth maps): depth pyramid on the device, photometric kernel in its RGB-D
+    form ((SO3, t) parameters, translation constant on the coarsest level), against the reference's own run."""
+    from pyslam_b200.pipelines import DenseRGBDPipeline
+    from pyslam_b200.sensors import RGBDCamera
+    g = load_golden('dense_rgbd_pipeline')
+    c = g['camera']
+    pipe = DenseRGBDPipeline(RGBDCamera(float(c[0]), float(c[1]), float(c[2]), float(c[3]), int(c[4]), int(c[5])))
+    pipe.track(g['im0'], g['depth0'])
+    kf = pipe.keyframes[0]
+    for l in range(int(g['levels'])):
+        assert np.array_equal(kf.depth[l], g['depth_%d' % l])
+    pipe.track(g['im1'], g['depth1'])
+    assert len(pipe.level_summaries) == int(g['n_solves'])
+    for k, (lvl, n_it, c0, c1) in enumerate(pipe.level_summaries):
+        h = g['history_%d' % k]
+        assert n_it == len(h) - 1, (k, n_it, len(h))
+        assert abs(c0 - h[0]) < 1e-6 * h[0] and abs(c1 - h[-1]) < 1e-6 * h[-1]
+    assert rel_err(B.rows_of([pipe.T_c_w[-1]])[0], g['T_final']) < 1e-6
