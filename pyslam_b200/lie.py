@@ -11,7 +11,7 @@ are used to *describe* a problem (initial values, measurements) and to hand
 results back; during `Problem.solve()` the poses live on the GPU as packed
 [R|t] rows and every exp/log/adjoint/retract on the hot path runs in
 csrc/lie.cuh.  Objects from a real `liegroups` install are accepted as well
-(duck-typed on `.rot.mat` / `.trans`, see pyslam_b200/lowering.py).
+(duck-typed on `.rot.mat` / `.trans`, see pyslam_b200/problem.py: Problem._lower).
 
 Conventions: tangent order [rho; phi]; left
 perturbation T <- exp(xi) T; small-angle branch when |angle| <= 1e-8.

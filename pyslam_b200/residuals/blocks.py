@@ -6,7 +6,7 @@ protocol `evaluate(params, compute_jacobians=None) -> residual |
 cells 3-4), so user code and tests can call a block directly.  `Problem.solve()`
 does NOT call these `evaluate` methods for the built-in types: it recognises the
 class (`BLOCK_KIND`), packs the measurement into SoA batches
-(pyslam_b200/lowering.py) and linearises them on the GPU (csrc/reproj.cuh,
+(pyslam_b200/problem.py: Problem._lower) and linearises them on the GPU (csrc/panel.cuh, csrc/reproj.cuh,
 csrc/posegraph.cuh).  Only residual types the library does not know are
 evaluated through this Python protocol and uploaded as dense blocks.
 
