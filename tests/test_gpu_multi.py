@@ -201,3 +201,35 @@ def test_nccl_sharded_matches_single_gpu(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     _run_processes(2, 'nccl', False, mode)
+
+
+@pytest.mark.timeout(600)
+def test_local_shards_general_path_and_losses():
+    """Shards whose landmarks do NOT form panels (tracks of 12 poses: materialised-W block kernels, separate retraction
+    kernel) under a Cauchy loss and lambda > 0, time-contiguous shards with contributor masks."""
+    from pyslam_b200 import configs, synthetic
+    from pyslam_b200.dist import connect_local, covisibility_pairs, iterate_local, shard_stereo_ba
+    full = synthetic.stereo_ba(30, 1500, track=12, seed=7)
+    full['loss'] = ('cauchy', 2.0)
+    eng1, _ = configs.ba_engine(full, 0)
+    eng1.finalize()
+    assert eng1.fused_info()[0] == 0
+    ref = [eng1.iterate(1e-2, True) for _ in range(3)]
+    pairs = covisibility_pairs(full['pose_idx'], full['pt_idx'])
+    engines, shards = [], []
+    for r in range(3):
+        d = shard_stereo_ba(full, r, 3, by_time=True)
+        e, _ = configs.ba_engine(d, 0)
+        e.add_coupling(3, pairs[:, 0], pairs[:, 1])
+        e.finalize()
+        engines.append(e); shards.append(d)
+    solvers = connect_local(engines)
+    for it in range(3):
+        for r in iterate_local(solvers, 1e-2, True):
+            np.testing.assert_allclose(r, ref[it], rtol=1e-8)
+    pts_ref = eng1.get_points()
+    for e, d in zip(engines, shards):
+        np.testing.assert_allclose(e.get_poses_se3(), eng1.get_poses_se3(), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(e.get_points(), pts_ref[d['lm_ids']], rtol=1e-9, atol=1e-11)
+    for e in engines + [eng1]:
+        e.close()
