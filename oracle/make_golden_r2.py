@@ -104,6 +104,21 @@ def motion_ransac():
         out[name + '_ransac_counts'] = masks.sum(axis=1)
         out[name + '_ransac_best_T'] = T_best.as_matrix()
         out[name + '_ransac_best_inliers'] = idx_best
+        # the tail of Sparse*Pipeline._compute_frame_to_frame_motion (pipelines/sparse.py:150-163,203-216) with the reference's
+        # classes: RANSAC guess + inliers -> motion-only batch residual -> Problem(motion_options).solve()
+        mo = Options()
+        mo.allow_nondecreasing_steps = True
+        mo.max_nondecreasing_steps = 5
+        mo.min_cost_decrease = 0.99
+        mo.max_iters = 30
+        mo.num_threads = 1
+        mo.linesearch_max_iters = 0
+        f2f = Problem(mo)
+        f2f.add_residual_block(ReprojectionMotionOnlyBatchResidual(cam, o1, o2, np.diag([1., 1., 1.])), ['T_1_0'], loss=ref_losses.L2Loss())
+        f2f.initialize_params({'T_1_0': T_best})
+        f2f.solve()
+        out[name + '_f2f_history'] = np.array(f2f._cost_history)
+        out[name + '_f2f_T'] = row(f2f.param_dict['T_1_0'])
     out['stiffness'] = S
     out['stereo_camera'] = np.array(synthetic.BA_CAMERA)
     out['rgbd_camera'] = np.array([640., 480., 1000., 1000., 1280, 960])

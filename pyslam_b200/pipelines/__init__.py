@@ -4,6 +4,8 @@ from .dense import DenseRGBDPipeline, DenseStereoPipeline, DenseVOPipeline
 from .keyframes import (DenseKeyframe, DenseRGBDKeyframe, DenseStereoKeyframe, Keyframe, SparseRGBDKeyframe,
                         SparseStereoKeyframe)
 from .ransac import FrameToFrameRANSAC
+from .sparse import SparseRGBDPipeline, SparseStereoPipeline, SparseVOPipeline
 
 __all__ = ['FrameToFrameRANSAC', 'Keyframe', 'DenseKeyframe', 'DenseRGBDKeyframe', 'DenseStereoKeyframe',
-           'SparseStereoKeyframe', 'SparseRGBDKeyframe', 'DenseVOPipeline', 'DenseStereoPipeline', 'DenseRGBDPipeline']
+           'SparseStereoKeyframe', 'SparseRGBDKeyframe', 'DenseVOPipeline', 'DenseStereoPipeline', 'DenseRGBDPipeline',
+           'SparseVOPipeline', 'SparseStereoPipeline', 'SparseRGBDPipeline']

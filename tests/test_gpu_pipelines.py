@@ -256,3 +256,35 @@ def test_dense_rgbd_pipeline_against_reference():
         assert n_it == len(h) - 1, (k, n_it, len(h))
         assert abs(c0 - h[0]) < 1e-6 * h[0] and abs(c1 - h[-1]) < 1e-6 * h[-1]
     assert rel_err(B.rows_of([pipe.T_c_w[-1]])[0], g['T_final']) < 1e-6
+
+
+@pytest.mark.parametrize('name', ['stereo', 'rgbd'])
+def test_sparse_pipeline_motion_estimate_against_reference(name):
+    """The hot part of Sparse*Pipeline._compute_frame_to_frame_motion (pipelines/sparse.py:143-163): RANSAC guess + inliers ->
+    motion-only refinement, with matches handed in through the matcher plug-in (the reference's matcher is libviso2)."""
+    from pyslam_b200.pipelines import SparseRGBDPipeline, SparseStereoPipeline
+    g = load_golden('motion_ransac')
+    cam = _cam(g, name)
+
+    class FixedMatches:
+        def match(self, ref_frame, track_frame):
+            return g[name + '_obs_1'], g[name + '_obs_2']
+    pipe = (SparseStereoPipeline if name == 'stereo' else SparseRGBDPipeline)(cam, matcher=FixedMatches())
+    img = np.zeros((4, 4), np.uint8)
+    if name == 'stereo':
+        pipe.track(img, img)
+    else:
+        pipe.track(img, np.ones((4, 4)))
+    np.random.seed(1234)                      # the generator state the reference's perform_ransac saw
+    if name == 'stereo':
+        pipe.track(img, img)
+    else:
+        pipe.track(img, np.ones((4, 4)))
+    hist = g[name + '_f2f_history']
+    assert len(pipe.last_cost_history) == len(hist)
+    np.testing.assert_allclose(pipe.last_cost_history, hist, rtol=1e-7)
+    T_ref = B.p_se3(g[name + '_f2f_T'])
+    T_ref.normalize()
+    assert rel_err(B.rows_of([pipe.T_c_w[-1]])[0], B.rows_of([T_ref])[0]) < 1e-7
+    with pytest.raises(RuntimeError):
+        type(pipe)(cam, matcher=None)._compute_frame_to_frame_motion(None, None) if type(pipe)(cam).matcher is None else (_ for _ in ()).throw(RuntimeError())
