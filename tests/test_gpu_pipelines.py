@@ -286,5 +286,7 @@ def test_sparse_pipeline_motion_estimate_against_reference(name):
     T_ref = B.p_se3(g[name + '_f2f_T'])
     T_ref.normalize()
     assert rel_err(B.rows_of([pipe.T_c_w[-1]])[0], B.rows_of([T_ref])[0]) < 1e-7
-    with pytest.raises(RuntimeError):
-        type(pipe)(cam, matcher=None)._compute_frame_to_frame_motion(None, None) if type(pipe)(cam).matcher is None else (_ for _ in ()).throw(RuntimeError())
+    bare = type(pipe)(cam)                      # without a matcher (and without libviso2) the pipeline says so
+    if bare.matcher is None:
+        with pytest.raises(RuntimeError):
+            bare._compute_frame_to_frame_motion(None, None)
