@@ -2,6 +2,7 @@
 // lowering (ordering / Schur partition / layout), the per-iteration kernel
 // schedule and the C ABI of include/bslam.h.  No CPU fallback exists anywhere
 // in this file: every arithmetic step of the iteration is a kernel launch.
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -1396,13 +1397,26 @@ int bslam_clear_blocks(bslam_solver* s) {
 
 // ------------------------------------------------------------------ lowering
 
+// BSLAM_FINALIZE_TIMING=1: wall time of the lowering stages on stderr (one-time cost per problem)
+#define FIN_T(name)                                                                                       \
+  do {                                                                                                    \
+    if (fin_timing) {                                                                                     \
+      const auto now = std::chrono::steady_clock::now();                                                  \
+      fprintf(stderr, "finalize %-16s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(now - fin_t0).count()); \
+      fin_t0 = now;                                                                                       \
+    }                                                                                                     \
+  } while (0)
+
 int bslam_finalize(bslam_solver* s) {
+  const bool fin_timing = getenv("BSLAM_FINALIZE_TIMING") != nullptr;
+  auto fin_t0 = std::chrono::steady_clock::now();
   NEED(s, "NULL solver");
   NEED(!s->finalized, "already finalized");
   CU(cudaSetDevice(s->device));
   const int N = (int)s->ob_pose.size();
   s->n_obs = N;
 
+  FIN_T("start");
   // ---- which points are eliminated by the Schur complement ----
   std::vector<uint8_t> by_reproj(s->n_pt, 0), by_dense(s->n_pt, 0);
   for (int i = 0; i < N; ++i) by_reproj[s->ob_pt[i]] = 1;
@@ -1419,12 +1433,19 @@ int bslam_finalize(bslam_solver* s) {
   // a landmark observed twice by the same pose goes through the generic (atomic) kernels: the block
   // kernels assume at most one observation per (pose, landmark)
   std::vector<uint8_t> dup_obs(s->n_pt, 0);
+  std::vector<int> obs_ptr(s->n_pt + 1, 0), obs_ids(N);      // observations of every point (CSR, registration order)
   {
-    std::vector<std::pair<int, int>> pp(N);
-    for (int i = 0; i < N; ++i) pp[i] = {s->ob_pt[i], s->ob_pose[i]};
-    std::sort(pp.begin(), pp.end());
-    for (int i = 1; i < N; ++i)
-      if (pp[i] == pp[i - 1]) dup_obs[pp[i].first] = 1;
+    for (int i = 0; i < N; ++i) obs_ptr[s->ob_pt[i] + 1]++;
+    for (int p = 0; p < s->n_pt; ++p) obs_ptr[p + 1] += obs_ptr[p];
+    std::vector<int> cur(obs_ptr.begin(), obs_ptr.end() - 1);
+    for (int i = 0; i < N; ++i) obs_ids[cur[s->ob_pt[i]]++] = i;
+    std::vector<int> seen_by(s->n_se3 + 1, -1);               // pose -> last point that stamped it
+    for (int p = 0; p < s->n_pt; ++p)
+      for (int k = obs_ptr[p]; k < obs_ptr[p + 1]; ++k) {
+        int& stamp = seen_by[s->ob_pose[obs_ids[k]]];
+        if (stamp == p) dup_obs[p] = 1;
+        stamp = p;
+      }
   }
   std::vector<int> regular, big, rest;
   for (int p = 0; p < s->n_pt; ++p) {
@@ -1443,6 +1464,7 @@ int bslam_finalize(bslam_solver* s) {
   }
   std::stable_sort(regular.begin(), regular.end(), [&](int a, int b) { return first_pose[a] < first_pose[b]; });
 
+  FIN_T("classify");
   // ---- dense landmark panels (panel.cuh) ----------------------------------------------
   // Greedy runs of consecutive regular landmarks: up to kPanelLm landmarks whose observing poses number
   // at most kPanelRows.  A run becomes a panel when its (row, landmark) grid is well filled (mode 1) or
@@ -1450,13 +1472,6 @@ int bslam_finalize(bslam_solver* s) {
   // come first in the internal order.
   struct HostPanel { int first, n_lms; std::vector<int> poses; int n_var; };
   std::vector<HostPanel> hpanels;
-  std::vector<int> obs_ptr(s->n_pt + 1, 0), obs_ids(N);
-  {
-    for (int i = 0; i < N; ++i) obs_ptr[s->ob_pt[i] + 1]++;
-    for (int p = 0; p < s->n_pt; ++p) obs_ptr[p + 1] += obs_ptr[p];
-    std::vector<int> cur(obs_ptr.begin(), obs_ptr.end() - 1);
-    for (int i = 0; i < N; ++i) obs_ids[cur[s->ob_pt[i]]++] = i;
-  }
   if (s->fused_mode > 0 && s->groups.size() < 65536) {
     // Panels of at most kPanelLm = 64 landmarks.  (32-landmark panels were measured for small landmark shards --
     // tools/panel_cap_study.py, BSLAM_PANEL_CAP -- and never won once every panel keeps two CTAs per SM resident.)
@@ -1529,6 +1544,7 @@ int bslam_finalize(bslam_solver* s) {
   s->pt_perm.assign(s->n_pt, -1);
   for (int q = 0; q < s->n_pt; ++q) s->pt_perm[s->pt_iperm[q]] = q;
 
+  FIN_T("panels");
   // ---- reduced-system layout ----------------------------------------------------------
   // The non-eliminated parameter blocks (SE3 poses, SE2 poses, vectors, remaining points,
   // in table order) are packed into "supernodes" of <= kNB (32) tangent dimensions; every
@@ -1633,6 +1649,7 @@ int bslam_finalize(bslam_solver* s) {
       a.erase(std::unique(a.begin(), a.end()), a.end());
     }
   }
+  FIN_T("supernodes+adj");
   // nested dissection by recursive bisection of the table order
   std::vector<int> sn_order;
   {
@@ -1753,6 +1770,7 @@ int bslam_finalize(bslam_solver* s) {
       if (h_c < h_best || (h_c == h_best && f_c < f_best)) { sn_order.swap(cand); h_best = h_c; f_best = f_c; }
     }
   }
+  FIN_T("ordering");
   // offsets
   s->se3_off.assign(s->n_se3, -1);
   s->se2_off.assign(s->n_se2, -1);
@@ -1806,11 +1824,16 @@ int bslam_finalize(bslam_solver* s) {
     CU(upload(s->d_tile_pose, idx, s->stream));
   }
 
+  FIN_T("offsets");
   // ---- observations sorted by internal point index (stable) ----
   std::vector<int> order(N);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int a, int b) { return s->pt_perm[s->ob_pt[a]] < s->pt_perm[s->ob_pt[b]]; });
+  {                                    // stable counting sort: the CSR above already groups by point in registration order
+    std::vector<int> at(s->n_pt + 1, 0);
+    for (int p = 0; p < s->n_pt; ++p) at[s->pt_perm[p] + 1] = obs_ptr[p + 1] - obs_ptr[p];
+    for (int q = 0; q < s->n_pt; ++q) at[q + 1] += at[q];
+    for (int p = 0; p < s->n_pt; ++p)
+      std::copy(obs_ids.begin() + obs_ptr[p], obs_ids.begin() + obs_ptr[p + 1], order.begin() + at[s->pt_perm[p]]);
+  }
   std::vector<double> ou(N), ov(N), od(N);
   std::vector<int> opose(N), opt(N), ogrp(N), lm_start(s->n_lm + 1, 0);
   for (int k = 0; k < N; ++k) {
@@ -1824,6 +1847,7 @@ int bslam_finalize(bslam_solver* s) {
   for (int q = 0; q < s->n_lm; ++q) lm_start[q + 1] += lm_start[q];
 
   // ---- panel grids: cell (row, landmark) -> observation, padded to kPanelLm landmarks per row ----
+  FIN_T("sort obs");
   std::vector<bs::PanelDesc> pdescs;
   std::vector<double> pobs;
   std::vector<unsigned short> pgrp;
@@ -1860,6 +1884,7 @@ int bslam_finalize(bslam_solver* s) {
   }
   if (pdescs.empty()) pdescs.push_back(bs::PanelDesc{});
 
+  FIN_T("panel grids");
   // ---- landmark blocks: whole landmarks, <= kBlkObs observations, bounded Schur operands ----
   // Inside a block the observations are re-ordered SLOT-MAJOR (grouped by pose, constant poses last):
   // a warp of the block kernels then reads one or two poses (shared-memory broadcasts) and the camera-side
@@ -1878,7 +1903,8 @@ int bslam_finalize(bslam_solver* s) {
   {
     int q = 0;
     std::vector<int> cur;                       // distinct variable poses of the block under construction
-    std::vector<int> slot_of, new_pos;
+    std::vector<int> slot_of, new_pos, pair_cnt, pair_slot, gen_pair;
+    std::vector<unsigned short> gen_combo;
     std::vector<double> tu, tv, td;
     std::vector<int> tpose, tpt, tgrp;
     s->nb_fused = 0;
@@ -1890,11 +1916,9 @@ int bslam_finalize(bslam_solver* s) {
       cur.clear();
       int q1 = q;
       while (q1 < q_lim && lm_start[q1 + 1] - b.obs_begin <= bs::kBlkObs) {
-        std::vector<int> trial = cur;
         for (int k = lm_start[q1]; k < lm_start[q1 + 1]; ++k)
-          if (s->se3_off[opose[k]] >= 0 && std::find(trial.begin(), trial.end(), opose[k]) == trial.end())
-            trial.push_back(opose[k]);
-        cur.swap(trial);
+          if (s->se3_off[opose[k]] >= 0 && std::find(cur.begin(), cur.end(), opose[k]) == cur.end())
+            cur.push_back(opose[k]);
         ++q1;
       }
       b.n_lms = q1 - q; b.n_obs = lm_start[q1] - b.obs_begin;
@@ -1935,7 +1959,11 @@ int bslam_finalize(bslam_solver* s) {
       // observations, (row observation, col observation) with the row pose the one at the larger reduced
       // offset (lower triangle); grouped by slot pair, longest pairs first (balanced round-robin over warps)
       {
-        std::map<std::pair<int, int>, std::vector<unsigned short>> by_pair;
+        // bucketed by slot pair with a stable counting pass (combos are generated in landmark order, which inside a
+        // pair is the order of their row positions)
+        const int ns = b.n_slots;
+        pair_cnt.assign((size_t)ns * ns + 1, 0);
+        gen_pair.clear(); gen_combo.clear();
         for (int l = 0; l < b.n_lms; ++l) {
           const int k0 = lm_start[b.lm_begin + l] - b.obs_begin, k1 = lm_start[b.lm_begin + l + 1] - b.obs_begin;
           for (int x = k0; x < k1; ++x) {
@@ -1944,17 +1972,29 @@ int bslam_finalize(bslam_solver* s) {
               if (slot_of[y] == 255) continue;
               int ro = x, co = y;
               if (s->se3_off[cur[slot_of[ro]]] < s->se3_off[cur[slot_of[co]]]) std::swap(ro, co);
-              by_pair[{slot_of[ro], slot_of[co]}].push_back((unsigned short)(new_pos[ro] | (new_pos[co] << 8)));
+              const int pk = slot_of[ro] * ns + slot_of[co];
+              gen_pair.push_back(pk);
+              gen_combo.push_back((unsigned short)(new_pos[ro] | (new_pos[co] << 8)));
+              pair_cnt[pk + 1]++;
             }
           }
         }
-        std::vector<std::pair<std::pair<int, int>, std::vector<unsigned short>>> pv(by_pair.begin(), by_pair.end());
+        std::vector<std::pair<std::pair<int, int>, std::vector<unsigned short>>> pv;
+        pair_slot.assign((size_t)ns * ns, -1);
+        for (int pk = 0; pk < ns * ns; ++pk)
+          if (pair_cnt[pk + 1] > 0) {
+            pair_slot[pk] = (int)pv.size();
+            pv.emplace_back(std::make_pair(pk / ns, pk % ns), std::vector<unsigned short>());
+            pv.back().second.reserve(pair_cnt[pk + 1]);
+          }
+        for (size_t k = 0; k < gen_pair.size(); ++k) pv[pair_slot[gen_pair[k]]].second.push_back(gen_combo[k]);
         std::stable_sort(pv.begin(), pv.end(), [](const auto& x, const auto& y) { return x.second.size() > y.second.size(); });
         const int cb0 = (int)sch_combos.size(), pb0 = (int)sch_pairs.size();
         for (auto& e : pv) {
           // combos -> runs of (row + i, col + i)
           std::vector<unsigned short>& cl = e.second;
-          std::sort(cl.begin(), cl.end(), [](unsigned short x, unsigned short y) { return (x & 255) != (y & 255) ? (x & 255) < (y & 255) : x < y; });
+          const auto by_row = [](unsigned short x, unsigned short y) { return (x & 255) != (y & 255) ? (x & 255) < (y & 255) : x < y; };
+          if (!std::is_sorted(cl.begin(), cl.end(), by_row)) std::sort(cl.begin(), cl.end(), by_row);
           const int rb0 = (int)sch_combos.size();
           for (size_t k = 0; k < cl.size();) {
             size_t k2 = k + 1;
@@ -2006,6 +2046,7 @@ int bslam_finalize(bslam_solver* s) {
   if (slot_pose.empty()) slot_pose.push_back(0);
   if (seg_start.empty()) seg_start.push_back(0);
 
+  FIN_T("lm blocks");
   // ---- dense-block structure ----
   s->dn_row_ptr.assign(1, 0); s->dn_col_ptr.assign(1, 0); s->dn_j_ptr.assign(1, 0);
   s->dn_col_index.clear();
@@ -2026,6 +2067,7 @@ int bslam_finalize(bslam_solver* s) {
     s->dn_j_ptr.push_back(s->dn_j_ptr.back() + (long long)s->dn_rows[b] * ncols);
   }
 
+  FIN_T("dense struct");
   // ---- device memory ----
   cudaStream_t st = s->stream;
   std::vector<double> pts_int(3 * (size_t)s->n_pt + 2, 0.0);    // + 2: a panel's point run is copied in 16-byte units
@@ -2141,7 +2183,9 @@ int bslam_finalize(bslam_solver* s) {
   CU(cudaMemsetAsync(s->d_red.p, 0, s->red_len() * sizeof(double), st));
   CU(cudaMemsetAsync(s->d_dx.p, 0, s->d_dx.n * sizeof(double), st));
   CU(cudaStreamSynchronize(st));
+  FIN_T("uploads");
   build_tile_mask(s, opose_lm, lm_start);
+  FIN_T("tile mask");
   s->h_opose_lm = opose_lm;
   s->h_lm_start = lm_start;
   s->finalized = true;

@@ -25,6 +25,7 @@ Extensions (default to reference behaviour): `Options.device`,
 `Problem.last_timings`.
 """
 import copy
+import operator
 import warnings
 
 import numpy as np
@@ -111,9 +112,9 @@ class _ReprojectionBatch:
 
     @staticmethod
     def _factorise(keys):
-        uniq = {}
-        inv = np.fromiter((uniq.setdefault(k, len(uniq)) for k in keys), np.int32, len(keys))
-        return list(uniq), inv
+        uniq = list(dict.fromkeys(keys))
+        index = dict(zip(uniq, range(len(uniq))))
+        return uniq, np.fromiter(map(index.__getitem__, keys), np.int32, len(keys))
 
 
 def _param_dof(p):
@@ -152,10 +153,24 @@ class Problem:
         self._covariance_matrix = None
         self._cost_history = []
         self._batches = []
+        self._point_blocks = []     # (keys, (n, 3) block, row views) of initialize_params
         self._engine = engine
         self._low = None
         self.last_timings = None
         self._timing = False
+
+    @property
+    def _update_partition_dict(self):
+        """key -> range in the update vector (problem.py:252-277); after a lowering it is materialised on first use
+        (10^5 range objects that the hot path never reads)."""
+        if self._partition is None and self._partition_src is not None:
+            keys, start, dof = self._partition_src
+            self._partition = {k: range(b, b + d) for k, b, d in zip(keys, start.tolist(), dof.tolist()) if b >= 0}
+        return self._partition
+
+    @_update_partition_dict.setter
+    def _update_partition_dict(self, value):
+        self._partition, self._partition_src = value, None
 
     # ------------------------------------------------------------------ building
     def add_residual_block(self, block, param_keys, loss=None):
@@ -175,7 +190,34 @@ class Problem:
 
     def initialize_params(self, param_dict):
         """problem.py:83-86 (values are deep-copied)."""
-        self.param_dict.update(copy.deepcopy(param_dict))
+        # Plain float 3-vectors (the 10^5 landmarks of a BA problem) are copied as the rows of ONE block: each
+        # parameter still is its own ndarray object, updated in place as the reference's `+=` does (problem.py:405-409),
+        # but the whole set moves to / from the device with a single copy (_upload_params / _download_params).
+        # Anything else, and any dict whose values alias each other, goes through copy.deepcopy as in the reference.
+        vals = list(param_dict.values())
+        if len({id(v) for v in vals}) != len(vals):
+            self.param_dict.update(copy.deepcopy(param_dict))
+        else:
+            nd, f64 = np.ndarray, np.float64
+            new = dict.fromkeys(param_dict)         # insertion order is the update-vector order (problem.py:252-277)
+            keys3, vals3 = [], []
+            for k, v in param_dict.items():
+                if type(v) is nd:
+                    if v.shape == (3,) and v.dtype == f64:
+                        keys3.append(k)
+                        vals3.append(v)
+                    else:
+                        new[k] = v.copy() if v.dtype != object else copy.deepcopy(v)
+                else:
+                    new[k] = copy.deepcopy(v)
+            if len(keys3) >= 64:
+                block = np.concatenate(vals3).reshape(len(keys3), 3)
+                views = list(block)
+                self._point_blocks.append((keys3, block, views))
+            else:
+                views = [v.copy() for v in vals3]
+            new.update(zip(keys3, views))
+            self.param_dict.update(new)
         self._low = None
 
     def set_parameters_constant(self, param_keys):
@@ -298,9 +340,10 @@ class Problem:
         for bt in self._batches:
             if loss_descriptor(bt.loss) is None or not _builtin_camera(bt.camera):
                 raise ValueError('add_reprojection_batch needs a built-in camera and loss')
-            for k in bt.pose_uniq + bt.point_uniq:
-                if k not in pd:
-                    raise KeyError('Parameter {} has not been initialized'.format(k))
+            if not pd.keys() >= set(bt.pose_uniq) or not pd.keys() >= set(bt.point_uniq):
+                for k in bt.pose_uniq + bt.point_uniq:
+                    if k not in pd:
+                        raise KeyError('Parameter {} has not been initialized'.format(k))
             point_keys.update(bt.point_uniq)
 
         # SO3 parameters live in the library's SO3 table when only fused (SO3, t) photometric blocks use them as
@@ -314,24 +357,45 @@ class Problem:
                 kinds[i] = ('dense',)
                 rot_keys.discard(keys[0])
 
-        # parameter tables, each in param_dict insertion order
-        low.table = {}                      # key -> (kind id, index)
-        low.keys = {'se3': [], 'se2': [], 'pt': [], 'vec': [], 'so3': []}
+        # parameter tables, each in param_dict insertion order.  Plain float arrays (the landmarks: 10^5 of them in a
+        # BA problem) are classified in bulk; every other parameter type goes through the per-object checks.
+        names = ('se3', 'se2', 'pt', 'vec', 'so3')
+        keys, vals = list(pd), list(pd.values())
+        n = len(keys)
+        nd = np.ndarray
+        dof = np.fromiter((len(v) if type(v) is nd else -1 for v in vals), np.int64, n)     # problem.py:257-266
+        code = np.full(n, 3, np.int8)                                                       # index into `names`
+        if point_keys:
+            code[np.fromiter(map(point_keys.__contains__, keys), bool, n)] = 2
         low.opaque = set()
-        for key, p in pd.items():
+        for i in np.flatnonzero(dof < 0):
+            key, p = keys[i], vals[i]
             g = group_of(p)
+            dof[i] = _param_dof(p)
             if g in ('se3', 'se2'):
-                name = g
+                code[i] = names.index(g)
             elif g == 'so3' and key in rot_keys:
-                name = 'so3'
-            elif g is None and key in point_keys:
-                name = 'pt'
+                code[i] = 4
+            elif g is None and code[i] == 2:
+                pass                        # a 3-vector held in a list / tuple
             else:
-                name = 'vec'
+                code[i] = 3
                 if g is not None or (hasattr(p, 'perturb') and hasattr(p, 'dof')):
                     low.opaque.add(key)     # manifold type the library has no kernel for
-            low.table[key] = (name, len(low.keys[name]))
-            low.keys[name].append(key)
+        variable = ~np.fromiter(map(const.__contains__, keys), bool, n) if const else np.ones(n, bool)
+        vdof = np.where(variable, dof, 0)
+        start = np.where(variable, np.cumsum(vdof) - vdof, -1)      # offset in the reference's update vector (problem.py:252-277)
+        stop = int(vdof.sum())
+        low.keys, low.starts = {}, {}
+        pos = np.empty(n, np.int64)
+        for c, name in enumerate(names):
+            ids = np.flatnonzero(code == c)
+            pos[ids] = np.arange(ids.size)
+            low.keys[name] = [keys[i] for i in ids] if ids.size != n else keys
+            low.starts[name] = np.stack([start[ids], dof[ids]], axis=1)     # per table entry: (start, dof), constants start at -1
+        low.table = dict(zip(keys, zip([names[c] for c in code.tolist()], pos.tolist())))     # key -> (table, index)
+        self._partition_src = (keys, start, dof)        # `_update_partition_dict` is built from this on first use
+        self._partition = None
         low.kinds = kinds
         low.dense_ids = [i for i, k in enumerate(kinds) if k[0] == 'dense']
         low.all_fused = not low.dense_ids
@@ -412,16 +476,17 @@ class Problem:
                     i2 = [low.table[self.block_param_keys[i][1]][1] for i in ids]
                     Tobs = np.array([_pose_row(self.residual_blocks[i].T_2_1_obs, n) for i in ids])
                     eng.add_pose_to_pose_blocks(grp, i1, i2, Tobs, S, gk[2][0], gk[2][1])
+        index_of = {name: dict(zip(low.keys[name], range(len(low.keys[name])))) for name in ('se3', 'pt')} if self._batches else {}
         for bt in self._batches:
             ld = loss_descriptor(bt.loss)
-            for k in bt.pose_uniq:
-                if low.table[k][0] != 'se3':
-                    raise ValueError('reprojection batch pose key {} is not an SE3 parameter'.format(k))
-            for k in bt.point_uniq:
-                if low.table[k][0] != 'pt':
-                    raise ValueError('reprojection batch point key {} is not a 3-vector parameter'.format(k))
-            pose_idx = np.fromiter((low.table[k][1] for k in bt.pose_uniq), np.int32, len(bt.pose_uniq))[bt.pose_inv]
-            pt_idx = np.fromiter((low.table[k][1] for k in bt.point_uniq), np.int32, len(bt.point_uniq))[bt.point_inv]
+            try:
+                pose_idx = np.array(list(map(index_of['se3'].__getitem__, bt.pose_uniq)), np.int32)[bt.pose_inv]
+            except KeyError as e:
+                raise ValueError('reprojection batch pose key {} is not an SE3 parameter'.format(e.args[0]))
+            try:
+                pt_idx = np.array(list(map(index_of['pt'].__getitem__, bt.point_uniq)), np.int32)[bt.point_inv]
+            except KeyError as e:
+                raise ValueError('reprojection batch point key {} is not a 3-vector parameter'.format(e.args[0]))
             eng.add_reprojection_blocks(pose_idx, pt_idx, bt.obs, bt.stiffness, bt.camera.intrinsics(), ld[0], ld[1])
 
         # --- host-evaluated blocks: structure ---
@@ -446,16 +511,22 @@ class Problem:
 
         # --- map the engine's internal update ordering to the reference's ---
         lay = eng.layout()
-        self._update_partition_dict = self._get_update_partition_dict()
         D = lay['dim']
-        total = sum(len(r) for r in self._update_partition_dict.values())
+        total = stop
         if total > D:      # D may exceed the sum of dofs: the reduced span contains padding entries
             raise RuntimeError('internal layout mismatch: {} vs {}'.format(total, D))
         src = np.empty(total, np.int64)
-        for key, r in self._update_partition_dict.items():
-            name, idx = low.table[key]
-            o = int(lay[name][idx])
-            src[r.start:r.stop] = np.arange(o, o + len(r))
+        for name, dof in (('se3', 6), ('se2', 3), ('so3', 3), ('pt', 3)):     # fixed-dof tables: one gather each
+            sd = low.starts[name]
+            if not len(sd):
+                continue
+            var = np.flatnonzero(sd[:, 0] >= 0)
+            if np.any(sd[var, 1] != dof):
+                raise RuntimeError('internal layout mismatch for {} parameters'.format(name))
+            src[sd[var, 0][:, None] + np.arange(dof)] = lay[name][var].astype(np.int64)[:, None] + np.arange(dof)
+        for (b, d), o in zip(low.starts['vec'].tolist(), lay['vec'].tolist()):
+            if b >= 0:
+                src[b:b + d] = np.arange(o, o + d)
         low.ref_from_internal = src
         low.dim = D
         low.layout = lay
@@ -465,6 +536,14 @@ class Problem:
         if key in self._low.opaque:
             return np.zeros(_param_dof(p))
         return np.atleast_1d(np.asarray(p, dtype=float)).ravel()
+
+    def _point_block(self, pd):
+        """The (n, 3) array whose rows ARE the point parameters of `pd` (same objects, table order), or None."""
+        ks = self._low.keys['pt']
+        for keys, block, views in self._point_blocks:
+            if len(keys) == len(ks) and keys == ks and all(map(operator.is_, map(pd.__getitem__, ks), views)):
+                return block
+        return None
 
     def _upload_params(self, pd, structure=False):
         """Host parameter objects -> device tables."""
@@ -480,10 +559,15 @@ class Problem:
             eng.set_rotations_so3(np.array([np.asarray(pd[k].mat, dtype=float).ravel() for k in ks['so3']]).reshape(-1, 9),
                                   flags(ks['so3']))
         if ks['pt'] or structure:
-            try:        # one conversion when every point already is a float 3-vector (the common case)
-                xyz = np.array([pd[k] for k in ks['pt']], dtype=float).reshape(len(ks['pt']), 3)
-            except ValueError:
-                xyz = np.array([np.asarray(pd[k], dtype=float).reshape(3) for k in ks['pt']]).reshape(-1, 3)
+            xyz = self._point_block(pd)
+            if xyz is None:
+                vals = [pd[k] for k in ks['pt']]
+                try:        # one pass when every point already is a float64 3-vector
+                    xyz = np.concatenate(vals).reshape(len(vals), 3) if vals else np.zeros((0, 3))
+                    if xyz.dtype != np.float64:
+                        raise ValueError
+                except ValueError:
+                    xyz = np.array([np.asarray(v, dtype=float).reshape(3) for v in vals]).reshape(-1, 3)
             eng.set_points(xyz, flags(ks['pt']))
         if ks['vec'] or structure:
             vals = [self._vec_values(k, pd[k]) for k in ks['vec']]
@@ -511,11 +595,15 @@ class Problem:
             for k, row in zip(ks['so3'], eng.get_rotations_so3()):
                 if k not in const:
                     pd[k].mat = row.reshape(3, 3).copy()
-        if ks['pt']:
+        block = self._point_block(pd) if ks['pt'] else None
+        if block is not None:
+            eng.get_points(out=block)       # the rows are the parameters (constant points come back unchanged)
+        elif ks['pt']:
+            f64, nd = np.float64, np.ndarray
             for k, row in zip(ks['pt'], eng.get_points()):
                 if k not in const:
                     p = pd[k]
-                    if type(p) is np.ndarray and p.shape == (3,) and p.dtype == np.float64:
+                    if type(p) is nd and p.dtype == f64 and p.shape == (3,):
                         p[:] = row                     # in place, as the reference's `+=` (problem.py:405-409)
                     else:
                         self._assign_vector(k, row)

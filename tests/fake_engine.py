@@ -68,7 +68,10 @@ class FakeEngine:
     def get_poses_se2(self):
         return self.tab['se2'].copy()
 
-    def get_points(self):
+    def get_points(self, out=None):
+        if out is not None:
+            out[...] = self.tab['pt']
+            return out
         return self.tab['pt'].copy()
 
     def get_vectors(self):
