@@ -259,3 +259,47 @@ def test_covariance_block_mapping():
     assert rel_err(p._covariance_matrix, o._covariance_matrix) < 1e-7
     pk, qk = B.ba_keys(gb)
     np.testing.assert_allclose(p.get_covariance_block(pk[2], qk[5]), o.get_covariance_block(pk[2], qk[5]), rtol=1e-6, atol=1e-10)
+
+
+def test_landmark_parameters_are_row_views_updated_in_place():
+    """initialize_params copies the float 3-vectors as rows of one block (single copy to / from the device) while
+    every parameter stays its own ndarray object, updated in place as the reference's `+=` does (problem.py:405-409);
+    replacing a parameter object, other shapes and aliased dicts fall back to the per-object path."""
+    rng = np.random.default_rng(0)
+    src = {'p%d' % i: rng.standard_normal(3) for i in range(100)}
+    src['scalar'] = np.array([1.0])
+    src['four'] = np.arange(4.0)
+    keep = {k: v.copy() for k, v in src.items()}
+    pr = pyslam_b200.Problem()
+    pr.initialize_params(src)
+    assert list(pr.param_dict) == list(src)                          # insertion order = update-vector order
+    for k, v in src.items():
+        assert pr.param_dict[k] is not v and np.array_equal(pr.param_dict[k], keep[k])
+    src['p3'][:] = 7.0                                               # deep copy: the caller's arrays are not shared
+    assert np.array_equal(pr.param_dict['p3'], keep['p3'])
+    keys, block, views = pr._point_blocks[0]
+    assert len(keys) == 100 and block.shape == (100, 3) and all(pr.param_dict[k] is v for k, v in zip(keys, views))
+    held = pr.param_dict['p5']
+    block[5] += 1.0                                                  # what a download does
+    assert np.array_equal(held, keep['p5'] + 1.0)
+    # aliased values: exactly copy.deepcopy (aliasing preserved), no block
+    a = np.zeros(3)
+    pr2 = pyslam_b200.Problem()
+    pr2.initialize_params({'x': a, 'y': a, **{'q%d' % i: np.ones(3) for i in range(80)}})
+    assert pr2.param_dict['x'] is pr2.param_dict['y'] and not pr2._point_blocks
+
+
+@pytest.mark.parametrize('replace', [False, True])
+def test_point_block_round_trip_through_the_engine(replace):
+    g = load_golden('ba_huber')
+    pr = B.product_ba_problem(g, bulk=True)
+    pk, qk = B.ba_keys(g)
+    if replace:      # a parameter object swapped behind the block's back: per-object path, same numbers
+        pr.param_dict[qk[2]] = np.array(pr.param_dict[qk[2]])
+    held = [pr.param_dict[k] for k in qk]
+    pr.solve()
+    assert (pr._point_block(pr.param_dict) is None) == (replace or len(qk) < 64)
+    assert all(pr.param_dict[k] is h for k, h in zip(qk, held))      # updated in place
+    assert rel_err(np.array(held), g['pts_final']) < 1e-8
+    ref = pr._get_update_partition_dict()
+    assert pr._update_partition_dict == ref and list(pr._update_partition_dict) == list(ref)
