@@ -22,8 +22,14 @@
 // followed by nt backward-substitution tasks x_k = X_kk^T (y_k - sum_{i>k} L_ik^T x_i).
 // The run time is the latency of the chain diag(k) -> L_ik -> diag(i) along the elimination
 // tree, not flops: diagonal tasks therefore take their (up to two) critical producers
-// through early-published C_ik tiles and form L_ik themselves (CholPlan::cscr).
-// Dependencies are flags in global memory (st.release / ld.acquire at gpu scope) compared
+// through early-published C_ik tiles and form L_ik themselves (CholPlan::cll), and every
+// transfer on that chain -- X_kk to the parent's diagonal task and to the column's
+// off-diagonal tasks, the early C tiles, x_k in the backward substitution -- travels as
+// (value, epoch) RECORDS written and polled with single 16-byte accesses (the LL protocol
+// of NCCL): one store and one polling load per hop instead of store, fence, flag store,
+// flag poll, load.  A diagonal task whose two children finish together takes both in one
+// pass.  (C4: 68 -> 54 us, profiles/r2_chol_micro.md.)
+// The other dependencies are flags in global memory (st.release / ld.acquire at gpu scope) compared
 // against a launch epoch the kernel advances itself (no memsets between launches); all
 // CTAs are co-resident and take tickets in increasing order of a topological order, so a
 // waiting CTA always waits on a ticket held by a running CTA (no deadlock).
@@ -73,12 +79,15 @@ struct CholPlan {
   const int* bwd_rows;   // rows i > k with a non-zero tile (i,k), descending
   int* ready;            // [(nt+1)*nt] epoch flags: tile final
   int* xready;           // [nt]       epoch flags: x_k final
-  int* cready;           // [kEarly nt] epoch flags: early C tile (slot e of row i) published
-  double* cscr;          // [kEarly nt][kNB*kNB] early C tiles.  The critical chain of the factorisation is
+  double* cll;           // [kEarly nt][kNB*kNB] records (value, launch epoch): early C tiles.  The critical chain is
                          //   diag(k) -> off(i,k): L_ik = C_ik X_kk^T -> diag(i): acc += L_ik L_ik^T
-                         // with a global-memory hop (store, fence, flag, poll, load) after each arrow.  C_ik is known
-                         // long before X_kk, so the diagonal task i forms L_ik itself from the early C_ik and X_kk
-                         // as soon as diag(k) posts: one hop and one tile task leave the chain per tree level.
+                         // with a global-memory hop after each arrow.  C_ik is known before X_kk, so the diagonal
+                         // task i forms L_ik itself from the early C_ik and X_kk as soon as diag(k) has stored X_kk:
+                         // one hop and one tile task leave the chain per tree level.
+  double* xll;           // [nt][kNB*kNB] records (value, launch epoch) of X_kk = L_kk^-1 for the parents' diagonal tasks, and
+  double* yll;           // [nt][kNB] records of x_k for the backward substitution: value and flag travel in ONE 16-byte
+                         // store (the LL protocol of NCCL), so the hop  producer -> consumer  on the critical chain is one
+                         // store and one (polling) load instead of store, fence, flag store, flag poll, load
   int* ticket;           // [0] ticket counter, [1] epoch of the last completed launch, [2] CTAs finished
                          // (the last CTA to finish resets [0], [2] and advances [1]: no memsets between launches)
   long long* trace;      // optional [n_tasks][4]: start, dependencies satisfied, end (globaltimer ns), SM id
@@ -126,6 +135,85 @@ BS_D int ld_acquire(const int* p) {
 }
 BS_D void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// (value, epoch) records, 16-byte aligned: written and read with single 16-byte accesses
+BS_D void st_rec(double* rec, double value, int epoch) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(rec), "l"(__double_as_longlong(value)), "l"((long long)epoch) : "memory");
+}
+// Tiles of kNB x kNB records (kLower: only the lower triangle is stored) -> shared memory: every thread polls the
+// records it needs, of both tiles when NT == 2, ALL in flight at once -- one L2 round trip after the producer's store lands
+template <bool kLower>
+BS_D void tile_to_records(double* R, const double* src, int epoch) {      // src: shared memory tile, leading dimension kLd
+  for (int q = threadIdx.x; q < kNB * kNB / 2; q += kCholThreads) {
+    const int r = q / (kNB / 2), c2 = (q % (kNB / 2)) << 1;
+    if (!kLower || c2 <= r) {
+      st_rec(R + 2 * (r * kNB + c2), src[r * kLd + c2], epoch);
+      st_rec(R + 2 * (r * kNB + c2 + 1), src[r * kLd + c2 + 1], epoch);
+    }
+  }
+}
+template <int NT, bool kLower>
+BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d1, int epoch) {
+  constexpr int kPer = kNB * kNB / 2 / kCholThreads;      // (row, column pair) slots per thread
+  long long v[NT][kPer][2], e[NT][kPer][2];
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < kPer; ++h) {
+        const int q = threadIdx.x + h * kCholThreads;
+        const int r = q / (kNB / 2), c2 = (q % (kNB / 2)) << 1;
+        const double* rec = (t ? R1 : R0) + 2 * (r * kNB + c2);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          v[t][h][w] = 0; e[t][h][w] = epoch;
+          if (!kLower || c2 <= r)          // lower triangle (the entry above a diagonal element is stored as 0)
+            asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v[t][h][w]), "=l"(e[t][h][w]) : "l"(rec + 2 * w) : "memory");
+        }
+      }
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int h = 0; h < kPer; ++h) ok = ok && e[t][h][0] == (long long)epoch && e[t][h][1] == (long long)epoch;
+    if (ok) break;
+    __nanosleep(64);
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int h = 0; h < kPer; ++h) {
+      const int q = threadIdx.x + h * kCholThreads;
+      const int r = q / (kNB / 2), c2 = (q % (kNB / 2)) << 1;
+      double* d = t ? d1 : d0;
+      d[r * kLd + c2] = __longlong_as_double(v[t][h][0]);
+      d[r * kLd + c2 + 1] = __longlong_as_double(v[t][h][1]);
+    }
+}
+
+BS_D int rec_epoch(const double* rec) {
+  long long v, e;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(rec) : "memory");
+  (void)v;
+  return (int)e;
+}
+// N records at rec[stride * i]: all loads in flight at once, repeated until every epoch matches
+template <int N>
+BS_D void ld_recs(const double* rec, int stride, int epoch, double (&out)[N]) {
+  long long v[N], e[N];
+  for (;;) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v[i]), "=l"(e[i]) : "l"(rec + (size_t)stride * i) : "memory");
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && e[i] == (long long)epoch;
+    if (ok) break;
+    __nanosleep(64);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = __longlong_as_double(v[i]);
 }
 
 // Block-wide wait until *flag == epoch.
@@ -200,17 +288,15 @@ BS_D void acc_foreach(F f) {
     for (int j = 0; j < kAccNJ; ++j) f(i, j, m0 + 8 * i + g, n0 + 8 * j + 2 * t);
 }
 
-// 1/sqrt(d) to full double precision: hardware approximation (MUFU.RSQ64H, ~2^-22) + two
-// Newton steps; ~2x shorter dependency chain than the library rsqrt() on the pivot critical path.
+// 1/sqrt(d) to full double precision: hardware approximation (MUFU.RSQ64H, relative error e ~ 2^-22) + ONE third-order
+// correction  y (1 + e/2 + 3 e^2 / 8),  e = 1 - d y^2  (error 5/16 e^3 ~ 2^-65): four dependent fp64 operations on the pivot
+// critical path instead of the six of two Newton steps (and ~3x fewer than the library rsqrt()).
 BS_D double fast_rsqrt(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double e = fma(-(d * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-  }
-  return y;
+  const double e = fma(-(d * y), y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
 }
 
 // ---- 16x16 building blocks (one warp each) ------------------------------------------------
@@ -388,10 +474,12 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
   extern __shared__ double smem[];
   double* sA = smem;
   double* sB = smem + kNB * kLd;
-  double* scol = smem + 2 * kNB * kLd;      // 64
+  double* sA2 = smem + 2 * kNB * kLd;       // second pair of tiles: both early tiles of a diagonal task at once
+  double* sB2 = smem + 3 * kNB * kLd;
+  double* scol = smem + 4 * kNB * kLd;      // 64
   double* srcp = scol + 64;                 // 64
   double* sred = srcp + 64;                 // kCholThreads
-  __shared__ int s_ticket, s_bad, s_epoch;
+  __shared__ int s_ticket, s_bad, s_epoch, s_pair;
   const int tid = threadIdx.x;
   const int nt = p.nt;
   if (tid == 0) s_epoch = ld_acquire(p.ticket + 1) + 1;
@@ -464,28 +552,71 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         __syncthreads();
         tile_mma_abt(sA, ti != tj ? sB : sA, acc);
       }
-      for (int e = 0; e < n_early; ++e) {
-        // last (critical) producer columns k: L_ik = C_ik X_kk^T formed here from the early C tile
-        const int k = p.klist[kend_l + e];
-        if (tid == 0) {
-          while (ld_acquire(p.cready + kEarly * ti + e) != epoch) __nanosleep(20);
-        } else if (tid == 32) {
-          while (ld_acquire(p.ready + k * nt + k) != epoch) __nanosleep(20);
+      // last (critical) producer columns k: L_ik = C_ik X_kk^T formed here from the early C tile and the records of X_kk.
+      // On the chain: ONE polling load per thread (all its records of X in flight at once), two MMAs, three barriers.
+      if (n_early > 0) {
+        const int k0 = p.klist[kend_l], k1 = p.klist[kend_l + n_early - 1];
+        const double* R0 = p.xll + (size_t)k0 * kNB * kNB * 2;
+        const double* R1 = p.xll + (size_t)k1 * kNB * kNB * 2;
+        // the C tiles are normally there before the X tiles: into shared memory first
+        __syncthreads();
+        {
+          const double* C0 = p.cll + (size_t)(kEarly * ti) * kNB * kNB * 2;
+          if (n_early == 2) tile_records<2, false>(C0, C0 + (size_t)kNB * kNB * 2, sA, sA2, epoch);
+          else tile_records<1, false>(C0, C0, sA, sA, epoch);
         }
-        __syncthreads();
-        tile_load(sA, p.cscr + (size_t)(kEarly * ti + e) * kNB * kNB, kNB, kNB);
-        tile_load(sB, Linv + (size_t)k * kNB * kNB, kNB, kNB);
-        __syncthreads();
-        TileAcc t_acc;
-        acc_zero(t_acc);
-        tile_mma_abt(sA, sB, t_acc);
-        __syncthreads();
-        acc_foreach([&](int i, int j, int r, int c) {
-          sA[r * kLd + c] = t_acc.c[i][j][0];
-          sA[r * kLd + c + 1] = t_acc.c[i][j][1];
-        });
-        __syncthreads();
-        tile_mma_abt(sA, sA, acc);
+        // a separator's two children usually finish together: take both X tiles in one pass unless the first child is clearly ahead
+        bool together = false;
+        if (n_early == 2) {
+          if (tid == 0) {
+            bool r0, r1;
+            for (;;) {
+              r0 = rec_epoch(R0) == epoch; r1 = rec_epoch(R1) == epoch;
+              if (r0 || r1) break;
+              __nanosleep(40);
+            }
+            s_pair = (r0 && !r1) ? 0 : 1;
+          }
+          __syncthreads();
+          together = s_pair != 0;
+        }
+        auto form = [&](double* sC, double* sX) {       // acc += (C X^T)(C X^T)^T
+          TileAcc t_acc;
+          acc_zero(t_acc);
+          tile_mma_abt(sC, sX, t_acc);
+          __syncthreads();
+          acc_foreach([&](int i, int j, int r, int c) {
+            sC[r * kLd + c] = t_acc.c[i][j][0];
+            sC[r * kLd + c + 1] = t_acc.c[i][j][1];
+          });
+          __syncthreads();
+          tile_mma_abt(sC, sC, acc);
+        };
+        if (together) {
+          tile_records<2, true>(R0, R1, sB, sB2, epoch);
+          __syncthreads();
+          TileAcc t0_acc, t1_acc;
+          acc_zero(t0_acc); acc_zero(t1_acc);
+          tile_mma_abt(sA, sB, t0_acc);
+          tile_mma_abt(sA2, sB2, t1_acc);
+          __syncthreads();
+          acc_foreach([&](int i, int j, int r, int c) {
+            sA[r * kLd + c] = t0_acc.c[i][j][0]; sA[r * kLd + c + 1] = t0_acc.c[i][j][1];
+            sA2[r * kLd + c] = t1_acc.c[i][j][0]; sA2[r * kLd + c + 1] = t1_acc.c[i][j][1];
+          });
+          __syncthreads();
+          tile_mma_abt(sA, sA, acc);
+          tile_mma_abt(sA2, sA2, acc);
+        } else {
+          tile_records<1, true>(R0, R0, sB, sB, epoch);
+          __syncthreads();
+          form(sA, sB);
+          if (n_early == 2) {
+            tile_records<1, true>(R1, R1, sB2, sB2, epoch);
+            __syncthreads();
+            form(sA2, sB2);
+          }
+        }
       }
       __syncthreads();
       if (p.trace && tid == 0) t1 = gtime();
@@ -496,16 +627,14 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
       });
       __syncthreads();
       if (ti != tj && task.early) {          // publish the early C tile for the diagonal task of row ti
-        double* Cs = p.cscr + (size_t)(kEarly * ti + task.early - 1) * kNB * kNB;
-        for (int e = tid; e < kNB * kNB / 2; e += kCholThreads) {
-          const int r = e / (kNB / 2), c2 = (e % (kNB / 2)) << 1;
-          *reinterpret_cast<double2*>(Cs + r * kNB + c2) = make_double2(sA[r * kLd + c2], sA[r * kLd + c2 + 1]);
-        }
-        post_flag(p.cready + kEarly * ti + task.early - 1, epoch);
+        tile_to_records<false>(p.cll + (size_t)(kEarly * ti + task.early - 1) * kNB * kNB * 2, sA, epoch);
       }
       if (ti == tj) {
         const int bad = tile_potrf_inv(sA, sB, scol, srcp, &s_bad);
         if (bad && tid == 0) red_add(scalars + 3 /*CHOL_FAIL*/, (double)bad);
+        {   // first out: the records the parent's diagonal task is polling
+          tile_to_records<true>(p.xll + (size_t)tj * kNB * kNB * 2, sB, epoch);
+        }
         double* Lk = Linv + (size_t)tj * kNB * kNB;
         for (int e = tid; e < kNB * kNB; e += kCholThreads) {
           const int r = e / kNB, c = e % kNB;
@@ -513,9 +642,11 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
           Lk[e] = sB[r * kLd + c];
         }
       } else {
-        wait_flag(p.ready + tj * nt + tj, epoch);
+        {
+          const double* Rj = p.xll + (size_t)tj * kNB * kNB * 2;
+          tile_records<1, true>(Rj, Rj, sB, sB, epoch);      // X_jj straight from the diagonal task's records
+        }
         if (p.trace && tid == 0) t1 = gtime();
-        tile_load(sB, Linv + (size_t)tj * kNB * kNB, kNB, kNB);
         __syncthreads();
         acc_zero(acc);
         tile_mma_abt(sA, sB, acc);            // L_ij = C X_jj^T
@@ -546,10 +677,11 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         const double* L = S + (size_t)(i * kNB + kR * grp) * ld + (size_t)k * kNB + c;
 #pragma unroll
         for (int r = 0; r < kR; ++r) lr[r] = __ldcg(L + (size_t)r * ld);
-        wait_flag(p.xready + i, epoch);
-        const double* xi = x + (size_t)i * kNB + kR * grp;
+        const double* xi = p.yll + 2 * ((size_t)i * kNB + kR * grp);      // records of x_i: polled, no flag
+        double xv[kR];
+        ld_recs<kR>(xi, 2, epoch, xv);
 #pragma unroll
-        for (int r = 0; r < kR; ++r) part = fma(lr[r], __ldcg(xi + r), part);
+        for (int r = 0; r < kR; ++r) part = fma(lr[r], xv[r], part);
       }
       wait_flag(p.ready + nt * nt + k, epoch);     // y_k (row 0 of the right-hand-side tile)
       if (p.trace && tid == 0) t1 = gtime();
@@ -573,6 +705,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
         double sum = 0.0;
 #pragma unroll
         for (int q = 0; q < kG; ++q) sum += sred[q * kNB + c];
+        st_rec(p.yll + 2 * ((size_t)k * kNB + c), sum, epoch);
         x[(size_t)k * kNB + c] = sum;
         scol[c] = sum;
       }
@@ -614,7 +747,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
   }
 }
 
-constexpr size_t kCholSmem = (2 * kNB * kLd + 64 + 64 + kCholThreads) * sizeof(double);
+constexpr size_t kCholSmem = (4 * kNB * kLd + 64 + 64 + kCholThreads) * sizeof(double);
 
 // Everything a linearisation needs cleared or refreshed, in ONE launch (each dependent launch inside the
 // iteration's CUDA graph costs 2-3 us of latency):

@@ -182,8 +182,8 @@ struct bslam_solver {
   bool plan_valid = false;
   int chol_epoch = 0, chol_grid = 0, n_tile_tasks = 0;
   DevBuf<bs::CholTask> d_tasks;
-  DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_cready, d_ticket;
-  DevBuf<double> d_cscr;                           // early C tiles of the diagonal tasks (CholPlan::cscr)
+  DevBuf<double> d_cll, d_xll, d_yll;     // (value, epoch) records of the factorisation's critical hops (CholPlan::xll / yll)
+  DevBuf<int> d_klist, d_bwd_ptr, d_bwd_rows, d_ready, d_xready, d_ticket;
   DevBuf<unsigned char> d_fill_mask;               // tile mask after symbolic fill-in
   DevBuf<long long> d_trace;                       // debug: per-task timestamps (bslam_debug_chol_trace)
   std::vector<bs::CholTask> h_tasks;
@@ -728,9 +728,12 @@ int build_chol_plan(bslam_solver* s) {
   CU(upload(s->d_bwd_rows, bwd_rows, st));
   CU(s->d_ready.alloc((size_t)(nt + 1) * nt));
   CU(s->d_xready.alloc(nt));
-  CU(s->d_cready.alloc((size_t)bs::kEarly * nt));
-  CU(s->d_cscr.alloc((size_t)bs::kEarly * nt * bs::kNB * bs::kNB));
-  CU(cudaMemsetAsync(s->d_cready.p, 0, s->d_cready.n * sizeof(int), st));
+  CU(s->d_cll.alloc((size_t)2 * bs::kEarly * nt * bs::kNB * bs::kNB));
+  CU(cudaMemsetAsync(s->d_cll.p, 0, s->d_cll.n * sizeof(double), st));
+  CU(s->d_xll.alloc((size_t)2 * nt * bs::kNB * bs::kNB));
+  CU(s->d_yll.alloc((size_t)2 * nt * bs::kNB));
+  CU(cudaMemsetAsync(s->d_xll.p, 0, s->d_xll.n * sizeof(double), st));
+  CU(cudaMemsetAsync(s->d_yll.p, 0, s->d_yll.n * sizeof(double), st));
   CU(s->d_ticket.alloc(4));                     // [ticket, epoch of the last completed launch, CTAs done]
   CU(cudaMemsetAsync(s->d_ticket.p, 0, 4 * sizeof(int), st));
   CU(cudaMemsetAsync(s->d_ready.p, 0, s->d_ready.n * sizeof(int), st));
@@ -760,7 +763,7 @@ int do_solve_reduced(bslam_solver* s, bool retract_poses = false) {
   p.n_tile_tasks = s->n_tile_tasks;
   p.tasks = s->d_tasks.p; p.klist = s->d_klist.p; p.bwd_ptr = s->d_bwd_ptr.p; p.bwd_rows = s->d_bwd_rows.p;
   p.ready = s->d_ready.p; p.xready = s->d_xready.p; p.ticket = s->d_ticket.p;
-  p.cready = s->d_cready.p; p.cscr = s->d_cscr.p;
+  p.cll = s->d_cll.p; p.xll = s->d_xll.p; p.yll = s->d_yll.p;
   p.trace = s->d_trace.p;
   p.rt_poses = retract_poses ? s->d_se3.p : nullptr;
   p.rt_pose_off = s->d_se3_off.p; p.rt_tile_ptr = s->d_tile_pose_ptr.p; p.rt_tile_pose = s->d_tile_pose.p;
