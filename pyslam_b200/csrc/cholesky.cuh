@@ -193,9 +193,9 @@ BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d
 }
 
 BS_D int rec_epoch(const double* rec) {
-  long long v, e;
+  [[maybe_unused]] long long v;
+  long long e;
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(rec) : "memory");
-  (void)v;
   return (int)e;
 }
 // N records at rec[stride * i]: all loads in flight at once, repeated until every epoch matches

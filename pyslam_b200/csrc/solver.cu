@@ -689,8 +689,30 @@ int build_chol_plan(bslam_solver* s) {
       for (int e = 0; e < T.early; ++e)
         tasks[tix[(size_t)T.i * nt + klist[T.kend - T.early + e]]].early = e + 1;
     }
+    // Ticket levels.  A diagonal task takes its early producers (i, k) as C tiles, which those tasks publish BEFORE they
+    // wait for diag(k): for the ticket order the diagonal task sits at the level of these tasks, right behind them
+    // (same level, same row, diagonal last), instead of two levels up behind every other task of the levels between --
+    // near the leaves, where a level holds more tasks than there are CTAs, it would otherwise get its CTA microseconds late.
+    std::vector<int> tlevel(tasks.size(), 0);
+    for (size_t t = 0; t < tasks.size(); ++t) {          // column-major: producers come first
+      const bs::CholTask& T = tasks[t];
+      const int n_early = T.i == T.j ? T.early : 0;
+      int lv = 0;
+      for (int kk = T.kbeg; kk < T.kend; ++kk) {
+        const int k = klist[kk];
+        const int add = kk >= T.kend - n_early ? 0 : 1;
+        lv = std::max(lv, tlevel[tix[(size_t)T.i * nt + k]] + add);
+        if (T.i != T.j) lv = std::max(lv, tlevel[tix[(size_t)T.j * nt + k]] + 1);
+      }
+      if (T.i != T.j) lv = std::max(lv, tlevel[tix[(size_t)T.j * nt + T.j]] + 1);
+      tlevel[t] = lv;
+    }
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      if (tlevel[x] != tlevel[y]) return tlevel[x] < tlevel[y];
+      if (tasks[x].i != tasks[y].i) return tasks[x].i < tasks[y].i;
+      return (tasks[x].i == tasks[x].j) < (tasks[y].i == tasks[y].j);
+    });
     std::vector<bs::CholTask> sorted(tasks.size());
     for (size_t t = 0; t < tasks.size(); ++t) sorted[t] = tasks[order[t]];
     tasks.swap(sorted);
