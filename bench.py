@@ -432,7 +432,7 @@ def run_ours(args):
                            'add_reprojection_batch of 600 000 blocks; lower_s = key -> table lowering + bslam_finalize (ordering, '
                            'panels, uploads), once per problem, measured on a second instance; solve_s_total = Problem.solve() on the fresh '
                            'problem: that lowering + eval_cost + iterations with the reference termination logic + download into the '
-                           '100 500 parameter objects -- the drop-in API is bound by the per-key Python lowering, not by the iterations'}
+                           '100 500 parameter objects -- the drop-in API is bound by the one-time lowering (bulk key handling in Python + bslam_finalize), not by the iterations'}
             del pr
         except Exception as ex:
             api = {'error': repr(ex)[:300]}
