@@ -25,9 +25,10 @@
 // through early-published C_ik tiles and form L_ik themselves (CholPlan::cll), and every
 // transfer on that chain -- X_kk to the parent's diagonal task and to the column's
 // off-diagonal tasks, the early C tiles, x_k in the backward substitution -- travels as
-// (value, epoch) RECORDS written and polled with single 16-byte accesses (the LL protocol
-// of NCCL): one store and one polling load per hop instead of store, fence, flag store,
-// flag poll, load.  A diagonal task whose two children finish together takes both in one
+// (value, tag) RECORDS written and polled with single 16-byte accesses (the LL protocol
+// of NCCL; tag = launch epoch XOR the value's bits, so that even a torn 16-byte access
+// cannot pair a stale value with a fresh tag): one store and one polling load per hop
+// instead of store, fence, flag store, flag poll, load.  A diagonal task whose two children finish together takes both in one
 // pass.  (C4: 68 -> 54 us, profiles/r2_chol_micro.md.)
 // The other dependencies are flags in global memory (st.release / ld.acquire at gpu scope) compared
 // against a launch epoch the kernel advances itself (no memsets between launches); all
@@ -84,7 +85,7 @@ struct CholPlan {
                          // with a global-memory hop after each arrow.  C_ik is known before X_kk, so the diagonal
                          // task i forms L_ik itself from the early C_ik and X_kk as soon as diag(k) has stored X_kk:
                          // one hop and one tile task leave the chain per tree level.
-  double* xll;           // [nt][kNB*kNB] records (value, launch epoch) of X_kk = L_kk^-1 for the parents' diagonal tasks, and
+  double* xll;           // [nt][kNB*kNB] records (value, tag: st_rec) of X_kk = L_kk^-1 for the parents' diagonal tasks, and
   double* yll;           // [nt][kNB] records of x_k for the backward substitution: value and flag travel in ONE 16-byte
                          // store (the LL protocol of NCCL), so the hop  producer -> consumer  on the critical chain is one
                          // store and one (polling) load instead of store, fence, flag store, flag poll, load
@@ -137,9 +138,13 @@ BS_D void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// (value, epoch) records, 16-byte aligned: written and read with single 16-byte accesses
+// (value, tag) records, 16-byte aligned, written and read with single 16-byte accesses; tag = epoch XOR the value's bits.
+// A record is accepted when tag XOR value == epoch, which makes the protocol independent of the 16 bytes being transferred
+// atomically: a torn read pairs the new value with the old tag (accepted only if that tag also fits the new value -- then
+// the value IS the new one) or the old value with the new tag (accepted only if old value == new value).
 BS_D void st_rec(double* rec, double value, int epoch) {
-  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(rec), "l"(__double_as_longlong(value)), "l"((long long)epoch) : "memory");
+  const long long bits = __double_as_longlong(value);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(rec), "l"(bits), "l"(bits ^ (long long)epoch) : "memory");
 }
 // Tiles of kNB x kNB records (kLower: only the lower triangle is stored) -> shared memory: every thread polls the
 // records it needs, of both tiles when NT == 2, ALL in flight at once -- one L2 round trip after the producer's store lands
@@ -168,7 +173,7 @@ BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d
         const double* rec = (t ? R1 : R0) + 2 * (r * kNB + c2);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          v[t][h][w] = 0; e[t][h][w] = epoch;
+          v[t][h][w] = 0; e[t][h][w] = epoch;      // not needed: passes the check below
           if (!kLower || c2 <= r)          // lower triangle (the entry above a diagonal element is stored as 0)
             asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v[t][h][w]), "=l"(e[t][h][w]) : "l"(rec + 2 * w) : "memory");
         }
@@ -176,7 +181,8 @@ BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d
 #pragma unroll
     for (int t = 0; t < NT; ++t)
 #pragma unroll
-      for (int h = 0; h < kPer; ++h) ok = ok && e[t][h][0] == (long long)epoch && e[t][h][1] == (long long)epoch;
+      for (int h = 0; h < kPer; ++h)
+        ok = ok && (e[t][h][0] ^ v[t][h][0]) == (long long)epoch && (e[t][h][1] ^ v[t][h][1]) == (long long)epoch;
     if (ok) break;
     __nanosleep(64);
   }
@@ -193,10 +199,9 @@ BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d
 }
 
 BS_D int rec_epoch(const double* rec) {
-  [[maybe_unused]] long long v;
-  long long e;
+  long long v, e;
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(rec) : "memory");
-  return (int)e;
+  return (int)(e ^ v);
 }
 // N records at rec[stride * i]: all loads in flight at once, repeated until every epoch matches
 template <int N>
@@ -208,7 +213,7 @@ BS_D void ld_recs(const double* rec, int stride, int epoch, double (&out)[N]) {
       asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(v[i]), "=l"(e[i]) : "l"(rec + (size_t)stride * i) : "memory");
     bool ok = true;
 #pragma unroll
-    for (int i = 0; i < N; ++i) ok = ok && e[i] == (long long)epoch;
+    for (int i = 0; i < N; ++i) ok = ok && (e[i] ^ v[i]) == (long long)epoch;
     if (ok) break;
     __nanosleep(64);
   }

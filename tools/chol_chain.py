@@ -1,4 +1,4 @@
-"""Critical chain of one traced chol_solve_kernel run on BASELINE config 4: the diagonal tasks in the order they
+"""Critical chain of one traced chol_solve_kernel run on BASELINE config 4 (or config 2 with the argument c2): the diagonal tasks in the order they
 finish, with the time since the previous link, plus the shape of the plan (tiles, levels)."""
 import sys
 import numpy as np
@@ -6,8 +6,14 @@ sys.path.insert(0, '.')
 import bench
 from pyslam_b200 import synthetic
 
-d = synthetic.stereo_ba(500, 100000, track=6, seed=0)
-eng, _ = bench.build_engine(d, 0)
+if 'c2' in sys.argv:      # BASELINE config 2: SE(2) pose graph, 1000 poses, 100 loop closures
+    from pyslam_b200 import configs
+    pr = configs.pose_graph_problem(synthetic.se2_pose_graph(1000, 100, seed=0), 'se2')
+    pr._ensure_lowered()
+    eng = pr._engine
+else:
+    d = synthetic.stereo_ba(500, 100000, track=6, seed=0)
+    eng, _ = bench.build_engine(d, 0)
 for _ in range(2):
     eng.linearize(fetch_cost=False); eng.reduce(0.); eng.solve_reduced(); eng.scalars()
 eng.linearize(fetch_cost=False); eng.reduce(0.)
