@@ -43,6 +43,9 @@
 
 namespace bs {
 
+#ifndef BSLAM_POLL_NS
+#define BSLAM_POLL_NS 64     // back-off between two polls of a record
+#endif
 #ifndef BSLAM_TILE
 #define BSLAM_TILE 32
 #endif
@@ -184,7 +187,7 @@ BS_D void tile_records(const double* R0, const double* R1, double* d0, double* d
       for (int h = 0; h < kPer; ++h)
         ok = ok && (e[t][h][0] ^ v[t][h][0]) == (long long)epoch && (e[t][h][1] ^ v[t][h][1]) == (long long)epoch;
     if (ok) break;
-    __nanosleep(64);
+    __nanosleep(BSLAM_POLL_NS);
   }
 #pragma unroll
   for (int t = 0; t < NT; ++t)
@@ -215,7 +218,7 @@ BS_D void ld_recs(const double* rec, int stride, int epoch, double (&out)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i) ok = ok && (e[i] ^ v[i]) == (long long)epoch;
     if (ok) break;
-    __nanosleep(64);
+    __nanosleep(BSLAM_POLL_NS);
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) out[i] = __longlong_as_double(v[i]);
@@ -578,7 +581,7 @@ chol_solve_kernel(double* __restrict__ S, int ld, double* __restrict__ Linv, dou
             for (;;) {
               r0 = rec_epoch(R0) == epoch; r1 = rec_epoch(R1) == epoch;
               if (r0 || r1) break;
-              __nanosleep(40);
+              __nanosleep(BSLAM_POLL_NS);
             }
             s_pair = (r0 && !r1) ? 0 : 1;
           }
