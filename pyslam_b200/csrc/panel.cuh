@@ -487,20 +487,39 @@ constexpr int kUnitsPerPanel = kPanelLm / 32;
 template <int kLoss>
 __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const PanelArgs a) {
   __shared__ double sred[2 * (kFinishThreads / 32)];
+  // per warp: the poses of the unit's rows at the linearisation point [8][12], after the update [8][12], and the
+  // pose updates of the variable rows [8][6] -- staged once per unit with lane-parallel loads (one latency), then
+  // read as broadcasts by the row loops (ncu: a quarter of the kernel's stall samples sat on the first use of a
+  // pose loaded inside the loops, another sixth on the row descriptors)
+  constexpr int kStage = 2 * 12 * kPanelRows + 6 * kPanelRows;
+  __shared__ double sStage[kFinishThreads / 32][kStage];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_warps = gridDim.x * (kFinishThreads / 32);
   const int n_units = a.n_panels * kUnitsPerPanel;
+  double* sP = sStage[warp];
+  double* sN = sP + 12 * kPanelRows;
+  double* sD = sN + 12 * kPanelRows;
   double cost = 0.0, dx2 = 0.0;
+  static_assert(sizeof(PanelDesc) == 32 + 16 * kPanelRows && sizeof(PanelRow) == 16, "descriptor read as 16-byte words");
 
   for (int unit = blockIdx.x * (kFinishThreads / 32) + warp; unit < n_units; unit += n_warps) {
     const int pn = unit / kUnitsPerPanel;
-    const PanelDesc* dsc = a.descs + pn;
-    const Panel pan = dsc->hdr;
+    // descriptor: header by every lane (one broadcast), row r by lane r -- both loads in flight together; the rows
+    // reach the other lanes through shuffles
+    const uint4* dw = reinterpret_cast<const uint4*>(a.descs + pn);
+    const uint4 hw = __ldg(dw);
+    uint4 myrow = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < kPanelRows) myrow = __ldg(dw + 2 + lane);
+    Panel pan;
+    pan.lm_begin = (int)hw.x; pan.n_lms = (int)hw.y; pan.n_rows = (int)hw.z; pan.n_var = (int)hw.w;
     const int half = unit % kUnitsPerPanel;
     const int j = 32 * half + lane;
     if (32 * half >= pan.n_lms) continue;                  // warp-uniform
     const bool valid = j < pan.n_lms;
     const size_t q = (size_t)pan.lm_begin + (valid ? j : 0);
+    unsigned row_mask[kPanelRows];
+#pragma unroll
+    for (int r = 0; r < kPanelRows; ++r) row_mask[r] = __shfl_sync(0xffffffffu, half ? myrow.w : myrow.z, r);
     // everything the unit reads from HBM, requested up front
     double ou[kPanelRows], ov[kPanelRows], od[kPanelRows];
     unsigned present = 0;
@@ -508,8 +527,7 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
     for (int r = 0; r < kPanelRows; ++r) {
       ou[r] = ov[r] = od[r] = 0.0;
       if (r < pan.n_rows) {
-        const PanelRow row = dsc->rows[r];
-        const unsigned m = half ? row.mask_hi : row.mask_lo;
+        const unsigned m = row_mask[r];
         if (valid && ((m >> lane) & 1u)) {
           const double* cellp = a.pobs + (size_t)pn * kPanelObs + r * kPanelLm + j;
           ou[r] = ld_stream(cellp); ov[r] = ld_stream(cellp + kPanelRows * kPanelLm); od[r] = ld_stream(cellp + 2 * kPanelRows * kPanelLm);
@@ -524,20 +542,43 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
 #pragma unroll
       for (int k = 0; k < 6; ++k) vi[k] = ld_stream(a.Vinv + 6 * q + k);
     }
+    // ---- poses and pose updates of the rows -> shared memory (all loads of a lane in flight together)
+    __syncwarp();                                          // the previous unit's readers are done
+    {
+      double vP[3], vN[3], vD[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int e = lane + 32 * i, r = min(e / 12, kPanelRows - 1), k = e - 12 * (e / 12);
+        const int pose = __shfl_sync(0xffffffffu, (int)myrow.x, r);
+        const bool on = e < 12 * pan.n_rows;
+        vP[i] = on ? __ldg(a.poses + 12 * (size_t)pose + k) : 0.0;
+        vN[i] = on && a.eval_cost ? __ldg(a.poses_new + 12 * (size_t)pose + k) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = lane + 32 * i, r = min(e / 6, kPanelRows - 1), k = e - 6 * (e / 6);
+        const int off = __shfl_sync(0xffffffffu, (int)myrow.y, r);
+        vD[i] = e < 6 * pan.n_var ? __ldg(a.dx_red + off + k) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { sP[lane + 32 * i] = vP[i]; sN[lane + 32 * i] = vN[i]; }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (lane + 32 * i < 6 * kPanelRows) sD[lane + 32 * i] = vD[i];
+    }
+    __syncwarp();
     // ---- sum over the rows of W^T dx_c
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
 #pragma unroll
     for (int r = 0; r < kPanelRows; ++r) {
       if (r >= pan.n_var) break;                           // constant poses carry no update (rows: variable poses first)
-      const PanelRow row = dsc->rows[r];                   // warp-uniform
       if (!((present >> r) & 1u)) continue;
       const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[((size_t)pn * kPanelRows + r) * kPanelLm + j]];
       double P[12], dxa[6], M[6], x, y, z;
-      const double* Pg = a.poses + 12 * (size_t)row.pose;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
+      for (int k = 0; k < 12; ++k) P[k] = sP[12 * r + k];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) dxa[k] = __ldg(a.dx_red + row.off + k);
+      for (int k = 0; k < 6; ++k) dxa[k] = sD[6 * r + k];
       reproj_M<kLoss>(grp, P, X, ou[r], ov[r], od[r], M, x, y, z);
       // e = d rho + B d phi,  B = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
       const double e0 = dxa[0] + z * dxa[4] - y * dxa[5];
@@ -568,12 +609,10 @@ __global__ void __launch_bounds__(kFinishThreads, 3) panel_finish_kernel(const P
       for (int r = 0; r < kPanelRows; ++r) {
         if (r >= pan.n_rows) break;
         if (!((present >> r) & 1u)) continue;
-        const PanelRow row = dsc->rows[r];
         const ReprojGroup& grp = kLoss >= 0 ? a.g0 : a.groups[a.pgrp[((size_t)pn * kPanelRows + r) * kPanelLm + j]];
         double P[12], rr[3];
-        const double* Pg = a.poses_new + 12 * (size_t)row.pose;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = __ldg(Pg + k);
+        for (int k = 0; k < 12; ++k) P[k] = sN[12 * r + k];
         reproj_residual_only(grp, P, Xn, ou[r], ov[r], od[r], rr);
 #pragma unroll
         for (int k = 0; k < 3; ++k) cost += loss_rho_t<kLoss>(grp.loss, rr[k]);
