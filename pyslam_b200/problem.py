@@ -25,6 +25,7 @@ Extensions (default to reference behaviour): `Options.device`,
 `Problem.last_timings`.
 """
 import copy
+import gc
 import operator
 import warnings
 
@@ -117,6 +118,21 @@ class _ReprojectionBatch:
         return uniq, np.fromiter(map(index.__getitem__, keys), np.int32, len(keys))
 
 
+class _gc_paused:
+    """Bulk construction of 10^5 small objects (row views, key lists, table entries) with the cyclic collector on makes
+    every generation-2 pass walk all of them again: the lowering of a BASELINE-size problem then takes 0.2 - 0.4 s
+    depending on what else the process holds.  None of the objects built here is cyclic."""
+
+    def __enter__(self):
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        if self.was:
+            gc.enable()
+        return False
+
+
 def _param_dof(p):
     """problem.py:257-266."""
     if hasattr(p, 'dof'):
@@ -197,7 +213,9 @@ class Problem:
         vals = list(param_dict.values())
         if len({id(v) for v in vals}) != len(vals):
             self.param_dict.update(copy.deepcopy(param_dict))
-        else:
+            self._low = None
+            return
+        with _gc_paused():
             nd, f64 = np.ndarray, np.float64
             new = dict.fromkeys(param_dict)         # insertion order is the update-vector order (problem.py:252-277)
             keys3, vals3 = [], []
@@ -253,7 +271,8 @@ class Problem:
         if self._engine is None:      # raises EngineError without the CUDA library / a GPU
             self._engine = _engine.Engine(getattr(self.options, 'device', 0))
         try:
-            return self._lower_impl()
+            with _gc_paused():
+                return self._lower_impl()
         except Exception:
             self._low = None
             raise
